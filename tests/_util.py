@@ -1,0 +1,39 @@
+"""Shared helpers for the parity tests (tolerances are the ones BASELINE.json:north_star states)."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# north_star: "within 1e-5 relative (fp32) or 2e-2 relative (bf16 GEMM variant)".
+# "relative" is taken against the tensor's scale (max |reference|): element-wise relative error is
+# meaningless for gradient entries that are themselves rounding noise around zero.
+RTOL_FP32 = 1e-5
+RTOL_BF16 = 2e-2
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def rel_err(got, ref):
+    got = torch.as_tensor(got).detach().double().cpu().reshape(-1)
+    ref = torch.as_tensor(ref).detach().double().cpu().reshape(-1)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if ref.numel() == 0:
+        return 0.0
+    scale = ref.abs().max().item()
+    if scale == 0.0:
+        scale = 1.0
+    return (got - ref).abs().max().item() / scale
+
+
+def assert_close(got, ref, rtol=RTOL_FP32, what=""):
+    e = rel_err(got, ref)
+    assert e <= rtol, f"{what}: scaled max error {e:.3e} > {rtol:.1e}"
+
+
+def sub(d, prefix):
+    return {k[len(prefix):]: v for k, v in d.items() if k.startswith(prefix)}
