@@ -1,0 +1,207 @@
+/*
+ * b200ppo.h — C ABI of the B200-native PPO hot path (libb200ppo.so).
+ *
+ * Drop-in boundary for aminrezaee/mujoco_reinforcement_learning's PPO update path.  The reference has
+ * no FFI of its own (it is pure Python over torch CPU operators), so every entry point below replaces
+ * a Python call site of the reference; the citation after "replaces:" is that call site, relative to
+ * the reference repository root.  Plain pointers and sizes only — no torch types.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers on the current CUDA device unless the name ends in `_host`.
+ *  - Tensors are dense, row-major, fp32 unless stated; bool tensors are one byte per element (torch.bool).
+ *  - Rollout buffers use the reference layout: env-major, time-minor ([N_envs, T], flat index n*T + t;
+ *    src/entities/algorithms/ppo.py:60,99).
+ *  - `stream` is a cudaStream_t (NULL = legacy default stream).  Calls only enqueue work; they never
+ *    synchronise the device unless documented (`*_host` entry points do).
+ *  - Return value: 0 on success, a negative B200PPO_E* code otherwise; `b200ppo_last_error()` returns a
+ *    thread-local message.  There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef B200PPO_H_
+#define B200PPO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PPO_VERSION 100
+
+#define B200PPO_OK 0
+#define B200PPO_EINVAL (-1)  /* bad argument (shape, alignment, null pointer) */
+#define B200PPO_ECUDA (-2)   /* CUDA runtime error, message in b200ppo_last_error() */
+#define B200PPO_ENOMEM (-3)
+#define B200PPO_ESTATE (-4)  /* call not valid for this context (e.g. batch larger than max_batch) */
+#define B200PPO_ENCCL (-5)
+
+#define B200PPO_MAX_LAYERS 8
+
+#define B200PPO_ACT_TANH 0
+#define B200PPO_ACT_RELU 1
+
+/* GEMM arithmetic of the actor/critic MLP. */
+#define B200PPO_PREC_FP32 0 /* fp32 FFMA everywhere: 1e-5 parity with the reference */
+#define B200PPO_PREC_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate / master weights: 2e-2 */
+
+typedef void* b200ppo_stream; /* cudaStream_t */
+typedef struct b200ppo_ctx b200ppo_ctx;
+
+/* One NetworkBlock: n_layers Linear layers, hidden activation after all but the last.
+ * replaces: src/models/network_block_creator.py:24-86 (no batch-norm / skip / end-normalisation: those
+ * branches are off on the PPO path). */
+typedef struct b200ppo_mlp_desc {
+  int32_t n_layers;                 /* Linear layers including the last one, 1..B200PPO_MAX_LAYERS */
+  int32_t in_dim;                   /* input features (obs_dim * window_length, flattened) */
+  int32_t dims[B200PPO_MAX_LAYERS]; /* output features of each Linear */
+  int32_t activation;               /* B200PPO_ACT_* applied after every hidden Linear */
+  int32_t final_tanh;               /* 1: out = out_scale * tanh(z_last) (linear/actor.py:28); 0: out = z_last */
+  float out_scale;                  /* network_config.output_max_value */
+} b200ppo_mlp_desc;
+
+/* Hyper-parameters read by the update step (src/main.py:41-54, src/entities/algorithms/ppo.py:95-137). */
+typedef struct b200ppo_hparams {
+  double learning_rate_actor;
+  double learning_rate_critic;
+  double beta1, beta2, adam_eps; /* torch.optim.Adam defaults 0.9, 0.999, 1e-8 (ppo_agent.py:15-18) */
+  double clip_epsilon;           /* ppo_config.clip_epsilon */
+  double entropy_eps;            /* ppo_config.entropy_eps */
+} b200ppo_hparams;
+
+int b200ppo_version(void);
+const char* b200ppo_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1 — advantage pipeline.
+ * replaces: PPO.calculate_advantages, src/entities/algorithms/ppo.py:62-91, and the torchrl call inside
+ *           it (torchrl 0.6.0 generalized_advantage_estimate, call site ppo.py:76-80).
+ *   reward        [N,T] fp32, or fp64 when reward_is_f64 (real rollouts: ppo.py:42-43)
+ *   value, next_value [N,T] fp32
+ *   terminated    [N,T] bool bytes
+ *   done          [N,T] bool bytes, or NULL = "terminated with the last step forced to 1" (ppo.py:70-72)
+ *   normalize_rewards / normalize_advantage: per-env over time, unbiased std, no epsilon, times
+ *   advantage_scaler (ppo.py:66-69, 81-88); normalize_advantage normalises BOTH outputs.
+ *   advantage, value_target [N,T] fp32 out.
+ */
+int b200ppo_gae(const void* reward, int reward_is_f64, const float* value, const float* next_value,
+                const uint8_t* terminated, const uint8_t* done, int64_t n_envs, int64_t n_steps, double gamma,
+                double lmbda, int normalize_rewards, int normalize_advantage, double advantage_scaler,
+                float* advantage, float* value_target, b200ppo_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2 — minibatch permutation gather.
+ * replaces: `shuffled_memory = memory[idx]` + the minibatch slice, ppo.py:103-106 (tensordict index).
+ * Gathers `count` rows idx[0..count) of the five leaves the update reads.  Bit-exact copies.
+ * idx is int64 (torch.randperm), values in [-n_rows, n_rows); out-of-range indices set *err_flag (device
+ * int32, may be NULL) to 1 and copy nothing for that row.
+ */
+int b200ppo_gather_minibatch(const int64_t* idx, int64_t count, int64_t n_rows, const float* obs, int64_t obs_dim,
+                             const float* action, int64_t act_dim, const float* logp, const float* advantage,
+                             const float* target, float* obs_out, float* action_out, float* logp_out,
+                             float* advantage_out, float* target_out, int32_t* err_flag, b200ppo_stream stream);
+
+/* Generic leaf gather: dst[i, :] = src[idx[i], :] for rows of row_bytes bytes (any dtype). */
+int b200ppo_gather_rows(const void* src, int64_t row_bytes, int64_t n_rows, const int64_t* idx, int64_t count,
+                        void* dst, int32_t* err_flag, b200ppo_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5 — Adam.
+ * replaces: torch.optim.Adam.step (single-tensor path) at ppo.py:122,135; built at ppo_agent.py:15-18.
+ * One segment of n contiguous fp32 parameters.  `step` is the 1-based step count of THIS update.
+ * grads may hold n_partials partial sums laid out [n_partials][partial_stride]; they are summed in
+ * index order before the update (n_partials = 1 for a plain gradient).
+ */
+int b200ppo_adam_step(float* params, const float* grads, int32_t n_partials, int64_t partial_stride,
+                      float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,
+                      double eps, int64_t step, b200ppo_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Actor-critic context: owns activations / gradient workspaces for batches up to max_batch.
+ * Parameter layout (one flat fp32 buffer owned by the caller):
+ *   actor:  for each layer l: W_l [dims[l], in_l] row-major (nn.Linear.weight), then b_l [dims[l]]
+ *           then actor_logstd [act_dim]
+ *   critic: same per-layer layout, appended after the actor segment.
+ * b200ppo_param_count / b200ppo_param_offset describe it (offsets in elements).
+ */
+int b200ppo_create(const b200ppo_mlp_desc* actor, const b200ppo_mlp_desc* critic, int64_t max_batch,
+                   int32_t precision, b200ppo_ctx** out);
+void b200ppo_destroy(b200ppo_ctx* ctx);
+int64_t b200ppo_param_count(const b200ppo_ctx* ctx);
+int64_t b200ppo_actor_param_count(const b200ppo_ctx* ctx); /* includes logstd; critic segment starts here */
+/* net: 0 actor, 1 critic; layer in [0,n_layers); what: 0 weight, 1 bias; (net 0, layer n_layers, what 0) = logstd */
+int64_t b200ppo_param_offset(const b200ppo_ctx* ctx, int32_t net, int32_t layer, int32_t what);
+
+/* K3 forward only.  replaces: Actor.forward (src/models/linear/actor.py:25-30) and Critic.forward
+ * (src/models/critic.py:22-25).  net: 0 actor → out [B, act_dim] = mean; 1 critic → out [B,1].
+ * saved (nullable) receives the hidden activations [sum(hidden dims)][B] needed by b200ppo_mlp_backward,
+ * layer after layer, each [B, dims[l]] row-major; size b200ppo_saved_size(ctx, net, B) floats. */
+int64_t b200ppo_saved_size(const b200ppo_ctx* ctx, int32_t net, int64_t batch);
+int b200ppo_mlp_forward(b200ppo_ctx* ctx, int32_t net, const float* params, const float* x, int64_t batch,
+                        float* out, float* saved, b200ppo_stream stream);
+/* K4 for the autograd façade: given dL/dout [B, out_dim] returns dL/dparams for that net (same layout as
+ * its parameter segment, logstd slot untouched) and optionally dL/dx (nullable). */
+int b200ppo_mlp_backward(b200ppo_ctx* ctx, int32_t net, const float* params, const float* x, const float* out,
+                         const float* saved, const float* grad_out, int64_t batch, float* grad_params,
+                         float* grad_x, b200ppo_stream stream);
+
+/* K6 — rollout inference.  replaces: ppo.py:22-26 (critic(s), actor(s), Normal.sample, log_prob.sum).
+ * noise (nullable) is the standard-normal draw [B, act_dim]: action = mean + exp(logstd) * noise; NULL →
+ * action = mean (test_phase, agent.py:36-38).  Any of mean/value/action/logp may be NULL. */
+int b200ppo_policy_infer(b200ppo_ctx* ctx, const float* params, const float* obs, int64_t batch,
+                         const float* noise, float* mean, float* value, float* action, float* logp,
+                         b200ppo_stream stream);
+
+/* "evaluate": ppo.py:109-115,125 — new log-prob [B], value [B], entropy (device scalar) for given actions. */
+int b200ppo_evaluate(b200ppo_ctx* ctx, const float* params, const float* obs, const float* action, int64_t batch,
+                     float* logp, float* value, float* entropy, b200ppo_stream stream);
+
+/* K3+K4 — losses and gradients of one minibatch, no optimiser step.
+ * replaces: ppo.py:109-134 minus the two optimizer.step() calls.
+ * grads [param_count] receives dL_actor/dθ_actor and dL_critic/dθ_critic; losses[0] = actor loss,
+ * losses[1] = critic loss (device). */
+int b200ppo_minibatch_grads(b200ppo_ctx* ctx, const float* params, const float* obs, const float* action,
+                            const float* old_logp, const float* advantage, const float* target, int64_t batch,
+                            const b200ppo_hparams* hp, float* grads, float* losses, b200ppo_stream stream);
+
+/* The trainer's update step.  replaces: PPO.train, ppo.py:93-154 (epochs × minibatches of
+ * gather → forward → losses → backward → two Adam steps), with the permutations supplied
+ * (`torch.randperm` stays the caller's, ppo.py:103, so indices are bit-exact).
+ *   obs [M,obs_dim] action [M,act_dim] old_logp/advantage/target [M]   — the flattened rollout
+ *   perms [epochs][M] int64
+ *   batch = training_config.batch_size; minibatches per epoch = floor(M / batch), the tail is dropped
+ *   (ppo.py:97-98,107-108); max_minibatches_per_epoch > 0 truncates an epoch (bounded benchmarking).
+ *   adam_step_io (host): Adam step count before the call; updated to the count after it.
+ *   losses_out (device, nullable) [epochs * minibatches][2] = (actor_loss, critic_loss) per minibatch.
+ */
+int b200ppo_train(b200ppo_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq, int64_t* adam_step_io,
+                  const float* obs, const float* action, const float* old_logp, const float* advantage,
+                  const float* target, int64_t n_samples, const int64_t* perms, int32_t epochs, int64_t batch,
+                  int64_t max_minibatches_per_epoch, const b200ppo_hparams* hp, float* losses_out,
+                  b200ppo_stream stream);
+
+/* End-to-end entry point with HOST buffers (pinned or pageable): advantage pipeline + PPO.train for one
+ * rollout.  Copies the rollout host→device, runs b200ppo_gae + b200ppo_train, copies the per-minibatch
+ * losses back and synchronises `stream`.  Parameters and Adam state stay on the device.
+ * replaces: PPO._iterate minus rollout, ppo.py:158-159. */
+int b200ppo_update_host(b200ppo_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq, int64_t* adam_step_io,
+                        const float* obs_host, const float* action_host, const float* old_logp_host,
+                        const float* reward_host, const float* value_host, const float* next_value_host,
+                        const uint8_t* terminated_host, int64_t n_envs, int64_t n_steps, double gamma, double lmbda,
+                        int normalize_rewards, int normalize_advantage, double advantage_scaler,
+                        const int64_t* perms_host, int32_t epochs, int64_t batch,
+                        int64_t max_minibatches_per_epoch, const b200ppo_hparams* hp, float* losses_host,
+                        b200ppo_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU).  The update is data-parallel over samples: every rank computes the
+ * gradient of its slice of each minibatch, gradients are summed over ranks (NCCL all-reduce over
+ * NVLink), every rank applies the same Adam step.  Loss means use the GLOBAL minibatch size.
+ * unique_id: the 128-byte ncclUniqueId from b200ppo_comm_unique_id on rank 0, distributed by the caller.
+ */
+int b200ppo_comm_unique_id(uint8_t id_out[128]);
+int b200ppo_comm_init(b200ppo_ctx* ctx, const uint8_t unique_id[128], int32_t rank, int32_t world_size);
+int b200ppo_comm_world(const b200ppo_ctx* ctx, int32_t* rank, int32_t* world_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PPO_H_ */

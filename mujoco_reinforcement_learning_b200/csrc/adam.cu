@@ -1,0 +1,127 @@
+// K5 — fused Adam (one launch for every parameter of actor and critic).
+//
+// replaces: torch.optim.Adam.step(), single-tensor CPU path (`_single_tensor_adam`, no amsgrad, no weight
+//           decay), called at src/entities/algorithms/ppo.py:122,135 for the optimisers built at
+//           src/entities/agents/ppo_agent.py:15-18.
+//
+// The reduction of the split-K weight-gradient partials is fused into the optimiser: the kernel sums
+// `n_partials` partial gradients in index order (deterministic), then applies the reference's update
+//   m = m + (1-b1)(g - m);  v = v*b2 + (1-b2)*g*g;  p += -(lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+// with the scalar factors computed in double on the host exactly as the Python code does.
+// Algorithmic bytes: 28 per parameter (read p,g,m,v; write p,m,v) when n_partials == 1.
+#include <math.h>
+
+#include "adam.cuh"
+
+namespace b200ppo {
+
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamScalars& s) {
+  m = __fadd_rn(m, __fmul_rn(s.one_minus_b1, __fsub_rn(g, m)));               // exp_avg.lerp_(grad, 1-beta1)
+  v = __fadd_rn(__fmul_rn(v, s.b2), __fmul_rn(__fmul_rn(s.one_minus_b2, g), g));  // mul_(b2).addcmul_(g,g,1-b2)
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s.bc2_sqrt), s.eps);
+  p = __fadd_rn(p, __fmul_rn(s.neg_step_size, __fdiv_rn(m, denom)));          // addcdiv_(m, denom, -step_size)
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ params, const float* __restrict__ grads, int n_partials, int64_t partial_stride,
+            float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t n, int64_t seg_split,
+            AdamScalars s0, AdamScalars s1, float* __restrict__ grad_out) {
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = tid; i < n4; i += nthreads) {
+    float4 g = *reinterpret_cast<const float4*>(grads + 4 * i);
+    for (int k = 1; k < n_partials; ++k) {
+      const float4 h = *reinterpret_cast<const float4*>(grads + k * partial_stride + 4 * i);
+      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+    }
+    float4 p = *reinterpret_cast<float4*>(params + 4 * i);
+    float4 m = *reinterpret_cast<float4*>(exp_avg + 4 * i);
+    float4 v = *reinterpret_cast<float4*>(exp_avg_sq + 4 * i);
+    const int64_t e = 4 * i;
+    adam_update(p.x, g.x, m.x, v.x, e + 0 < seg_split ? s0 : s1);
+    adam_update(p.y, g.y, m.y, v.y, e + 1 < seg_split ? s0 : s1);
+    adam_update(p.z, g.z, m.z, v.z, e + 2 < seg_split ? s0 : s1);
+    adam_update(p.w, g.w, m.w, v.w, e + 3 < seg_split ? s0 : s1);
+    *reinterpret_cast<float4*>(params + 4 * i) = p;
+    *reinterpret_cast<float4*>(exp_avg + 4 * i) = m;
+    *reinterpret_cast<float4*>(exp_avg_sq + 4 * i) = v;
+    if (grad_out != nullptr) *reinterpret_cast<float4*>(grad_out + 4 * i) = g;
+  }
+  for (int64_t e = 4 * n4 + tid; e < n; e += nthreads) {  // tail (n % 4)
+    float g = grads[e];
+    for (int k = 1; k < n_partials; ++k) g += grads[k * partial_stride + e];
+    float p = params[e], m = exp_avg[e], v = exp_avg_sq[e];
+    adam_update(p, g, m, v, e < seg_split ? s0 : s1);
+    params[e] = p; exp_avg[e] = m; exp_avg_sq[e] = v;
+    if (grad_out != nullptr) grad_out[e] = g;
+  }
+}
+
+// Sum partials only (used before the NCCL all-reduce and by the grads-only entry point).
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ grads, int n_partials, int64_t partial_stride, int64_t n,
+                       float* __restrict__ out) {
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t e = tid; e < n; e += nthreads) {
+    float g = grads[e];
+    for (int k = 1; k < n_partials; ++k) g += grads[k * partial_stride + e];
+    out[e] = g;
+  }
+}
+
+AdamScalars make_adam_scalars(double lr, double beta1, double beta2, double eps, int64_t step) {
+  AdamScalars s;
+  const double bc1 = 1.0 - pow(beta1, double(step));
+  const double bc2 = 1.0 - pow(beta2, double(step));
+  s.one_minus_b1 = float(1.0 - beta1);
+  s.b2 = float(beta2);
+  s.one_minus_b2 = float(1.0 - beta2);
+  s.bc2_sqrt = float(sqrt(bc2));
+  s.eps = float(eps);
+  s.neg_step_size = float(-(lr / bc1));
+  return s;
+}
+
+static inline unsigned ew_grid(int64_t work_items) {
+  int64_t blocks = (work_items + 255) / 256;
+  const int64_t cap = int64_t(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  return unsigned(blocks < 1 ? 1 : blocks);
+}
+
+int launch_adam(float* params, const float* grads, int n_partials, int64_t partial_stride, float* exp_avg,
+                float* exp_avg_sq, int64_t n, int64_t seg_split, const AdamScalars& s0, const AdamScalars& s1,
+                float* grad_out, cudaStream_t st) {
+  if (n == 0) return B200PPO_OK;
+  adam_kernel<<<ew_grid((n + 3) / 4), 256, 0, st>>>(params, grads, n_partials, partial_stride, exp_avg, exp_avg_sq, n,
+                                                    seg_split, s0, s1, grad_out);
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
+
+int launch_reduce_partials(const float* grads, int n_partials, int64_t partial_stride, int64_t n, float* out,
+                           cudaStream_t st) {
+  if (n == 0) return B200PPO_OK;
+  reduce_partials_kernel<<<ew_grid(n), 256, 0, st>>>(grads, n_partials, partial_stride, n, out);
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
+
+}  // namespace b200ppo
+
+using namespace b200ppo;
+
+extern "C" B2_EXPORT int b200ppo_adam_step(float* params, const float* grads, int32_t n_partials, int64_t partial_stride,
+                                 float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,
+                                 double eps, int64_t step, b200ppo_stream stream) {
+  B2_CHECK_ARG(params && grads && exp_avg && exp_avg_sq, "b200ppo_adam_step: null pointer");
+  B2_CHECK_ARG(n >= 0 && n_partials >= 1 && step >= 1, "b200ppo_adam_step: bad n/n_partials/step");
+  B2_CHECK_ARG(aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq) &&
+                   (n_partials == 1 || partial_stride % 4 == 0),
+               "b200ppo_adam_step: buffers must be 16-byte aligned");
+  const AdamScalars s = make_adam_scalars(lr, beta1, beta2, eps, step);
+  return launch_adam(params, grads, n_partials, partial_stride, exp_avg, exp_avg_sq, n, n, s, s, nullptr,
+                     static_cast<cudaStream_t>(stream));
+}

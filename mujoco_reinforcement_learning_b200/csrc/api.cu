@@ -1,0 +1,671 @@
+// C-ABI entry points and host-side orchestration of the actor-critic update (see include/b200ppo.h).
+//
+// replaces: the Python control flow of PPO.train (src/entities/algorithms/ppo.py:93-154) and the
+//           per-call glue of Actor/Critic.forward (src/models/linear/actor.py:25-30, src/models/critic.py:22-25).
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "adam.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ppo_loss.cuh"
+
+namespace b200ppo {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+constexpr int64_t kParamAlign = 32;  // every parameter tensor starts on a 128-byte boundary of the flat buffer
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct Net {
+  b200ppo_mlp_desc d;
+  int64_t w_off[B200PPO_MAX_LAYERS], b_off[B200PPO_MAX_LAYERS];
+  int64_t seg_begin, seg_end;  // [begin, end) in the flat buffer (actor: includes logstd)
+  int64_t hidden_sum;          // sum of hidden widths
+  int in_dim(int l) const { return l == 0 ? d.in_dim : d.dims[l - 1]; }
+  int out_dim() const { return d.dims[d.n_layers - 1]; }
+  int64_t act_off(int l, int64_t B) const {  // hidden activation l (l < n_layers-1) inside an acts buffer
+    int64_t s = 0;
+    for (int i = 0; i < l; ++i) s += d.dims[i];
+    return s * B;
+  }
+  int64_t dz_off(int l, int64_t B) const { return act_off(l, B); }  // dZ buffer also holds the last layer
+};
+
+// NCCL is resolved at run time from the library torch already loaded (no link-time dependency).
+struct NcclApi {
+  struct Id128 { char b[128]; };  // ncclUniqueId, passed by value
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.AllReduce) return B200PPO_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    set_error("NCCL not found: %s", dlerror());
+    return B200PPO_ENCCL;
+  }
+  g_nccl.handle = h;
+  *(void**)(&g_nccl.GetUniqueId) = dlsym(h, "ncclGetUniqueId");
+  *(void**)(&g_nccl.CommInitRank) = dlsym(h, "ncclCommInitRank");
+  *(void**)(&g_nccl.AllReduce) = dlsym(h, "ncclAllReduce");
+  *(void**)(&g_nccl.CommDestroy) = dlsym(h, "ncclCommDestroy");
+  *(void**)(&g_nccl.GetErrorString) = dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+    set_error("NCCL symbols missing");
+    return B200PPO_ENCCL;
+  }
+  return B200PPO_OK;
+}
+
+}  // namespace b200ppo
+
+using namespace b200ppo;
+
+struct b200ppo_ctx {
+  Net net[2];
+  int64_t logstd_off = 0, n_params = 0, n_actor = 0;
+  int64_t max_batch = 0;
+  int precision = 0;
+  int max_split = 1;
+  float* ws_act[2] = {nullptr, nullptr};
+  float* ws_dz[2] = {nullptr, nullptr};
+  float* ws_out[2] = {nullptr, nullptr};
+  float* gpart = nullptr;       // [max_split][n_params]
+  float* grad_flat = nullptr;   // [n_params + 4]: summed gradient + (actor_loss, critic_loss) for the all-reduce
+  float* loss_partials = nullptr;
+  unsigned* ticket = nullptr;
+  float* scratch = nullptr;     // [8] losses / entropy scratch
+  int32_t* err_flag = nullptr;
+  // shuffled-epoch buffers (train)
+  float *sh_obs = nullptr, *sh_act = nullptr, *sh_logp = nullptr, *sh_adv = nullptr, *sh_tgt = nullptr;
+  int64_t sh_cap = 0;
+  // device staging of the host entry point
+  struct {
+    float *obs = nullptr, *act = nullptr, *logp = nullptr, *rew = nullptr, *val = nullptr, *nval = nullptr;
+    float *adv = nullptr, *tgt = nullptr, *losses = nullptr;
+    uint8_t* term = nullptr;
+    int64_t* perms = nullptr;
+    int64_t rows = 0, perm_elems = 0, loss_elems = 0;
+  } host;
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+namespace b200ppo {
+
+static int layout_net(Net& n, const b200ppo_mlp_desc* d, int64_t& cursor) {
+  B2_CHECK_ARG(d->n_layers >= 1 && d->n_layers <= B200PPO_MAX_LAYERS, "n_layers %d out of range", d->n_layers);
+  B2_CHECK_ARG(d->in_dim > 0, "in_dim must be positive");
+  B2_CHECK_ARG(d->activation == B200PPO_ACT_TANH || d->activation == B200PPO_ACT_RELU, "unknown activation %d", d->activation);
+  n.d = *d;
+  n.seg_begin = cursor;
+  n.hidden_sum = 0;
+  for (int l = 0; l < d->n_layers; ++l) {
+    B2_CHECK_ARG(d->dims[l] > 0, "layer %d has non-positive width", l);
+    n.w_off[l] = cursor;
+    cursor = align_up(cursor + int64_t(d->dims[l]) * n.in_dim(l), kParamAlign);
+    n.b_off[l] = cursor;
+    cursor = align_up(cursor + d->dims[l], kParamAlign);
+    if (l < d->n_layers - 1) n.hidden_sum += d->dims[l];
+  }
+  n.seg_end = cursor;
+  return B200PPO_OK;
+}
+
+template <typename T>
+static int dev_alloc(T** p, int64_t elems, bool zero = false) {
+  *p = nullptr;
+  if (elems <= 0) elems = 1;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), size_t(elems) * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%lld bytes) failed: %s", (long long)(elems * sizeof(T)), cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? B200PPO_ENOMEM : B200PPO_ECUDA;
+  }
+  if (zero) B2_CUDA(cudaMemset(*p, 0, size_t(elems) * sizeof(T)));
+  return B200PPO_OK;
+}
+
+template <typename T>
+static void dev_free(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+__global__ void tanh_scale_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, float scale,
+                                      int64_t n, float* __restrict__ dz) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float th = out[i] / scale;
+    dz[i] = grad_out[i] * scale * (1.f - th * th);
+  }
+}
+
+__global__ void copy2_kernel(const float* __restrict__ src, float* __restrict__ dst) {
+  if (threadIdx.x < 2) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+// ---- forward -----------------------------------------------------------------------------------------
+// nets: bit 0 actor, bit 1 critic.  acts[n]: hidden activations (dense for `B` rows); outs[n]: [B, out_dim].
+static int forward_nets(const b200ppo_ctx* ctx, const float* params, const float* x, int64_t B, int nets,
+                        float* const acts[2], float* const outs[2], cudaStream_t st) {
+  int maxL = 0;
+  for (int n = 0; n < 2; ++n)
+    if (nets & (1 << n)) maxL = std::max(maxL, ctx->net[n].d.n_layers);
+  for (int l = 0; l < maxL; ++l) {
+    GemmGroup g{};
+    int64_t large_tiles = 0;
+    GemmProblem probs[2];
+    int np = 0;
+    for (int n = 0; n < 2; ++n) {
+      const Net& N = ctx->net[n];
+      if (!(nets & (1 << n)) || l >= N.d.n_layers) continue;
+      const bool last = (l == N.d.n_layers - 1);
+      GemmProblem p{};
+      p.A = (l == 0) ? x : acts[n] + N.act_off(l - 1, B);
+      p.a_sm = N.in_dim(l); p.a_sk = 1;
+      p.B = params + N.w_off[l];
+      p.b_sn = N.in_dim(l); p.b_sk = 1;
+      p.bias = params + N.b_off[l];
+      p.C = last ? outs[n] : acts[n] + N.act_off(l, B);
+      p.ldc = N.d.dims[l];
+      p.M = int(B); p.N = N.d.dims[l]; p.K = N.in_dim(l);
+      p.out_scale = N.d.out_scale;
+      if (last) p.epilogue = N.d.final_tanh ? EPI_BIAS_TANH_SCALE : EPI_BIAS;
+      else p.epilogue = N.d.activation == B200PPO_ACT_TANH ? EPI_BIAS_TANH : EPI_BIAS_RELU;
+      large_tiles += int64_t((p.M + 127) / 128) * ((p.N + 127) / 128);
+      if (p.N < 96) large_tiles = -(1ll << 40);
+      probs[np++] = p;
+    }
+    const bool large = large_tiles >= (2 * num_sms()) / 3;
+    for (int i = 0; i < np; ++i) gemm_group_add(g, probs[i], large ? 128 : 64, large ? 128 : 64, 1);
+    B2_TRY(launch_gemm_group(g, large, st));
+  }
+  return B200PPO_OK;
+}
+
+static int pick_split(const b200ppo_ctx* ctx, int64_t tiles, int64_t K) {
+  if (tiles <= 0) return 1;
+  int64_t s = (4ll * num_sms() + tiles - 1) / tiles;
+  s = std::min<int64_t>(s, std::max<int64_t>(1, K / 64));
+  s = std::min<int64_t>(s, ctx->max_split);
+  return int(std::max<int64_t>(1, s));
+}
+
+// ---- backward ----------------------------------------------------------------------------------------
+// dz[n] holds dL/dz of every layer; the last layer's block must be filled on entry.  Weight / bias gradients go
+// to gpart as `*split_out` split-K partials laid out like the parameter buffer.  grad_x[n] (nullable): dL/dx.
+static int backward_nets(const b200ppo_ctx* ctx, const float* params, const float* x, int64_t B, int nets,
+                         float* const acts[2], float* const dz[2], float* gpart, int* split_out,
+                         float* const grad_x[2], cudaStream_t st) {
+  int maxL = 0;
+  for (int n = 0; n < 2; ++n)
+    if (nets & (1 << n)) maxL = std::max(maxL, ctx->net[n].d.n_layers);
+  // dgrad chain, grouped by distance from the output
+  for (int s = 0; s < maxL; ++s) {
+    GemmProblem probs[2];
+    int np = 0;
+    int64_t large_tiles = 0;
+    for (int n = 0; n < 2; ++n) {
+      const Net& N = ctx->net[n];
+      if (!(nets & (1 << n))) continue;
+      const int l = N.d.n_layers - 1 - s;
+      if (l < 0) continue;
+      if (l == 0 && (grad_x == nullptr || grad_x[n] == nullptr)) continue;
+      GemmProblem p{};
+      p.A = dz[n] + N.dz_off(l, B);
+      p.a_sm = N.d.dims[l]; p.a_sk = 1;
+      p.B = params + N.w_off[l];
+      p.b_sn = 1; p.b_sk = N.in_dim(l);
+      p.M = int(B); p.N = N.in_dim(l); p.K = N.d.dims[l];
+      p.ldc = N.in_dim(l);
+      if (l == 0) {
+        p.C = grad_x[n];
+        p.epilogue = EPI_STORE;
+      } else {
+        p.C = dz[n] + N.dz_off(l - 1, B);
+        p.aux = acts[n] + N.act_off(l - 1, B);
+        p.ld_aux = N.d.dims[l - 1];
+        p.epilogue = N.d.activation == B200PPO_ACT_TANH ? EPI_DTANH : EPI_DRELU;
+      }
+      large_tiles += int64_t((p.M + 127) / 128) * ((p.N + 127) / 128);
+      if (p.N < 96) large_tiles = -(1ll << 40);
+      probs[np++] = p;
+    }
+    if (np == 0) continue;
+    const bool large = large_tiles >= (2 * num_sms()) / 3;
+    GemmGroup g{};
+    for (int i = 0; i < np; ++i) gemm_group_add(g, probs[i], large ? 128 : 64, large ? 128 : 64, 1);
+    B2_TRY(launch_gemm_group(g, large, st));
+  }
+  // every weight / bias gradient in one grouped split-K launch
+  if (gpart != nullptr) {
+    GemmProblem probs[kMaxGemmProblems];
+    int np = 0;
+    int64_t tiles = 0;
+    for (int n = 0; n < 2; ++n) {
+      const Net& N = ctx->net[n];
+      if (!(nets & (1 << n))) continue;
+      for (int l = 0; l < N.d.n_layers; ++l) {
+        GemmProblem p{};
+        p.A = dz[n] + N.dz_off(l, B);
+        p.a_sm = 1; p.a_sk = N.d.dims[l];
+        p.B = (l == 0) ? x : acts[n] + N.act_off(l - 1, B);
+        p.b_sn = 1; p.b_sk = N.in_dim(l);
+        p.M = N.d.dims[l]; p.N = N.in_dim(l); p.K = int(B);
+        p.C = gpart + N.w_off[l];
+        p.ldc = N.in_dim(l);
+        p.bias_grad = gpart + N.b_off[l];
+        p.c_split_stride = ctx->n_params;
+        p.epilogue = EPI_STORE;
+        tiles += int64_t((p.M + 63) / 64) * ((p.N + 63) / 64);
+        probs[np++] = p;
+      }
+    }
+    const int split = pick_split(ctx, tiles, B);
+    GemmGroup g{};
+    for (int i = 0; i < np; ++i) gemm_group_add(g, probs[i], 64, 64, split);
+    B2_TRY(launch_gemm_group(g, false, st));
+    if (split_out) *split_out = split;
+  }
+  return B200PPO_OK;
+}
+
+static int check_batch(const b200ppo_ctx* ctx, int64_t B, const char* who) {
+  if (ctx == nullptr) {
+    set_error("%s: null context", who);
+    return B200PPO_EINVAL;
+  }
+  if (B < 0 || B > ctx->max_batch) {
+    set_error("%s: batch %lld exceeds the context's max_batch %lld", who, (long long)B, (long long)ctx->max_batch);
+    return B200PPO_ESTATE;
+  }
+  return B200PPO_OK;
+}
+
+// forward + losses + backward of one minibatch; gradients left as split-K partials in ctx->gpart.
+static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float* obs, const float* action,
+                             const float* old_logp, const float* adv, const float* tgt, int64_t B,
+                             const b200ppo_hparams* hp, float* losses_dev, int* split_out, cudaStream_t st) {
+  float* acts[2] = {ctx->ws_act[0], ctx->ws_act[1]};
+  float* outs[2] = {ctx->ws_out[0], ctx->ws_out[1]};
+  float* dz[2] = {ctx->ws_dz[0], ctx->ws_dz[1]};
+  B2_TRY(forward_nets(ctx, params, obs, B, 3, acts, outs, st));
+  const Net& Na = ctx->net[0];
+  const Net& Nc = ctx->net[1];
+  LossArgs la{};
+  la.mean = outs[0]; la.logstd = params + ctx->logstd_off; la.action = action; la.old_logp = old_logp;
+  la.advantage = adv; la.value = outs[1]; la.target = tgt; la.batch = B; la.act_dim = Na.out_dim();
+  la.final_tanh = Na.d.final_tanh; la.out_scale = Na.d.out_scale;
+  la.clip_eps = float(hp->clip_epsilon); la.ent_coef = float(hp->entropy_eps);
+  la.inv_global_batch = 1.f / float(B * ctx->world);
+  la.rank_share = 1.f / float(ctx->world);
+  la.dz_actor = dz[0] + Na.dz_off(Na.d.n_layers - 1, B);
+  la.dv = dz[1] + Nc.dz_off(Nc.d.n_layers - 1, B);
+  la.partials = ctx->loss_partials; la.ticket = ctx->ticket;
+  la.losses = losses_dev; la.logstd_grad = ctx->gpart + ctx->logstd_off;
+  B2_TRY(launch_ppo_loss(la, st));
+  B2_TRY(backward_nets(ctx, params, obs, B, 3, acts, dz, ctx->gpart, split_out, nullptr, st));
+  return B200PPO_OK;
+}
+
+static int ensure_shuffle_capacity(b200ppo_ctx* ctx, int64_t rows) {
+  if (rows <= ctx->sh_cap) return B200PPO_OK;
+  B2_CUDA(cudaDeviceSynchronize());
+  dev_free(ctx->sh_obs); dev_free(ctx->sh_act); dev_free(ctx->sh_logp); dev_free(ctx->sh_adv); dev_free(ctx->sh_tgt);
+  ctx->sh_cap = 0;
+  const int D = ctx->net[0].d.in_dim, A = ctx->net[0].out_dim();
+  B2_TRY(dev_alloc(&ctx->sh_obs, rows * D));
+  B2_TRY(dev_alloc(&ctx->sh_act, rows * A));
+  B2_TRY(dev_alloc(&ctx->sh_logp, rows));
+  B2_TRY(dev_alloc(&ctx->sh_adv, rows));
+  B2_TRY(dev_alloc(&ctx->sh_tgt, rows));
+  ctx->sh_cap = rows;
+  return B200PPO_OK;
+}
+
+int launch_gather_chunked(const int64_t* idx, int64_t count, int64_t n_rows, int64_t chunk, int64_t chunk_stride,
+                          int64_t chunk_offset, const float* obs, int obs_dim, const float* act, int act_dim,
+                          const float* logp, const float* adv, const float* tgt, float* obs_o, float* act_o,
+                          float* logp_o, float* adv_o, float* tgt_o, int32_t* err_flag, cudaStream_t st);
+
+}  // namespace b200ppo
+
+// =========================================================================================================
+extern "C" B2_EXPORT int b200ppo_version(void) { return B200PPO_VERSION; }
+extern "C" B2_EXPORT const char* b200ppo_last_error(void) { return g_err; }
+
+extern "C" B2_EXPORT int b200ppo_create(const b200ppo_mlp_desc* actor, const b200ppo_mlp_desc* critic, int64_t max_batch,
+                              int32_t precision, b200ppo_ctx** out) {
+  B2_CHECK_ARG(actor && critic && out, "b200ppo_create: null pointer");
+  B2_CHECK_ARG(max_batch > 0 && max_batch < (1ll << 30), "b200ppo_create: bad max_batch");
+  B2_CHECK_ARG(precision == B200PPO_PREC_FP32 || precision == B200PPO_PREC_BF16, "b200ppo_create: bad precision");
+  B2_CHECK_ARG(actor->in_dim == critic->in_dim, "actor and critic must read the same observation");
+  B2_CHECK_ARG(critic->dims[critic->n_layers > 0 ? critic->n_layers - 1 : 0] == 1, "critic output width must be 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("b200ppo_create: no CUDA device (this library has no CPU fallback)");
+    return B200PPO_ECUDA;
+  }
+  b200ppo_ctx* c = new b200ppo_ctx();
+  int64_t cursor = 0;
+  int r = layout_net(c->net[0], actor, cursor);
+  if (r == B200PPO_OK) {
+    c->logstd_off = cursor;
+    cursor = align_up(cursor + c->net[0].out_dim(), kParamAlign);
+    c->net[0].seg_end = cursor;
+    c->n_actor = cursor;
+    r = layout_net(c->net[1], critic, cursor);
+  }
+  if (r != B200PPO_OK) { delete c; return r; }
+  c->n_params = cursor;
+  c->max_batch = max_batch;
+  c->precision = precision;
+  c->max_split = 32;
+  const int64_t Bm = max_batch;
+  for (int n = 0; n < 2 && r == B200PPO_OK; ++n) {
+    const Net& N = c->net[n];
+    r = dev_alloc(&c->ws_act[n], Bm * N.hidden_sum);
+    if (r == B200PPO_OK) r = dev_alloc(&c->ws_dz[n], Bm * (N.hidden_sum + N.out_dim()));
+    if (r == B200PPO_OK) r = dev_alloc(&c->ws_out[n], Bm * N.out_dim());
+  }
+  if (r == B200PPO_OK) r = dev_alloc(&c->gpart, int64_t(c->max_split) * c->n_params, true);
+  if (r == B200PPO_OK) r = dev_alloc(&c->grad_flat, c->n_params + 4, true);
+  if (r == B200PPO_OK) r = dev_alloc(&c->loss_partials, int64_t(loss_grid_size(Bm)) * (2 + c->net[0].out_dim()));
+  if (r == B200PPO_OK) r = dev_alloc(&c->ticket, 1, true);
+  if (r == B200PPO_OK) r = dev_alloc(&c->scratch, 8, true);
+  if (r == B200PPO_OK) r = dev_alloc(&c->err_flag, 1, true);
+  if (r != B200PPO_OK) { b200ppo_destroy(c); return r; }
+  *out = c;
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
+  if (!c) return;
+  cudaDeviceSynchronize();
+  for (int n = 0; n < 2; ++n) { dev_free(c->ws_act[n]); dev_free(c->ws_dz[n]); dev_free(c->ws_out[n]); }
+  dev_free(c->gpart); dev_free(c->grad_flat); dev_free(c->loss_partials); dev_free(c->ticket); dev_free(c->scratch);
+  dev_free(c->err_flag);
+  dev_free(c->sh_obs); dev_free(c->sh_act); dev_free(c->sh_logp); dev_free(c->sh_adv); dev_free(c->sh_tgt);
+  dev_free(c->host.obs); dev_free(c->host.act); dev_free(c->host.logp); dev_free(c->host.rew); dev_free(c->host.val);
+  dev_free(c->host.nval); dev_free(c->host.adv); dev_free(c->host.tgt); dev_free(c->host.losses); dev_free(c->host.term);
+  dev_free(c->host.perms);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  delete c;
+}
+
+extern "C" B2_EXPORT int64_t b200ppo_param_count(const b200ppo_ctx* c) { return c ? c->n_params : 0; }
+extern "C" B2_EXPORT int64_t b200ppo_actor_param_count(const b200ppo_ctx* c) { return c ? c->n_actor : 0; }
+
+extern "C" B2_EXPORT int64_t b200ppo_param_offset(const b200ppo_ctx* c, int32_t net, int32_t layer, int32_t what) {
+  if (!c || net < 0 || net > 1) return -1;
+  const Net& N = c->net[net];
+  if (net == 0 && layer == N.d.n_layers && what == 0) return c->logstd_off;
+  if (layer < 0 || layer >= N.d.n_layers || what < 0 || what > 1) return -1;
+  return what == 0 ? N.w_off[layer] : N.b_off[layer];
+}
+
+extern "C" B2_EXPORT int64_t b200ppo_saved_size(const b200ppo_ctx* c, int32_t net, int64_t batch) {
+  if (!c || net < 0 || net > 1) return -1;
+  return c->net[net].hidden_sum * batch;
+}
+
+extern "C" B2_EXPORT int b200ppo_mlp_forward(b200ppo_ctx* ctx, int32_t net, const float* params, const float* x, int64_t batch,
+                                   float* out, float* saved, b200ppo_stream stream) {
+  B2_TRY(check_batch(ctx, batch, "b200ppo_mlp_forward"));
+  B2_CHECK_ARG((net == 0 || net == 1) && params && x && out, "b200ppo_mlp_forward: bad argument");
+  if (batch == 0) return B200PPO_OK;
+  float* acts[2] = {ctx->ws_act[0], ctx->ws_act[1]};
+  float* outs[2] = {nullptr, nullptr};
+  if (saved) acts[net] = saved;
+  outs[net] = out;
+  return forward_nets(ctx, params, x, batch, 1 << net, acts, outs, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" B2_EXPORT int b200ppo_mlp_backward(b200ppo_ctx* ctx, int32_t net, const float* params, const float* x,
+                                    const float* out, const float* saved, const float* grad_out, int64_t batch,
+                                    float* grad_params, float* grad_x, b200ppo_stream stream) {
+  B2_TRY(check_batch(ctx, batch, "b200ppo_mlp_backward"));
+  B2_CHECK_ARG((net == 0 || net == 1) && params && x && out && saved && grad_out && grad_params,
+               "b200ppo_mlp_backward: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Net& N = ctx->net[net];
+  const int64_t n_seg = (net == 0 ? ctx->logstd_off : N.seg_end) - N.seg_begin;
+  if (batch == 0) {
+    B2_CUDA(cudaMemsetAsync(grad_params, 0, size_t(n_seg) * sizeof(float), st));
+    return B200PPO_OK;
+  }
+  float* acts[2] = {nullptr, nullptr};
+  float* dz[2] = {nullptr, nullptr};
+  float* gx[2] = {nullptr, nullptr};
+  acts[net] = const_cast<float*>(saved);
+  dz[net] = ctx->ws_dz[net];
+  gx[net] = grad_x;
+  float* dz_last = dz[net] + N.dz_off(N.d.n_layers - 1, batch);
+  const int64_t n_out = batch * N.out_dim();
+  if (N.d.final_tanh) {
+    tanh_scale_bwd_kernel<<<unsigned((n_out + 255) / 256), 256, 0, st>>>(grad_out, out, N.d.out_scale, n_out, dz_last);
+    B2_LAUNCH_CHECK();
+  } else {
+    B2_CUDA(cudaMemcpyAsync(dz_last, grad_out, size_t(n_out) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  int split = 1;
+  B2_TRY(backward_nets(ctx, params, x, batch, 1 << net, acts, dz, ctx->gpart, &split, gx, st));
+  return launch_reduce_partials(ctx->gpart + N.seg_begin, split, ctx->n_params, n_seg, grad_params, st);
+}
+
+extern "C" B2_EXPORT int b200ppo_policy_infer(b200ppo_ctx* ctx, const float* params, const float* obs, int64_t batch,
+                                    const float* noise, float* mean, float* value, float* action, float* logp,
+                                    b200ppo_stream stream) {
+  B2_TRY(check_batch(ctx, batch, "b200ppo_policy_infer"));
+  B2_CHECK_ARG(params && obs, "b200ppo_policy_infer: null pointer");
+  if (batch == 0) return B200PPO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* acts[2] = {ctx->ws_act[0], ctx->ws_act[1]};
+  float* outs[2] = {mean ? mean : ctx->ws_out[0], value ? value : ctx->ws_out[1]};
+  const bool need_actor = mean || action || logp;
+  const int nets = (need_actor ? 1 : 0) | (value ? 2 : 0);
+  if (nets == 0) return B200PPO_OK;
+  B2_TRY(forward_nets(ctx, params, obs, batch, nets, acts, outs, st));
+  if (action || logp)
+    B2_TRY(launch_sample_logp(outs[0], params + ctx->logstd_off, noise, batch, ctx->net[0].out_dim(), action, logp, st));
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_evaluate(b200ppo_ctx* ctx, const float* params, const float* obs, const float* action,
+                                int64_t batch, float* logp, float* value, float* entropy, b200ppo_stream stream) {
+  B2_TRY(check_batch(ctx, batch, "b200ppo_evaluate"));
+  B2_CHECK_ARG(params && obs && action && batch > 0, "b200ppo_evaluate: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* acts[2] = {ctx->ws_act[0], ctx->ws_act[1]};
+  float* outs[2] = {ctx->ws_out[0], value ? value : ctx->ws_out[1]};
+  B2_TRY(forward_nets(ctx, params, obs, batch, 3, acts, outs, st));
+  LossArgs la{};
+  la.mean = outs[0]; la.logstd = params + ctx->logstd_off; la.action = action; la.batch = batch;
+  la.act_dim = ctx->net[0].out_dim(); la.final_tanh = ctx->net[0].d.final_tanh; la.out_scale = ctx->net[0].d.out_scale;
+  la.inv_global_batch = 1.f / float(batch); la.rank_share = 1.f;
+  la.logp_out = logp; la.entropy_out = entropy;
+  la.partials = ctx->loss_partials; la.ticket = ctx->ticket;
+  return launch_ppo_loss(la, st);
+}
+
+extern "C" B2_EXPORT int b200ppo_minibatch_grads(b200ppo_ctx* ctx, const float* params, const float* obs, const float* action,
+                                       const float* old_logp, const float* advantage, const float* target,
+                                       int64_t batch, const b200ppo_hparams* hp, float* grads, float* losses,
+                                       b200ppo_stream stream) {
+  B2_TRY(check_batch(ctx, batch, "b200ppo_minibatch_grads"));
+  B2_CHECK_ARG(params && obs && action && old_logp && advantage && target && hp && grads && batch > 0,
+               "b200ppo_minibatch_grads: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int split = 1;
+  B2_TRY(minibatch_fwd_bwd(ctx, params, obs, action, old_logp, advantage, target, batch, hp,
+                           losses ? losses : ctx->scratch, &split, st));
+  return launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, grads, st);
+}
+
+extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq,
+                             int64_t* adam_step_io, const float* obs, const float* action, const float* old_logp,
+                             const float* advantage, const float* target, int64_t n_samples, const int64_t* perms,
+                             int32_t epochs, int64_t batch, int64_t max_minibatches_per_epoch,
+                             const b200ppo_hparams* hp, float* losses_out, b200ppo_stream stream) {
+  B2_CHECK_ARG(ctx && params && exp_avg && exp_avg_sq && adam_step_io && obs && action && old_logp && advantage &&
+                   target && perms && hp,
+               "b200ppo_train: null pointer");
+  B2_CHECK_ARG(epochs >= 0 && batch > 0 && n_samples >= 0, "b200ppo_train: bad sizes");
+  B2_CHECK_ARG(batch % ctx->world == 0, "b200ppo_train: batch %lld not divisible by world size %d", (long long)batch, ctx->world);
+  const int64_t lb = batch / ctx->world;  // rows of each minibatch owned by this rank
+  B2_TRY(check_batch(ctx, lb, "b200ppo_train"));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t nb = n_samples / batch;  // int(T*N / batch_size): the tail is dropped (ppo.py:97-98,107-108)
+  if (max_minibatches_per_epoch > 0) nb = std::min(nb, max_minibatches_per_epoch);
+  if (nb == 0 || epochs == 0) return B200PPO_OK;
+  B2_TRY(ensure_shuffle_capacity(ctx, nb * lb));
+  const int D = ctx->net[0].d.in_dim, A = ctx->net[0].out_dim();
+  int64_t step = *adam_step_io;
+  for (int e = 0; e < epochs; ++e) {
+    // shuffled_memory = memory[idx] restricted to the rows this rank will consume
+    B2_TRY(launch_gather_chunked(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
+                                 obs, D, action, A, old_logp, advantage, target, ctx->sh_obs, ctx->sh_act, ctx->sh_logp,
+                                 ctx->sh_adv, ctx->sh_tgt, ctx->err_flag, st));
+    for (int64_t i = 0; i < nb; ++i) {
+      const int64_t r0 = i * lb;
+      float* loss_slot = losses_out ? losses_out + (int64_t(e) * nb + i) * 2 : ctx->scratch;
+      int split = 1;
+      ++step;
+      const AdamScalars sa = make_adam_scalars(hp->learning_rate_actor, hp->beta1, hp->beta2, hp->adam_eps, step);
+      const AdamScalars sc = make_adam_scalars(hp->learning_rate_critic, hp->beta1, hp->beta2, hp->adam_eps, step);
+      if (ctx->world == 1) {
+        B2_TRY(minibatch_fwd_bwd(ctx, params, ctx->sh_obs + r0 * D, ctx->sh_act + r0 * A, ctx->sh_logp + r0,
+                                 ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp, loss_slot, &split, st));
+        B2_TRY(launch_adam(params, ctx->gpart, split, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor,
+                           sa, sc, nullptr, st));
+      } else {
+        float* red_losses = ctx->grad_flat + ctx->n_params;
+        B2_TRY(minibatch_fwd_bwd(ctx, params, ctx->sh_obs + r0 * D, ctx->sh_act + r0 * A, ctx->sh_logp + r0,
+                                 ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp, red_losses, &split, st));
+        B2_TRY(launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, ctx->grad_flat, st));
+        const int rc = g_nccl.AllReduce(ctx->grad_flat, ctx->grad_flat, size_t(ctx->n_params + 4), /*ncclFloat32*/ 7,
+                                        /*ncclSum*/ 0, ctx->comm, st);
+        if (rc != 0) {
+          set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+          return B200PPO_ENCCL;
+        }
+        B2_TRY(launch_adam(params, ctx->grad_flat, 1, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor,
+                           sa, sc, nullptr, st));
+        copy2_kernel<<<1, 32, 0, st>>>(red_losses, loss_slot);
+        B2_LAUNCH_CHECK();
+      }
+    }
+  }
+  *adam_step_io = step;
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_update_host(b200ppo_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq,
+                                   int64_t* adam_step_io, const float* obs_host, const float* action_host,
+                                   const float* old_logp_host, const float* reward_host, const float* value_host,
+                                   const float* next_value_host, const uint8_t* terminated_host, int64_t n_envs,
+                                   int64_t n_steps, double gamma, double lmbda, int normalize_rewards,
+                                   int normalize_advantage, double advantage_scaler, const int64_t* perms_host,
+                                   int32_t epochs, int64_t batch, int64_t max_minibatches_per_epoch,
+                                   const b200ppo_hparams* hp, float* losses_host, b200ppo_stream stream) {
+  B2_CHECK_ARG(ctx && obs_host && action_host && old_logp_host && reward_host && value_host && next_value_host &&
+                   terminated_host && perms_host && hp,
+               "b200ppo_update_host: null pointer");
+  B2_CHECK_ARG(n_envs > 0 && n_steps > 0 && epochs > 0 && batch > 0, "b200ppo_update_host: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t M = n_envs * n_steps;
+  const int D = ctx->net[0].d.in_dim, A = ctx->net[0].out_dim();
+  auto& h = ctx->host;
+  if (h.rows < M) {
+    B2_CUDA(cudaDeviceSynchronize());
+    dev_free(h.obs); dev_free(h.act); dev_free(h.logp); dev_free(h.rew); dev_free(h.val); dev_free(h.nval);
+    dev_free(h.adv); dev_free(h.tgt); dev_free(h.term);
+    h.rows = 0;
+    B2_TRY(dev_alloc(&h.obs, M * D)); B2_TRY(dev_alloc(&h.act, M * A)); B2_TRY(dev_alloc(&h.logp, M));
+    B2_TRY(dev_alloc(&h.rew, M)); B2_TRY(dev_alloc(&h.val, M)); B2_TRY(dev_alloc(&h.nval, M));
+    B2_TRY(dev_alloc(&h.adv, M)); B2_TRY(dev_alloc(&h.tgt, M)); B2_TRY(dev_alloc(&h.term, M));
+    h.rows = M;
+  }
+  if (h.perm_elems < int64_t(epochs) * M) {
+    B2_CUDA(cudaDeviceSynchronize());
+    dev_free(h.perms);
+    B2_TRY(dev_alloc(&h.perms, int64_t(epochs) * M));
+    h.perm_elems = int64_t(epochs) * M;
+  }
+  int64_t nb = M / batch;
+  if (max_minibatches_per_epoch > 0) nb = std::min(nb, max_minibatches_per_epoch);
+  const int64_t n_loss = int64_t(epochs) * nb * 2;
+  if (h.loss_elems < n_loss) {
+    B2_CUDA(cudaDeviceSynchronize());
+    dev_free(h.losses);
+    B2_TRY(dev_alloc(&h.losses, n_loss));
+    h.loss_elems = n_loss;
+  }
+  const auto H2D = cudaMemcpyHostToDevice;
+  B2_CUDA(cudaMemcpyAsync(h.rew, reward_host, size_t(M) * 4, H2D, st));
+  B2_CUDA(cudaMemcpyAsync(h.val, value_host, size_t(M) * 4, H2D, st));
+  B2_CUDA(cudaMemcpyAsync(h.nval, next_value_host, size_t(M) * 4, H2D, st));
+  B2_CUDA(cudaMemcpyAsync(h.term, terminated_host, size_t(M), H2D, st));
+  B2_TRY(b200ppo_gae(h.rew, 0, h.val, h.nval, h.term, nullptr, n_envs, n_steps, gamma, lmbda, normalize_rewards,
+                     normalize_advantage, advantage_scaler, h.adv, h.tgt, stream));
+  B2_CUDA(cudaMemcpyAsync(h.obs, obs_host, size_t(M) * D * 4, H2D, st));
+  B2_CUDA(cudaMemcpyAsync(h.act, action_host, size_t(M) * A * 4, H2D, st));
+  B2_CUDA(cudaMemcpyAsync(h.logp, old_logp_host, size_t(M) * 4, H2D, st));
+  B2_CUDA(cudaMemcpyAsync(h.perms, perms_host, size_t(epochs) * M * 8, H2D, st));
+  B2_TRY(b200ppo_train(ctx, params, exp_avg, exp_avg_sq, adam_step_io, h.obs, h.act, h.logp, h.adv, h.tgt, M, h.perms,
+                       epochs, batch, max_minibatches_per_epoch, hp, h.losses, stream));
+  if (losses_host && n_loss > 0)
+    B2_CUDA(cudaMemcpyAsync(losses_host, h.losses, size_t(n_loss) * 4, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  return B200PPO_OK;
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------------------
+extern "C" B2_EXPORT int b200ppo_comm_unique_id(uint8_t id_out[128]) {
+  B2_TRY(load_nccl());
+  const int rc = g_nccl.GetUniqueId(id_out);
+  if (rc != 0) { set_error("ncclGetUniqueId failed (%d)", rc); return B200PPO_ENCCL; }
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_comm_init(b200ppo_ctx* ctx, const uint8_t unique_id[128], int32_t rank, int32_t world_size) {
+  B2_CHECK_ARG(ctx && unique_id && world_size >= 1 && rank >= 0 && rank < world_size, "b200ppo_comm_init: bad argument");
+  if (world_size == 1) { ctx->rank = 0; ctx->world = 1; return B200PPO_OK; }
+  B2_TRY(load_nccl());
+  NcclApi::Id128 id;
+  memcpy(id.b, unique_id, 128);
+  void* comm = nullptr;
+  const int rc = g_nccl.CommInitRank(&comm, world_size, id, rank);
+  if (rc != 0) {
+    set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return B200PPO_ENCCL;
+  }
+  ctx->comm = comm; ctx->rank = rank; ctx->world = world_size;
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_comm_world(const b200ppo_ctx* ctx, int32_t* rank, int32_t* world_size) {
+  B2_CHECK_ARG(ctx, "b200ppo_comm_world: null context");
+  if (rank) *rank = ctx->rank;
+  if (world_size) *world_size = ctx->world;
+  return B200PPO_OK;
+}

@@ -1,0 +1,73 @@
+// Shared helpers for libb200ppo (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "b200ppo.h"
+
+#define B2_EXPORT __attribute__((visibility("default")))
+
+namespace b200ppo {
+
+void set_error(const char* fmt, ...);
+
+#define B2_CHECK_ARG(cond, ...)           \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::b200ppo::set_error(__VA_ARGS__);  \
+      return B200PPO_EINVAL;              \
+    }                                     \
+  } while (0)
+
+#define B2_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      ::b200ppo::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return B200PPO_ECUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+
+#define B2_LAUNCH_CHECK() B2_CUDA(cudaGetLastError())
+
+#define B2_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != B200PPO_OK) return _r; \
+  } while (0)
+
+inline int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Streaming 128-bit accesses: data touched once, keep it out of L1.
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace b200ppo

@@ -1,0 +1,219 @@
+"""K3/K4/K6 + trainer parity through the C ABI: forward, evaluate, inference, losses, gradients,
+post-Adam parameters — against the reference's own outputs (tests/golden) and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import mujoco_reinforcement_learning_b200 as pkg
+from oracle import ppo_oracle as O
+from tests._util import RTOL_FP32, assert_close, load_golden, sub
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TRAIN_CASES = ["train_tanh64", "train_relu3", "train_tanh96"]
+ACT = {"tanh": torch.nn.Tanh, "relu": torch.nn.ReLU}
+
+
+def make_pair(obs_dim, act_dim, hidden, critic_hidden, activation, out_max=1.0, batch=64, epochs=1, lr=1e-4, clip=0.1,
+              ent=1e-4, n_envs=1, steps=1, init=None, seed=0, max_batch=None):
+    """(oracle agent on CPU, CUDA agent) holding identical parameters."""
+    cfg = O.OracleConfig(obs_dim=obs_dim, act_dim=act_dim, actor_hidden=list(hidden), critic_hidden=list(critic_hidden),
+                         activation=activation, output_max_value=out_max, learning_rate=lr, batch_size=batch,
+                         epochs=epochs, clip_epsilon=clip, entropy_eps=ent)
+    torch.manual_seed(seed)
+    oracle = O.OracleAgent(cfg)
+    if init is not None:
+        oracle.networks.load_state_dict({k: torch.from_numpy(v) for k, v in init.items()})
+    run = pkg.Run(training_config=pkg.TrainingConfig(learning_rate=lr, batch_size=batch, epochs_per_iteration=epochs),
+                  ppo_config=pkg.PPOConfig(clip_epsilon=clip, entropy_eps=ent),
+                  environment_config=pkg.EnvironmentConfig(maximum_timesteps=steps, num_envs=n_envs, window_length=1),
+                  network_config=pkg.NetworkConfig(input_shape=obs_dim, output_shape=act_dim, output_max_value=out_max,
+                                                   activation_class=ACT[activation], num_linear_layers=len(hidden),
+                                                   linear_hidden_shapes=list(hidden),
+                                                   critic_hidden_shapes=list(critic_hidden)))
+    agent = pkg.PPOAgent(run, max_batch=max_batch or max(batch, 1024))
+    agent.networks.load_state_dict(oracle.networks.state_dict())
+    assert agent.engine.params_are_bound()
+    return oracle, agent, run
+
+
+def from_golden(name):
+    g = load_golden(name)
+    B, epochs, lr, clip, ent, out_max = g["cfg"]
+    init, mem = sub(g, "init/"), sub(g, "mem/")
+    n_envs, steps = mem["action_log_prob"].shape
+    D = init["actor.actor.first_layers.0.weight"].shape[1]
+    A = init["actor.actor_logstd"].shape[0]
+    oracle, agent, run = make_pair(D, A, [int(h) for h in g["hidden"]], [128, 128], str(g["activation"]), float(out_max),
+                                   int(B), int(epochs), float(lr), float(clip), float(ent), n_envs, steps, init)
+    return g, mem, oracle, agent, run
+
+
+def flat_mem(mem):
+    M = mem["action_log_prob"].size
+    t = lambda k, *s: torch.from_numpy(mem[k]).reshape(M, *s)
+    return {"current_state": t("current_state", -1), "action": t("action", -1), "action_log_prob": t("action_log_prob"),
+            "advantage": t("advantage", 1), "current_state_value_target": t("current_state_value_target", 1)}
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_forward_evaluate_infer_vs_oracle(name):
+    g, mem, oracle, agent, run = from_golden(name)
+    fm = flat_mem(mem)
+    obs, act = fm["current_state"], fm["action"]
+    with torch.no_grad():
+        mean_ref, std_ref = oracle.networks["actor"](obs)
+        v_ref = oracle.networks["critic"](obs)
+        dist = torch.distributions.Normal(mean_ref, std_ref)
+        mean, std = agent.networks["actor"](obs.to(DEV))
+        v = agent.get_state_value(obs.to(DEV))
+    assert mean.shape == mean_ref.shape and std.shape == std_ref.shape and v.shape == v_ref.shape
+    assert_close(mean, mean_ref, RTOL_FP32, "mean")
+    assert_close(std, std_ref, RTOL_FP32, "std")
+    assert_close(v, v_ref, RTOL_FP32, "value")
+    logp, ent, val = agent.evaluate(obs.to(DEV), act.to(DEV))
+    assert_close(logp, dist.log_prob(act).sum(1), RTOL_FP32, "logp")
+    assert_close(ent, dist.entropy().mean(), RTOL_FP32, "entropy")
+    assert_close(val, v_ref, RTOL_FP32, "value(evaluate)")
+    noise = torch.randn(obs.shape[0], act.shape[1], generator=torch.Generator().manual_seed(3))
+    a, lp, vv = agent.act_fused(obs.to(DEV), noise.to(DEV))
+    a_ref = mean_ref + std_ref * noise
+    assert_close(a, a_ref, RTOL_FP32, "sampled action")
+    assert_close(lp, dist.log_prob(a_ref).sum(1), 1e-4, "rollout logp")  # (a-mean) cancellation: a few ulp of |a|
+    assert_close(vv, v_ref, RTOL_FP32, "rollout value")
+    a_test, _, _ = agent.act_fused(obs.to(DEV), test_phase=True)
+    assert_close(a_test, mean_ref, RTOL_FP32, "test-phase action")
+    act_sample, d2 = agent.act(obs.to(DEV), return_dist=True)
+    assert act_sample.shape == mean_ref.shape
+    assert_close(d2.log_prob(act.to(DEV)).sum(1), dist.log_prob(act).sum(1), RTOL_FP32, "dist.log_prob")
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_minibatch_losses_and_gradients_vs_oracle(name):
+    g, mem, oracle, agent, run = from_golden(name)
+    fm = flat_mem(mem)
+    idx = torch.from_numpy(g["perms"][0])[:oracle.cfg.batch_size]
+    b = {k: v[idx] for k, v in fm.items()}
+    al, cl, grads_ref, _, _ = O.minibatch_grads(oracle, b["current_state"], b["action"], b["action_log_prob"],
+                                                b["advantage"], b["current_state_value_target"])
+    eng = agent.engine
+    hp = eng.hparams(1e-4, 1e-4, oracle.cfg.clip_epsilon, oracle.cfg.entropy_eps)
+    losses, grads = eng.minibatch_grads(*(b[k].to(DEV) for k in ("current_state", "action", "action_log_prob", "advantage",
+                                                                  "current_state_value_target")), hp)
+    assert abs(losses[0].item() - al) <= RTOL_FP32 * max(1.0, abs(al))
+    assert abs(losses[1].item() - cl) <= RTOL_FP32 * max(1.0, abs(cl))
+    names = [n for n, _ in agent.networks.named_parameters()]
+    by_name = eng.grads_by_name(grads, names)
+    assert sorted(by_name) == sorted(grads_ref)
+    for k, ref in grads_ref.items():
+        assert_close(by_name[k], ref, RTOL_FP32, f"grad {k}")
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_autograd_facade_matches_oracle_autograd(name):
+    g, mem, oracle, agent, run = from_golden(name)
+    fm = flat_mem(mem)
+    obs, act = fm["current_state"][:50], fm["action"][:50]
+    w = torch.randn(50, act.shape[1], generator=torch.Generator().manual_seed(9))
+    mean_ref, _ = oracle.networks["actor"](obs)
+    v_ref = oracle.networks["critic"](obs)
+    ((mean_ref * w).sum() + (v_ref ** 2).sum()).backward()
+    x = obs.to(DEV).requires_grad_(True)
+    mean, std = agent.networks["actor"](x)
+    v = agent.get_state_value(x)
+    ((mean * w.to(DEV)).sum() + (v ** 2).sum() + std.sum()).backward()
+    ref = dict(oracle.networks.named_parameters())
+    for n, p in agent.networks.named_parameters():
+        if n == "actor.actor_logstd":
+            assert_close(p.grad, 50 * p.detach().exp(), RTOL_FP32, n)
+            continue
+        assert_close(p.grad, ref[n].grad, RTOL_FP32, f"autograd {n}")
+    assert x.grad is not None and x.grad.shape == x.shape
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_train_matches_reference_outputs(name):
+    """PPO.train on the CUDA path vs the REFERENCE'S OWN final state (same inputs, same permutations)."""
+    g, mem, oracle, agent, run = from_golden(name)
+    n_envs, steps = mem["action_log_prob"].shape
+    memory = pkg.RolloutMemory({k: torch.from_numpy(v).to(DEV) for k, v in mem.items() if v.dtype != np.float64
+                                or k == "reward"}, (n_envs, steps))
+    algo = pkg.PPO(type("H", (), {"run": run})(), agent)
+    al, cl = algo.train(memory, perms=torch.from_numpy(g["perms"]))
+    final = sub(g, "final/")
+    for k, v in agent.networks.state_dict().items():
+        assert_close(v, final[k], RTOL_FP32, f"param {k}")
+        init = g["init/" + k]
+        assert_close(v.cpu().numpy() - init, final[k] - init, 5e-3, f"update of {k}")  # p - p0 cancels ~3 digits
+    for oname, opt in agent.optimizers.items():
+        sd = opt.state_dict()
+        assert abs(sd["param_groups"][0]["lr"] - float(g[f"opt/{oname}/lr"])) < 1e-12  # scheduler stepped once
+        for pid, st in sd["state"].items():
+            assert_close(st["exp_avg"], g[f"opt/{oname}/{pid}/exp_avg"], RTOL_FP32, f"{oname}/{pid}/exp_avg")
+            assert_close(st["exp_avg_sq"], g[f"opt/{oname}/{pid}/exp_avg_sq"], RTOL_FP32, f"{oname}/{pid}/exp_avg_sq")
+            assert float(st["step"]) == float(g[f"opt/{oname}/{pid}/step"])
+    np.testing.assert_allclose([al, cl], g["logged_losses"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape", [dict(D=376, A=17, H=[256, 256], N=16, T=64, B=500),    # Humanoid dims, reference B
+                                   dict(D=27, A=8, H=[256, 256], N=32, T=32, B=256),      # Ant dims
+                                   dict(D=11, A=3, H=[64, 64], N=16, T=256, B=4096),      # Hopper config, one big batch
+                                   dict(D=17, A=6, H=[64, 64], N=1, T=2048, B=500)])      # HalfCheetah config
+def test_train_vs_oracle_on_baseline_shapes(shape):
+    D, A, H, N, T, B = (shape[k] for k in "DAHNTB")
+    oracle, agent, run = make_pair(D, A, H, H, "tanh", batch=B, epochs=1, n_envs=N, steps=T, seed=4, max_batch=B)
+    roll = O.synthetic_rollout(N, T, D, A, seed=77)
+    adv, tgt = O.calculate_advantages(roll["reward"], roll["current_state_value"], roll["next_state_value"],
+                                      roll["terminated"], 0.99, 0.98)
+    M = N * T
+    fm = {"current_state": roll["current_state"].reshape(M, D), "action": roll["action"].reshape(M, A),
+          "advantage": adv.reshape(M, 1), "current_state_value_target": tgt.reshape(M, 1)}
+    with torch.no_grad():
+        mean, std = oracle.networks["actor"](fm["current_state"])
+        fm["action_log_prob"] = torch.distributions.Normal(mean, std).log_prob(fm["action"]).sum(1) + 0.02 * torch.randn(M)
+    perms = [torch.randperm(M, generator=torch.Generator().manual_seed(8))]
+    max_mb = 3
+    ref_losses = O.ppo_train(oracle, fm, perms, max_minibatches=max_mb)
+    memory = pkg.RolloutMemory({"current_state": roll["current_state"].to(DEV), "action": roll["action"].to(DEV),
+                                "action_log_prob": fm["action_log_prob"].reshape(N, T).to(DEV),
+                                "advantage": adv.to(DEV), "current_state_value_target": tgt.to(DEV)}, (N, T))
+    algo = pkg.PPO(type("H", (), {"run": run})(), agent)
+    algo.train(memory, perms=torch.stack(perms), max_minibatches_per_epoch=max_mb)
+    got = algo.last_losses.cpu().numpy()
+    np.testing.assert_allclose(got, np.array(ref_losses), rtol=1e-5, atol=1e-6)
+    ref_sd = oracle.networks.state_dict()
+    for k, v in agent.networks.state_dict().items():
+        assert_close(v, ref_sd[k], RTOL_FP32, f"param {k}")
+
+
+def test_checkpoint_round_trip_and_reference_key_names(tmp_path):
+    oracle, agent, run = make_pair(12, 4, [32, 32], [32, 32], "tanh")
+    run.experiment_path = str(tmp_path)
+    keys = list(agent.networks.state_dict().keys())
+    assert keys[0] == "actor.actor_logstd" or "actor.actor.first_layers.0.weight" in keys
+    assert "critic.network.last_layer.bias" in keys and "actor.actor_logstd" in keys
+    before = {k: v.clone() for k, v in agent.networks.state_dict().items()}
+    agent.engine.exp_avg.normal_()
+    agent.engine.adam_step = 17
+    agent.save()
+    opt_sd = torch.load(f"{tmp_path}/networks/0/optimizer_actor.pth")
+    assert set(opt_sd) == {"state", "param_groups"} and float(opt_sd["state"][0]["step"]) == 17.0
+    # the reference's stock torch.optim.Adam can load it
+    ref_opt = torch.optim.Adam(oracle.networks["actor"].parameters(), lr=1e-4)
+    ref_opt.load_state_dict(opt_sd)
+    saved_m = agent.engine.exp_avg.clone()
+    with torch.no_grad():
+        agent.engine.flat.zero_()
+        agent.engine.exp_avg.zero_()
+    agent.engine.adam_step = 0
+    agent.load()
+    for k, v in agent.networks.state_dict().items():
+        assert torch.equal(v, before[k])
+    assert agent.engine.params_are_bound() and agent.engine.adam_step == 17
+    assert torch.equal(agent.engine.exp_avg, saved_m)
+
+
+def test_batch_larger_than_engine_capacity_is_an_error():
+    _, agent, _ = make_pair(8, 2, [16, 16], [16, 16], "tanh", max_batch=32)
+    with pytest.raises(RuntimeError, match="max_batch"):
+        agent.get_state_value(torch.zeros(33, 8, device=DEV))
