@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""PPO-update benchmark on the Humanoid shape (BASELINE.json metric/config), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one PPO iteration's update over one synthetic rollout: the advantage pipeline
+(`PPO.calculate_advantages`) followed by `epochs` epochs of permutation-gather + minibatch
+forward/loss/backward/Adam (`PPO.train`).  `value` = samples pushed through the update per second with the
+rollout already resident in HBM; `e2e` = the same through the C-ABI host-buffer entry point
+(`b200ppo_update_host`: pinned host rollout -> device, update, losses -> host).  With N GPUs every rank owns a
+slab of `envs` environments (weak scaling): the slabs are all-gathered after the GAE scan, every rank takes its
+1/N slice of every global minibatch (global permutation, as the reference indexes), gradients are summed by an
+NCCL all-reduce per minibatch.
+
+`--impl reference` times the CPU oracle port of the reference's path (`oracle/ppo_oracle.py`: the reference's
+own torch CPU operators) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OBS_DIM, ACT_DIM, HIDDEN = 376, 17, [256, 256]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_rollout(n_envs, steps, seed):
+    from oracle.ppo_oracle import synthetic_rollout  # synthetic-input generator only (shared with the tests)
+    return synthetic_rollout(n_envs, steps, OBS_DIM, ACT_DIM, seed=seed)
+
+
+def flops_per_sample():
+    macs = 0
+    for out in (ACT_DIM, 1):
+        dims = [OBS_DIM] + HIDDEN + [out]
+        macs += sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    first = 2 * OBS_DIM * HIDDEN[0]  # no dgrad into the observations (two nets)
+    return {"fwd": 2 * macs, "dgrad": 2 * macs - 2 * first, "wgrad": 2 * macs, "total": 6 * macs - 2 * first}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args, config):
+    """CPU arm: the oracle port of the reference path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ppo_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.minibatch
+    cfg = O.OracleConfig(obs_dim=OBS_DIM, act_dim=ACT_DIM, actor_hidden=HIDDEN, critic_hidden=HIDDEN, batch_size=B, epochs=1)
+    torch.manual_seed(0)
+    agent = O.OracleAgent(cfg)
+    roll = make_rollout(args.envs, args.rollout_steps, 1234 + 3)
+    M = args.envs * args.rollout_steps
+    with torch.no_grad():
+        mean, std = agent.networks["actor"](roll["current_state"].reshape(M, OBS_DIM))
+        logp = torch.distributions.Normal(mean, std).log_prob(roll["action"].reshape(M, ACT_DIM)).sum(1)
+    mb = max(1, min(M // B, args.ref_minibatches if args.ref_minibatches > 0 else max(1, (64 * 4096) // B)))
+
+    def step(seed):
+        adv, tgt = O.calculate_advantages(roll["reward"], roll["current_state_value"], roll["next_state_value"],
+                                          roll["terminated"], 0.99, 0.98)
+        fm = {"current_state": roll["current_state"].reshape(M, OBS_DIM), "action": roll["action"].reshape(M, ACT_DIM),
+              "action_log_prob": logp, "advantage": adv.reshape(M, 1), "current_state_value_target": tgt.reshape(M, 1)}
+        perm = torch.randperm(M, generator=torch.Generator().manual_seed(seed))
+        O.ppo_train(agent, fm, [perm], max_minibatches=mb)
+
+    for w in range(args.warmup):
+        step(w)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step(100 + k)
+    dt = time.perf_counter() - t0
+    value = args.steps * mb * B / dt
+    sample = (f"per step: full GAE over {args.envs}x{args.rollout_steps} + permutation gather of all leaves + the first "
+              f"{mb} of {M // B} minibatches of one epoch (torch CPU, {cores} threads)")
+    line = {"impl": "reference", "metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def cuda_time(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts), min(ts)
+
+
+def hbm_kernel_lines(pk):
+    """Roofline of the HBM-bound kernels at sizes that do not fit the 126 MB L2 (SURVEY.md §8d cache caveat)."""
+    import mujoco_reinforcement_learning_b200 as pkg
+    out = {}
+    dev = "cuda"
+    # K1 at the sweep's large end: 65536 envs x 1024 steps = 1.48 GB algorithmic
+    n, t = 65536, 1024
+    r, v, vn = (torch.randn(n, t, 1, device=dev) for _ in range(3))
+    term = torch.rand(n, t, device=dev) < 0.01
+    med, best = cuda_time(lambda: pkg.calculate_advantages(r, v, vn, term, 0.99, 0.98), 10)
+    gb = 22 * n * t / 1e9
+    out["gae_65536x1024"] = {"bytes": 22 * n * t, "ms": med, "GBps": gb / (med * 1e-3), "frac": gb / (med * 1e-3) / pk["hbm"]}
+    medn, _ = cuda_time(lambda: pkg.calculate_advantages(r, v, vn, term, 0.99, 0.98, normalize_advantage=True), 5)
+    out["gae_65536x1024_normalized"] = {"bytes": 22 * n * t, "ms": medn, "GBps": gb / (medn * 1e-3), "frac": gb / (medn * 1e-3) / pk["hbm"]}
+    del r, v, vn, term
+    # K1 at the Humanoid shape (11.5 MB: L2 resident, reported as time)
+    n, t = 4096, 128
+    r, v, vn = (torch.randn(n, t, 1, device=dev) for _ in range(3))
+    term = torch.rand(n, t, device=dev) < 0.01
+    med, best = cuda_time(lambda: pkg.calculate_advantages(r, v, vn, term, 0.99, 0.98), 20)
+    out["gae_4096x128"] = {"bytes": 22 * n * t, "ms": med, "GBps": 22 * n * t / 1e9 / (med * 1e-3), "note": "L2-resident (11.5 MB)"}
+    del r, v, vn, term
+    # K2: one epoch's gather at the Humanoid shape, 1.665 GB algorithmic
+    m = 4096 * 128
+    obs, act = torch.randn(m, OBS_DIM, device=dev), torch.randn(m, ACT_DIM, device=dev)
+    s = torch.randn(m, device=dev)
+    idx = torch.randperm(m, device=dev)
+    med, best = cuda_time(lambda: pkg.gather_minibatch(idx, obs, act, s, s, s, check=False), 10)
+    by = (2 * (4 * OBS_DIM + 4 * ACT_DIM + 12) + 8) * m
+    out["gather_epoch_524288"] = {"bytes": by, "ms": med, "GBps": by / 1e9 / (med * 1e-3), "frac": by / 1e9 / (med * 1e-3) / pk["hbm"]}
+    del obs, act, s, idx
+    # K5 on a 64M-parameter vector (1.79 GB) and on the real 329k-parameter set
+    for n_par, key in ((64 * 1024 * 1024, "adam_64M"), (329251, "adam_329k")):
+        p, g, mm, vv = (torch.randn(n_par, device=dev) for _ in range(4))
+        vv.abs_()
+        med, best = cuda_time(lambda: pkg.adam_step_(p, g, mm, vv, 10, 1e-4), 10)
+        by = 28 * n_par
+        out[key] = {"bytes": by, "ms": med, "GBps": by / 1e9 / (med * 1e-3)}
+        if n_par > 10 ** 7:
+            out[key]["frac"] = out[key]["GBps"] / pk["hbm"]
+        else:
+            out[key]["note"] = "L2-resident (9.2 MB): launch/latency bound"
+        del p, g, mm, vv
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_baseline(args):
+    """Bounded CPU sample of the same workload through the oracle port (rank 0, N=1 only)."""
+    from oracle import ppo_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.minibatch
+    M = args.envs * args.rollout_steps
+    cfg = O.OracleConfig(obs_dim=OBS_DIM, act_dim=ACT_DIM, actor_hidden=HIDDEN, critic_hidden=HIDDEN, batch_size=B, epochs=1)
+    torch.manual_seed(0)
+    agent = O.OracleAgent(cfg)
+    roll = make_rollout(args.envs, args.rollout_steps, 1234 + 3)
+    logp = torch.zeros(M)
+    mb = max(1, min(M // B, (48 * 4096) // B))
+    t0 = time.perf_counter()
+    adv, tgt = O.calculate_advantages(roll["reward"], roll["current_state_value"], roll["next_state_value"],
+                                      roll["terminated"], 0.99, 0.98)
+    t_gae = time.perf_counter() - t0
+    fm = {"current_state": roll["current_state"].reshape(M, OBS_DIM), "action": roll["action"].reshape(M, ACT_DIM),
+          "action_log_prob": logp, "advantage": adv.reshape(M, 1), "current_state_value_target": tgt.reshape(M, 1)}
+    perm = torch.randperm(M, generator=torch.Generator().manual_seed(1))
+    O.ppo_train(agent, fm, [perm], max_minibatches=2)  # warm-up
+    t0 = time.perf_counter()
+    O.ppo_train(agent, fm, [perm], max_minibatches=mb)
+    dt = time.perf_counter() - t0
+    return {"value": mb * B / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port (torch CPU ops of the reference), {cores} threads: gather of one epoch + first {mb} of "
+                      f"{M // B} minibatches; GAE {args.envs}x{args.rollout_steps} separately {t_gae * 1e3:.1f} ms "
+                      f"({22 * M / 1e9 / t_gae:.2f} GB/s)"}
+
+
+def run_b200(args, config):
+    import torch.distributed as dist
+
+    import mujoco_reinforcement_learning_b200 as pkg
+    from mujoco_reinforcement_learning_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    lib = _lib.load()
+
+    n_envs, T, B, E = args.envs, args.rollout_steps, args.minibatch, args.epochs
+    M_local, M = n_envs * T, n_envs * T * world
+    GB = B * world
+    run = pkg.Run(training_config=pkg.TrainingConfig(learning_rate=1e-4, batch_size=GB, epochs_per_iteration=E),
+                  ppo_config=pkg.PPOConfig(), environment_config=pkg.EnvironmentConfig(maximum_timesteps=T, num_envs=n_envs * world),
+                  network_config=pkg.NetworkConfig(input_shape=OBS_DIM, output_shape=ACT_DIM, linear_hidden_shapes=HIDDEN),
+                  device=str(dev), gemm_precision=args.precision)
+    torch.manual_seed(0)  # identical initial parameters on every rank
+    agent = pkg.PPOAgent(run, max_batch=max(B, 4096))
+    eng = agent.engine
+    if world > 1:
+        from mujoco_reinforcement_learning_b200 import distributed as D
+        D.init_engine_comm(eng)
+    algo = pkg.PPO(type("Helper", (), {"run": run})(), agent)
+
+    roll = make_rollout(n_envs, T, 1234 + 3 + rank)
+    host = {k: roll[k].contiguous() for k in ("current_state", "action", "reward", "current_state_value", "next_state_value", "terminated")}
+    d = {k: v.to(dev) for k, v in host.items()}
+    obs_flat = d["current_state"].reshape(M_local, OBS_DIM)
+    logp = torch.empty(M_local, device=dev)
+    for s in range(0, M_local, eng.max_batch):  # old log-prob under the initial policy
+        lp, _, _ = eng.evaluate(obs_flat[s:s + eng.max_batch], d["action"].reshape(M_local, ACT_DIM)[s:s + eng.max_batch])
+        logp[s:s + eng.max_batch] = lp
+    d["action_log_prob"] = logp.reshape(n_envs, T)
+    host["action_log_prob"] = d["action_log_prob"].cpu()
+    n_total_steps = args.warmup + args.steps + 1
+    gperm = torch.Generator().manual_seed(99)
+    perms_host = [torch.stack([torch.randperm(M, generator=gperm) for _ in range(E)]) for _ in range(n_total_steps)]
+    perms_dev = [p.to(dev) for p in perms_host]
+    hp = eng.hparams(1e-4, 1e-4, 0.1, 1e-4)
+    nb = M // GB
+    samples_per_step = E * nb * GB
+
+    def step_device(i):
+        mem = pkg.RolloutMemory(dict(d), (n_envs, T))
+        algo.calculate_advantages(mem)
+        fields = {"current_state": mem["current_state"].reshape(M_local, OBS_DIM), "action": mem["action"].reshape(M_local, ACT_DIM),
+                  "action_log_prob": mem["action_log_prob"].reshape(M_local), "advantage": mem["advantage"].reshape(M_local),
+                  "current_state_value_target": mem["current_state_value_target"].reshape(M_local)}
+        if world > 1:
+            fields = D.all_gather_fields(fields)
+        return eng.train(fields["current_state"], fields["action"], fields["action_log_prob"], fields["advantage"],
+                         fields["current_state_value_target"], perms_dev[i], GB, hp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.b200ppo_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(args.steps):
+        losses = step_device(args.warmup + k)
+    ev1.record()
+    barrier()
+    launches = lib.b200ppo_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = args.steps * samples_per_step / (ms * 1e-3)
+    final_losses = losses[-1].tolist()
+
+    # ---- e2e through the C ABI with host buffers (single GPU: the host entry point is per-rank) --------------
+    e2e = None
+    if world == 1:
+        pin = {k: v.pin_memory() for k, v in host.items()}
+        pin_perms = [p.pin_memory() for p in perms_host]
+        loss_host = torch.empty((E * nb, 2), dtype=torch.float32).pin_memory()
+        step_io = C.c_int64(eng.adam_step)
+
+        def step_host(i):
+            _lib.check(lib.b200ppo_update_host(eng._ctx, _lib.ptr(eng.flat), _lib.ptr(eng.exp_avg), _lib.ptr(eng.exp_avg_sq),
+                                               C.byref(step_io), C.c_void_p(pin["current_state"].data_ptr()),
+                                               C.c_void_p(pin["action"].data_ptr()), C.c_void_p(pin["action_log_prob"].data_ptr()),
+                                               C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["current_state_value"].data_ptr()),
+                                               C.c_void_p(pin["next_state_value"].data_ptr()),
+                                               C.c_void_p(pin["terminated"].data_ptr()), n_envs, T, 0.99, 0.98, 0, 0, 1.0,
+                                               C.c_void_p(pin_perms[i].data_ptr()), E, B, 0, C.byref(hp),
+                                               C.c_void_p(loss_host.data_ptr()), _lib.stream_ptr()), "b200ppo_update_host")
+
+        for i in range(max(1, min(args.warmup, 2))):
+            step_host(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            step_host(args.warmup + k)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        eng.adam_step = int(step_io.value)
+        h2d = sum(v.numel() * v.element_size() for v in host.values()) + perms_host[0].numel() * 8
+        e2e = {"value": args.steps * samples_per_step / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": dt / args.steps * 1e3,
+               "api": "b200ppo_update_host (C ABI, pinned host buffers)"}
+
+    # ---- per-kernel-class device time of one step (CUDA events on the launching stream) ----------------------
+    _lib.check(lib.b200ppo_profile_begin(eng._ctx))
+    ga, gb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mem = pkg.RolloutMemory(dict(d), (n_envs, T))
+    ga.record(); algo.calculate_advantages(mem); gb_.record()
+    step_device(args.warmup + args.steps)
+    ms_c = (C.c_double * 8)()
+    n_c = (C.c_int64 * 8)()
+    _lib.check(lib.b200ppo_profile_end(eng._ctx, ms_c, n_c))
+    prof = {name: {"ms": ms_c[i], "groups": int(n_c[i])} for i, name in enumerate(_lib.PROF_CLASSES) if n_c[i]}
+    prof["gae"] = {"ms": ga.elapsed_time(gb_), "groups": 1}
+    fl = flops_per_sample()
+    lb_rows = E * nb * B  # rows this rank pushed through the GEMMs in the profiled step
+    gemm_ms = sum(prof[k]["ms"] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad") if k in prof)
+    gemm_flops = fl["total"] * lb_rows
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    total_prof_ms = sum(v["ms"] for v in prof.values())
+    for k, v in prof.items():
+        v["share"] = v["ms"] / total_prof_ms if total_prof_ms else 0.0
+    for k, key in (("gemm_fwd", "fwd"), ("gemm_dgrad", "dgrad"), ("gemm_wgrad", "wgrad")):
+        if k in prof and prof[k]["ms"] > 0:
+            prof[k]["TFLOPs"] = fl[key] * lb_rows / (prof[k]["ms"] * 1e-3) / 1e12
+    if "gather" in prof and prof["gather"]["ms"] > 0:
+        by = (2 * (4 * OBS_DIM + 4 * ACT_DIM + 12) + 8) * (E * nb * B)
+        prof["gather"]["GBps"] = by / 1e9 / (prof["gather"]["ms"] * 1e-3)
+        prof["gather"]["frac_hbm"] = prof["gather"]["GBps"] / pk["hbm"]
+    roofline = {"kernel": "gemm_group_kernel (actor+critic MLP forward/dgrad/wgrad, fp32 FFMA)" if args.precision == "fp32"
+                else "tcgen05 bf16 GEMMs (actor+critic MLP forward/dgrad/wgrad)",
+                "bound": "tensor", "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tensor_sustained"], "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
+                "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
+                "flops_per_sample": fl["total"], "launch_groups": sum(prof[k]["groups"] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad") if k in prof)}
+
+    line = {"metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic", "config": config,
+            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernel_classes": prof,
+            "final_losses": final_losses, "samples_per_step": samples_per_step}
+    if rank == 0:
+        if not args.no_kernels:
+            line["hbm_kernels"] = hbm_kernel_lines(pk)
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--rollout-steps", type=int, default=128)
+    ap.add_argument("--minibatch", type=int, default=4096, help="minibatch rows per GPU (global = N x this)")
+    ap.add_argument("--epochs", type=int, default=10, help="epochs_per_iteration (reference default, main.py:45)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--ref-minibatches", type=int, default=0, help="reference arm: minibatches per step (0 = auto)")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the HBM-kernel roofline mini-benchmarks")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "Humanoid-v4 shape PPO update (BASELINE.json configs[3]): GAE + epochs x (permutation gather + "
+                          "minibatch actor-critic forward/loss/backward/Adam)",
+              "envs_per_gpu": args.envs, "rollout_steps": args.rollout_steps, "obs_dim": OBS_DIM, "act_dim": ACT_DIM,
+              "hidden": HIDDEN, "activation": "tanh", "gemm": args.precision, "minibatch_per_gpu": args.minibatch, "epochs_per_step": args.epochs,
+              "parallelism": f"dp{max(world, 1)} (env-slab sharding, grad all-reduce)" if world > 1 else "single GPU",
+              "cache": "inputs larger than L2 (788 MB observation buffer re-gathered every epoch); no explicit flush"}
+    if args.impl == "reference":
+        run_reference(args, config)
+    else:
+        run_b200(args, config)
+
+
+if __name__ == "__main__":
+    main()

@@ -192,6 +192,26 @@ int b200ppo_update_host(b200ppo_ctx* ctx, float* params, float* exp_avg, float* 
                         b200ppo_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Instrumentation (used by bench.py; no reference counterpart).
+ * b200ppo_launch_count: CUDA kernels this library has launched in this process so far.
+ * b200ppo_profile_begin/end: between the two calls every kernel group launched by b200ppo_train on this
+ * context is bracketed by CUDA events on its stream; _end synchronises and returns, per class, the summed
+ * device time in ms and the number of timed groups (a forward "group" is one launch per layer).
+ */
+#define B200PPO_PROF_GATHER 0
+#define B200PPO_PROF_GEMM_FWD 1
+#define B200PPO_PROF_LOSS 2
+#define B200PPO_PROF_GEMM_DGRAD 3
+#define B200PPO_PROF_GEMM_WGRAD 4
+#define B200PPO_PROF_ADAM 5
+#define B200PPO_PROF_ALLREDUCE 6
+#define B200PPO_PROF_OTHER 7
+#define B200PPO_PROF_CLASSES 8
+int64_t b200ppo_launch_count(void);
+int b200ppo_profile_begin(b200ppo_ctx* ctx);
+int b200ppo_profile_end(b200ppo_ctx* ctx, double ms_out[B200PPO_PROF_CLASSES], int64_t launches_out[B200PPO_PROF_CLASSES]);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The update is data-parallel over samples: every rank computes the
  * gradient of its slice of each minibatch, gradients are summed over ranks (NCCL all-reduce over
  * NVLink), every rank applies the same Adam step.  Loss means use the GLOBAL minibatch size.

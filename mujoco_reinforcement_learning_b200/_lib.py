@@ -25,6 +25,7 @@ c_ptr = C.c_void_p
 MAX_LAYERS = 8
 ACT_TANH, ACT_RELU = 0, 1
 PREC_FP32, PREC_BF16 = 0, 1
+PROF_CLASSES = ("gather", "gemm_fwd", "loss", "gemm_dgrad", "gemm_wgrad", "adam", "allreduce", "other")
 
 
 class MlpDesc(C.Structure):
@@ -78,6 +79,9 @@ SIGNATURES = {
     "b200ppo_update_host": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, C.POINTER(c_i64), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                     c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_dbl, c_i32, c_i32, c_dbl, c_ptr, c_i32, c_i64,
                                     c_i64, C.POINTER(HParams), c_ptr, c_ptr]),
+    "b200ppo_launch_count": (c_i64, []),
+    "b200ppo_profile_begin": (c_i32, [c_ptr]),
+    "b200ppo_profile_end": (c_i32, [c_ptr, C.POINTER(c_dbl), C.POINTER(c_i64)]),
     "b200ppo_comm_unique_id": (c_i32, [c_ptr]),
     "b200ppo_comm_init": (c_i32, [c_ptr, c_ptr, c_i32, c_i32]),
     "b200ppo_comm_world": (c_i32, [c_ptr, C.POINTER(c_i32), C.POINTER(c_i32)]),

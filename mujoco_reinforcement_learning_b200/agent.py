@@ -24,7 +24,7 @@ class FusedAdam(torch.optim.Adam):
 
     def __init__(self, engine: ActorCriticEngine, net_id: int, lr: float):
         self.engine, self.net_id = engine, net_id
-        params = [p for p, _ in engine.named_slots(net_id)]
+        params = [p for p, _ in engine.module_slots(net_id)]  # torch's numbering: module.parameters() order
         super().__init__(params, lr=lr, foreach=False)
         self.bind_state()
 

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "adam.cuh"
@@ -24,6 +25,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 constexpr int64_t kParamAlign = 32;  // every parameter tensor starts on a 128-byte boundary of the flat buffer
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -76,11 +80,30 @@ static int load_nccl() {
   return B200PPO_OK;
 }
 
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline numbers).
+struct Profiler {
+  bool on = false;
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  void begin(int cls, cudaStream_t st) {
+    if (!on) return;
+    Rec r{cls, nullptr, nullptr};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(recs.back().b, st);
+  }
+};
+
 }  // namespace b200ppo
 
 using namespace b200ppo;
 
 struct b200ppo_ctx {
+  Profiler prof;
   Net net[2];
   int64_t logstd_off = 0, n_params = 0, n_actor = 0;
   int64_t max_batch = 0;
@@ -111,6 +134,14 @@ struct b200ppo_ctx {
 };
 
 namespace b200ppo {
+
+#define PROF(ctx, cls, st, expr)          \
+  do {                                    \
+    (ctx)->prof.begin(cls, st);           \
+    int _pr = (expr);                     \
+    (ctx)->prof.end(st);                  \
+    if (_pr != B200PPO_OK) return _pr;    \
+  } while (0)
 
 static int layout_net(Net& n, const b200ppo_mlp_desc* d, int64_t& cursor) {
   B2_CHECK_ARG(d->n_layers >= 1 && d->n_layers <= B200PPO_MAX_LAYERS, "n_layers %d out of range", d->n_layers);
@@ -213,7 +244,7 @@ static int pick_split(const b200ppo_ctx* ctx, int64_t tiles, int64_t K) {
 // ---- backward ----------------------------------------------------------------------------------------
 // dz[n] holds dL/dz of every layer; the last layer's block must be filled on entry.  Weight / bias gradients go
 // to gpart as `*split_out` split-K partials laid out like the parameter buffer.  grad_x[n] (nullable): dL/dx.
-static int backward_nets(const b200ppo_ctx* ctx, const float* params, const float* x, int64_t B, int nets,
+static int backward_nets(b200ppo_ctx* ctx, const float* params, const float* x, int64_t B, int nets,
                          float* const acts[2], float* const dz[2], float* gpart, int* split_out,
                          float* const grad_x[2], cudaStream_t st) {
   int maxL = 0;
@@ -254,7 +285,7 @@ static int backward_nets(const b200ppo_ctx* ctx, const float* params, const floa
     const bool large = large_tiles >= (2 * num_sms()) / 3;
     GemmGroup g{};
     for (int i = 0; i < np; ++i) gemm_group_add(g, probs[i], large ? 128 : 64, large ? 128 : 64, 1);
-    B2_TRY(launch_gemm_group(g, large, st));
+    PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, launch_gemm_group(g, large, st));
   }
   // every weight / bias gradient in one grouped split-K launch
   if (gpart != nullptr) {
@@ -283,7 +314,7 @@ static int backward_nets(const b200ppo_ctx* ctx, const float* params, const floa
     const int split = pick_split(ctx, tiles, B);
     GemmGroup g{};
     for (int i = 0; i < np; ++i) gemm_group_add(g, probs[i], 64, 64, split);
-    B2_TRY(launch_gemm_group(g, false, st));
+    PROF(ctx, B200PPO_PROF_GEMM_WGRAD, st, launch_gemm_group(g, false, st));
     if (split_out) *split_out = split;
   }
   return B200PPO_OK;
@@ -308,7 +339,7 @@ static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float*
   float* acts[2] = {ctx->ws_act[0], ctx->ws_act[1]};
   float* outs[2] = {ctx->ws_out[0], ctx->ws_out[1]};
   float* dz[2] = {ctx->ws_dz[0], ctx->ws_dz[1]};
-  B2_TRY(forward_nets(ctx, params, obs, B, 3, acts, outs, st));
+  PROF(ctx, B200PPO_PROF_GEMM_FWD, st, forward_nets(ctx, params, obs, B, 3, acts, outs, st));
   const Net& Na = ctx->net[0];
   const Net& Nc = ctx->net[1];
   LossArgs la{};
@@ -322,7 +353,7 @@ static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float*
   la.dv = dz[1] + Nc.dz_off(Nc.d.n_layers - 1, B);
   la.partials = ctx->loss_partials; la.ticket = ctx->ticket;
   la.losses = losses_dev; la.logstd_grad = ctx->gpart + ctx->logstd_off;
-  B2_TRY(launch_ppo_loss(la, st));
+  PROF(ctx, B200PPO_PROF_LOSS, st, launch_ppo_loss(la, st));
   B2_TRY(backward_nets(ctx, params, obs, B, 3, acts, dz, ctx->gpart, split_out, nullptr, st));
   return B200PPO_OK;
 }
@@ -542,9 +573,10 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
   int64_t step = *adam_step_io;
   for (int e = 0; e < epochs; ++e) {
     // shuffled_memory = memory[idx] restricted to the rows this rank will consume
-    B2_TRY(launch_gather_chunked(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
-                                 obs, D, action, A, old_logp, advantage, target, ctx->sh_obs, ctx->sh_act, ctx->sh_logp,
-                                 ctx->sh_adv, ctx->sh_tgt, ctx->err_flag, st));
+    PROF(ctx, B200PPO_PROF_GATHER, st,
+         launch_gather_chunked(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
+                               obs, D, action, A, old_logp, advantage, target, ctx->sh_obs, ctx->sh_act, ctx->sh_logp,
+                               ctx->sh_adv, ctx->sh_tgt, ctx->err_flag, st));
     for (int64_t i = 0; i < nb; ++i) {
       const int64_t r0 = i * lb;
       float* loss_slot = losses_out ? losses_out + (int64_t(e) * nb + i) * 2 : ctx->scratch;
@@ -555,21 +587,26 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
       if (ctx->world == 1) {
         B2_TRY(minibatch_fwd_bwd(ctx, params, ctx->sh_obs + r0 * D, ctx->sh_act + r0 * A, ctx->sh_logp + r0,
                                  ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp, loss_slot, &split, st));
-        B2_TRY(launch_adam(params, ctx->gpart, split, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor,
-                           sa, sc, nullptr, st));
+        PROF(ctx, B200PPO_PROF_ADAM, st,
+             launch_adam(params, ctx->gpart, split, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa,
+                         sc, nullptr, st));
       } else {
         float* red_losses = ctx->grad_flat + ctx->n_params;
         B2_TRY(minibatch_fwd_bwd(ctx, params, ctx->sh_obs + r0 * D, ctx->sh_act + r0 * A, ctx->sh_logp + r0,
                                  ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp, red_losses, &split, st));
-        B2_TRY(launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, ctx->grad_flat, st));
+        PROF(ctx, B200PPO_PROF_OTHER, st,
+             launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, ctx->grad_flat, st));
+        ctx->prof.begin(B200PPO_PROF_ALLREDUCE, st);
         const int rc = g_nccl.AllReduce(ctx->grad_flat, ctx->grad_flat, size_t(ctx->n_params + 4), /*ncclFloat32*/ 7,
                                         /*ncclSum*/ 0, ctx->comm, st);
+        ctx->prof.end(st);
         if (rc != 0) {
           set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
           return B200PPO_ENCCL;
         }
-        B2_TRY(launch_adam(params, ctx->grad_flat, 1, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor,
-                           sa, sc, nullptr, st));
+        PROF(ctx, B200PPO_PROF_ADAM, st,
+             launch_adam(params, ctx->grad_flat, 1, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa,
+                         sc, nullptr, st));
         copy2_kernel<<<1, 32, 0, st>>>(red_losses, loss_slot);
         B2_LAUNCH_CHECK();
       }
@@ -636,6 +673,35 @@ extern "C" B2_EXPORT int b200ppo_update_host(b200ppo_ctx* ctx, float* params, fl
   if (losses_host && n_loss > 0)
     B2_CUDA(cudaMemcpyAsync(losses_host, h.losses, size_t(n_loss) * 4, cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
+  return B200PPO_OK;
+}
+
+// ---- instrumentation -----------------------------------------------------------------------------------
+extern "C" B2_EXPORT int64_t b200ppo_launch_count(void) { return g_launches.load(); }
+
+extern "C" B2_EXPORT int b200ppo_profile_begin(b200ppo_ctx* ctx) {
+  B2_CHECK_ARG(ctx, "b200ppo_profile_begin: null context");
+  for (auto& r : ctx->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  ctx->prof.recs.clear();
+  ctx->prof.on = true;
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_profile_end(b200ppo_ctx* ctx, double ms_out[B200PPO_PROF_CLASSES],
+                                             int64_t launches_out[B200PPO_PROF_CLASSES]) {
+  B2_CHECK_ARG(ctx && ms_out && launches_out, "b200ppo_profile_end: null pointer");
+  ctx->prof.on = false;
+  B2_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < B200PPO_PROF_CLASSES; ++i) { ms_out[i] = 0.0; launches_out[i] = 0; }
+  for (auto& r : ctx->prof.recs) {
+    float ms = 0.f;
+    if (r.b != nullptr && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms_out[r.cls] += ms;
+      launches_out[r.cls] += 1;
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  ctx->prof.recs.clear();
   return B200PPO_OK;
 }
 

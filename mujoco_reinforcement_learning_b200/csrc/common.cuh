@@ -11,6 +11,7 @@
 namespace b200ppo {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define B2_CHECK_ARG(cond, ...)           \
   do {                                    \
@@ -29,7 +30,12 @@ void set_error(const char* fmt, ...);
     }                                                                                              \
   } while (0)
 
-#define B2_LAUNCH_CHECK() B2_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by this: counts it, then checks the launch
+#define B2_LAUNCH_CHECK()                \
+  do {                                   \
+    ::b200ppo::count_launch();           \
+    B2_CUDA(cudaGetLastError());         \
+  } while (0)
 
 #define B2_TRY(expr)            \
   do {                          \

@@ -220,10 +220,10 @@ extern "C" B2_EXPORT int b200ppo_gae(const void* reward, int reward_is_f64, cons
                            const uint8_t* terminated, const uint8_t* done, int64_t n_envs, int64_t n_steps,
                            double gamma, double lmbda, int normalize_rewards, int normalize_advantage,
                            double advantage_scaler, float* advantage, float* value_target, b200ppo_stream stream) {
-  B2_CHECK_ARG(reward && value && next_value && terminated && advantage && value_target, "b200ppo_gae: null pointer");
   B2_CHECK_ARG(n_envs >= 0 && n_steps >= 0 && n_steps < (1ll << 30), "b200ppo_gae: bad shape [%lld,%lld]",
                (long long)n_envs, (long long)n_steps);
   if (n_envs == 0 || n_steps == 0) return B200PPO_OK;
+  B2_CHECK_ARG(reward && value && next_value && terminated && advantage && value_target, "b200ppo_gae: null pointer");
   B2_CHECK_ARG((n_envs + 3) / 4 < (1ll << 31), "b200ppo_gae: too many envs");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float g = float(gamma);          // gamma * int tensor -> float32 tensor

@@ -1,0 +1,56 @@
+"""Multi-GPU plumbing (one process per GPU, `torch.distributed` for rendezvous, NCCL over NVLink for data).
+
+The update is data-parallel over samples: every rank owns a slab of environments for the
+rollout and the GAE scan (no communication: the recurrence and the normalisation run along time only); the
+slabs are all-gathered once per rollout so that the reference's GLOBAL permutation stays bit-exact; every rank
+then consumes rows [r*B/G, (r+1)*B/G) of each global minibatch and the flat fp32 gradient (+ the two loss
+partials) is summed with one NCCL all-reduce per minibatch inside `b200ppo_train`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def rank_rows(minibatch_index: int, global_batch: int, world: int, rank: int) -> range:
+    """Permutation slots of global minibatch `minibatch_index` consumed by `rank` (same arithmetic as the
+    chunked gather in csrc/gather.cu)."""
+    lb = global_batch // world
+    start = minibatch_index * global_batch + rank * lb
+    return range(start, start + lb)
+
+
+def init_engine_comm(engine, group=None) -> None:
+    """Create the engine's NCCL communicator: rank 0 makes the unique id, torch.distributed carries it."""
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lib = _lib.load()
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        _lib.check(lib.b200ppo_comm_unique_id(buf), "b200ppo_comm_unique_id")
+    backend = dist.get_backend(group)
+    dev = engine.device if backend == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0, group=group)
+    ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+    with torch.cuda.device(engine.device):
+        _lib.check(lib.b200ppo_comm_init(engine._ctx, ident, rank, world), "b200ppo_comm_init")
+    engine.rank, engine.world = rank, world
+
+
+def all_gather_fields(fields: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
+    """All-gather every leaf along dim 0 (rank-major = env-major: rank r's envs land at rows [r*N_local, ...))."""
+    world = dist.get_world_size(group)
+    out = {}
+    for k, v in fields.items():
+        v = v.contiguous()
+        full = torch.empty((world * v.shape[0], *v.shape[1:]), dtype=v.dtype, device=v.device)
+        dist.all_gather_into_tensor(full, v, group=group)
+        out[k] = full
+    return out

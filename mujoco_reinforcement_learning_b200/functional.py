@@ -24,6 +24,8 @@ def _gae_rows(reward, value, next_value, terminated, done, gamma, lmbda, normali
     rows, steps = value.shape
     adv = torch.empty_like(value)
     tgt = torch.empty_like(value)
+    if value.numel() == 0:
+        return adv, tgt
     _lib.check(
         lib.b200ppo_gae(_lib.ptr(reward), int(reward.dtype == torch.float64), _lib.ptr(value), _lib.ptr(next_value),
                         _lib.ptr(terminated), _lib.ptr(done), rows, steps, float(gamma), float(lmbda),
@@ -124,6 +126,8 @@ def gather_minibatch(idx, obs, action, logp, advantage, target, check: bool = Tr
     o = torch.empty((cnt, obs2.shape[1]), dtype=torch.float32, device=obs.device)
     a = torch.empty((cnt, act2.shape[1]), dtype=torch.float32, device=obs.device)
     lp, ad, tg = (torch.empty(cnt, dtype=torch.float32, device=obs.device) for _ in range(3))
+    if cnt == 0:
+        return o, a, lp, ad, tg
     err = torch.zeros(1, dtype=torch.int32, device=obs.device)
     _lib.check(
         lib.b200ppo_gather_minibatch(_lib.ptr(idx.contiguous()), cnt, m, _lib.ptr(obs2), obs2.shape[1], _lib.ptr(act2),

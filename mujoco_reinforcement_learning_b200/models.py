@@ -223,8 +223,16 @@ class ActorCriticEngine:
         return (0, self.n_actor) if net_id == 0 else (self.n_actor, self.n_params)
 
     def named_slots(self, net_id: int):
+        """(parameter, offset) of one net in flat-buffer order (logstd last for the actor)."""
         n_actor_slots = 2 * len(self.actor.actor.dims) + 1
         return self.slots[:n_actor_slots] if net_id == 0 else self.slots[n_actor_slots:]
+
+    def module_slots(self, net_id: int):
+        """(parameter, offset) in `module.parameters()` order — the order torch.optim.Adam numbers its state in
+        (the actor's own `actor_logstd` comes before its sub-module's tensors)."""
+        off = {id(p): o for p, o in self.slots}
+        module = self.actor if net_id == 0 else self.critic
+        return [(p, off[id(p)]) for p in module.parameters()]
 
     # -- raw calls ---------------------------------------------------------------------------------------
     def _check_x(self, x: torch.Tensor) -> torch.Tensor:
@@ -323,8 +331,10 @@ class ActorCriticEngine:
                    "b200ppo_minibatch_grads")
         return losses, grads
 
-    def grads_by_name(self, grads: torch.Tensor, names: Sequence[str]):
-        return {n: grads[off:off + p.numel()].view(p.shape) for n, (p, off) in zip(names, self.slots)}
+    def grads_by_name(self, grads: torch.Tensor, named_parameters):
+        """Split a flat gradient into {name: tensor} for an iterable of (name, parameter)."""
+        off = {id(p): o for p, o in self.slots}
+        return {n: grads[off[id(p)]:off[id(p)] + p.numel()].view(p.shape) for n, p in named_parameters}
 
     def train(self, obs, action, old_logp, advantage, target, perms, batch: int, hp: _lib.HParams,
               max_minibatches_per_epoch: int = 0) -> torch.Tensor:
