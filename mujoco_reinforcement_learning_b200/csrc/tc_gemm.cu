@@ -1,0 +1,464 @@
+// Grouped bf16 GEMM on tcgen05 tensor cores — the throughput arithmetic of the actor/critic MLP (2e-2 variant).
+//
+// replaces: aten::addmm / aten::mm of NetworkBlock.forward (src/models/network_block_creator.py:74-86) and of the
+//           autograd backward of ppo.py:121,134, for the hidden layers.
+//
+// Per CTA (192 threads, one 128 x BN output tile, BN in {64,128,256}):
+//   warp 0  TMA producer : cp.async.bulk.tensor 2-D boxes (128-byte swizzle) of A and B into a 4-stage smem ring,
+//                          completion on per-stage mbarriers; out-of-bounds rows/columns are zero-filled by TMA,
+//                          so ragged M/N/K need no padding in global memory.
+//   warp 1  MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x 4 per
+//                          stage into a TMEM accumulator (BN fp32 columns), tcgen05.commit frees the stage.
+//   warps 2-5 epilogue   : tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused bias + tanh/relu, or
+//                          activation-derivative multiply (dgrad), or fp32 split-K partial store (wgrad) with
+//                          the bias gradient read off an appended ones-column of the B operand.
+// Operands may be K-major or MN-major (UMMA descriptor major bits), so forward (X W^T), dgrad (dZ W via a
+// transposed bf16 weight copy) and wgrad (dZ^T X, both operands MN-major) share the kernel with no transposes
+// of activations.
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "tc_gemm.cuh"
+
+namespace b200ppo {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;  // bf16 elements: 128 bytes = one swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// 64-bit shared-memory matrix descriptor (sm_100): 128-byte swizzle, version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;  // descriptor version (Blackwell)
+  d |= uint64_t(2) << 61;  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGroup grp) {
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + TC_STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int pi = 0;
+#pragma unroll 1
+  for (int i = 1; i < grp.count; ++i)
+    if (int(blockIdx.x) >= grp.p[i].tile_begin) pi = i;
+  const TcProblem& P = grp.p[pi];
+  int local = int(blockIdx.x) - P.tile_begin;
+  const int tiles_mn = P.tiles_m * P.tiles_n;
+  const int split = local / tiles_mn;
+  local -= split * tiles_mn;
+  const int m0 = (local / P.tiles_n) * TC_BM, n0 = (local % P.tiles_n) * BN;
+  const int total_kt = (P.K + TC_BK - 1) / TC_BK;
+  const int kt_begin = split * P.k_tiles_per_split;
+  const int kt_end = min(total_kt, kt_begin + P.k_tiles_per_split);
+  const bool has_k = kt_end > kt_begin;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && has_k) {  // ===== TMA producer =====
+      for (int kt = kt_begin, it = 0; kt < kt_end; ++kt, ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], TC_A_BYTES + B_BYTES);
+        uint8_t* a = sA + s * TC_A_BYTES;
+        uint8_t* b = sB + s * B_BYTES;
+        if (!P.a_mn_major) {
+          tma_load_2d(a, &P.tmA, &full_bar[s], kt * TC_BK, m0);
+        } else {
+          tma_load_2d(a, &P.tmA, &full_bar[s], m0, kt * TC_BK);
+          tma_load_2d(a + 64 * TC_BK * 2, &P.tmA, &full_bar[s], m0 + 64, kt * TC_BK);
+        }
+        if (!P.b_mn_major) {
+          tma_load_2d(b, &P.tmB, &full_bar[s], kt * TC_BK, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b + j * 64 * TC_BK * 2, &P.tmB, &full_bar[s], n0 + 64 * j, kt * TC_BK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (has_k) {  // ===== MMA issuer =====
+      // instruction descriptor: D fp32, A/B bf16, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(P.a_mn_major != 0) << 15) |
+                             (uint32_t(P.b_mn_major != 0) << 16) | (uint32_t(BN >> 3) << 17) | (uint32_t(TC_BM >> 4) << 24);
+      // K-major SW128: 8-row groups 1024 B apart; one K=16 step = +32 B inside the swizzle row.
+      // MN-major SW128: K atoms (8 k-rows x 128 B) 1024 B apart (SBO), 64-wide MN atoms BK*128 B apart (LBO);
+      //                 one K=16 step = +2048 B.
+      const uint32_t a_lbo = P.a_mn_major ? TC_BK * 128 : 0, b_lbo = P.b_mn_major ? TC_BK * 128 : 0;
+      const uint32_t a_kstep = P.a_mn_major ? 2048 : 32, b_kstep = P.b_mn_major ? 2048 : 32;
+      for (int kt = kt_begin, it = 0; kt < kt_end; ++kt, ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(sA + s * TC_A_BYTES), b_addr = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            umma_bf16(tmem_base, umma_desc(a_addr + k * a_kstep, a_lbo, 1024), umma_desc(b_addr + k * b_kstep, b_lbo, 1024),
+                      idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (kt == kt_end - 1) umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+      }
+    }
+  } else {  // ===== epilogue warps 2..5 =====
+    if (has_k) {
+      mbar_wait(tmem_full_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < P.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      if (has_k) {
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      const int nb = n0 + c * 32;
+      if (!row_ok || nb >= P.N) continue;
+      const bool full = nb + 32 <= P.N;
+      float h[32];
+      if (P.epilogue == TC_EPI_FWD) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float z = __uint_as_float(v[j]) + ((full || nb + j < P.N) ? __ldg(P.bias + nb + j) : 0.f);
+          h[j] = P.act == B200PPO_ACT_TANH ? tanhf(z) : fmaxf(z, 0.f);
+        }
+      } else if (P.epilogue == TC_EPI_DGRAD) {
+        const __nv_bfloat16* ap = P.aux + int64_t(m) * P.ld_aux + nb;
+        float a[32];
+        if (full && (P.ld_aux % 8 == 0)) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(ap) + u);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[t]);
+              a[u * 8 + t * 2] = __low2float(b2);
+              a[u * 8 + t * 2 + 1] = __high2float(b2);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = (nb + j < P.N) ? __bfloat162float(ap[j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float g = __uint_as_float(v[j]);
+          h[j] = P.act == B200PPO_ACT_TANH ? g * (1.f - a[j] * a[j]) : (a[j] > 0.f ? g : 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = __uint_as_float(v[j]);
+      }
+      if (P.out_bf16 != nullptr) {
+        __nv_bfloat16* op = P.out_bf16 + int64_t(m) * P.ld_bf16 + nb;
+        if (full && (P.ld_bf16 % 8 == 0)) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            reinterpret_cast<uint4*>(op)[u] = make_uint4(pack_bf16(h[u * 8], h[u * 8 + 1]), pack_bf16(h[u * 8 + 2], h[u * 8 + 3]),
+                                                         pack_bf16(h[u * 8 + 4], h[u * 8 + 5]), pack_bf16(h[u * 8 + 6], h[u * 8 + 7]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < P.N) op[j] = __float2bfloat16_rn(h[j]);
+        }
+      }
+      if (P.out_f32 != nullptr) {
+        float* base = P.out_f32 + int64_t(split) * P.split_stride;
+        const int ncols = P.bias_col >= 0 ? P.bias_col : P.N;  // columns that belong to the matrix proper
+        float* op = base + int64_t(m) * P.ld_f32 + nb;
+        if (nb + 32 <= ncols && (P.ld_f32 % 4 == 0) && (P.split_stride % 4 == 0)) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) reinterpret_cast<float4*>(op)[u] = make_float4(h[u * 4], h[u * 4 + 1], h[u * 4 + 2], h[u * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < ncols) op[j] = h[j];
+        }
+        if (P.bias_col >= nb && P.bias_col < nb + 32 && P.bias_grad != nullptr) {
+          float bg = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j == P.bias_col) bg = h[j];
+          P.bias_grad[int64_t(split) * P.split_stride + m] = bg;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::mutex g_map_mutex;
+static std::map<std::tuple<const void*, int64_t, int64_t, int64_t, int, int>, CUtensorMap> g_map_cache;
+
+int tc_init() {
+  if (g_encode) return B200PPO_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  B2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return B200PPO_ECUDA;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return B200PPO_OK;
+}
+
+static int make_map(CUtensorMap* out, const __nv_bfloat16* ptr, int64_t inner, int64_t outer, int64_t pitch, int box_inner,
+                    int box_outer) {
+  B2_TRY(tc_init());
+  auto key = std::make_tuple(static_cast<const void*>(ptr), inner, outer, pitch, box_inner, box_outer);
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) {
+    *out = it->second;
+    return B200PPO_OK;
+  }
+  B2_CHECK_ARG(aligned16(ptr) && (pitch * 2) % 16 == 0 && inner > 0 && outer > 0, "tensor map: base/pitch must be 16-byte aligned");
+  cuuint64_t gdim[2] = {cuuint64_t(inner), cuuint64_t(outer)};
+  cuuint64_t gstride[1] = {cuuint64_t(pitch * 2)};
+  cuuint32_t box[2] = {cuuint32_t(box_inner), cuuint32_t(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  const CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for extents [%lld,%lld] pitch %lld box [%d,%d]", int(r), (long long)inner,
+              (long long)outer, (long long)pitch, box_inner, box_outer);
+    return B200PPO_ECUDA;
+  }
+  if (g_map_cache.size() > 65536) g_map_cache.clear();
+  g_map_cache.emplace(key, m);
+  *out = m;
+  return B200PPO_OK;
+}
+
+int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B, int bn, int split_k) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return B200PPO_OK;
+  B2_CHECK_ARG(g.count < kMaxTcProblems, "too many problems in one tensor-core group");
+  p.a_mn_major = A.mn_major;
+  p.b_mn_major = B.mn_major;
+  if (!A.mn_major) B2_TRY(make_map(&p.tmA, A.ptr, p.K, p.M, A.pitch, TC_BK, TC_BM));
+  else B2_TRY(make_map(&p.tmA, A.ptr, p.M, p.K, A.pitch, 64, TC_BK));
+  if (!B.mn_major) B2_TRY(make_map(&p.tmB, B.ptr, p.K, p.N, B.pitch, TC_BK, bn));
+  else B2_TRY(make_map(&p.tmB, B.ptr, p.N, p.K, B.pitch, 64, TC_BK));
+  const int total_kt = (p.K + TC_BK - 1) / TC_BK;
+  if (split_k < 1) split_k = 1;
+  if (split_k > total_kt) split_k = total_kt;
+  p.split_k = split_k;
+  p.k_tiles_per_split = (total_kt + split_k - 1) / split_k;
+  p.tiles_m = (p.M + TC_BM - 1) / TC_BM;
+  p.tiles_n = (p.N + bn - 1) / bn;
+  p.tile_begin = g.total_tiles;
+  g.total_tiles += p.tiles_m * p.tiles_n * split_k;
+  g.p[g.count++] = p;
+  return B200PPO_OK;
+}
+
+template <int BN>
+static int launch_bn(const TcGroup& g, cudaStream_t st) {
+  constexpr int smem = TC_STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    B2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  tc_gemm_kernel<BN><<<g.total_tiles, TC_THREADS, smem, st>>>(g);
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
+
+int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st) {
+  if (g.total_tiles == 0) return B200PPO_OK;
+  switch (bn) {
+    case 64: return launch_bn<64>(g, st);
+    case 128: return launch_bn<128>(g, st);
+    case 256: return launch_bn<256>(g, st);
+  }
+  set_error("unsupported tensor-core N tile %d", bn);
+  return B200PPO_EINVAL;
+}
+
+int tc_pick_bn(int64_t tiles_m_total, int N) {
+  // widest N tile that still gives every SM a CTA
+  const int sms = num_sms();
+  for (int bn : {256, 128}) {
+    if (N >= bn && tiles_m_total * ((N + bn - 1) / bn) >= sms) return bn;
+  }
+  if (N > 64 && tiles_m_total * ((N + 127) / 128) * 2 >= sms) return 128;
+  return 64;
+}
+
+// ---- debug entry point: C = A * B^T through the tensor-core kernel (used by the GPU tests) -------------------------
+__global__ void cast_pad_bf16_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t pitch,
+                                     __nv_bfloat16* __restrict__ dst) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * pitch) return;
+  const int64_t r = i / pitch, c = i % pitch;
+  dst[i] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+}
+
+__global__ void sum_splits_kernel(const float* __restrict__ part, int splits, int64_t stride, int64_t n, float* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += part[k * stride + i];
+  out[i] = s;
+}
+
+}  // namespace b200ppo
+
+using namespace b200ppo;
+
+extern "C" B2_EXPORT int b200ppo_debug_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                                               int32_t a_mn_major, int32_t b_mn_major, int32_t bn, int32_t split_k,
+                                               b200ppo_stream stream) {
+  B2_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "b200ppo_debug_tc_gemm: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto pad8 = [](int64_t x) { return (x + 7) / 8 * 8; };
+  // global arrays: K-major operand [MN][K]; MN-major operand [K][MN]
+  const int64_t a_rows = a_mn_major ? K : M, a_cols = a_mn_major ? M : K;
+  const int64_t b_rows = b_mn_major ? K : N, b_cols = b_mn_major ? N : K;
+  const int64_t a_pitch = pad8(a_cols), b_pitch = pad8(b_cols);
+  __nv_bfloat16 *Ab = nullptr, *Bb = nullptr;
+  float* part = nullptr;
+  if (split_k < 1) split_k = 1;
+  B2_CUDA(cudaMalloc(&Ab, a_rows * a_pitch * 2));
+  B2_CUDA(cudaMalloc(&Bb, b_rows * b_pitch * 2));
+  const int64_t mn = int64_t(M) * N, stride = (mn + 3) / 4 * 4;
+  B2_CUDA(cudaMalloc(&part, size_t(split_k) * stride * 4));
+  cast_pad_bf16_kernel<<<unsigned((a_rows * a_pitch + 255) / 256), 256, 0, st>>>(A, a_rows, a_cols, a_pitch, Ab);
+  B2_LAUNCH_CHECK();
+  cast_pad_bf16_kernel<<<unsigned((b_rows * b_pitch + 255) / 256), 256, 0, st>>>(B, b_rows, b_cols, b_pitch, Bb);
+  B2_LAUNCH_CHECK();
+  TcGroup g{};
+  TcProblem p{};
+  p.M = M; p.N = N; p.K = K;
+  p.epilogue = TC_EPI_STORE;
+  p.out_f32 = part; p.ld_f32 = N; p.split_stride = stride; p.bias_col = -1;
+  int rc = tc_group_add(g, p, TcOperand{Ab, a_pitch, a_mn_major}, TcOperand{Bb, b_pitch, b_mn_major}, bn, split_k);
+  if (rc == B200PPO_OK) rc = launch_tc_group(g, bn, st);
+  if (rc == B200PPO_OK) {
+    sum_splits_kernel<<<unsigned((mn + 255) / 256), 256, 0, st>>>(part, g.p[0].split_k, stride, mn, C);
+    count_launch();
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(Ab); cudaFree(Bb); cudaFree(part);
+  {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    g_map_cache.clear();  // the temporaries above are gone
+  }
+  if (rc != B200PPO_OK) return rc;
+  B2_CUDA(cudaGetLastError());
+  return B200PPO_OK;
+}

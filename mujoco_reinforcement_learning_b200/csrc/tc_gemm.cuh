@@ -1,0 +1,57 @@
+// Grouped bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators, TMA operand staging).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace b200ppo {
+
+enum TcEpilogue : int {
+  TC_EPI_FWD = 0,    // h = act(acc + bias[n]) -> bf16 (and optionally fp32)
+  TC_EPI_DGRAD = 1,  // dz = acc * act'(aux[m,n]) -> bf16
+  TC_EPI_STORE = 2,  // fp32 store of a split-K partial; column `bias_col` is routed to bias_grad[m]
+};
+
+// C[m,n] = sum_k A(m,k) * B(n,k), bf16 operands, fp32 accumulation in TMEM.
+// K-major operand: global bf16 [rows = M or N][k], k contiguous.   MN-major operand: global bf16 [k][M or N].
+struct TcProblem {
+  CUtensorMap tmA, tmB;
+  int M, N, K;
+  int a_mn_major, b_mn_major;
+  int tiles_m, tiles_n, split_k, k_tiles_per_split, tile_begin;
+  int epilogue, act;
+  const float* bias;
+  __nv_bfloat16* out_bf16;
+  int ld_bf16;
+  float* out_f32;
+  int ld_f32;
+  int64_t split_stride;
+  const __nv_bfloat16* aux;
+  int ld_aux;
+  float* bias_grad;
+  int bias_col;  // -1: none
+};
+
+constexpr int kMaxTcProblems = 4;
+
+struct TcGroup {
+  TcProblem p[kMaxTcProblems];
+  int count;
+  int total_tiles;
+};
+
+// Operand description handed to tc_group_add (device pointers to bf16, pitches in elements).
+struct TcOperand {
+  const __nv_bfloat16* ptr;
+  int64_t pitch;   // elements between consecutive rows of the global array
+  int mn_major;    // 0: array is [MN][K] (K contiguous); 1: array is [K][MN] (MN contiguous)
+};
+
+int tc_init();  // resolves cuTensorMapEncodeTiled; returns B200PPO_OK or an error
+// bn: N tile (64, 128 or 256).  Fills tensor maps (cached) and tile bookkeeping.
+int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B, int bn, int split_k);
+int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st);
+int tc_pick_bn(int64_t rows_total_tiles_m, int N);
+
+}  // namespace b200ppo

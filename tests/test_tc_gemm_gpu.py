@@ -1,0 +1,43 @@
+"""tcgen05 GEMM kernel (bf16 operands, fp32 TMEM accumulation) vs torch on the same bf16-rounded operands."""
+import pytest
+import torch
+
+from mujoco_reinforcement_learning_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CASES = [
+    # M, N, K, a_mn, b_mn, bn, split
+    (128, 128, 64, 0, 0, 128, 1),
+    (128, 64, 16, 0, 0, 64, 1),
+    (256, 256, 256, 0, 0, 256, 1),
+    (4096, 256, 376, 0, 0, 128, 1),      # forward layer 1 (K not a multiple of 64: TMA zero fill)
+    (500, 256, 256, 0, 0, 64, 1),        # ragged M
+    (300, 200, 100, 0, 0, 128, 1),       # ragged everything
+    (128, 128, 64, 1, 1, 128, 1),        # both operands MN-major (wgrad form)
+    (128, 128, 128, 1, 0, 128, 1),
+    (128, 128, 128, 0, 1, 64, 1),
+    (256, 377, 4096, 1, 1, 128, 8),      # wgrad layer 1 with the ones-column, split-K
+    (256, 257, 500, 1, 1, 64, 3),        # wgrad layer 2, ragged K
+    (64, 27, 1000, 1, 1, 64, 2),
+]
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,bn,split", CASES)
+def test_tc_gemm_matches_torch(M, N, K, a_mn, b_mn, bn, split):
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((K, M) if a_mn else (M, K), device=DEV, generator=g)
+    B = torch.randn((K, N) if b_mn else (N, K), device=DEV, generator=g)
+    C = torch.full((M, N), float("nan"), device=DEV)
+    _lib.check(lib.b200ppo_debug_tc_gemm(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, a_mn, b_mn, bn, split,
+                                         _lib.stream_ptr()), "debug_tc_gemm")
+    Ab = A.bfloat16().double()
+    Bb = B.bfloat16().double()
+    Am = Ab.t() if a_mn else Ab
+    Bm = Bb.t() if b_mn else Bb
+    ref = Am @ Bm.t()
+    err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert torch.isfinite(C).all()
+    assert err < 2e-5, f"scaled max error {err:.3e}"  # same bf16 operands, fp32 vs fp64 accumulation only
