@@ -11,9 +11,12 @@
 #include <vector>
 
 #include "adam.cuh"
+#include "cast.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
+#include "heads.cuh"
 #include "ppo_loss.cuh"
+#include "tc_gemm.cuh"
 
 namespace b200ppo {
 
@@ -129,6 +132,18 @@ struct b200ppo_ctx {
     int64_t* perms = nullptr;
     int64_t rows = 0, perm_elems = 0, loss_elems = 0;
   } host;
+  // bf16 operands of the tensor-core path (precision == B200PPO_PREC_BF16); hidden layers only
+  struct {
+    __nv_bfloat16* H[2][B200PPO_MAX_LAYERS] = {};   // hidden activations [max_batch, pitchH], ones in column dims[l]
+    __nv_bfloat16* dZ[2][B200PPO_MAX_LAYERS] = {};  // dL/dz of every layer [max_batch, pitchZ]
+    __nv_bfloat16* W[2][B200PPO_MAX_LAYERS] = {};   // W_l   [dims[l], pitchW]
+    __nv_bfloat16* WT[2][B200PPO_MAX_LAYERS] = {};  // W_l^T [in_l, pitchZ] (l >= 1)
+    int pitchH[2][B200PPO_MAX_LAYERS] = {}, pitchZ[2][B200PPO_MAX_LAYERS] = {}, pitchW[2][B200PPO_MAX_LAYERS] = {};
+    __nv_bfloat16* X = nullptr;      // [max_batch, pitchX] staged observations (grads-only entry point)
+    __nv_bfloat16* sh_obs = nullptr; // [sh_cap, pitchX] shuffled observations of an epoch
+    int pitchX = 0;
+    WeightCastGroup casts{};
+  } bf;
   void* comm = nullptr;
   int rank = 0, world = 1;
 };
@@ -197,7 +212,7 @@ __global__ void copy2_kernel(const float* __restrict__ src, float* __restrict__ 
 // ---- forward -----------------------------------------------------------------------------------------
 // nets: bit 0 actor, bit 1 critic.  acts[n]: hidden activations (dense for `B` rows); outs[n]: [B, out_dim].
 static int forward_nets(const b200ppo_ctx* ctx, const float* params, const float* x, int64_t B, int nets,
-                        float* const acts[2], float* const outs[2], cudaStream_t st) {
+                        float* const acts[2], float* const outs[2], cudaStream_t st, bool skip_last = false) {
   int maxL = 0;
   for (int n = 0; n < 2; ++n)
     if (nets & (1 << n)) maxL = std::max(maxL, ctx->net[n].d.n_layers);
@@ -210,6 +225,7 @@ static int forward_nets(const b200ppo_ctx* ctx, const float* params, const float
       const Net& N = ctx->net[n];
       if (!(nets & (1 << n)) || l >= N.d.n_layers) continue;
       const bool last = (l == N.d.n_layers - 1);
+      if (last && skip_last) continue;
       GemmProblem p{};
       p.A = (l == 0) ? x : acts[n] + N.act_off(l - 1, B);
       p.a_sm = N.in_dim(l); p.a_sk = 1;
@@ -226,6 +242,7 @@ static int forward_nets(const b200ppo_ctx* ctx, const float* params, const float
       if (p.N < 96) large_tiles = -(1ll << 40);
       probs[np++] = p;
     }
+    if (np == 0) continue;
     const bool large = large_tiles >= (2 * num_sms()) / 3;
     for (int i = 0; i < np; ++i) gemm_group_add(g, probs[i], large ? 128 : 64, large ? 128 : 64, 1);
     B2_TRY(launch_gemm_group(g, large, st));
@@ -246,12 +263,13 @@ static int pick_split(const b200ppo_ctx* ctx, int64_t tiles, int64_t K) {
 // to gpart as `*split_out` split-K partials laid out like the parameter buffer.  grad_x[n] (nullable): dL/dx.
 static int backward_nets(b200ppo_ctx* ctx, const float* params, const float* x, int64_t B, int nets,
                          float* const acts[2], float* const dz[2], float* gpart, int* split_out,
-                         float* const grad_x[2], cudaStream_t st) {
+                         float* const grad_x[2], cudaStream_t st, bool skip_last_dgrad = false) {
   int maxL = 0;
   for (int n = 0; n < 2; ++n)
     if (nets & (1 << n)) maxL = std::max(maxL, ctx->net[n].d.n_layers);
-  // dgrad chain, grouped by distance from the output
-  for (int s = 0; s < maxL; ++s) {
+  // dgrad chain, grouped by distance from the output (s = 0: through the output layer — done by the fused heads
+  // kernel when skip_last_dgrad)
+  for (int s = skip_last_dgrad ? 1 : 0; s < maxL; ++s) {
     GemmProblem probs[2];
     int np = 0;
     int64_t large_tiles = 0;
@@ -320,6 +338,159 @@ static int backward_nets(b200ppo_ctx* ctx, const float* params, const float* x, 
   return B200PPO_OK;
 }
 
+
+static inline int pad8(int x) { return (x + 7) / 8 * 8; }
+
+// bf16 operands of the tensor-core path.  Every Linear of both nets runs on tcgen05 (the 17- and 1-wide output
+// layers too: a mostly-empty 128x64 tile costs less than a latency-bound SIMT pass).
+static int alloc_bf16_workspaces(b200ppo_ctx* c) {
+  B2_TRY(tc_init());
+  auto& bf = c->bf;
+  const int64_t Bm = c->max_batch;
+  bf.pitchX = pad8(c->net[0].d.in_dim + 1);
+  B2_TRY(dev_alloc(&bf.X, Bm * bf.pitchX));
+  B2_TRY(launch_init_ones_column(bf.X, Bm, bf.pitchX, c->net[0].d.in_dim, nullptr));
+  bf.casts.count = 0;
+  bf.casts.max_elems = 0;
+  for (int n = 0; n < 2; ++n) {
+    const Net& N = c->net[n];
+    B2_CHECK_ARG(N.d.n_layers >= 2, "the bf16 tensor-core path needs at least one hidden layer per network");
+    for (int l = 0; l < N.d.n_layers; ++l) {
+      const bool last = l == N.d.n_layers - 1;
+      bf.pitchZ[n][l] = pad8(N.d.dims[l]);
+      bf.pitchW[n][l] = pad8(N.in_dim(l));
+      if (!last) {  // hidden activation with the ones-column the wgrad reads the bias gradient from
+        bf.pitchH[n][l] = pad8(N.d.dims[l] + 1);
+        B2_TRY(dev_alloc(&bf.H[n][l], Bm * bf.pitchH[n][l]));
+        B2_TRY(launch_init_ones_column(bf.H[n][l], Bm, bf.pitchH[n][l], N.d.dims[l], nullptr));
+      }
+      B2_TRY(dev_alloc(&bf.dZ[n][l], Bm * bf.pitchZ[n][l], true));
+      B2_TRY(dev_alloc(&bf.W[n][l], int64_t(N.d.dims[l]) * bf.pitchW[n][l], true));
+      if (l >= 1) B2_TRY(dev_alloc(&bf.WT[n][l], int64_t(N.in_dim(l)) * bf.pitchZ[n][l], true));
+      WeightCast& w = bf.casts.w[bf.casts.count++];
+      w.src = nullptr;  // the parameter base is a per-call argument: filled in by cast_weights()
+      w.dst = bf.W[n][l]; w.dst_t = bf.WT[n][l];
+      w.out = N.d.dims[l]; w.in = N.in_dim(l); w.pitch = bf.pitchW[n][l]; w.pitch_t = bf.pitchZ[n][l];
+      bf.casts.max_elems = std::max(bf.casts.max_elems, w.out * w.in);
+    }
+  }
+  B2_CUDA(cudaDeviceSynchronize());
+  return B200PPO_OK;
+}
+
+static int cast_weights(b200ppo_ctx* ctx, const float* params, cudaStream_t st) {
+  WeightCastGroup g = ctx->bf.casts;
+  int k = 0;
+  for (int n = 0; n < 2; ++n)
+    for (int l = 0; l < ctx->net[n].d.n_layers; ++l) g.w[k++].src = params + ctx->net[n].w_off[l];
+  return launch_cast_weights(g, st);
+}
+
+// forward of both nets on the tensor cores; hidden activations in bf16 (+ ones column), outputs in fp32.
+static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_bfloat16* xb, int64_t B,
+                             float* const outs[2], cudaStream_t st) {
+  auto& bf = ctx->bf;
+  int maxL = 0;
+  for (int n = 0; n < 2; ++n) maxL = std::max(maxL, ctx->net[n].d.n_layers);
+  for (int l = 0; l < maxL; ++l) {
+    TcGroup g{};
+    int maxN = 0, nets_here = 0;
+    for (int n = 0; n < 2; ++n)
+      if (l < ctx->net[n].d.n_layers) { maxN = std::max(maxN, ctx->net[n].d.dims[l]); ++nets_here; }
+    const int bn = tc_pick_bn(int64_t((B + 127) / 128) * nets_here, maxN);
+    for (int n = 0; n < 2; ++n) {
+      const Net& N = ctx->net[n];
+      if (l >= N.d.n_layers) continue;
+      const bool last = l == N.d.n_layers - 1;
+      TcProblem p{};
+      p.M = int(B); p.N = N.d.dims[l]; p.K = N.in_dim(l);
+      p.epilogue = TC_EPI_FWD;
+      p.bias = params + N.b_off[l];
+      p.bias_col = -1;
+      if (last) {
+        p.act = N.d.final_tanh ? TC_ACT_TANH_SCALE : TC_ACT_NONE;
+        p.out_scale = N.d.out_scale;
+        p.out_f32 = outs[n]; p.ld_f32 = N.d.dims[l];
+      } else {
+        p.act = N.d.activation;
+        p.out_bf16 = bf.H[n][l]; p.ld_bf16 = bf.pitchH[n][l];
+      }
+      TcOperand A{l == 0 ? xb : bf.H[n][l - 1], l == 0 ? bf.pitchX : bf.pitchH[n][l - 1], 0};
+      TcOperand Bop{bf.W[n][l], bf.pitchW[n][l], 0};
+      B2_TRY(tc_group_add(g, p, A, Bop, bn, 1));
+    }
+    PROF(ctx, B200PPO_PROF_GEMM_FWD, st, launch_tc_group(g, bn, st));
+  }
+  return B200PPO_OK;
+}
+
+// backward of both nets on the tensor cores.  bf.dZ[n][L-1] (dL/dz of the output layers, bf16) is filled on entry.
+static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t B, float* gpart, int* split_out,
+                              cudaStream_t st) {
+  auto& bf = ctx->bf;
+  int maxL = 0;
+  for (int n = 0; n < 2; ++n) maxL = std::max(maxL, ctx->net[n].d.n_layers);
+  // dgrads, deepest first: dZ_{l-1} = (dZ_l W_l) * act'(H_{l-1}),  B operand = W_l^T (K-major bf16 copy)
+  for (int s = 0; s < maxL; ++s) {
+    TcGroup g{};
+    int maxN = 0, nets_here = 0;
+    for (int n = 0; n < 2; ++n) {
+      const int l = ctx->net[n].d.n_layers - 1 - s;
+      if (l >= 1) { maxN = std::max(maxN, ctx->net[n].in_dim(l)); ++nets_here; }
+    }
+    if (nets_here == 0) break;
+    const int bn = tc_pick_bn(int64_t((B + 127) / 128) * nets_here, maxN);
+    for (int n = 0; n < 2; ++n) {
+      const Net& N = ctx->net[n];
+      const int l = N.d.n_layers - 1 - s;
+      if (l < 1) continue;
+      TcProblem p{};
+      p.M = int(B); p.N = N.in_dim(l); p.K = N.d.dims[l];
+      p.epilogue = TC_EPI_DGRAD; p.act = N.d.activation;
+      p.aux = bf.H[n][l - 1]; p.ld_aux = bf.pitchH[n][l - 1];
+      p.out_bf16 = bf.dZ[n][l - 1]; p.ld_bf16 = bf.pitchZ[n][l - 1];
+      p.bias_col = -1;
+      TcOperand A{bf.dZ[n][l], bf.pitchZ[n][l], 0};
+      TcOperand Bop{bf.WT[n][l], bf.pitchZ[n][l], 0};
+      B2_TRY(tc_group_add(g, p, A, Bop, bn, 1));
+    }
+    PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, launch_tc_group(g, bn, st));
+  }
+  // every weight / bias gradient: dW_l = dZ_l^T [H_{l-1} | 1], both operands MN-major, split-K over the batch
+  int64_t tiles = 0;
+  int maxN = 0;
+  for (int n = 0; n < 2; ++n)
+    for (int l = 0; l < ctx->net[n].d.n_layers; ++l) {
+      tiles += int64_t((ctx->net[n].d.dims[l] + 127) / 128) * ((ctx->net[n].in_dim(l) + 1 + 127) / 128);
+      maxN = std::max(maxN, ctx->net[n].in_dim(l) + 1);
+    }
+  int split = int(std::min<int64_t>(std::max<int64_t>(1, (2ll * num_sms() + tiles - 1) / std::max<int64_t>(tiles, 1)), ctx->max_split));
+  split = int(std::min<int64_t>(split, (B + 63) / 64));
+  if (split < 1) split = 1;
+  const int bn = maxN > 64 ? 128 : 64;
+  TcGroup g{};
+  for (int n = 0; n < 2; ++n) {
+    const Net& N = ctx->net[n];
+    for (int l = 0; l < N.d.n_layers; ++l) {
+      TcProblem p{};
+      p.M = N.d.dims[l]; p.N = N.in_dim(l) + 1; p.K = int(B);
+      p.epilogue = TC_EPI_STORE;
+      p.out_f32 = gpart + N.w_off[l]; p.ld_f32 = N.in_dim(l); p.split_stride = ctx->n_params;
+      p.bias_grad = gpart + N.b_off[l]; p.bias_col = N.in_dim(l);
+      TcOperand A{bf.dZ[n][l], bf.pitchZ[n][l], 1};
+      TcOperand Bop{l == 0 ? xb : bf.H[n][l - 1], l == 0 ? bf.pitchX : bf.pitchH[n][l - 1], 1};
+      if (g.count == kMaxTcProblems) {
+        PROF(ctx, B200PPO_PROF_GEMM_WGRAD, st, launch_tc_group(g, bn, st));
+        g = TcGroup{};
+      }
+      B2_TRY(tc_group_add(g, p, A, Bop, bn, split));
+    }
+  }
+  PROF(ctx, B200PPO_PROF_GEMM_WGRAD, st, launch_tc_group(g, bn, st));
+  if (split_out) *split_out = split;
+  return B200PPO_OK;
+}
+
 static int check_batch(const b200ppo_ctx* ctx, int64_t B, const char* who) {
   if (ctx == nullptr) {
     set_error("%s: null context", who);
@@ -333,38 +504,80 @@ static int check_batch(const b200ppo_ctx* ctx, int64_t B, const char* who) {
 }
 
 // forward + losses + backward of one minibatch; gradients left as split-K partials in ctx->gpart.
-static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float* obs, const float* action,
-                             const float* old_logp, const float* adv, const float* tgt, int64_t B,
-                             const b200ppo_hparams* hp, float* losses_dev, int* split_out, cudaStream_t st) {
-  float* acts[2] = {ctx->ws_act[0], ctx->ws_act[1]};
-  float* outs[2] = {ctx->ws_out[0], ctx->ws_out[1]};
-  float* dz[2] = {ctx->ws_dz[0], ctx->ws_dz[1]};
-  PROF(ctx, B200PPO_PROF_GEMM_FWD, st, forward_nets(ctx, params, obs, B, 3, acts, outs, st));
+static void fill_loss_args(const b200ppo_ctx* ctx, LossArgs& la, const float* params, const float* mean, const float* value,
+                           const float* action, const float* old_logp, const float* adv, const float* tgt, int64_t B,
+                           const b200ppo_hparams* hp) {
   const Net& Na = ctx->net[0];
-  const Net& Nc = ctx->net[1];
-  LossArgs la{};
-  la.mean = outs[0]; la.logstd = params + ctx->logstd_off; la.action = action; la.old_logp = old_logp;
-  la.advantage = adv; la.value = outs[1]; la.target = tgt; la.batch = B; la.act_dim = Na.out_dim();
+  la.mean = mean; la.logstd = params + ctx->logstd_off; la.action = action; la.old_logp = old_logp;
+  la.advantage = adv; la.value = value; la.target = tgt; la.batch = B; la.act_dim = Na.out_dim();
   la.final_tanh = Na.d.final_tanh; la.out_scale = Na.d.out_scale;
   la.clip_eps = float(hp->clip_epsilon); la.ent_coef = float(hp->entropy_eps);
   la.inv_global_batch = 1.f / float(B * ctx->world);
   la.rank_share = 1.f / float(ctx->world);
-  la.dz_actor = dz[0] + Na.dz_off(Na.d.n_layers - 1, B);
-  la.dv = dz[1] + Nc.dz_off(Nc.d.n_layers - 1, B);
-  la.partials = ctx->loss_partials; la.ticket = ctx->ticket;
-  la.losses = losses_dev; la.logstd_grad = ctx->gpart + ctx->logstd_off;
-  PROF(ctx, B200PPO_PROF_LOSS, st, launch_ppo_loss(la, st));
-  B2_TRY(backward_nets(ctx, params, obs, B, 3, acts, dz, ctx->gpart, split_out, nullptr, st));
-  return B200PPO_OK;
+}
+
+// obs: fp32 rows (fp32 path) — or obs_b: bf16 rows with the ones-column (tensor-core path).
+static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float* obs, const __nv_bfloat16* obs_b,
+                             const float* action, const float* old_logp, const float* adv, const float* tgt, int64_t B,
+                             const b200ppo_hparams* hp, float* losses_dev, int* split_out, cudaStream_t st) {
+  float* acts[2] = {ctx->ws_act[0], ctx->ws_act[1]};
+  float* outs[2] = {ctx->ws_out[0], ctx->ws_out[1]};
+  float* dz[2] = {ctx->ws_dz[0], ctx->ws_dz[1]};
+  const Net& Na = ctx->net[0];
+  const Net& Nc = ctx->net[1];
+  const int La = Na.d.n_layers, Lc = Nc.d.n_layers;
+  if (ctx->precision == B200PPO_PREC_BF16) {
+    // tcgen05 everywhere: forward (L launches), loss seeds (1), dgrads (L-1), all wgrads (1)
+    B2_TRY(forward_nets_bf16(ctx, params, obs_b, B, outs, st));
+    LossArgs la{};
+    fill_loss_args(ctx, la, params, outs[0], outs[1], action, old_logp, adv, tgt, B, hp);
+    la.dz_actor_bf16 = ctx->bf.dZ[0][La - 1]; la.dz_actor_pitch = ctx->bf.pitchZ[0][La - 1];
+    la.dv_bf16 = ctx->bf.dZ[1][Lc - 1]; la.dv_pitch = ctx->bf.pitchZ[1][Lc - 1];
+    la.partials = ctx->loss_partials; la.ticket = ctx->ticket;
+    la.losses = losses_dev; la.logstd_grad = ctx->gpart + ctx->logstd_off;
+    PROF(ctx, B200PPO_PROF_LOSS, st, launch_ppo_loss(la, st));
+    return backward_nets_bf16(ctx, obs_b, B, ctx->gpart, split_out, st);
+  }
+  const bool heads = La >= 2 && Lc >= 2 && heads_supported(Na.out_dim(), Na.d.dims[La - 2], Nc.d.dims[Lc - 2]);
+  PROF(ctx, B200PPO_PROF_GEMM_FWD, st, forward_nets(ctx, params, obs, B, 3, acts, outs, st, heads));
+  if (heads) {
+    HeadsArgs h{};
+    h.h_a = acts[0] + Na.act_off(La - 2, B); h.h_c = acts[1] + Nc.act_off(Lc - 2, B);
+    h.w3a = params + Na.w_off[La - 1]; h.b3a = params + Na.b_off[La - 1];
+    h.w3c = params + Nc.w_off[Lc - 1]; h.b3c = params + Nc.b_off[Lc - 1];
+    h.logstd = params + ctx->logstd_off;
+    h.action = action; h.old_logp = old_logp; h.advantage = adv; h.target = tgt;
+    h.batch = B; h.act_dim = Na.out_dim(); h.hid_a = Na.d.dims[La - 2]; h.hid_c = Nc.d.dims[Lc - 2];
+    h.act = Na.d.activation; h.act_c = Nc.d.activation;
+    h.final_tanh = Na.d.final_tanh; h.out_scale = Na.d.out_scale;
+    h.clip_eps = float(hp->clip_epsilon); h.ent_coef = float(hp->entropy_eps);
+    h.inv_global_batch = 1.f / float(B * ctx->world); h.rank_share = 1.f / float(ctx->world);
+    h.dz3_f32 = dz[0] + Na.dz_off(La - 1, B); h.dv_f32 = dz[1] + Nc.dz_off(Lc - 1, B);
+    h.dz_a_f32 = dz[0] + Na.dz_off(La - 2, B); h.dz_c_f32 = dz[1] + Nc.dz_off(Lc - 2, B);
+    h.partials = ctx->loss_partials; h.ticket = ctx->ticket;
+    h.losses = losses_dev; h.logstd_grad = ctx->gpart + ctx->logstd_off;
+    PROF(ctx, B200PPO_PROF_LOSS, st, launch_heads(h, st));
+  } else {
+    LossArgs la{};
+    fill_loss_args(ctx, la, params, outs[0], outs[1], action, old_logp, adv, tgt, B, hp);
+    la.dz_actor = dz[0] + Na.dz_off(La - 1, B);
+    la.dv = dz[1] + Nc.dz_off(Lc - 1, B);
+    la.partials = ctx->loss_partials; la.ticket = ctx->ticket;
+    la.losses = losses_dev; la.logstd_grad = ctx->gpart + ctx->logstd_off;
+    PROF(ctx, B200PPO_PROF_LOSS, st, launch_ppo_loss(la, st));
+  }
+  return backward_nets(ctx, params, obs, B, 3, acts, dz, ctx->gpart, split_out, nullptr, st, heads);
 }
 
 static int ensure_shuffle_capacity(b200ppo_ctx* ctx, int64_t rows) {
   if (rows <= ctx->sh_cap) return B200PPO_OK;
   B2_CUDA(cudaDeviceSynchronize());
   dev_free(ctx->sh_obs); dev_free(ctx->sh_act); dev_free(ctx->sh_logp); dev_free(ctx->sh_adv); dev_free(ctx->sh_tgt);
+  dev_free(ctx->bf.sh_obs);
   ctx->sh_cap = 0;
   const int D = ctx->net[0].d.in_dim, A = ctx->net[0].out_dim();
-  B2_TRY(dev_alloc(&ctx->sh_obs, rows * D));
+  if (ctx->precision == B200PPO_PREC_BF16) B2_TRY(dev_alloc(&ctx->bf.sh_obs, rows * ctx->bf.pitchX));
+  else B2_TRY(dev_alloc(&ctx->sh_obs, rows * D));
   B2_TRY(dev_alloc(&ctx->sh_act, rows * A));
   B2_TRY(dev_alloc(&ctx->sh_logp, rows));
   B2_TRY(dev_alloc(&ctx->sh_adv, rows));
@@ -377,6 +590,10 @@ int launch_gather_chunked(const int64_t* idx, int64_t count, int64_t n_rows, int
                           int64_t chunk_offset, const float* obs, int obs_dim, const float* act, int act_dim,
                           const float* logp, const float* adv, const float* tgt, float* obs_o, float* act_o,
                           float* logp_o, float* adv_o, float* tgt_o, int32_t* err_flag, cudaStream_t st);
+int launch_gather_chunked_bf16(const int64_t* idx, int64_t count, int64_t n_rows, int64_t chunk, int64_t chunk_stride,
+                               int64_t chunk_offset, const float* obs, int obs_dim, const float* act, int act_dim,
+                               const float* logp, const float* adv, const float* tgt, __nv_bfloat16* obs_o, int pitch,
+                               float* act_o, float* logp_o, float* adv_o, float* tgt_o, int32_t* err_flag, cudaStream_t st);
 
 }  // namespace b200ppo
 
@@ -420,10 +637,12 @@ extern "C" B2_EXPORT int b200ppo_create(const b200ppo_mlp_desc* actor, const b20
   }
   if (r == B200PPO_OK) r = dev_alloc(&c->gpart, int64_t(c->max_split) * c->n_params, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->grad_flat, c->n_params + 4, true);
-  if (r == B200PPO_OK) r = dev_alloc(&c->loss_partials, int64_t(loss_grid_size(Bm)) * (2 + c->net[0].out_dim()));
+  if (r == B200PPO_OK)
+    r = dev_alloc(&c->loss_partials, int64_t(std::max(loss_grid_size(Bm), 8 * num_sms())) * (2 + c->net[0].out_dim()));
   if (r == B200PPO_OK) r = dev_alloc(&c->ticket, 1, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->scratch, 8, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->err_flag, 1, true);
+  if (r == B200PPO_OK && precision == B200PPO_PREC_BF16) r = alloc_bf16_workspaces(c);
   if (r != B200PPO_OK) { b200ppo_destroy(c); return r; }
   *out = c;
   return B200PPO_OK;
@@ -435,6 +654,9 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   for (int n = 0; n < 2; ++n) { dev_free(c->ws_act[n]); dev_free(c->ws_dz[n]); dev_free(c->ws_out[n]); }
   dev_free(c->gpart); dev_free(c->grad_flat); dev_free(c->loss_partials); dev_free(c->ticket); dev_free(c->scratch);
   dev_free(c->err_flag);
+  for (int n = 0; n < 2; ++n)
+    for (int l = 0; l < B200PPO_MAX_LAYERS; ++l) { dev_free(c->bf.H[n][l]); dev_free(c->bf.dZ[n][l]); dev_free(c->bf.W[n][l]); dev_free(c->bf.WT[n][l]); }
+  dev_free(c->bf.X); dev_free(c->bf.sh_obs);
   dev_free(c->sh_obs); dev_free(c->sh_act); dev_free(c->sh_logp); dev_free(c->sh_adv); dev_free(c->sh_tgt);
   dev_free(c->host.obs); dev_free(c->host.act); dev_free(c->host.logp); dev_free(c->host.rew); dev_free(c->host.val);
   dev_free(c->host.nval); dev_free(c->host.adv); dev_free(c->host.tgt); dev_free(c->host.losses); dev_free(c->host.term);
@@ -547,7 +769,11 @@ extern "C" B2_EXPORT int b200ppo_minibatch_grads(b200ppo_ctx* ctx, const float* 
                "b200ppo_minibatch_grads: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int split = 1;
-  B2_TRY(minibatch_fwd_bwd(ctx, params, obs, action, old_logp, advantage, target, batch, hp,
+  if (ctx->precision == B200PPO_PREC_BF16) {
+    B2_TRY(cast_weights(ctx, params, st));
+    B2_TRY(launch_cast_rows_ones(obs, batch, ctx->net[0].d.in_dim, ctx->bf.X, ctx->bf.pitchX, st));
+  }
+  B2_TRY(minibatch_fwd_bwd(ctx, params, obs, ctx->bf.X, action, old_logp, advantage, target, batch, hp,
                            losses ? losses : ctx->scratch, &split, st));
   return launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, grads, st);
 }
@@ -571,12 +797,21 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
   B2_TRY(ensure_shuffle_capacity(ctx, nb * lb));
   const int D = ctx->net[0].d.in_dim, A = ctx->net[0].out_dim();
   int64_t step = *adam_step_io;
+  const bool tc = ctx->precision == B200PPO_PREC_BF16;
+  const int PX = ctx->bf.pitchX;
+  if (tc) PROF(ctx, B200PPO_PROF_OTHER, st, cast_weights(ctx, params, st));
   for (int e = 0; e < epochs; ++e) {
     // shuffled_memory = memory[idx] restricted to the rows this rank will consume
-    PROF(ctx, B200PPO_PROF_GATHER, st,
-         launch_gather_chunked(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
-                               obs, D, action, A, old_logp, advantage, target, ctx->sh_obs, ctx->sh_act, ctx->sh_logp,
-                               ctx->sh_adv, ctx->sh_tgt, ctx->err_flag, st));
+    if (tc)
+      PROF(ctx, B200PPO_PROF_GATHER, st,
+           launch_gather_chunked_bf16(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
+                                      obs, D, action, A, old_logp, advantage, target, ctx->bf.sh_obs, PX, ctx->sh_act,
+                                      ctx->sh_logp, ctx->sh_adv, ctx->sh_tgt, ctx->err_flag, st));
+    else
+      PROF(ctx, B200PPO_PROF_GATHER, st,
+           launch_gather_chunked(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
+                                 obs, D, action, A, old_logp, advantage, target, ctx->sh_obs, ctx->sh_act, ctx->sh_logp,
+                                 ctx->sh_adv, ctx->sh_tgt, ctx->err_flag, st));
     for (int64_t i = 0; i < nb; ++i) {
       const int64_t r0 = i * lb;
       float* loss_slot = losses_out ? losses_out + (int64_t(e) * nb + i) * 2 : ctx->scratch;
@@ -585,15 +820,18 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
       const AdamScalars sa = make_adam_scalars(hp->learning_rate_actor, hp->beta1, hp->beta2, hp->adam_eps, step);
       const AdamScalars sc = make_adam_scalars(hp->learning_rate_critic, hp->beta1, hp->beta2, hp->adam_eps, step);
       if (ctx->world == 1) {
-        B2_TRY(minibatch_fwd_bwd(ctx, params, ctx->sh_obs + r0 * D, ctx->sh_act + r0 * A, ctx->sh_logp + r0,
-                                 ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp, loss_slot, &split, st));
+        B2_TRY(minibatch_fwd_bwd(ctx, params, tc ? nullptr : ctx->sh_obs + r0 * D, tc ? ctx->bf.sh_obs + r0 * PX : nullptr,
+                                 ctx->sh_act + r0 * A, ctx->sh_logp + r0, ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp,
+                                 loss_slot, &split, st));
         PROF(ctx, B200PPO_PROF_ADAM, st,
              launch_adam(params, ctx->gpart, split, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa,
                          sc, nullptr, st));
+        if (tc) PROF(ctx, B200PPO_PROF_OTHER, st, cast_weights(ctx, params, st));
       } else {
         float* red_losses = ctx->grad_flat + ctx->n_params;
-        B2_TRY(minibatch_fwd_bwd(ctx, params, ctx->sh_obs + r0 * D, ctx->sh_act + r0 * A, ctx->sh_logp + r0,
-                                 ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp, red_losses, &split, st));
+        B2_TRY(minibatch_fwd_bwd(ctx, params, tc ? nullptr : ctx->sh_obs + r0 * D, tc ? ctx->bf.sh_obs + r0 * PX : nullptr,
+                                 ctx->sh_act + r0 * A, ctx->sh_logp + r0, ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp,
+                                 red_losses, &split, st));
         PROF(ctx, B200PPO_PROF_OTHER, st,
              launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, ctx->grad_flat, st));
         ctx->prof.begin(B200PPO_PROF_ALLREDUCE, st);
@@ -607,6 +845,7 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
         PROF(ctx, B200PPO_PROF_ADAM, st,
              launch_adam(params, ctx->grad_flat, 1, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa,
                          sc, nullptr, st));
+        if (tc) PROF(ctx, B200PPO_PROF_OTHER, st, cast_weights(ctx, params, st));
         copy2_kernel<<<1, 32, 0, st>>>(red_losses, loss_slot);
         B2_LAUNCH_CHECK();
       }

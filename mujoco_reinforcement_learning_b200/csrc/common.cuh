@@ -76,4 +76,31 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+
+// Final combine of per-CTA partials [n_cta][width] by the last CTA: thread (part, c) sums a contiguous slice of
+// CTAs with independent (pipelined) L2 loads, then the slices are added in slice order — a fixed order, so the
+// result is deterministic, without the serial chain of L2 round trips a single thread per column would pay.
+template <int THREADS>
+__device__ __forceinline__ float combine_partials(const float* partials, unsigned n_cta, int width, int c_out, float* s_scratch) {
+  // s_scratch: THREADS floats.  Returns the total of column c_out to threads with threadIdx.x == c_out (< width).
+  constexpr int COLS = 64;                 // columns handled per slice row (width <= 64)
+  constexpr int PARTS = THREADS / COLS;    // slices
+  const int tid = threadIdx.x, c = tid % COLS, part = tid / COLS;
+  float s = 0.f;
+  if (c < width && part < PARTS) {
+    const unsigned per = (n_cta + PARTS - 1) / PARTS;
+    const unsigned k0 = part * per, k1 = min(n_cta, k0 + per);
+#pragma unroll 4
+    for (unsigned k = k0; k < k1; ++k) s += __ldcg(partials + size_t(k) * width + c);
+  }
+  s_scratch[tid] = s;
+  __syncthreads();
+  float total = 0.f;
+  if (tid < width) {
+    for (int p = 0; p < PARTS; ++p) total += s_scratch[p * COLS + tid];
+  }
+  (void)c_out;
+  return total;
+}
+
 }  // namespace b200ppo

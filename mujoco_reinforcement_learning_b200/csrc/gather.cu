@@ -8,6 +8,8 @@
 // allocation): each source row is touched exactly once per epoch.  The scalar leaves and the short action
 // row ride along in the same warp so a minibatch costs one launch.
 // Algorithmic bytes per sample: 2*(4*D + 4*A + 12) + 8  (SURVEY.md §8d).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b200ppo {
@@ -70,6 +72,47 @@ gather_minibatch_kernel(const int64_t* __restrict__ idx, int64_t count, int64_t 
   }
 }
 
+// Same gather, observations emitted as bf16 rows of pitch `pitch` elements with a 1.0 in column obs_dim (the
+// ones-column from which the tensor-core wgrad reads the bias gradient); the other leaves stay fp32.
+__global__ void __launch_bounds__(256)
+gather_minibatch_bf16_kernel(const int64_t* __restrict__ idx, int64_t count, int64_t n_rows, int64_t chunk,
+                             int64_t chunk_stride, int64_t chunk_offset, const float* __restrict__ obs, int obs_dim,
+                             const float* __restrict__ act, int act_dim, const float* __restrict__ logp,
+                             const float* __restrict__ adv, const float* __restrict__ tgt,
+                             __nv_bfloat16* __restrict__ obs_o, int pitch, float* __restrict__ act_o,
+                             float* __restrict__ logp_o, float* __restrict__ adv_o, float* __restrict__ tgt_o,
+                             int32_t* err_flag, int vec4) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int64_t i = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); i < count;
+       i += int64_t(gridDim.x) * warps_per_block) {
+    const int64_t pos = (chunk == count) ? i + chunk_offset : (i / chunk) * chunk_stride + chunk_offset + i % chunk;
+    const int64_t s = resolve_index(idx, pos, n_rows, err_flag);
+    if (s < 0) continue;
+    const float* src = obs + s * obs_dim;
+    __nv_bfloat16* dst = obs_o + i * pitch;
+    if (vec4) {
+      const int n4 = obs_dim >> 2;
+      for (int k = lane; k < n4; k += 32) {
+        const float4 v = ldg_stream4(src + 4 * k);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 w;
+        w.x = *reinterpret_cast<const uint32_t*>(&lo);
+        w.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dst + 4 * k) = w;
+      }
+    } else {
+      for (int k = lane; k < obs_dim; k += 32) dst[k] = __float2bfloat16_rn(__ldg(src + k));
+    }
+    for (int k = obs_dim + lane; k < pitch; k += 32) dst[k] = __float2bfloat16_rn(k == obs_dim ? 1.f : 0.f);
+    if (act != nullptr)
+      for (int k = lane; k < act_dim; k += 32) act_o[i * act_dim + k] = __ldg(act + s * act_dim + k);
+    if (lane == 0 && logp != nullptr) logp_o[i] = __ldg(logp + s);
+    if (lane == 1 && adv != nullptr) adv_o[i] = __ldg(adv + s);
+    if (lane == 2 && tgt != nullptr) tgt_o[i] = __ldg(tgt + s);
+  }
+}
+
 // Generic leaf gather on raw bytes (16-byte chunks when possible).
 template <typename ChunkT>
 __global__ void __launch_bounds__(256)
@@ -103,6 +146,20 @@ int launch_gather_chunked(const int64_t* idx, int64_t count, int64_t n_rows, int
     gather_minibatch_kernel<true><<<grid, block, 0, st>>>(idx, count, n_rows, chunk, chunk_stride, chunk_offset, obs, obs_dim, act, act_dim, logp, adv, tgt, obs_o, act_o, logp_o, adv_o, tgt_o, err_flag);
   else
     gather_minibatch_kernel<false><<<grid, block, 0, st>>>(idx, count, n_rows, chunk, chunk_stride, chunk_offset, obs, obs_dim, act, act_dim, logp, adv, tgt, obs_o, act_o, logp_o, adv_o, tgt_o, err_flag);
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
+
+int launch_gather_chunked_bf16(const int64_t* idx, int64_t count, int64_t n_rows, int64_t chunk, int64_t chunk_stride,
+                               int64_t chunk_offset, const float* obs, int obs_dim, const float* act, int act_dim,
+                               const float* logp, const float* adv, const float* tgt, __nv_bfloat16* obs_o, int pitch,
+                               float* act_o, float* logp_o, float* adv_o, float* tgt_o, int32_t* err_flag, cudaStream_t st) {
+  if (count == 0) return B200PPO_OK;
+  const int vec = (obs_dim % 4 == 0) && aligned16(obs) && (pitch % 4 == 0) && ((uintptr_t)obs_o % 8 == 0);
+  dim3 block(256), grid(gather_grid(count, 8));
+  gather_minibatch_bf16_kernel<<<grid, block, 0, st>>>(idx, count, n_rows, chunk, chunk_stride, chunk_offset, obs, obs_dim,
+                                                       act, act_dim, logp, adv, tgt, obs_o, pitch, act_o, logp_o, adv_o,
+                                                       tgt_o, err_flag, vec);
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }

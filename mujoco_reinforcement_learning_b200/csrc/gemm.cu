@@ -207,6 +207,12 @@ gemm_group_kernel(const __grid_constant__ GemmGroup grp) {
           const float aux = (need_aux && ok) ? __ldg(P.aux + int64_t(m) * P.ld_aux + n + j) : 0.f;
           out[j] = apply_epilogue(acc[gi * 4 + i][gj * 4 + j], epi, bias, aux, P.out_scale);
         }
+        if (P.C_bf16 != nullptr) {
+          __nv_bfloat16* bp = P.C_bf16 + int64_t(m) * P.ldc_bf16 + n;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < P.N) bp[j] = __float2bfloat16_rn(out[j]);
+        }
         float* cp = Cbase + int64_t(m) * P.ldc + n;
         if (P.c_vec && n + 3 < P.N) {
           *reinterpret_cast<float4*>(cp) = make_float4(out[0], out[1], out[2], out[3]);

@@ -1,5 +1,7 @@
 // Grouped fp32 GEMM used by the actor/critic MLP forward, dgrad and wgrad (fp32-parity path).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b200ppo {
@@ -25,6 +27,8 @@ struct GemmProblem {
   const float* bias;
   const float* aux;
   float* bias_grad;  // wgrad only: bias_grad[m] = sum_k A(m,k) (per split), nullable
+  __nv_bfloat16* C_bf16;  // optional bf16 mirror of C (operand of the tensor-core path), row pitch ldc_bf16
+  int ldc_bf16;
   int64_t a_sm, a_sk, b_sn, b_sk;
   int64_t c_split_stride;  // elements between split-K partials (applies to C and bias_grad)
   int M, N, K;

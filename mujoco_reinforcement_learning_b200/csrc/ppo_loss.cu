@@ -45,7 +45,8 @@ ppo_loss_seed_kernel(LossArgs a) {
       lp += -(d * d) / s_two_var[j] - s_logsig[j] - kLogSqrt2Pi;
     }
     if (a.logp_out != nullptr) a.logp_out[b] = lp;
-    if (a.dz_actor != nullptr) {
+    const bool want_seed = a.dz_actor != nullptr || a.dz_actor_bf16 != nullptr;
+    if (want_seed) {
       const float adv = a.advantage[b];
       const float ratio = expf(lp - a.old_logp[b]);
       const float lo = 1.f - a.clip_eps, hi = 1.f + a.clip_eps;
@@ -58,7 +59,8 @@ ppo_loss_seed_kernel(LossArgs a) {
       const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
       const float g_ratio = -(w1 * adv + (1.f - w1) * adv * in_range) * a.inv_global_batch;
       const float g_lp = g_ratio * ratio;
-      float* dz = a.dz_actor + b * A;
+      float* dz = a.dz_actor != nullptr ? a.dz_actor + b * A : nullptr;
+      __nv_bfloat16* dzb = a.dz_actor_bf16 != nullptr ? a.dz_actor_bf16 + b * a.dz_actor_pitch : nullptr;
       for (int j = 0; j < A; ++j) {
         const float d = ac[j] - mu[j];
         const float dn = d * s_inv_var[j];
@@ -67,17 +69,23 @@ ppo_loss_seed_kernel(LossArgs a) {
           const float th = mu[j] / a.out_scale;
           dmu *= a.out_scale * (1.f - th * th);
         }
-        dz[j] = dmu;
+        if (dz != nullptr) dz[j] = dmu;
+        if (dzb != nullptr) dzb[j] = __float2bfloat16_rn(dmu);
         s_dl[tid * A + j] = g_lp * (d * dn - 1.f);
       }
+      if (dzb != nullptr)
+        for (int j = A; j < a.dz_actor_pitch; ++j) dzb[j] = __float2bfloat16_rn(0.f);
     }
-    if (a.dv != nullptr) {
+    if (a.dv != nullptr || a.dv_bf16 != nullptr) {
       const float e = a.value[b] - a.target[b];
       const float ae = fabsf(e);
       hub = ae < 1.f ? 0.5f * e * e : ae - 0.5f;
-      a.dv[b] = fminf(fmaxf(e, -1.f), 1.f) * a.inv_global_batch;
+      const float dvv = fminf(fmaxf(e, -1.f), 1.f) * a.inv_global_batch;
+      if (a.dv != nullptr) a.dv[b] = dvv;
+      if (a.dv_bf16 != nullptr)
+        for (int j = 0; j < a.dv_pitch; ++j) a.dv_bf16[b * a.dv_pitch + j] = __float2bfloat16_rn(j == 0 ? dvv : 0.f);
     }
-  } else if (a.dz_actor != nullptr) {
+  } else if (a.dz_actor != nullptr || a.dz_actor_bf16 != nullptr) {
     for (int j = 0; j < A; ++j) s_dl[tid * A + j] = 0.f;
   }
   if (a.partials == nullptr) return;
@@ -92,7 +100,7 @@ ppo_loss_seed_kernel(LossArgs a) {
     for (int w = 0; w < kLossThreads / 32; ++w) { x += s_red[0][w]; y += s_red[1][w]; }
     part[0] = x; part[1] = y;
   }
-  if (a.dz_actor != nullptr) {
+  if (a.dz_actor != nullptr || a.dz_actor_bf16 != nullptr) {
     for (int j = tid; j < A; j += kLossThreads) {
       float s = 0.f;
       for (int r = 0; r < kLossThreads; ++r) s += s_dl[r * A + j];
@@ -105,11 +113,11 @@ ppo_loss_seed_kernel(LossArgs a) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // last CTA: combine the per-CTA partials in CTA order
-  const volatile float* vp = a.partials;
+  // last CTA: combine the per-CTA partials (fixed order)
   for (int c = tid; c < 2 + A; c += kLossThreads) {
     float s = 0.f;
-    for (unsigned k = 0; k < gridDim.x; ++k) s += vp[int64_t(k) * (2 + A) + c];
+#pragma unroll 8
+    for (unsigned k = 0; k < gridDim.x; ++k) s += __ldcg(a.partials + int64_t(k) * (2 + A) + c);
     if (c == 0) {
       float ent = 0.f;  // mean over [B, A] of 0.5 + 0.5*log(2*pi) + log(sigma_j): the row is constant in b
       for (int j = 0; j < A; ++j) ent += 0.5f + kLogSqrt2Pi + s_logsig[j];

@@ -1,5 +1,7 @@
 // Internal interface of the loss / gradient-seed kernels (ppo_loss.cu).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b200ppo {
@@ -24,6 +26,9 @@ struct LossArgs {
   float* logp_out;      // [B] new log-prob
   float* dz_actor;      // [B, A] dL_actor / d z_last
   float* dv;            // [B]    dL_critic / d value
+  __nv_bfloat16* dz_actor_bf16;  // [B, dz_actor_pitch] bf16 copy for the tensor-core dgrad / wgrad (padding zeroed)
+  __nv_bfloat16* dv_bf16;        // [B, dv_pitch]
+  int dz_actor_pitch, dv_pitch;
   float* partials;      // [grid][2 + A] scratch
   unsigned* ticket;     // zero-initialised counter, self-resetting
   float* losses;        // [2] actor_loss, critic_loss

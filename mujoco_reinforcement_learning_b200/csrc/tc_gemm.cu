@@ -3,13 +3,14 @@
 // replaces: aten::addmm / aten::mm of NetworkBlock.forward (src/models/network_block_creator.py:74-86) and of the
 //           autograd backward of ppo.py:121,134, for the hidden layers.
 //
-// Per CTA (192 threads, one 128 x BN output tile, BN in {64,128,256}):
+// Per CTA (320 threads, one 128 x BN output tile, BN in {64,128,256}):
 //   warp 0  TMA producer : cp.async.bulk.tensor 2-D boxes (128-byte swizzle) of A and B into a 4-stage smem ring,
 //                          completion on per-stage mbarriers; out-of-bounds rows/columns are zero-filled by TMA,
 //                          so ragged M/N/K need no padding in global memory.
 //   warp 1  MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x 4 per
 //                          stage into a TMEM accumulator (BN fp32 columns), tcgen05.commit frees the stage.
-//   warps 2-5 epilogue   : tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused bias + tanh/relu, or
+//   warps 2-9 epilogue   : tcgen05.ld 32x32b.x32 (one accumulator row per thread, two warps per TMEM lane quarter
+//                          splitting the columns), fused bias + MUFU tanh / relu, or
 //                          activation-derivative multiply (dgrad), or fp32 split-K partial store (wgrad) with
 //                          the bias gradient read off an appended ones-column of the B operand.
 // Operands may be K-major or MN-major (UMMA descriptor major bits), so forward (X W^T), dgrad (dZ W via a
@@ -26,7 +27,8 @@ namespace b200ppo {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // bf16 elements: 128 bytes = one swizzle row
 constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                        // two per TMEM lane quarter, each takes half of the columns
+constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;    // + TMA producer warp + MMA issuer warp
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -90,6 +92,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// MUFU.TANH: one instruction, max relative error ~2^-11 — below bf16's 2^-8 resolution of the stored activation
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         __syncwarp();
       }
     }
-  } else {  // ===== epilogue warps 2..5 =====
+  } else {  // ===== epilogue warps 2..9 =====
     if (has_k) {
       mbar_wait(tmem_full_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -202,8 +211,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int m = m0 + q * 32 + lane;
     const bool row_ok = m < P.M;
+    constexpr int CHUNKS = BN / 32;
+    constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
+    const int c_begin = ((warp - 2) >> 2) * CH_PER_WARP;
+    const int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       uint32_t v[32];
       if (has_k) {
         tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
@@ -216,10 +229,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const bool full = nb + 32 <= P.N;
       float h[32];
       if (P.epilogue == TC_EPI_FWD) {
+        float bias[32];
+        if (full) {  // bias segments start on 128-byte boundaries of the flat parameter buffer
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float z = __uint_as_float(v[j]) + ((full || nb + j < P.N) ? __ldg(P.bias + nb + j) : 0.f);
-          h[j] = P.act == B200PPO_ACT_TANH ? tanhf(z) : fmaxf(z, 0.f);
+          for (int u = 0; u < 8; ++u) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(P.bias + nb) + u);
+            bias[u * 4] = t.x; bias[u * 4 + 1] = t.y; bias[u * 4 + 2] = t.z; bias[u * 4 + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bias[j] = nb + j < P.N ? __ldg(P.bias + nb + j) : 0.f;
+        }
+        if (P.act == B200PPO_ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h[j] = tanh_fast(__uint_as_float(v[j]) + bias[j]);
+        } else if (P.act == B200PPO_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h[j] = fmaxf(__uint_as_float(v[j]) + bias[j], 0.f);
+        } else if (P.act == TC_ACT_TANH_SCALE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h[j] = P.out_scale * tanh_fast(__uint_as_float(v[j]) + bias[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h[j] = __uint_as_float(v[j]) + bias[j];
         }
       } else if (P.epilogue == TC_EPI_DGRAD) {
         const __nv_bfloat16* ap = P.aux + int64_t(m) * P.ld_aux + nb;

