@@ -456,18 +456,34 @@ static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t
     }
     PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, launch_tc_group(g, bn, st));
   }
-  // every weight / bias gradient: dW_l = dZ_l^T [H_{l-1} | 1], both operands MN-major, split-K over the batch
-  int64_t tiles = 0;
-  int maxN = 0;
-  for (int n = 0; n < 2; ++n)
-    for (int l = 0; l < ctx->net[n].d.n_layers; ++l) {
-      tiles += int64_t((ctx->net[n].d.dims[l] + 127) / 128) * ((ctx->net[n].in_dim(l) + 1 + 127) / 128);
-      maxN = std::max(maxN, ctx->net[n].in_dim(l) + 1);
+  // every weight / bias gradient: dW_l = dZ_l^T [H_{l-1} | 1], both operands MN-major, split-K over the batch.
+  // N tile: the width that wastes the least padded MMA work over all problems (N = in+1 is 257 / 377 for 256 / 376
+  // inputs: 192-wide tiles cover both in two tiles where 128-wide ones need three); split-K: as many splits as fill
+  // ONE wave of resident CTAs — one CTA more than a wave would double the kernel's duration.
+  int bn = 64;
+  {
+    int maxN = 0;
+    for (int n = 0; n < 2; ++n)
+      for (int l = 0; l < ctx->net[n].d.n_layers; ++l) maxN = std::max(maxN, ctx->net[n].in_dim(l) + 1);
+    if (maxN > 64) {
+      int64_t best = -1;
+      for (int cand : {128, 192, 256}) {
+        int64_t work = 0;
+        for (int n = 0; n < 2; ++n)
+          for (int l = 0; l < ctx->net[n].d.n_layers; ++l)
+            work += int64_t((ctx->net[n].d.dims[l] + 127) / 128) * ((ctx->net[n].in_dim(l) + 1 + cand - 1) / cand) * cand;
+        if (best < 0 || work < best) { best = work; bn = cand; }
+      }
     }
-  int split = int(std::min<int64_t>(std::max<int64_t>(1, (2ll * num_sms() + tiles - 1) / std::max<int64_t>(tiles, 1)), ctx->max_split));
+  }
+  int64_t tiles = 0;
+  for (int n = 0; n < 2; ++n)
+    for (int l = 0; l < ctx->net[n].d.n_layers; ++l)
+      tiles += int64_t((ctx->net[n].d.dims[l] + 127) / 128) * ((ctx->net[n].in_dim(l) + 1 + bn - 1) / bn);
+  const int64_t slots = int64_t(num_sms()) * tc_ctas_per_sm(bn);
+  int split = int(std::min<int64_t>(std::max<int64_t>(1, slots / std::max<int64_t>(tiles, 1)), ctx->max_split));
   split = int(std::min<int64_t>(split, (B + 63) / 64));
   if (split < 1) split = 1;
-  const int bn = maxN > 64 ? 128 : 64;
   TcGroup g{};
   for (int n = 0; n < 2; ++n) {
     const Net& N = ctx->net[n];

@@ -26,7 +26,10 @@ namespace b200ppo {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // bf16 elements: 128 bytes = one swizzle row
-constexpr int TC_STAGES = 4;
+// smem ring depth: K loops here are 1-6 tiles for forward/dgrad, so 3 stages already cover them, and 3 x 32 KB lets
+// two CTAs share an SM (BN <= 128): one CTA's epilogue then overlaps the other's TMA/MMA main loop.
+template <int BN> struct TcCfg { static constexpr int STAGES = BN <= 128 ? 3 : 4; static constexpr int CTAS_PER_SM = BN <= 128 ? 2 : 1; };
+int tc_ctas_per_sm(int bn) { return bn <= 128 ? 2 : 1; }
 constexpr int TC_EPI_WARPS = 8;                        // two per TMEM lane quarter, each takes half of the columns
 constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;    // + TMA producer warp + MMA issuer warp
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
@@ -94,6 +97,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // MUFU.TANH: one instruction, max relative error ~2^-11 — below bf16's 2^-8 resolution of the stored activation
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -107,9 +121,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGroup grp) {
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_kernel(const __grid_constant__ TcGroup grp) {
+  constexpr int TC_STAGES = TcCfg<BN>::STAGES;
   constexpr int B_BYTES = BN * TC_BK * 2;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));  // power of two
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -204,114 +219,143 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       }
     }
   } else {  // ===== epilogue warps 2..9 =====
+    // Problem fields into registers once (the indexed constant-bank loads of `P.` inside the column loop showed up
+    // as long-scoreboard stalls), and everything the epilogue reads from global memory — the activation operand of
+    // the dgrad, the bias of the forward — is requested BEFORE waiting for the accumulator, so that latency hides
+    // behind the TMA/MMA main loop.
+    const int epi = P.epilogue, act = P.act, Mrows = P.M, Ncols = P.N;
+    const float* __restrict__ bias_p = P.bias;
+    __nv_bfloat16* __restrict__ outb = P.out_bf16;
+    float* __restrict__ outf = P.out_f32 != nullptr ? P.out_f32 + int64_t(split) * P.split_stride : nullptr;
+    float* __restrict__ bgrad = P.bias_grad != nullptr ? P.bias_grad + int64_t(split) * P.split_stride : nullptr;
+    const __nv_bfloat16* __restrict__ auxp = P.aux;
+    const int ld_bf16 = P.ld_bf16, ld_f32 = P.ld_f32, ld_aux = P.ld_aux, bias_col = P.bias_col;
+    const bool f32_vec = (P.ld_f32 % 4 == 0) && (P.split_stride % 4 == 0);
+    const float out_scale = P.out_scale;
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < Mrows;
+    // 16 accumulator columns per step (keeps the epilogue under the 102-register budget of two CTAs per SM)
+    constexpr int CW = 16;
+    constexpr int CHUNKS = BN / CW;
+    constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
+    const int c_begin = ((warp - 2) >> 2) * CH_PER_WARP;
+    const int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
+    const bool aux_vec = (ld_aux % 8 == 0);
+
+    uint4 pre[2];  // prefetched 32 bytes of the dgrad's activation row for the NEXT step
+    auto prefetch_aux = [&](int c) {
+      const int nb = n0 + c * CW;
+      if (epi == TC_EPI_DGRAD && row_ok && c < c_end && nb + CW <= Ncols && aux_vec) {
+        const uint4* ap = reinterpret_cast<const uint4*>(auxp + int64_t(m) * ld_aux + nb);
+        pre[0] = __ldg(ap);
+        pre[1] = __ldg(ap + 1);
+      }
+    };
+    prefetch_aux(c_begin);
     if (has_k) {
       mbar_wait(tmem_full_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < P.M;
-    constexpr int CHUNKS = BN / 32;
-    constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
-    const int c_begin = ((warp - 2) >> 2) * CH_PER_WARP;
-    const int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
-      uint32_t v[32];
+      uint32_t v[CW];
       if (has_k) {
-        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
+        tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * CW), v);
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
+        for (int j = 0; j < CW; ++j) v[j] = 0u;
       }
-      const int nb = n0 + c * 32;
-      if (!row_ok || nb >= P.N) continue;
-      const bool full = nb + 32 <= P.N;
-      float h[32];
-      if (P.epilogue == TC_EPI_FWD) {
-        float bias[32];
-        if (full) {  // bias segments start on 128-byte boundaries of the flat parameter buffer
+      const int nb = n0 + c * CW;
+      const bool live = row_ok && nb < Ncols;
+      const bool full = nb + CW <= Ncols;
+      float h[CW];
+      if (epi == TC_EPI_FWD) {
+        if (live) {
+          if (full) {  // bias segments start on 128-byte boundaries of the flat parameter buffer
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(P.bias + nb) + u);
-            bias[u * 4] = t.x; bias[u * 4 + 1] = t.y; bias[u * 4 + 2] = t.z; bias[u * 4 + 3] = t.w;
+            for (int u = 0; u < CW / 4; ++u) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(bias_p + nb) + u);
+              h[u * 4] = t.x; h[u * 4 + 1] = t.y; h[u * 4 + 2] = t.z; h[u * 4 + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) h[j] = nb + j < Ncols ? __ldg(bias_p + nb + j) : 0.f;
           }
-        } else {
+          if (act == B200PPO_ACT_TANH) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) bias[j] = nb + j < P.N ? __ldg(P.bias + nb + j) : 0.f;
+            for (int j = 0; j < CW; ++j) h[j] = tanh_fast(__uint_as_float(v[j]) + h[j]);
+          } else if (act == B200PPO_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) h[j] = fmaxf(__uint_as_float(v[j]) + h[j], 0.f);
+          } else if (act == TC_ACT_TANH_SCALE) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) h[j] = out_scale * tanh_fast(__uint_as_float(v[j]) + h[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) h[j] = __uint_as_float(v[j]) + h[j];
+          }
         }
-        if (P.act == B200PPO_ACT_TANH) {
+      } else if (epi == TC_EPI_DGRAD) {
+        if (live && full && aux_vec) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) h[j] = tanh_fast(__uint_as_float(v[j]) + bias[j]);
-        } else if (P.act == B200PPO_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) h[j] = fmaxf(__uint_as_float(v[j]) + bias[j], 0.f);
-        } else if (P.act == TC_ACT_TANH_SCALE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) h[j] = P.out_scale * tanh_fast(__uint_as_float(v[j]) + bias[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) h[j] = __uint_as_float(v[j]) + bias[j];
-        }
-      } else if (P.epilogue == TC_EPI_DGRAD) {
-        const __nv_bfloat16* ap = P.aux + int64_t(m) * P.ld_aux + nb;
-        float a[32];
-        if (full && (P.ld_aux % 8 == 0)) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint4 w = __ldg(reinterpret_cast<const uint4*>(ap) + u);
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t ww[4] = {pre[u].x, pre[u].y, pre[u].z, pre[u].w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[t]);
-              a[u * 8 + t * 2] = __low2float(b2);
-              a[u * 8 + t * 2 + 1] = __high2float(b2);
+              h[u * 8 + t * 2] = __low2float(b2);
+              h[u * 8 + t * 2 + 1] = __high2float(b2);
             }
           }
-        } else {
+        } else if (live) {
+          const __nv_bfloat16* ap = auxp + int64_t(m) * ld_aux + nb;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] = (nb + j < P.N) ? __bfloat162float(ap[j]) : 0.f;
+          for (int j = 0; j < CW; ++j) h[j] = (nb + j < Ncols) ? __bfloat162float(ap[j]) : 0.f;
         }
+        prefetch_aux(c + 1);  // next step's activation row in flight while this one is finished and stored
+        if (live) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float g = __uint_as_float(v[j]);
-          h[j] = P.act == B200PPO_ACT_TANH ? g * (1.f - a[j] * a[j]) : (a[j] > 0.f ? g : 0.f);
+          for (int j = 0; j < CW; ++j) {
+            const float g = __uint_as_float(v[j]);
+            h[j] = act == B200PPO_ACT_TANH ? g * (1.f - h[j] * h[j]) : (h[j] > 0.f ? g : 0.f);
+          }
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < CW; ++j) h[j] = __uint_as_float(v[j]);
       }
-      if (P.out_bf16 != nullptr) {
-        __nv_bfloat16* op = P.out_bf16 + int64_t(m) * P.ld_bf16 + nb;
-        if (full && (P.ld_bf16 % 8 == 0)) {
+      if (!live) continue;
+      if (outb != nullptr) {
+        __nv_bfloat16* op = outb + int64_t(m) * ld_bf16 + nb;
+        if (full && (ld_bf16 % 8 == 0)) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < CW / 8; ++u)
             reinterpret_cast<uint4*>(op)[u] = make_uint4(pack_bf16(h[u * 8], h[u * 8 + 1]), pack_bf16(h[u * 8 + 2], h[u * 8 + 3]),
                                                          pack_bf16(h[u * 8 + 4], h[u * 8 + 5]), pack_bf16(h[u * 8 + 6], h[u * 8 + 7]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < P.N) op[j] = __float2bfloat16_rn(h[j]);
+          for (int j = 0; j < CW; ++j)
+            if (nb + j < Ncols) op[j] = __float2bfloat16_rn(h[j]);
         }
       }
-      if (P.out_f32 != nullptr) {
-        float* base = P.out_f32 + int64_t(split) * P.split_stride;
-        const int ncols = P.bias_col >= 0 ? P.bias_col : P.N;  // columns that belong to the matrix proper
-        float* op = base + int64_t(m) * P.ld_f32 + nb;
-        if (nb + 32 <= ncols && (P.ld_f32 % 4 == 0) && (P.split_stride % 4 == 0)) {
+      if (outf != nullptr) {
+        const int ncols = bias_col >= 0 ? bias_col : Ncols;  // columns that belong to the matrix proper
+        float* op = outf + int64_t(m) * ld_f32 + nb;
+        if (nb + CW <= ncols && f32_vec) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) reinterpret_cast<float4*>(op)[u] = make_float4(h[u * 4], h[u * 4 + 1], h[u * 4 + 2], h[u * 4 + 3]);
+          for (int u = 0; u < CW / 4; ++u) reinterpret_cast<float4*>(op)[u] = make_float4(h[u * 4], h[u * 4 + 1], h[u * 4 + 2], h[u * 4 + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < CW; ++j)
             if (nb + j < ncols) op[j] = h[j];
         }
-        if (P.bias_col >= nb && P.bias_col < nb + 32 && P.bias_grad != nullptr) {
+        if (bias_col >= nb && bias_col < nb + CW && bgrad != nullptr) {
           float bg = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j == P.bias_col) bg = h[j];
-          P.bias_grad[int64_t(split) * P.split_stride + m] = bg;
+          for (int j = 0; j < CW; ++j)
+            if (nb + j == bias_col) bg = h[j];
+          bgrad[m] = bg;
         }
       }
     }
@@ -399,7 +443,7 @@ int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B
 
 template <int BN>
 static int launch_bn(const TcGroup& g, cudaStream_t st) {
-  constexpr int smem = TC_STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256;
+  constexpr int smem = TcCfg<BN>::STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     B2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -415,6 +459,7 @@ int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st) {
   switch (bn) {
     case 64: return launch_bn<64>(g, st);
     case 128: return launch_bn<128>(g, st);
+    case 192: return launch_bn<192>(g, st);
     case 256: return launch_bn<256>(g, st);
   }
   set_error("unsupported tensor-core N tile %d", bn);
@@ -422,13 +467,10 @@ int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st) {
 }
 
 int tc_pick_bn(int64_t tiles_m_total, int N) {
-  // widest N tile that still gives every SM a CTA
-  const int sms = num_sms();
-  for (int bn : {256, 128}) {
-    if (N >= bn && tiles_m_total * ((N + bn - 1) / bn) >= sms) return bn;
-  }
-  if (N > 64 && tiles_m_total * ((N + 127) / 128) * 2 >= sms) return 128;
-  return 64;
+  // 128-wide tiles run two CTAs per SM (epilogue of one overlaps the main loop of the other); narrower only when
+  // the problem is narrow or would leave SMs idle
+  (void)tiles_m_total;
+  return N > 64 ? 128 : 64;
 }
 
 // ---- debug entry point: C = A * B^T through the tensor-core kernel (used by the GPU tests) -------------------------

@@ -58,5 +58,6 @@ int tc_init();  // resolves cuTensorMapEncodeTiled; returns B200PPO_OK or an err
 int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B, int bn, int split_k);
 int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st);
 int tc_pick_bn(int64_t rows_total_tiles_m, int N);
+int tc_ctas_per_sm(int bn);  // resident CTAs per SM of the bn-wide kernel instance
 
 }  // namespace b200ppo

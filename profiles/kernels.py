@@ -12,6 +12,7 @@ import mujoco_reinforcement_learning_b200 as pkg  # noqa: E402
 
 which = sys.argv[1]
 precision = sys.argv[sys.argv.index("--precision") + 1] if "--precision" in sys.argv else "fp32"
+batch = int(sys.argv[sys.argv.index("--batch") + 1]) if "--batch" in sys.argv else 4096
 dev = "cuda"
 torch.manual_seed(0)
 if which in ("gae", "gae_norm"):
@@ -33,7 +34,7 @@ elif which == "adam":
     for i in range(3):
         pkg.adam_step_(p, g, m_, v_, i + 1, 1e-4)
 elif which == "update":
-    B, N, T = 4096, 512, 64
+    B, N, T = batch, max(512, batch // 64 * 2), 64
     run = pkg.Run(training_config=pkg.TrainingConfig(batch_size=B, epochs_per_iteration=1),
                   environment_config=pkg.EnvironmentConfig(maximum_timesteps=T, num_envs=N),
                   network_config=pkg.NetworkConfig(input_shape=376, output_shape=17, linear_hidden_shapes=[256, 256]),

@@ -21,6 +21,12 @@ CASES = [
     (256, 377, 4096, 1, 1, 128, 8),      # wgrad layer 1 with the ones-column, split-K
     (256, 257, 500, 1, 1, 64, 3),        # wgrad layer 2, ragged K
     (64, 27, 1000, 1, 1, 64, 2),
+    (256, 377, 2048, 1, 1, 192, 4),      # 192-wide tiles: N = 377 in two tiles
+    (256, 257, 1024, 1, 1, 192, 3),
+    (17, 257, 4096, 1, 1, 192, 5),       # output-layer wgrad: M = act_dim
+    (1000, 192, 200, 0, 0, 192, 1),
+    (4096, 256, 17, 0, 0, 128, 1),       # output-layer dgrad: K = act_dim
+    (4096, 17, 256, 0, 0, 64, 1),        # output-layer forward: N = act_dim
 ]
 
 
