@@ -397,7 +397,11 @@ static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_b
     int maxN = 0, nets_here = 0;
     for (int n = 0; n < 2; ++n)
       if (l < ctx->net[n].d.n_layers) { maxN = std::max(maxN, ctx->net[n].d.dims[l]); ++nets_here; }
-    const int bn = tc_pick_bn(int64_t((B + 127) / 128) * nets_here, maxN);
+    int maxK = 0;
+    for (int n = 0; n < 2; ++n)
+      if (l < ctx->net[n].d.n_layers) maxK = std::max(maxK, ctx->net[n].in_dim(l));
+    const bool ws = tc_ws_applicable(int64_t((B + 127) / 128) * nets_here, maxN, maxK);
+    const int bn = ws ? tc_ws_bn(maxN) : tc_pick_bn(int64_t((B + 127) / 128) * nets_here, maxN);
     for (int n = 0; n < 2; ++n) {
       const Net& N = ctx->net[n];
       if (l >= N.d.n_layers) continue;
@@ -419,7 +423,7 @@ static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_b
       TcOperand Bop{bf.W[n][l], bf.pitchW[n][l], 0};
       B2_TRY(tc_group_add(g, p, A, Bop, bn, 1));
     }
-    PROF(ctx, B200PPO_PROF_GEMM_FWD, st, launch_tc_group(g, bn, st));
+    PROF(ctx, B200PPO_PROF_GEMM_FWD, st, ws ? launch_tc_ws(g, st) : launch_tc_group(g, bn, st));
   }
   return B200PPO_OK;
 }
@@ -439,7 +443,13 @@ static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t
       if (l >= 1) { maxN = std::max(maxN, ctx->net[n].in_dim(l)); ++nets_here; }
     }
     if (nets_here == 0) break;
-    const int bn = tc_pick_bn(int64_t((B + 127) / 128) * nets_here, maxN);
+    int maxK = 0;
+    for (int n = 0; n < 2; ++n) {
+      const int l = ctx->net[n].d.n_layers - 1 - s;
+      if (l >= 1) maxK = std::max(maxK, ctx->net[n].d.dims[l]);
+    }
+    const bool ws = tc_ws_applicable(int64_t((B + 127) / 128) * nets_here, maxN, maxK);
+    const int bn = ws ? tc_ws_bn(maxN) : tc_pick_bn(int64_t((B + 127) / 128) * nets_here, maxN);
     for (int n = 0; n < 2; ++n) {
       const Net& N = ctx->net[n];
       const int l = N.d.n_layers - 1 - s;
@@ -454,7 +464,7 @@ static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t
       TcOperand Bop{bf.WT[n][l], bf.pitchZ[n][l], 0};
       B2_TRY(tc_group_add(g, p, A, Bop, bn, 1));
     }
-    PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, launch_tc_group(g, bn, st));
+    PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, ws ? launch_tc_ws(g, st) : launch_tc_group(g, bn, st));
   }
   // every weight / bias gradient: dW_l = dZ_l^T [H_{l-1} | 1], both operands MN-major, split-K over the batch.
   // N tile: the width that wastes the least padded MMA work over all problems (N = in+1 is 257 / 377 for 256 / 376

@@ -20,105 +20,14 @@
 #include <mutex>
 #include <tuple>
 
-#include "tc_gemm.cuh"
+#include "tc_common.cuh"
 
 namespace b200ppo {
 
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;  // bf16 elements: 128 bytes = one swizzle row
 // smem ring depth: K loops here are 1-6 tiles for forward/dgrad, so 3 stages already cover them, and 3 x 32 KB lets
 // two CTAs share an SM (BN <= 128): one CTA's epilogue then overlaps the other's TMA/MMA main loop.
 template <int BN> struct TcCfg { static constexpr int STAGES = BN <= 128 ? 3 : 4; static constexpr int CTAS_PER_SM = BN <= 128 ? 2 : 1; };
 int tc_ctas_per_sm(int bn) { return bn <= 128 ? 2 : 1; }
-constexpr int TC_EPI_WARPS = 8;                        // two per TMEM lane quarter, each takes half of the columns
-constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;    // + TMA producer warp + MMA issuer warp
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// 64-bit shared-memory matrix descriptor (sm_100): 128-byte swizzle, version 1.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
-  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= uint64_t(1) << 46;  // descriptor version (Blackwell)
-  d |= uint64_t(2) << 61;  // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// MUFU.TANH: one instruction, max relative error ~2^-11 — below bf16's 2^-8 resolution of the stored activation
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_kernel(const __grid_constant__ TcGroup grp) {
@@ -219,146 +128,7 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
       }
     }
   } else {  // ===== epilogue warps 2..9 =====
-    // Problem fields into registers once (the indexed constant-bank loads of `P.` inside the column loop showed up
-    // as long-scoreboard stalls), and everything the epilogue reads from global memory — the activation operand of
-    // the dgrad, the bias of the forward — is requested BEFORE waiting for the accumulator, so that latency hides
-    // behind the TMA/MMA main loop.
-    const int epi = P.epilogue, act = P.act, Mrows = P.M, Ncols = P.N;
-    const float* __restrict__ bias_p = P.bias;
-    __nv_bfloat16* __restrict__ outb = P.out_bf16;
-    float* __restrict__ outf = P.out_f32 != nullptr ? P.out_f32 + int64_t(split) * P.split_stride : nullptr;
-    float* __restrict__ bgrad = P.bias_grad != nullptr ? P.bias_grad + int64_t(split) * P.split_stride : nullptr;
-    const __nv_bfloat16* __restrict__ auxp = P.aux;
-    const int ld_bf16 = P.ld_bf16, ld_f32 = P.ld_f32, ld_aux = P.ld_aux, bias_col = P.bias_col;
-    const bool f32_vec = (P.ld_f32 % 4 == 0) && (P.split_stride % 4 == 0);
-    const float out_scale = P.out_scale;
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < Mrows;
-    // 16 accumulator columns per step (keeps the epilogue under the 102-register budget of two CTAs per SM)
-    constexpr int CW = 16;
-    constexpr int CHUNKS = BN / CW;
-    constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
-    const int c_begin = ((warp - 2) >> 2) * CH_PER_WARP;
-    const int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
-    const bool aux_vec = (ld_aux % 8 == 0);
-
-    uint4 pre[2];  // prefetched 32 bytes of the dgrad's activation row for the NEXT step
-    auto prefetch_aux = [&](int c) {
-      const int nb = n0 + c * CW;
-      if (epi == TC_EPI_DGRAD && row_ok && c < c_end && nb + CW <= Ncols && aux_vec) {
-        const uint4* ap = reinterpret_cast<const uint4*>(auxp + int64_t(m) * ld_aux + nb);
-        pre[0] = __ldg(ap);
-        pre[1] = __ldg(ap + 1);
-      }
-    };
-    prefetch_aux(c_begin);
-    if (has_k) {
-      mbar_wait(tmem_full_bar, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-#pragma unroll 1
-    for (int c = c_begin; c < c_end; ++c) {
-      uint32_t v[CW];
-      if (has_k) {
-        tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * CW), v);
-      } else {
-#pragma unroll
-        for (int j = 0; j < CW; ++j) v[j] = 0u;
-      }
-      const int nb = n0 + c * CW;
-      const bool live = row_ok && nb < Ncols;
-      const bool full = nb + CW <= Ncols;
-      float h[CW];
-      if (epi == TC_EPI_FWD) {
-        if (live) {
-          if (full) {  // bias segments start on 128-byte boundaries of the flat parameter buffer
-#pragma unroll
-            for (int u = 0; u < CW / 4; ++u) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(bias_p + nb) + u);
-              h[u * 4] = t.x; h[u * 4 + 1] = t.y; h[u * 4 + 2] = t.z; h[u * 4 + 3] = t.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) h[j] = nb + j < Ncols ? __ldg(bias_p + nb + j) : 0.f;
-          }
-          if (act == B200PPO_ACT_TANH) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) h[j] = tanh_fast(__uint_as_float(v[j]) + h[j]);
-          } else if (act == B200PPO_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) h[j] = fmaxf(__uint_as_float(v[j]) + h[j], 0.f);
-          } else if (act == TC_ACT_TANH_SCALE) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) h[j] = out_scale * tanh_fast(__uint_as_float(v[j]) + h[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) h[j] = __uint_as_float(v[j]) + h[j];
-          }
-        }
-      } else if (epi == TC_EPI_DGRAD) {
-        if (live && full && aux_vec) {
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const uint32_t ww[4] = {pre[u].x, pre[u].y, pre[u].z, pre[u].w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[t]);
-              h[u * 8 + t * 2] = __low2float(b2);
-              h[u * 8 + t * 2 + 1] = __high2float(b2);
-            }
-          }
-        } else if (live) {
-          const __nv_bfloat16* ap = auxp + int64_t(m) * ld_aux + nb;
-#pragma unroll
-          for (int j = 0; j < CW; ++j) h[j] = (nb + j < Ncols) ? __bfloat162float(ap[j]) : 0.f;
-        }
-        prefetch_aux(c + 1);  // next step's activation row in flight while this one is finished and stored
-        if (live) {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const float g = __uint_as_float(v[j]);
-            h[j] = act == B200PPO_ACT_TANH ? g * (1.f - h[j] * h[j]) : (h[j] > 0.f ? g : 0.f);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < CW; ++j) h[j] = __uint_as_float(v[j]);
-      }
-      if (!live) continue;
-      if (outb != nullptr) {
-        __nv_bfloat16* op = outb + int64_t(m) * ld_bf16 + nb;
-        if (full && (ld_bf16 % 8 == 0)) {
-#pragma unroll
-          for (int u = 0; u < CW / 8; ++u)
-            reinterpret_cast<uint4*>(op)[u] = make_uint4(pack_bf16(h[u * 8], h[u * 8 + 1]), pack_bf16(h[u * 8 + 2], h[u * 8 + 3]),
-                                                         pack_bf16(h[u * 8 + 4], h[u * 8 + 5]), pack_bf16(h[u * 8 + 6], h[u * 8 + 7]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < CW; ++j)
-            if (nb + j < Ncols) op[j] = __float2bfloat16_rn(h[j]);
-        }
-      }
-      if (outf != nullptr) {
-        const int ncols = bias_col >= 0 ? bias_col : Ncols;  // columns that belong to the matrix proper
-        float* op = outf + int64_t(m) * ld_f32 + nb;
-        if (nb + CW <= ncols && f32_vec) {
-#pragma unroll
-          for (int u = 0; u < CW / 4; ++u) reinterpret_cast<float4*>(op)[u] = make_float4(h[u * 4], h[u * 4 + 1], h[u * 4 + 2], h[u * 4 + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < CW; ++j)
-            if (nb + j < ncols) op[j] = h[j];
-        }
-        if (bias_col >= nb && bias_col < nb + CW && bgrad != nullptr) {
-          float bg = 0.f;
-#pragma unroll
-          for (int j = 0; j < CW; ++j)
-            if (nb + j == bias_col) bg = h[j];
-          bgrad[m] = bg;
-        }
-      }
-    }
+    tc_epilogue<BN>(P, split, tmem_base, has_k, m0, n0, warp, lane, tmem_full_bar, 0);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -520,8 +290,10 @@ extern "C" B2_EXPORT int b200ppo_debug_tc_gemm(const float* A, const float* B, f
   p.M = M; p.N = N; p.K = K;
   p.epilogue = TC_EPI_STORE;
   p.out_f32 = part; p.ld_f32 = N; p.split_stride = stride; p.bias_col = -1;
+  const bool ws = bn < 0;  // bn = -1: the persistent weights-stationary kernel
+  if (ws) bn = tc_ws_bn(N);
   int rc = tc_group_add(g, p, TcOperand{Ab, a_pitch, a_mn_major}, TcOperand{Bb, b_pitch, b_mn_major}, bn, split_k);
-  if (rc == B200PPO_OK) rc = launch_tc_group(g, bn, st);
+  if (rc == B200PPO_OK) rc = ws ? launch_tc_ws(g, st) : launch_tc_group(g, bn, st);
   if (rc == B200PPO_OK) {
     sum_splits_kernel<<<unsigned((mn + 255) / 256), 256, 0, st>>>(part, g.p[0].split_k, stride, mn, C);
     count_launch();

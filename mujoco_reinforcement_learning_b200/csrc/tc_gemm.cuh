@@ -58,6 +58,10 @@ int tc_init();  // resolves cuTensorMapEncodeTiled; returns B200PPO_OK or an err
 int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B, int bn, int split_k);
 int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st);
 int tc_pick_bn(int64_t rows_total_tiles_m, int N);
-int tc_ctas_per_sm(int bn);  // resident CTAs per SM of the bn-wide kernel instance
+int tc_ctas_per_sm(int bn);
+// Persistent weights-stationary variant (tc_ws.cu) for forward / dgrad groups with many row tiles.
+bool tc_ws_applicable(int64_t total_tiles_m, int maxN, int maxK);
+int tc_ws_bn(int maxN);
+int launch_tc_ws(const TcGroup& g, cudaStream_t st);  // resident CTAs per SM of the bn-wide kernel instance
 
 }  // namespace b200ppo

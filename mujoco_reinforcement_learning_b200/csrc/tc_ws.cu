@@ -1,0 +1,198 @@
+// Persistent, weights-stationary tcgen05 GEMM for the forward and dgrad passes of the MLP (large minibatches).
+//
+// C[M, N] = A[M, K] * W[N, K]^T with M = minibatch rows (tens of thousands), N <= 256, K <= 384: the weight matrix
+// is a few hundred KB at most, the activations are what streams.  The tile-per-CTA kernel (tc_gemm.cu) re-reads the
+// weight tile for every 128 rows, which makes it L2->SM bandwidth bound (64 FLOP per byte staged).  Here a CTA
+// loads its problem's whole W into shared memory ONCE (TMA, 128-byte swizzle, K-major), then walks over its share
+// of the 128-row tiles: only A moves (4x the arithmetic intensity), the accumulator is double-buffered in TMEM
+// (2 x BN columns) so the epilogue of tile t overlaps the MMAs of tile t+1.
+//   warp 0      TMA producer: W once, then the A k-blocks of every tile through an n-stage mbarrier ring
+//   warp 1      MMA issuer (one lane): tcgen05.mma M=128, N=BN, K=16, commit -> frees the A stage / publishes the tile
+//   warps 2-9   epilogue (shared with tc_gemm.cu): tcgen05.ld, bias + MUFU tanh | act' multiply, bf16/fp32 stores
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace b200ppo {
+
+struct WsGroup {
+  TcProblem p[2];
+  int count;
+  int cta_begin[3];  // CTAs [cta_begin[i], cta_begin[i+1]) serve problem i
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_constant__ WsGroup grp, int a_stages) {
+  constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  constexpr int W_KB_BYTES = BN * TC_BK * 2;  // one 64-wide k-block of W
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pi = (grp.count > 1 && int(blockIdx.x) >= grp.cta_begin[1]) ? 1 : 0;
+  const TcProblem& P = grp.p[pi];
+  const int cta_local = int(blockIdx.x) - grp.cta_begin[pi];
+  const int ctas = grp.cta_begin[pi + 1] - grp.cta_begin[pi];
+  const int KB = (P.K + TC_BK - 1) / TC_BK;
+  const int tiles_m = P.tiles_m;
+
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + size_t(KB) * W_KB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + size_t(a_stages) * TC_A_BYTES);
+  uint64_t* w_full = bars;
+  uint64_t* a_full = bars + 1;
+  uint64_t* a_empty = a_full + a_stages;
+  uint64_t* acc_full = a_empty + a_stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(w_full, 1);
+    for (int s = 0; s < a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(w_full, uint32_t(KB) * W_KB_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + size_t(kb) * W_KB_BYTES, &P.tmB, w_full, kb * TC_BK, 0);
+      int it = 0;
+      for (int tile = cta_local; tile < tiles_m; tile += ctas) {
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % a_stages;
+          const uint32_t ph = (it / a_stages) & 1;
+          mbar_wait(&a_empty[s], ph ^ 1);
+          mbar_expect_tx(&a_full[s], TC_A_BYTES);
+          tma_load_2d(sA + size_t(s) * TC_A_BYTES, &P.tmA, &a_full[s], kb * TC_BK, tile * TC_BM);
+        }
+      }
+    }
+  } else if (warp == 1) {  // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(TC_BM >> 4) << 24);
+    mbar_wait(w_full, 0);
+    int it = 0, t = 0;
+    for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
+      const int buf = t & 1;
+      mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % a_stages;
+        const uint32_t ph = (it / a_stages) & 1;
+        mbar_wait(&a_full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(sA + size_t(s) * TC_A_BYTES), b_addr = smem_u32(sW + size_t(kb) * W_KB_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(tmem_base + uint32_t(buf * BN), umma_desc(a_addr + k * 32, 0, 1024), umma_desc(b_addr + k * 32, 0, 1024), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&a_empty[s]);
+          if (kb == KB - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {  // ===== epilogue warps =====
+    int t = 0;
+    for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
+      const int buf = t & 1;
+      tc_epilogue<BN>(P, 0, tmem_base + uint32_t(buf * BN), true, tile * TC_BM, 0, warp, lane, &acc_full[buf], uint32_t((t >> 1) & 1));
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+constexpr int kWsMaxSmem = 227 * 1024;
+
+// N tile and A-ring depth for a group, or bn = 0 when the weights-stationary kernel does not apply.
+static void ws_plan(int maxN, int maxK, int* bn_out, int* stages_out) {
+  *bn_out = 0;
+  *stages_out = 0;
+  if (maxN > 256) return;
+  const int bn = maxN > 128 ? 256 : (maxN > 64 ? 128 : 64);
+  const int kb = (maxK + TC_BK - 1) / TC_BK;
+  const int64_t w_bytes = int64_t(kb) * bn * TC_BK * 2;
+  const int64_t avail = kWsMaxSmem - 1024 - 512 - w_bytes;
+  int stages = int(avail / TC_A_BYTES);
+  if (stages < 2) return;
+  if (stages > 8) stages = 8;
+  *bn_out = bn;
+  *stages_out = stages;
+}
+
+bool tc_ws_applicable(int64_t total_tiles_m, int maxN, int maxK) {
+  int bn, st;
+  ws_plan(maxN, maxK, &bn, &st);
+  // persistence pays once every CTA owns at least ~two row tiles; below that the one-tile kernel has more CTAs
+  return bn != 0 && total_tiles_m >= 2ll * num_sms();
+}
+
+int tc_ws_bn(int maxN) { return maxN > 128 ? 256 : (maxN > 64 ? 128 : 64); }
+
+template <int BN>
+static int launch_ws_bn(const WsGroup& g, int stages, int kb_max, int grid, cudaStream_t st) {
+  const int smem = kb_max * BN * TC_BK * 2 + stages * TC_A_BYTES + 1024 + 512;
+  static int configured = 0;
+  if (configured < smem) {
+    B2_CUDA(cudaFuncSetAttribute(tc_ws_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  tc_ws_kernel<BN><<<grid, TC_THREADS, smem, st>>>(g, stages);
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
+
+// g: one or two forward / dgrad problems built with tc_group_add(..., bn = tc_ws_bn(maxN), split 1), K-major operands.
+int launch_tc_ws(const TcGroup& g, cudaStream_t st) {
+  B2_CHECK_ARG(g.count >= 1 && g.count <= 2, "weights-stationary launch takes one or two problems");
+  int maxN = 0, maxK = 0;
+  int64_t tiles = 0;
+  for (int i = 0; i < g.count; ++i) {
+    B2_CHECK_ARG(!g.p[i].a_mn_major && !g.p[i].b_mn_major && g.p[i].split_k == 1, "weights-stationary kernel: K-major, no split-K");
+    maxN = std::max(maxN, g.p[i].N);
+    maxK = std::max(maxK, g.p[i].K);
+    tiles += g.p[i].tiles_m;
+  }
+  int bn, stages;
+  ws_plan(maxN, maxK, &bn, &stages);
+  B2_CHECK_ARG(bn != 0, "weights do not fit in shared memory");
+  WsGroup w{};
+  w.count = g.count;
+  const int grid = int(std::min<int64_t>(num_sms(), tiles));
+  int begin = 0;
+  for (int i = 0; i < g.count; ++i) {
+    w.p[i] = g.p[i];
+    w.cta_begin[i] = begin;
+    int share = (i == g.count - 1) ? grid - begin : int((int64_t(grid) * g.p[i].tiles_m + tiles / 2) / tiles);
+    if (share < 1) share = 1;
+    begin += share;
+  }
+  w.cta_begin[g.count] = grid;
+  const int kb_max = (maxK + TC_BK - 1) / TC_BK;
+  switch (bn) {
+    case 64: return launch_ws_bn<64>(w, stages, kb_max, grid, st);
+    case 128: return launch_ws_bn<128>(w, stages, kb_max, grid, st);
+    default: return launch_ws_bn<256>(w, stages, kb_max, grid, st);
+  }
+}
+
+}  // namespace b200ppo

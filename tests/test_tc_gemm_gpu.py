@@ -27,6 +27,11 @@ CASES = [
     (1000, 192, 200, 0, 0, 192, 1),
     (4096, 256, 17, 0, 0, 128, 1),       # output-layer dgrad: K = act_dim
     (4096, 17, 256, 0, 0, 64, 1),        # output-layer forward: N = act_dim
+    (40000, 256, 376, 0, 0, -1, 1),      # weights-stationary persistent kernel: forward layer 1 (W = 192 KB in smem)
+    (40000, 256, 256, 0, 0, -1, 1),      # forward / dgrad layer 2
+    (33000, 17, 256, 0, 0, -1, 1),       # narrow output layer
+    (20000, 100, 130, 0, 0, -1, 1),      # ragged N, K
+    (300, 256, 256, 0, 0, -1, 1),        # fewer tiles than CTAs
 ]
 
 
