@@ -401,7 +401,7 @@ static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_b
     for (int n = 0; n < 2; ++n)
       if (l < ctx->net[n].d.n_layers) maxK = std::max(maxK, ctx->net[n].in_dim(l));
     const bool ws = tc_ws_applicable(int64_t((B + 127) / 128) * nets_here, maxN, maxK);
-    const int bn = ws ? tc_ws_bn(maxN) : tc_pick_bn(int64_t((B + 127) / 128) * nets_here, maxN);
+    const int bn = ws ? tc_ws_bn(maxN, maxK) : tc_pick_bn(int64_t((B + 127) / 128) * nets_here, maxN);
     for (int n = 0; n < 2; ++n) {
       const Net& N = ctx->net[n];
       if (l >= N.d.n_layers) continue;
@@ -449,7 +449,7 @@ static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t
       if (l >= 1) maxK = std::max(maxK, ctx->net[n].d.dims[l]);
     }
     const bool ws = tc_ws_applicable(int64_t((B + 127) / 128) * nets_here, maxN, maxK);
-    const int bn = ws ? tc_ws_bn(maxN) : tc_pick_bn(int64_t((B + 127) / 128) * nets_here, maxN);
+    const int bn = ws ? tc_ws_bn(maxN, maxK) : tc_pick_bn(int64_t((B + 127) / 128) * nets_here, maxN);
     for (int n = 0; n < 2; ++n) {
       const Net& N = ctx->net[n];
       const int l = N.d.n_layers - 1 - s;

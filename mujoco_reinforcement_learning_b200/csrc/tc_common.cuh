@@ -99,13 +99,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // Epilogue of one 128 x BN accumulator tile, executed by the 8 epilogue warps (warp index 2..9 of the CTA).
 template <int BN>
 __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint32_t tmem_acc, bool has_k, int m0, int n0, int warp,
-                                            int lane, uint64_t* tmem_full_bar, uint32_t full_parity) {
+                                            int lane, uint64_t* tmem_full_bar, uint32_t full_parity, const float* bias_s) {
     // Problem fields into registers once (the indexed constant-bank loads of `P.` inside the column loop showed up
     // as long-scoreboard stalls), and everything the epilogue reads from global memory — the activation operand of
     // the dgrad, the bias of the forward — is requested BEFORE waiting for the accumulator, so that latency hides
     // behind the TMA/MMA main loop.
     const int epi = P.epilogue, act = P.act, Mrows = P.M, Ncols = P.N;
-    const float* __restrict__ bias_p = P.bias;
     __nv_bfloat16* __restrict__ outb = P.out_bf16;
     float* __restrict__ outf = P.out_f32 != nullptr ? P.out_f32 + int64_t(split) * P.split_stride : nullptr;
     float* __restrict__ bgrad = P.bias_grad != nullptr ? P.bias_grad + int64_t(split) * P.split_stride : nullptr;
@@ -153,15 +152,11 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
       float h[CW];
       if (epi == TC_EPI_FWD) {
         if (live) {
-          if (full) {  // bias segments start on 128-byte boundaries of the flat parameter buffer
+          // bias of this CTA's columns was staged in shared memory once (broadcast reads, no global latency here)
 #pragma unroll
-            for (int u = 0; u < CW / 4; ++u) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(bias_p + nb) + u);
-              h[u * 4] = t.x; h[u * 4 + 1] = t.y; h[u * 4 + 2] = t.z; h[u * 4 + 3] = t.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) h[j] = nb + j < Ncols ? __ldg(bias_p + nb + j) : 0.f;
+          for (int u = 0; u < CW / 4; ++u) {
+            const float4 t = *reinterpret_cast<const float4*>(bias_s + (nb - n0) + u * 4);
+            h[u * 4] = t.x; h[u * 4 + 1] = t.y; h[u * 4 + 2] = t.z; h[u * 4 + 3] = t.w;
           }
           if (act == B200PPO_ACT_TANH) {
 #pragma unroll
@@ -240,6 +235,187 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
         }
       }
     }
+}
+
+
+// Stage the bias of columns [n0, n0 + bn) into shared memory (zeros beyond N or when the problem has no bias).
+__device__ __forceinline__ void tc_stage_bias(const TcProblem& P, int n0, int bn, float* bias_s, int tid, int nthreads) {
+  for (int j = tid; j < bn; j += nthreads)
+    bias_s[j] = (P.bias != nullptr && P.epilogue == TC_EPI_FWD && n0 + j < P.N) ? __ldg(P.bias + n0 + j) : 0.f;
+}
+
+// ---- shared-memory staged epilogue ---------------------------------------------------------------------------------
+// tcgen05.ld hands every thread one accumulator ROW, so storing straight from registers makes each warp-wide store
+// touch 32 different 128-byte lines (32 L1 wavefronts per instruction) — measured as THE bottleneck of the forward and
+// dgrad kernels.  Instead each epilogue warp owns a 4 KB staging tile (32 rows x 128 B, 16-byte units XOR-swizzled by
+// row & 7 so both the row-per-thread phase and the line-per-8-threads phase are bank-conflict free): results go
+// registers -> staging -> global with every instruction writing four full 128-byte lines; the dgrad's activation
+// operand comes in through the same tile the same way.
+constexpr int TC_STAGE_BYTES = 4096;  // per epilogue warp
+
+__device__ __forceinline__ uint32_t stage_off(int row, int unit) { return uint32_t(row * 128 + ((unit ^ (row & 7)) << 4)); }
+
+// dgrad: request this warp's 32 x (BN/2) slab of the activation operand into its staging tile with cp.async (16 bytes
+// per lane, 8 lanes per 128-byte line) and commit the group; nothing waits here, so the request overlaps the MMAs.
+// Only for BN <= 128 (the slab is then a single 128-byte-row group).  Always commits (possibly empty) so that the
+// caller's group counting stays uniform.
+template <int BN>
+__device__ __forceinline__ void tc_issue_aux(const TcProblem& P, int m0, int n0, int warp, int lane, uint8_t* stage, bool valid) {
+  static_assert(BN <= 128, "staged dgrad needs BN <= 128");
+  if (valid && P.epilogue == TC_EPI_DGRAD) {
+    constexpr int WCOLS = BN / 2;
+    const int q = warp & 3;
+    const int mq = m0 + q * 32;
+    const int nbg = n0 + ((warp - 2) >> 2) * WCOLS;
+    constexpr int upr = WCOLS >> 3;
+    const uint32_t sbase = smem_u32(stage);
+    const __nv_bfloat16* auxp = P.aux;
+    const int ld_aux = P.ld_aux;
+#pragma unroll
+    for (int idx = lane; idx < 32 * upr; idx += 32) {
+      const int row = idx / upr, unit = idx - row * upr;
+      const bool ok = mq + row < P.M && nbg + unit * 8 < P.N;
+      const __nv_bfloat16* src = auxp + int64_t(ok ? mq + row : 0) * ld_aux + (ok ? nbg + unit * 8 : 0);
+      const uint32_t bytes = ok ? 16u : 0u;  // src-size 0: zero fill
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + stage_off(row, unit)), "l"(src), "r"(bytes) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_staged(const TcProblem& P, int split, uint32_t tmem_acc, bool has_k, int m0, int n0,
+                                                   int warp, int lane, uint64_t* tmem_full_bar, uint32_t full_parity,
+                                                   uint8_t* stage, const float* bias_s, int aux_groups_in_flight) {
+  const int epi = P.epilogue, act = P.act, Mrows = P.M, Ncols = P.N;
+  __nv_bfloat16* __restrict__ outb = P.out_bf16;
+  float* __restrict__ outf = P.out_f32 != nullptr ? P.out_f32 + int64_t(split) * P.split_stride : nullptr;
+  float* __restrict__ bgrad = P.bias_grad != nullptr ? P.bias_grad + int64_t(split) * P.split_stride : nullptr;
+  const __nv_bfloat16* __restrict__ auxp = P.aux;
+  const int ld_bf16 = P.ld_bf16, ld_f32 = P.ld_f32, ld_aux = P.ld_aux, bias_col = P.bias_col;
+  const float out_scale = P.out_scale;
+  const int q = warp & 3;                 // TMEM lane quarter of this warp
+  const int mq = m0 + q * 32;             // first row of the warp's 32-row slab
+  const int m = mq + lane;
+  const bool f32_out = (epi == TC_EPI_STORE);
+  const int ncols_mat = f32_out ? (bias_col >= 0 ? bias_col : Ncols) : Ncols;  // columns stored through the staging tile
+  constexpr int WCOLS = BN / 2;           // columns per epilogue warp
+  const int col0 = ((warp - 2) >> 2) * WCOLS;
+  const int GW = f32_out ? 32 : 64;       // columns per 128-byte staging row
+  const uint32_t sbase = smem_u32(stage);
+
+  // dgrad: the activation tile was requested with cp.async by tc_issue_aux (this tile's group is the older one)
+  if (epi == TC_EPI_DGRAD) {
+    if (aux_groups_in_flight > 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  if (has_k) {
+    mbar_wait(tmem_full_bar, full_parity);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+#pragma unroll 1
+  for (int gc = 0; gc < WCOLS; gc += GW) {
+    const int gcols = (WCOLS - gc) < GW ? (WCOLS - gc) : GW;
+    const int nbg = n0 + col0 + gc;
+    __syncwarp();
+#pragma unroll 1
+    for (int s = 0; s < gcols / 16; ++s) {
+      uint32_t v[16];
+      if (has_k) {
+        tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(col0 + gc + s * 16), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      const int nb = nbg + s * 16;
+      float h[16];
+      if (epi == TC_EPI_FWD) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 t = *reinterpret_cast<const float4*>(bias_s + (nb - n0) + u * 4);
+          h[u * 4] = t.x; h[u * 4 + 1] = t.y; h[u * 4 + 2] = t.z; h[u * 4 + 3] = t.w;
+        }
+        if (act == B200PPO_ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) h[j] = tanh_fast(__uint_as_float(v[j]) + h[j]);
+        } else if (act == B200PPO_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) h[j] = fmaxf(__uint_as_float(v[j]) + h[j], 0.f);
+        } else if (act == TC_ACT_TANH_SCALE) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) h[j] = out_scale * tanh_fast(__uint_as_float(v[j]) + h[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) h[j] = __uint_as_float(v[j]) + h[j];
+        }
+      } else if (epi == TC_EPI_DGRAD) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(sbase + stage_off(lane, s * 2 + u)) : "memory");
+          const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[t]);
+            h[u * 8 + t * 2] = __low2float(b2);
+            h[u * 8 + t * 2 + 1] = __high2float(b2);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float g = __uint_as_float(v[j]);
+          h[j] = act == B200PPO_ACT_TANH ? g * (1.f - h[j] * h[j]) : (h[j] > 0.f ? g : 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h[j] = __uint_as_float(v[j]);
+        if (bgrad != nullptr && bias_col >= nb && bias_col < nb + 16 && m < Mrows) {
+          float bg = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j == bias_col) bg = h[j];
+          bgrad[m] = bg;
+        }
+      }
+      if (f32_out) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + stage_off(lane, s * 4 + u)), "r"(__float_as_uint(h[u * 4])),
+                       "r"(__float_as_uint(h[u * 4 + 1])), "r"(__float_as_uint(h[u * 4 + 2])), "r"(__float_as_uint(h[u * 4 + 3]))
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + stage_off(lane, s * 2 + u)), "r"(pack_bf16(h[u * 8], h[u * 8 + 1])),
+                       "r"(pack_bf16(h[u * 8 + 2], h[u * 8 + 3])), "r"(pack_bf16(h[u * 8 + 4], h[u * 8 + 5])),
+                       "r"(pack_bf16(h[u * 8 + 6], h[u * 8 + 7]))
+                       : "memory");
+      }
+    }
+    __syncwarp();
+    // staging -> global: 8 consecutive lanes write one full 128-byte line
+    const int upr = f32_out ? (gcols >> 2) : (gcols >> 3);
+    const int cpu = f32_out ? 4 : 8;  // columns per 16-byte unit
+    for (int idx = lane; idx < 32 * upr; idx += 32) {
+      const int row = idx / upr, unit = idx - row * upr;
+      const int col = nbg + unit * cpu;
+      if (mq + row < Mrows && col < ncols_mat) {
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(sbase + stage_off(row, unit)) : "memory");
+        if (f32_out) *reinterpret_cast<uint4*>(outf + int64_t(mq + row) * ld_f32 + col) = make_uint4(w0, w1, w2, w3);
+        else *reinterpret_cast<uint4*>(outb + int64_t(mq + row) * ld_bf16 + col) = make_uint4(w0, w1, w2, w3);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Host-evaluated: may this problem use the staged epilogue (16-byte aligned rows and whole units inside the matrix)?
+inline bool tc_can_stage(const TcProblem& p) {
+  if (p.epilogue == TC_EPI_STORE) return false;  // measured: staging the fp32 split-K partials does not pay (58 vs 50 us)
+  const bool out_ok = p.out_bf16 != nullptr && p.out_f32 == nullptr && p.ld_bf16 % 8 == 0 && p.N % 8 == 0 && aligned16(p.out_bf16);
+  if (p.epilogue == TC_EPI_DGRAD) return out_ok && p.aux != nullptr && p.ld_aux % 8 == 0 && aligned16(p.aux);
+  return out_ok;
 }
 
 }  // namespace b200ppo

@@ -24,9 +24,13 @@
 
 namespace b200ppo {
 
-// smem ring depth: K loops here are 1-6 tiles for forward/dgrad, so 3 stages already cover them, and 3 x 32 KB lets
-// two CTAs share an SM (BN <= 128): one CTA's epilogue then overlaps the other's TMA/MMA main loop.
-template <int BN> struct TcCfg { static constexpr int STAGES = BN <= 128 ? 3 : 4; static constexpr int CTAS_PER_SM = BN <= 128 ? 2 : 1; };
+// smem ring depth: K loops are 1-6 tiles for forward/dgrad, so for BN <= 128 two 32 KB stages + the 32 KB epilogue
+// staging area let two CTAs share an SM (one CTA's epilogue overlaps the other's TMA/MMA main loop); the wide tiles
+// used by the long-K weight-gradient GEMM run one CTA per SM with a deeper ring.
+template <int BN> struct TcCfg {
+  static constexpr int STAGES = BN <= 128 ? 2 : (BN <= 192 ? 4 : 3);
+  static constexpr int CTAS_PER_SM = BN <= 128 ? 2 : 1;
+};
 int tc_ctas_per_sm(int bn) { return bn <= 128 ? 2 : 1; }
 
 template <int BN>
@@ -42,6 +46,8 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // BN floats
+  uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 1024;                        // TC_EPI_WARPS x 4 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -60,6 +66,7 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   const int kt_end = min(total_kt, kt_begin + P.k_tiles_per_split);
   const bool has_k = kt_end > kt_begin;
 
+  tc_stage_bias(P, n0, BN, bias_s, threadIdx.x, TC_THREADS);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -128,7 +135,15 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
       }
     }
   } else {  // ===== epilogue warps 2..9 =====
-    tc_epilogue<BN>(P, split, tmem_base, has_k, m0, n0, warp, lane, tmem_full_bar, 0);
+    if constexpr (BN <= 128) {
+      if (P.staged) {
+        uint8_t* st = stage_area + (warp - 2) * TC_STAGE_BYTES;
+        tc_issue_aux<BN>(P, m0, n0, warp, lane, st, true);
+        tc_epilogue_staged<BN>(P, split, tmem_base, has_k, m0, n0, warp, lane, tmem_full_bar, 0, st, bias_s, 0);
+      } else {
+        tc_epilogue<BN>(P, split, tmem_base, has_k, m0, n0, warp, lane, tmem_full_bar, 0, bias_s);
+      }
+    } else tc_epilogue<BN>(P, split, tmem_base, has_k, m0, n0, warp, lane, tmem_full_bar, 0, bias_s);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -206,6 +221,7 @@ int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B
   p.tiles_m = (p.M + TC_BM - 1) / TC_BM;
   p.tiles_n = (p.N + bn - 1) / bn;
   p.tile_begin = g.total_tiles;
+  p.staged = tc_can_stage(p) ? 1 : 0;
   g.total_tiles += p.tiles_m * p.tiles_n * split_k;
   g.p[g.count++] = p;
   return B200PPO_OK;
@@ -213,7 +229,7 @@ int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B
 
 template <int BN>
 static int launch_bn(const TcGroup& g, cudaStream_t st) {
-  constexpr int smem = TcCfg<BN>::STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256;
+  constexpr int smem = TcCfg<BN>::STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256 + 1024 + TC_EPI_WARPS * TC_STAGE_BYTES;
   static bool configured = false;
   if (!configured) {
     B2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -291,7 +307,7 @@ extern "C" B2_EXPORT int b200ppo_debug_tc_gemm(const float* A, const float* B, f
   p.epilogue = TC_EPI_STORE;
   p.out_f32 = part; p.ld_f32 = N; p.split_stride = stride; p.bias_col = -1;
   const bool ws = bn < 0;  // bn = -1: the persistent weights-stationary kernel
-  if (ws) bn = tc_ws_bn(N);
+  if (ws) bn = tc_ws_bn(N, K);
   int rc = tc_group_add(g, p, TcOperand{Ab, a_pitch, a_mn_major}, TcOperand{Bb, b_pitch, b_mn_major}, bn, split_k);
   if (rc == B200PPO_OK) rc = ws ? launch_tc_ws(g, st) : launch_tc_group(g, bn, st);
   if (rc == B200PPO_OK) {

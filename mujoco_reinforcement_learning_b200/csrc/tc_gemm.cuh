@@ -36,6 +36,7 @@ struct TcProblem {
   float* bias_grad;
   int bias_col;  // -1: none
   float out_scale;
+  int staged;  // epilogue goes through the shared-memory staging tile (set by tc_group_add)
 };
 
 constexpr int kMaxTcProblems = 6;
@@ -61,7 +62,7 @@ int tc_pick_bn(int64_t rows_total_tiles_m, int N);
 int tc_ctas_per_sm(int bn);
 // Persistent weights-stationary variant (tc_ws.cu) for forward / dgrad groups with many row tiles.
 bool tc_ws_applicable(int64_t total_tiles_m, int maxN, int maxK);
-int tc_ws_bn(int maxN);
+int tc_ws_bn(int maxN, int maxK);
 int launch_tc_ws(const TcGroup& g, cudaStream_t st);  // resident CTAs per SM of the bn-wide kernel instance
 
 }  // namespace b200ppo

@@ -15,10 +15,15 @@
 
 namespace b200ppo {
 
+constexpr int kWsMaxSlots = 4;
+
+// A slot = (problem, N tile): its CTAs keep that BN-wide slice of the problem's W in shared memory.
 struct WsGroup {
   TcProblem p[2];
   int count;
-  int cta_begin[3];  // CTAs [cta_begin[i], cta_begin[i+1]) serve problem i
+  int n_slots;
+  int slot_prob[kWsMaxSlots], slot_n0[kWsMaxSlots];
+  int cta_begin[kWsMaxSlots + 1];  // CTAs [cta_begin[i], cta_begin[i+1]) serve slot i
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -32,10 +37,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pi = (grp.count > 1 && int(blockIdx.x) >= grp.cta_begin[1]) ? 1 : 0;
-  const TcProblem& P = grp.p[pi];
-  const int cta_local = int(blockIdx.x) - grp.cta_begin[pi];
-  const int ctas = grp.cta_begin[pi + 1] - grp.cta_begin[pi];
+  int slot = 0;
+#pragma unroll 1
+  for (int i = 1; i < grp.n_slots; ++i)
+    if (int(blockIdx.x) >= grp.cta_begin[i]) slot = i;
+  const TcProblem& P = grp.p[grp.slot_prob[slot]];
+  const int n0 = grp.slot_n0[slot];
+  const int cta_local = int(blockIdx.x) - grp.cta_begin[slot];
+  const int ctas = grp.cta_begin[slot + 1] - grp.cta_begin[slot];
   const int KB = (P.K + TC_BK - 1) / TC_BK;
   const int tiles_m = P.tiles_m;
 
@@ -48,7 +57,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
   uint64_t* acc_full = a_empty + a_stages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // BN floats
+  uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 1024;                  // TC_EPI_WARPS x 4 KB
 
+  tc_stage_bias(P, n0, BN, bias_s, threadIdx.x, TC_THREADS);
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
     for (int s = 0; s < a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -66,7 +78,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       mbar_expect_tx(w_full, uint32_t(KB) * W_KB_BYTES);
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + size_t(kb) * W_KB_BYTES, &P.tmB, w_full, kb * TC_BK, 0);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + size_t(kb) * W_KB_BYTES, &P.tmB, w_full, kb * TC_BK, n0);
       int it = 0;
       for (int tile = cta_local; tile < tiles_m; tile += ctas) {
         for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -105,12 +117,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
     }
   } else {  // ===== epilogue warps =====
     int t = 0;
-    for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
-      const int buf = t & 1;
-      tc_epilogue<BN>(P, 0, tmem_base + uint32_t(buf * BN), true, tile * TC_BM, 0, warp, lane, &acc_full[buf], uint32_t((t >> 1) & 1));
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    if constexpr (BN <= 128) {
+      // two staging tiles per warp: while tile t is finished and stored from one, the dgrad's activation slab of tile
+      // t + ctas is already streaming into the other (cp.async), i.e. behind the MMAs of the next tile
+      uint8_t* st[2] = {stage_area + (warp - 2) * 2 * TC_STAGE_BYTES, stage_area + (warp - 2) * 2 * TC_STAGE_BYTES + TC_STAGE_BYTES};
+      if (P.staged) tc_issue_aux<BN>(P, cta_local * TC_BM, n0, warp, lane, st[0], cta_local < tiles_m);
+      for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
+        const int buf = t & 1;
+        if (P.staged) {
+          const int next = tile + ctas;
+          tc_issue_aux<BN>(P, next * TC_BM, n0, warp, lane, st[buf ^ 1], next < tiles_m);
+          tc_epilogue_staged<BN>(P, 0, tmem_base + uint32_t(buf * BN), true, tile * TC_BM, n0, warp, lane, &acc_full[buf],
+                                 uint32_t((t >> 1) & 1), st[buf], bias_s, 1);
+        } else {
+          tc_epilogue<BN>(P, 0, tmem_base + uint32_t(buf * BN), true, tile * TC_BM, n0, warp, lane, &acc_full[buf], uint32_t((t >> 1) & 1), bias_s);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+      for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
+        const int buf = t & 1;
+        tc_epilogue<BN>(P, 0, tmem_base + uint32_t(buf * BN), true, tile * TC_BM, n0, warp, lane, &acc_full[buf], uint32_t((t >> 1) & 1), bias_s);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -122,21 +156,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
 }
 
 constexpr int kWsMaxSmem = 227 * 1024;
+constexpr int kWsFixedSmem = 1024 + 512 + 1024 + 2 * TC_EPI_WARPS * TC_STAGE_BYTES;  // staging is double-buffered here  // alignment slack + barriers + epilogue staging
 
 // N tile and A-ring depth for a group, or bn = 0 when the weights-stationary kernel does not apply.
+// N tile <= 128: each epilogue warp then owns 64 columns = ONE 128-byte staging row, so the dgrad's whole activation
+// tile is requested in a single burst before the accumulator is awaited (and W slices of <= 96 KB leave a deep A ring).
 static void ws_plan(int maxN, int maxK, int* bn_out, int* stages_out) {
   *bn_out = 0;
   *stages_out = 0;
-  if (maxN > 256) return;
-  const int bn = maxN > 128 ? 256 : (maxN > 64 ? 128 : 64);
   const int kb = (maxK + TC_BK - 1) / TC_BK;
-  const int64_t w_bytes = int64_t(kb) * bn * TC_BK * 2;
-  const int64_t avail = kWsMaxSmem - 1024 - 512 - w_bytes;
-  int stages = int(avail / TC_A_BYTES);
-  if (stages < 2) return;
-  if (stages > 8) stages = 8;
-  *bn_out = bn;
-  *stages_out = stages;
+  for (int bn : {128, 64}) {
+    if (bn > 64 && maxN <= bn / 2) continue;  // a narrower tile covers N
+    const int64_t w_bytes = int64_t(kb) * bn * TC_BK * 2;
+    const int64_t avail = kWsMaxSmem - kWsFixedSmem - w_bytes;
+    int stages = int(avail / TC_A_BYTES);
+    if (stages < 3) continue;
+    if ((maxN + bn - 1) / bn * 2 > kWsMaxSlots) continue;
+    *bn_out = bn;
+    *stages_out = stages > 8 ? 8 : stages;
+    return;
+  }
 }
 
 bool tc_ws_applicable(int64_t total_tiles_m, int maxN, int maxK) {
@@ -146,11 +185,15 @@ bool tc_ws_applicable(int64_t total_tiles_m, int maxN, int maxK) {
   return bn != 0 && total_tiles_m >= 2ll * num_sms();
 }
 
-int tc_ws_bn(int maxN) { return maxN > 128 ? 256 : (maxN > 64 ? 128 : 64); }
+int tc_ws_bn(int maxN, int maxK) {
+  int bn, st;
+  ws_plan(maxN, maxK, &bn, &st);
+  return bn;
+}
 
 template <int BN>
 static int launch_ws_bn(const WsGroup& g, int stages, int kb_max, int grid, cudaStream_t st) {
-  const int smem = kb_max * BN * TC_BK * 2 + stages * TC_A_BYTES + 1024 + 512;
+  const int smem = kb_max * BN * TC_BK * 2 + stages * TC_A_BYTES + kWsFixedSmem;
   static int configured = 0;
   if (configured < smem) {
     B2_CUDA(cudaFuncSetAttribute(tc_ws_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -161,37 +204,46 @@ static int launch_ws_bn(const WsGroup& g, int stages, int kb_max, int grid, cuda
   return B200PPO_OK;
 }
 
-// g: one or two forward / dgrad problems built with tc_group_add(..., bn = tc_ws_bn(maxN), split 1), K-major operands.
+// g: one or two forward / dgrad problems built with tc_group_add(..., bn = tc_ws_bn(maxN, maxK), split 1), K-major.
 int launch_tc_ws(const TcGroup& g, cudaStream_t st) {
   B2_CHECK_ARG(g.count >= 1 && g.count <= 2, "weights-stationary launch takes one or two problems");
   int maxN = 0, maxK = 0;
-  int64_t tiles = 0;
   for (int i = 0; i < g.count; ++i) {
     B2_CHECK_ARG(!g.p[i].a_mn_major && !g.p[i].b_mn_major && g.p[i].split_k == 1, "weights-stationary kernel: K-major, no split-K");
     maxN = std::max(maxN, g.p[i].N);
     maxK = std::max(maxK, g.p[i].K);
-    tiles += g.p[i].tiles_m;
   }
   int bn, stages;
   ws_plan(maxN, maxK, &bn, &stages);
   B2_CHECK_ARG(bn != 0, "weights do not fit in shared memory");
   WsGroup w{};
   w.count = g.count;
-  const int grid = int(std::min<int64_t>(num_sms(), tiles));
-  int begin = 0;
+  int64_t work = 0;  // row tiles summed over slots
   for (int i = 0; i < g.count; ++i) {
     w.p[i] = g.p[i];
-    w.cta_begin[i] = begin;
-    int share = (i == g.count - 1) ? grid - begin : int((int64_t(grid) * g.p[i].tiles_m + tiles / 2) / tiles);
+    for (int n0 = 0; n0 < g.p[i].N; n0 += bn) {
+      w.slot_prob[w.n_slots] = i;
+      w.slot_n0[w.n_slots] = n0;
+      ++w.n_slots;
+      work += g.p[i].tiles_m;
+    }
+  }
+  const int grid = int(std::min<int64_t>(num_sms(), work));
+  int begin = 0;
+  for (int sidx = 0; sidx < w.n_slots; ++sidx) {
+    w.cta_begin[sidx] = begin;
+    const int64_t tiles = g.p[w.slot_prob[sidx]].tiles_m;
+    int share = (sidx == w.n_slots - 1) ? grid - begin : int((int64_t(grid) * tiles + work / 2) / work);
     if (share < 1) share = 1;
     begin += share;
   }
-  w.cta_begin[g.count] = grid;
+  w.cta_begin[w.n_slots] = std::max(begin, grid);
   const int kb_max = (maxK + TC_BK - 1) / TC_BK;
+  const int total = w.cta_begin[w.n_slots];
   switch (bn) {
-    case 64: return launch_ws_bn<64>(w, stages, kb_max, grid, st);
-    case 128: return launch_ws_bn<128>(w, stages, kb_max, grid, st);
-    default: return launch_ws_bn<256>(w, stages, kb_max, grid, st);
+    case 64: return launch_ws_bn<64>(w, stages, kb_max, total, st);
+    case 128: return launch_ws_bn<128>(w, stages, kb_max, total, st);
+    default: return launch_ws_bn<256>(w, stages, kb_max, total, st);
   }
 }
 
