@@ -13,18 +13,30 @@ namespace b200ppo {
 constexpr float kLogSqrt2Pi = 0.91893853320467274178f;  // math.log(math.sqrt(2*math.pi))
 constexpr int kLossThreads = 128;
 
-// dynamic smem: [A] sigma-derived constants x3, then [kLossThreads][A] logstd-gradient contributions
+// One thread per sample row, but every global access is a block-wide contiguous slab copy: the 128 rows a CTA owns
+// are adjacent in the row-major [B, A] arrays, so `mean`, `action` and the gradient seeds move through shared memory
+// with fully coalesced 128-byte lines (rows of A = 17 floats would otherwise cost one line per thread).
+// dynamic smem: 3 x [A] sigma constants | mean [T][A] | action [T][A] | dz fp32 [T][A] (also the logstd-gradient
+// contributions after use) | dl [T][A] | dz bf16 [T][pitch]
 __global__ void __launch_bounds__(kLossThreads)
 ppo_loss_seed_kernel(LossArgs a) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int A = a.act_dim;
-  float* s_logsig = smem;           // log(sigma_j) as torch computes it: log(exp(logstd))
-  float* s_inv_var = smem + A;      // 1 / sigma_j^2
-  float* s_two_var = smem + 2 * A;  // 2 * sigma_j^2
-  float* s_dl = smem + 3 * A;       // [kLossThreads][A]
+  float* s_logsig = smem;
+  float* s_inv_var = smem + A;
+  float* s_two_var = smem + 2 * A;
+  float* s_mean = smem + 3 * A;
+  float* s_act = s_mean + kLossThreads * A;
+  float* s_dz = s_act + kLossThreads * A;
+  float* s_dl = s_dz + kLossThreads * A;
+  __nv_bfloat16* s_dzb = reinterpret_cast<__nv_bfloat16*>(s_dl + kLossThreads * A);
   __shared__ float s_red[2][kLossThreads / 32];
+  __shared__ float s_comb[kLossThreads];
   __shared__ bool s_last;
   const int tid = threadIdx.x;
+  const int64_t b0 = int64_t(blockIdx.x) * kLossThreads;
+  const int64_t remaining = a.batch - b0;
+  const int rows = remaining < kLossThreads ? int(remaining) : kLossThreads;
   for (int j = tid; j < A; j += kLossThreads) {
     const float sig = expf(a.logstd[j]);
     const float var = sig * sig;
@@ -32,20 +44,25 @@ ppo_loss_seed_kernel(LossArgs a) {
     s_inv_var[j] = 1.f / var;
     s_two_var[j] = 2.f * var;
   }
+  for (int i = tid; i < rows * A; i += kLossThreads) {
+    s_mean[i] = __ldg(a.mean + b0 * A + i);
+    s_act[i] = __ldg(a.action + b0 * A + i);
+  }
   __syncthreads();
-  const int64_t b = int64_t(blockIdx.x) * kLossThreads + tid;
-  const bool active = b < a.batch;
+  const int64_t b = b0 + tid;
+  const bool active = tid < rows;
+  const bool want_seed = a.dz_actor != nullptr || a.dz_actor_bf16 != nullptr;
+  const int pitch = a.dz_actor_pitch;
   float surr = 0.f, hub = 0.f;
   if (active) {
-    const float* mu = a.mean + b * A;
-    const float* ac = a.action + b * A;
+    const float* mu = s_mean + tid * A;
+    const float* ac = s_act + tid * A;
     float lp = 0.f;
     for (int j = 0; j < A; ++j) {
       const float d = ac[j] - mu[j];
       lp += -(d * d) / s_two_var[j] - s_logsig[j] - kLogSqrt2Pi;
     }
     if (a.logp_out != nullptr) a.logp_out[b] = lp;
-    const bool want_seed = a.dz_actor != nullptr || a.dz_actor_bf16 != nullptr;
     if (want_seed) {
       const float adv = a.advantage[b];
       const float ratio = expf(lp - a.old_logp[b]);
@@ -59,8 +76,6 @@ ppo_loss_seed_kernel(LossArgs a) {
       const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
       const float g_ratio = -(w1 * adv + (1.f - w1) * adv * in_range) * a.inv_global_batch;
       const float g_lp = g_ratio * ratio;
-      float* dz = a.dz_actor != nullptr ? a.dz_actor + b * A : nullptr;
-      __nv_bfloat16* dzb = a.dz_actor_bf16 != nullptr ? a.dz_actor_bf16 + b * a.dz_actor_pitch : nullptr;
       for (int j = 0; j < A; ++j) {
         const float d = ac[j] - mu[j];
         const float dn = d * s_inv_var[j];
@@ -69,12 +84,12 @@ ppo_loss_seed_kernel(LossArgs a) {
           const float th = mu[j] / a.out_scale;
           dmu *= a.out_scale * (1.f - th * th);
         }
-        if (dz != nullptr) dz[j] = dmu;
-        if (dzb != nullptr) dzb[j] = __float2bfloat16_rn(dmu);
+        s_dz[tid * A + j] = dmu;
+        if (a.dz_actor_bf16 != nullptr) s_dzb[tid * pitch + j] = __float2bfloat16_rn(dmu);
         s_dl[tid * A + j] = g_lp * (d * dn - 1.f);
       }
-      if (dzb != nullptr)
-        for (int j = A; j < a.dz_actor_pitch; ++j) dzb[j] = __float2bfloat16_rn(0.f);
+      if (a.dz_actor_bf16 != nullptr)
+        for (int j = A; j < pitch; ++j) s_dzb[tid * pitch + j] = __float2bfloat16_rn(0.f);
     }
     if (a.dv != nullptr || a.dv_bf16 != nullptr) {
       const float e = a.value[b] - a.target[b];
@@ -82,11 +97,27 @@ ppo_loss_seed_kernel(LossArgs a) {
       hub = ae < 1.f ? 0.5f * e * e : ae - 0.5f;
       const float dvv = fminf(fmaxf(e, -1.f), 1.f) * a.inv_global_batch;
       if (a.dv != nullptr) a.dv[b] = dvv;
-      if (a.dv_bf16 != nullptr)
-        for (int j = 0; j < a.dv_pitch; ++j) a.dv_bf16[b * a.dv_pitch + j] = __float2bfloat16_rn(j == 0 ? dvv : 0.f);
+      if (a.dv_bf16 != nullptr) {  // [B, dv_pitch] with the value in column 0: 16 bytes per row when dv_pitch == 8
+        if (a.dv_pitch == 8) {
+          const __nv_bfloat162 v0 = __floats2bfloat162_rn(dvv, 0.f);
+          *reinterpret_cast<uint4*>(a.dv_bf16 + b * 8) = make_uint4(*reinterpret_cast<const uint32_t*>(&v0), 0u, 0u, 0u);
+        } else {
+          for (int j = 0; j < a.dv_pitch; ++j) a.dv_bf16[b * a.dv_pitch + j] = __float2bfloat16_rn(j == 0 ? dvv : 0.f);
+        }
+      }
     }
-  } else if (a.dz_actor != nullptr || a.dz_actor_bf16 != nullptr) {
+  } else if (want_seed) {
     for (int j = 0; j < A; ++j) s_dl[tid * A + j] = 0.f;
+  }
+  __syncthreads();
+  if (want_seed) {  // coalesced slab stores of the seeds
+    if (a.dz_actor != nullptr)
+      for (int i = tid; i < rows * A; i += kLossThreads) a.dz_actor[b0 * A + i] = s_dz[i];
+    if (a.dz_actor_bf16 != nullptr) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(s_dzb);  // pitch is even: whole 32-bit words
+      uint32_t* dst = reinterpret_cast<uint32_t*>(a.dz_actor_bf16 + b0 * pitch);
+      for (int i = tid; i < rows * pitch / 2; i += kLossThreads) dst[i] = src[i];
+    }
   }
   if (a.partials == nullptr) return;
 
@@ -100,7 +131,7 @@ ppo_loss_seed_kernel(LossArgs a) {
     for (int w = 0; w < kLossThreads / 32; ++w) { x += s_red[0][w]; y += s_red[1][w]; }
     part[0] = x; part[1] = y;
   }
-  if (a.dz_actor != nullptr || a.dz_actor_bf16 != nullptr) {
+  if (want_seed) {
     for (int j = tid; j < A; j += kLossThreads) {
       float s = 0.f;
       for (int r = 0; r < kLossThreads; ++r) s += s_dl[r * A + j];
@@ -113,11 +144,10 @@ ppo_loss_seed_kernel(LossArgs a) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // last CTA: combine the per-CTA partials (fixed order)
-  for (int c = tid; c < 2 + A; c += kLossThreads) {
-    float s = 0.f;
-#pragma unroll 8
-    for (unsigned k = 0; k < gridDim.x; ++k) s += __ldcg(a.partials + int64_t(k) * (2 + A) + c);
+  // last CTA: combine the per-CTA partials (fixed order, pipelined loads)
+  const float s = combine_partials<kLossThreads>(a.partials, gridDim.x, 2 + A, tid, s_comb);
+  const int c = tid;
+  if (c < 2 + A) {
     if (c == 0) {
       float ent = 0.f;  // mean over [B, A] of 0.5 + 0.5*log(2*pi) + log(sigma_j): the row is constant in b
       for (int j = 0; j < A; ++j) ent += 0.5f + kLogSqrt2Pi + s_logsig[j];
@@ -152,7 +182,10 @@ sample_logp_kernel(const float* __restrict__ mean, const float* __restrict__ log
 
 int launch_ppo_loss(const LossArgs& a, cudaStream_t st) {
   if (a.batch == 0) return B200PPO_OK;
-  const size_t smem = sizeof(float) * (3 * size_t(a.act_dim) + size_t(kLossThreads) * a.act_dim);
+  const int pitch = a.dz_actor_bf16 != nullptr ? a.dz_actor_pitch : 0;
+  B2_CHECK_ARG(a.act_dim + 2 <= 64, "act_dim %d too large for the loss kernel (<= 62)", a.act_dim);
+  B2_CHECK_ARG(pitch % 2 == 0, "bf16 seed pitch must be even");
+  const size_t smem = sizeof(float) * (3 * size_t(a.act_dim) + 4 * size_t(kLossThreads) * a.act_dim) + size_t(kLossThreads) * pitch * 2 + 16;
   if (smem > 48 * 1024) {
     static bool attr_set = false;
     if (!attr_set) {
