@@ -58,15 +58,101 @@ adam_kernel(float* __restrict__ params, const float* __restrict__ grads, int n_p
   }
 }
 
+struct CastTable {
+  int64_t begin[2 * B200PPO_MAX_LAYERS], end[2 * B200PPO_MAX_LAYERS];  // element range of each matrix in the flat buffer
+  __nv_bfloat16* dst[2 * B200PPO_MAX_LAYERS];
+  __nv_bfloat16* dst_t[2 * B200PPO_MAX_LAYERS];
+  int in[2 * B200PPO_MAX_LAYERS], pitch[2 * B200PPO_MAX_LAYERS], pitch_t[2 * B200PPO_MAX_LAYERS];
+  int count;
+};
+
+// Block-level finish of the fused-epilogue loss partials: s_lc[0] = sum surrogate, [1] = sum huber, [2+j] = logstd grads.
+__device__ __forceinline__ void combine_losses(const LossCombine& lc, float* s_lc, float* s_scr) {
+  const int tid = threadIdx.x;
+  const float s = combine_partials<256>(lc.partials, unsigned(lc.n_cta), 2 + lc.act_dim, tid, s_scr);
+  if (tid < 2 + lc.act_dim) s_lc[tid] = tid < 2 ? s : s - lc.ent_coef * lc.rank_share / float(lc.act_dim);
+  if (tid == 0 && lc.losses_out != nullptr) {
+    float ent = 0.f;  // mean over [B, A] of 0.5 + 0.5 log(2 pi) + log sigma_j
+    for (int j = 0; j < lc.act_dim; ++j) ent += 0.5f + 0.91893853320467274178f + logf(expf(lc.logstd[j]));
+    ent /= float(lc.act_dim);
+    lc.losses_out[0] = -s * lc.inv_global_batch - lc.ent_coef * ent * lc.rank_share;
+  }
+  if (tid == 1 && lc.losses_out != nullptr) lc.losses_out[1] = s * lc.inv_global_batch;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, int n_partials, int64_t partial_stride,
+                 float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t n, int64_t seg_split, AdamScalars s0,
+                 AdamScalars s1, const __grid_constant__ CastTable ct, const __grid_constant__ LossCombine lc) {
+  __shared__ float s_lc[64];
+  __shared__ float s_scr[256];
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  const int64_t n4 = n >> 2;  // the flat buffer is padded to a multiple of 32 elements
+  // the block whose grid-stride chunks contain actor_logstd finishes the loss partials (before anything is updated)
+  const bool lc_owner = lc.partials != nullptr && int64_t(blockIdx.x) == ((lc.logstd_off >> 2) / blockDim.x) % gridDim.x;
+  if (lc_owner) combine_losses(lc, s_lc, s_scr);
+  for (int64_t i = tid; i < n4; i += nthreads) {
+    float4 g = *reinterpret_cast<const float4*>(grads + 4 * i);
+    for (int k = 1; k < n_partials; ++k) {
+      const float4 h = *reinterpret_cast<const float4*>(grads + k * partial_stride + 4 * i);
+      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+    }
+    if (lc_owner && 4 * i + 3 >= lc.logstd_off && 4 * i < lc.logstd_off + lc.act_dim) {
+      const int64_t r = 4 * i - lc.logstd_off;
+      if (r + 0 >= 0 && r + 0 < lc.act_dim) g.x = s_lc[2 + r + 0];
+      if (r + 1 >= 0 && r + 1 < lc.act_dim) g.y = s_lc[2 + r + 1];
+      if (r + 2 >= 0 && r + 2 < lc.act_dim) g.z = s_lc[2 + r + 2];
+      if (r + 3 >= 0 && r + 3 < lc.act_dim) g.w = s_lc[2 + r + 3];
+    }
+    float4 p = *reinterpret_cast<float4*>(params + 4 * i);
+    float4 m = *reinterpret_cast<float4*>(exp_avg + 4 * i);
+    float4 v = *reinterpret_cast<float4*>(exp_avg_sq + 4 * i);
+    const int64_t e = 4 * i;
+    adam_update(p.x, g.x, m.x, v.x, e + 0 < seg_split ? s0 : s1);
+    adam_update(p.y, g.y, m.y, v.y, e + 1 < seg_split ? s0 : s1);
+    adam_update(p.z, g.z, m.z, v.z, e + 2 < seg_split ? s0 : s1);
+    adam_update(p.w, g.w, m.w, v.w, e + 3 < seg_split ? s0 : s1);
+    *reinterpret_cast<float4*>(params + 4 * i) = p;
+    *reinterpret_cast<float4*>(exp_avg + 4 * i) = m;
+    *reinterpret_cast<float4*>(exp_avg_sq + 4 * i) = v;
+    // bf16 shadow copies of the matrix this float4 belongs to (tensors start on 32-element boundaries, so a float4
+    // never straddles two tensors; it may straddle two rows when `in` is not a multiple of 4)
+    int k = -1;
+#pragma unroll 1
+    for (int c = 0; c < ct.count; ++c)
+      if (e >= ct.begin[c] && e < ct.end[c]) k = c;
+    if (k >= 0) {
+      const float pv[4] = {p.x, p.y, p.z, p.w};
+      const int in = ct.in[k];
+      const int64_t rel = e - ct.begin[k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (e + j >= ct.end[k]) break;
+        const int o = int((rel + j) / in), c2 = int((rel + j) - int64_t(o) * in);
+        const __nv_bfloat16 b = __float2bfloat16_rn(pv[j]);
+        ct.dst[k][int64_t(o) * ct.pitch[k] + c2] = b;
+        if (ct.dst_t[k] != nullptr) ct.dst_t[k][int64_t(c2) * ct.pitch_t[k] + o] = b;
+      }
+    }
+  }
+}
+
 // Sum partials only (used before the NCCL all-reduce and by the grads-only entry point).
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ grads, int n_partials, int64_t partial_stride, int64_t n,
-                       float* __restrict__ out) {
+                       float* __restrict__ out, const __grid_constant__ LossCombine lc) {
+  __shared__ float s_lc[64];
+  __shared__ float s_scr[256];
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  const bool lc_owner = lc.partials != nullptr && int64_t(blockIdx.x) == (lc.logstd_off / blockDim.x) % gridDim.x;
+  if (lc_owner) combine_losses(lc, s_lc, s_scr);
   for (int64_t e = tid; e < n; e += nthreads) {
     float g = grads[e];
     for (int k = 1; k < n_partials; ++k) g += grads[k * partial_stride + e];
+    if (lc_owner && e >= lc.logstd_off && e < lc.logstd_off + lc.act_dim) g = s_lc[2 + (e - lc.logstd_off)];
     out[e] = g;
   }
 }
@@ -101,10 +187,33 @@ int launch_adam(float* params, const float* grads, int n_partials, int64_t parti
   return B200PPO_OK;
 }
 
-int launch_reduce_partials(const float* grads, int n_partials, int64_t partial_stride, int64_t n, float* out,
-                           cudaStream_t st) {
+int launch_adam_cast(float* params, const float* grads, int n_partials, int64_t partial_stride, float* exp_avg,
+                     float* exp_avg_sq, int64_t n, int64_t seg_split, const AdamScalars& s0, const AdamScalars& s1,
+                     const WeightCastGroup& casts, const LossCombine& lc, cudaStream_t st) {
   if (n == 0) return B200PPO_OK;
-  reduce_partials_kernel<<<ew_grid(n), 256, 0, st>>>(grads, n_partials, partial_stride, n, out);
+  B2_CHECK_ARG(lc.partials == nullptr || (lc.act_dim + 2 <= 64 && lc.logstd_off % 4 == 0), "loss combine: act_dim <= 62");
+  B2_CHECK_ARG(n % 4 == 0, "fused Adam + cast expects the padded flat parameter buffer");
+  CastTable ct{};
+  ct.count = casts.count;
+  for (int k = 0; k < casts.count; ++k) {
+    const WeightCast& w = casts.w[k];
+    ct.begin[k] = w.src - params;
+    ct.end[k] = ct.begin[k] + int64_t(w.out) * w.in;
+    B2_CHECK_ARG(ct.begin[k] >= 0 && ct.end[k] <= n, "weight cast source outside the parameter buffer");
+    ct.dst[k] = w.dst; ct.dst_t[k] = w.dst_t;
+    ct.in[k] = w.in; ct.pitch[k] = w.pitch; ct.pitch_t[k] = w.pitch_t;
+  }
+  adam_cast_kernel<<<ew_grid(n / 4), 256, 0, st>>>(params, grads, n_partials, partial_stride, exp_avg, exp_avg_sq, n, seg_split,
+                                                  s0, s1, ct, lc);
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
+
+int launch_reduce_partials(const float* grads, int n_partials, int64_t partial_stride, int64_t n, float* out,
+                           cudaStream_t st, const LossCombine* lc) {
+  if (n == 0) return B200PPO_OK;
+  const LossCombine none{};
+  reduce_partials_kernel<<<ew_grid(n), 256, 0, st>>>(grads, n_partials, partial_stride, n, out, lc ? *lc : none);
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }

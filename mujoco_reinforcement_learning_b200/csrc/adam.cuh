@@ -1,5 +1,6 @@
 // Internal interface of the fused Adam kernel (adam.cu).
 #pragma once
+#include "cast.cuh"
 #include "common.cuh"
 
 namespace b200ppo {
@@ -18,7 +19,25 @@ int launch_adam(float* params, const float* grads, int n_partials, int64_t parti
                 float* exp_avg_sq, int64_t n, int64_t seg_split, const AdamScalars& s0, const AdamScalars& s1,
                 float* grad_out, cudaStream_t st);
 
+// When the loss sums come out of the fused PPO epilogues as per-CTA partials (tc_common.cuh), the kernel that consumes
+// the gradients also finishes them: fixed-order sum over the CTAs, the two loss values, and d loss / d logstd.
+struct LossCombine {
+  const float* partials = nullptr;  // [n_cta][2 + act_dim]; nullptr = nothing to combine
+  int n_cta = 0, act_dim = 0;
+  int64_t logstd_off = 0;           // element offset of actor_logstd in the flat buffers
+  const float* logstd = nullptr;    // current actor_logstd (for the entropy term)
+  float inv_global_batch = 0.f, ent_coef = 0.f, rank_share = 1.f;
+  float* losses_out = nullptr;      // [2]
+};
+
+// Same update, and in the same pass the bf16 shadow copies of the hidden/output weight matrices that the tensor-core
+// GEMMs read (W and W^T, see cast.cuh) are re-emitted from the freshly updated fp32 master values: no separate cast
+// launch, no second read of the parameters.  `casts.w[k].src` must point into `params`.
+int launch_adam_cast(float* params, const float* grads, int n_partials, int64_t partial_stride, float* exp_avg,
+                     float* exp_avg_sq, int64_t n, int64_t seg_split, const AdamScalars& s0, const AdamScalars& s1,
+                     const WeightCastGroup& casts, const LossCombine& lc, cudaStream_t st);
+
 int launch_reduce_partials(const float* grads, int n_partials, int64_t partial_stride, int64_t n, float* out,
-                           cudaStream_t st);
+                           cudaStream_t st, const LossCombine* lc = nullptr);
 
 }  // namespace b200ppo

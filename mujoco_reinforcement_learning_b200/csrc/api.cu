@@ -118,6 +118,7 @@ struct b200ppo_ctx {
   float* gpart = nullptr;       // [max_split][n_params]
   float* grad_flat = nullptr;   // [n_params + 4]: summed gradient + (actor_loss, critic_loss) for the all-reduce
   float* loss_partials = nullptr;
+  int64_t loss_partial_rows = 0;
   unsigned* ticket = nullptr;
   float* scratch = nullptr;     // [8] losses / entropy scratch
   int32_t* err_flag = nullptr;
@@ -378,17 +379,28 @@ static int alloc_bf16_workspaces(b200ppo_ctx* c) {
   return B200PPO_OK;
 }
 
-static int cast_weights(b200ppo_ctx* ctx, const float* params, cudaStream_t st) {
+static WeightCastGroup cast_group(const b200ppo_ctx* ctx, const float* params) {
   WeightCastGroup g = ctx->bf.casts;
   int k = 0;
   for (int n = 0; n < 2; ++n)
     for (int l = 0; l < ctx->net[n].d.n_layers; ++l) g.w[k++].src = params + ctx->net[n].w_off[l];
-  return launch_cast_weights(g, st);
+  return g;
+}
+
+static int cast_weights(b200ppo_ctx* ctx, const float* params, cudaStream_t st) {
+  return launch_cast_weights(cast_group(ctx, params), st);
 }
 
 // forward of both nets on the tensor cores; hidden activations in bf16 (+ ones column), outputs in fp32.
+// The minibatch leaves the fused PPO epilogues of the output layers consume (nullptr = plain forward).
+struct PpoFuse {
+  const float *action, *old_logp, *advantage, *target;
+  const b200ppo_hparams* hp;
+  int loss_ctas;  // out: CTAs that wrote a row of loss partials
+};
+
 static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_bfloat16* xb, int64_t B,
-                             float* const outs[2], cudaStream_t st) {
+                             float* const outs[2], cudaStream_t st, PpoFuse* fuse = nullptr) {
   auto& bf = ctx->bf;
   int maxL = 0;
   for (int n = 0; n < 2; ++n) maxL = std::max(maxL, ctx->net[n].d.n_layers);
@@ -411,7 +423,19 @@ static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_b
       p.epilogue = TC_EPI_FWD;
       p.bias = params + N.b_off[l];
       p.bias_col = -1;
-      if (last) {
+      if (last && fuse != nullptr) {
+        p.epilogue = n == 0 ? TC_EPI_PPO_ACTOR : TC_EPI_PPO_CRITIC;
+        p.out_scale = N.d.out_scale;
+        p.ppo.logstd = params + ctx->logstd_off;
+        p.ppo.action = fuse->action; p.ppo.old_logp = fuse->old_logp; p.ppo.advantage = fuse->advantage;
+        p.ppo.target = fuse->target;
+        p.ppo.dz_out = bf.dZ[n][l]; p.ppo.dz_pitch = bf.pitchZ[n][l];
+        p.ppo.partials = ctx->loss_partials;
+        p.ppo.act_dim = ctx->net[0].out_dim();
+        p.ppo.final_tanh = N.d.final_tanh;
+        p.ppo.clip_eps = float(fuse->hp->clip_epsilon);
+        p.ppo.inv_global_batch = 1.f / float(B * ctx->world);
+      } else if (last) {
         p.act = N.d.final_tanh ? TC_ACT_TANH_SCALE : TC_ACT_NONE;
         p.out_scale = N.d.out_scale;
         p.out_f32 = outs[n]; p.ld_f32 = N.d.dims[l];
@@ -423,7 +447,9 @@ static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_b
       TcOperand Bop{bf.W[n][l], bf.pitchW[n][l], 0};
       B2_TRY(tc_group_add(g, p, A, Bop, bn, 1));
     }
-    PROF(ctx, B200PPO_PROF_GEMM_FWD, st, ws ? launch_tc_ws(g, st) : launch_tc_group(g, bn, st));
+    int grid = 0;
+    PROF(ctx, B200PPO_PROF_GEMM_FWD, st, ws ? launch_tc_ws(g, st, &grid) : launch_tc_group(g, bn, st, &grid));
+    if (fuse != nullptr && l == maxL - 1) fuse->loss_ctas = grid;
   }
   return B200PPO_OK;
 }
@@ -543,9 +569,13 @@ static void fill_loss_args(const b200ppo_ctx* ctx, LossArgs& la, const float* pa
 }
 
 // obs: fp32 rows (fp32 path) — or obs_b: bf16 rows with the ones-column (tensor-core path).
+// *loss_ctas_out > 0: the loss sums were left as that many rows of ctx->loss_partials (fused epilogues) and the kernel
+// that consumes the gradients must finish them (LossCombine); 0: losses_dev and the logstd gradient are already final.
 static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float* obs, const __nv_bfloat16* obs_b,
                              const float* action, const float* old_logp, const float* adv, const float* tgt, int64_t B,
-                             const b200ppo_hparams* hp, float* losses_dev, int* split_out, cudaStream_t st) {
+                             const b200ppo_hparams* hp, float* losses_dev, int* split_out, int* loss_ctas_out,
+                             cudaStream_t st) {
+  *loss_ctas_out = 0;
   float* acts[2] = {ctx->ws_act[0], ctx->ws_act[1]};
   float* outs[2] = {ctx->ws_out[0], ctx->ws_out[1]};
   float* dz[2] = {ctx->ws_dz[0], ctx->ws_dz[1]};
@@ -553,7 +583,15 @@ static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float*
   const Net& Nc = ctx->net[1];
   const int La = Na.d.n_layers, Lc = Nc.d.n_layers;
   if (ctx->precision == B200PPO_PREC_BF16) {
-    // tcgen05 everywhere: forward (L launches), loss seeds (1), dgrads (L-1), all wgrads (1)
+    // tcgen05 everywhere: forward (L launches; PPO loss fused into the output layers' epilogue), dgrads (L-1), wgrads (1)
+    const bool same_depth = La == Lc;  // both output layers in the same launch
+    if (same_depth && tc_ppo_fits(Na.out_dim()) && Na.out_dim() <= 32 &&
+        int64_t(2 * ((B + 127) / 128) + 8) <= ctx->loss_partial_rows) {
+      PpoFuse fuse{action, old_logp, adv, tgt, hp, 0};
+      B2_TRY(forward_nets_bf16(ctx, params, obs_b, B, outs, st, &fuse));
+      *loss_ctas_out = fuse.loss_ctas;
+      return backward_nets_bf16(ctx, obs_b, B, ctx->gpart, split_out, st);
+    }
     B2_TRY(forward_nets_bf16(ctx, params, obs_b, B, outs, st));
     LossArgs la{};
     fill_loss_args(ctx, la, params, outs[0], outs[1], action, old_logp, adv, tgt, B, hp);
@@ -593,6 +631,22 @@ static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float*
     PROF(ctx, B200PPO_PROF_LOSS, st, launch_ppo_loss(la, st));
   }
   return backward_nets(ctx, params, obs, B, 3, acts, dz, ctx->gpart, split_out, nullptr, st, heads);
+}
+
+static LossCombine make_loss_combine(const b200ppo_ctx* ctx, const float* params, int loss_ctas, int64_t B,
+                                     const b200ppo_hparams* hp, float* losses_out) {
+  LossCombine lc{};
+  if (loss_ctas <= 0) return lc;
+  lc.partials = ctx->loss_partials;
+  lc.n_cta = loss_ctas;
+  lc.act_dim = ctx->net[0].out_dim();
+  lc.logstd_off = ctx->logstd_off;
+  lc.logstd = params + ctx->logstd_off;
+  lc.inv_global_batch = 1.f / float(B * ctx->world);
+  lc.ent_coef = float(hp->entropy_eps);
+  lc.rank_share = 1.f / float(ctx->world);
+  lc.losses_out = losses_out;
+  return lc;
 }
 
 static int ensure_shuffle_capacity(b200ppo_ctx* ctx, int64_t rows) {
@@ -663,8 +717,8 @@ extern "C" B2_EXPORT int b200ppo_create(const b200ppo_mlp_desc* actor, const b20
   }
   if (r == B200PPO_OK) r = dev_alloc(&c->gpart, int64_t(c->max_split) * c->n_params, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->grad_flat, c->n_params + 4, true);
-  if (r == B200PPO_OK)
-    r = dev_alloc(&c->loss_partials, int64_t(std::max(loss_grid_size(Bm), 8 * num_sms())) * (2 + c->net[0].out_dim()));
+  c->loss_partial_rows = std::max<int64_t>(std::max(loss_grid_size(Bm), 8 * num_sms()), 2 * ((Bm + 127) / 128) + 8);
+  if (r == B200PPO_OK) r = dev_alloc(&c->loss_partials, c->loss_partial_rows * (2 + c->net[0].out_dim()), true);
   if (r == B200PPO_OK) r = dev_alloc(&c->ticket, 1, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->scratch, 8, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->err_flag, 1, true);
@@ -799,9 +853,12 @@ extern "C" B2_EXPORT int b200ppo_minibatch_grads(b200ppo_ctx* ctx, const float* 
     B2_TRY(cast_weights(ctx, params, st));
     B2_TRY(launch_cast_rows_ones(obs, batch, ctx->net[0].d.in_dim, ctx->bf.X, ctx->bf.pitchX, st));
   }
-  B2_TRY(minibatch_fwd_bwd(ctx, params, obs, ctx->bf.X, action, old_logp, advantage, target, batch, hp,
-                           losses ? losses : ctx->scratch, &split, st));
-  return launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, grads, st);
+  int loss_ctas = 0;
+  float* loss_dst = losses ? losses : ctx->scratch;
+  B2_TRY(minibatch_fwd_bwd(ctx, params, obs, ctx->bf.X, action, old_logp, advantage, target, batch, hp, loss_dst, &split,
+                           &loss_ctas, st));
+  const LossCombine lc = make_loss_combine(ctx, params, loss_ctas, batch, hp, loss_dst);
+  return launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, grads, st, &lc);
 }
 
 extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq,
@@ -841,25 +898,31 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
     for (int64_t i = 0; i < nb; ++i) {
       const int64_t r0 = i * lb;
       float* loss_slot = losses_out ? losses_out + (int64_t(e) * nb + i) * 2 : ctx->scratch;
-      int split = 1;
+      int split = 1, loss_ctas = 0;
       ++step;
       const AdamScalars sa = make_adam_scalars(hp->learning_rate_actor, hp->beta1, hp->beta2, hp->adam_eps, step);
       const AdamScalars sc = make_adam_scalars(hp->learning_rate_critic, hp->beta1, hp->beta2, hp->adam_eps, step);
       if (ctx->world == 1) {
         B2_TRY(minibatch_fwd_bwd(ctx, params, tc ? nullptr : ctx->sh_obs + r0 * D, tc ? ctx->bf.sh_obs + r0 * PX : nullptr,
                                  ctx->sh_act + r0 * A, ctx->sh_logp + r0, ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp,
-                                 loss_slot, &split, st));
-        PROF(ctx, B200PPO_PROF_ADAM, st,
-             launch_adam(params, ctx->gpart, split, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa,
-                         sc, nullptr, st));
-        if (tc) PROF(ctx, B200PPO_PROF_OTHER, st, cast_weights(ctx, params, st));
+                                 loss_slot, &split, &loss_ctas, st));
+        if (tc)  // Adam + bf16 re-cast of the weights (+ the finish of the fused-epilogue loss partials) in one pass
+          PROF(ctx, B200PPO_PROF_ADAM, st,
+               launch_adam_cast(params, ctx->gpart, split, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor,
+                                sa, sc, cast_group(ctx, params), make_loss_combine(ctx, params, loss_ctas, lb, hp, loss_slot),
+                                st));
+        else
+          PROF(ctx, B200PPO_PROF_ADAM, st,
+               launch_adam(params, ctx->gpart, split, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa,
+                           sc, nullptr, st));
       } else {
         float* red_losses = ctx->grad_flat + ctx->n_params;
         B2_TRY(minibatch_fwd_bwd(ctx, params, tc ? nullptr : ctx->sh_obs + r0 * D, tc ? ctx->bf.sh_obs + r0 * PX : nullptr,
                                  ctx->sh_act + r0 * A, ctx->sh_logp + r0, ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp,
-                                 red_losses, &split, st));
+                                 red_losses, &split, &loss_ctas, st));
+        const LossCombine lc = make_loss_combine(ctx, params, loss_ctas, lb, hp, red_losses);
         PROF(ctx, B200PPO_PROF_OTHER, st,
-             launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, ctx->grad_flat, st));
+             launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, ctx->grad_flat, st, &lc));
         ctx->prof.begin(B200PPO_PROF_ALLREDUCE, st);
         const int rc = g_nccl.AllReduce(ctx->grad_flat, ctx->grad_flat, size_t(ctx->n_params + 4), /*ncclFloat32*/ 7,
                                         /*ncclSum*/ 0, ctx->comm, st);
@@ -868,10 +931,14 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
           set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
           return B200PPO_ENCCL;
         }
-        PROF(ctx, B200PPO_PROF_ADAM, st,
-             launch_adam(params, ctx->grad_flat, 1, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa,
-                         sc, nullptr, st));
-        if (tc) PROF(ctx, B200PPO_PROF_OTHER, st, cast_weights(ctx, params, st));
+        if (tc)
+          PROF(ctx, B200PPO_PROF_ADAM, st,
+               launch_adam_cast(params, ctx->grad_flat, 1, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor,
+                                sa, sc, cast_group(ctx, params), LossCombine{}, st));
+        else
+          PROF(ctx, B200PPO_PROF_ADAM, st,
+               launch_adam(params, ctx->grad_flat, 1, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa,
+                           sc, nullptr, st));
         copy2_kernel<<<1, 32, 0, st>>>(red_losses, loss_slot);
         B2_LAUNCH_CHECK();
       }

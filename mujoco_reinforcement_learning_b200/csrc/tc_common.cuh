@@ -241,7 +241,7 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
 // Stage the bias of columns [n0, n0 + bn) into shared memory (zeros beyond N or when the problem has no bias).
 __device__ __forceinline__ void tc_stage_bias(const TcProblem& P, int n0, int bn, float* bias_s, int tid, int nthreads) {
   for (int j = tid; j < bn; j += nthreads)
-    bias_s[j] = (P.bias != nullptr && P.epilogue == TC_EPI_FWD && n0 + j < P.N) ? __ldg(P.bias + n0 + j) : 0.f;
+    bias_s[j] = (P.bias != nullptr && P.epilogue != TC_EPI_DGRAD && P.epilogue != TC_EPI_STORE && n0 + j < P.N) ? __ldg(P.bias + n0 + j) : 0.f;
 }
 
 // ---- shared-memory staged epilogue ---------------------------------------------------------------------------------
@@ -416,6 +416,198 @@ inline bool tc_can_stage(const TcProblem& p) {
   const bool out_ok = p.out_bf16 != nullptr && p.out_f32 == nullptr && p.ld_bf16 % 8 == 0 && p.N % 8 == 0 && aligned16(p.out_bf16);
   if (p.epilogue == TC_EPI_DGRAD) return out_ok && p.aux != nullptr && p.ld_aux % 8 == 0 && aligned16(p.aux);
   return out_ok;
+}
+
+// ---- fused PPO-loss epilogues of the output layers ---------------------------------------------------------------------
+constexpr float kTcLogSqrt2Pi = 0.91893853320467274178f;
+
+struct PpoAcc {  // per-thread running sums over the tiles a CTA processes
+  float surr, hub;
+  float dl[32];
+  __device__ __forceinline__ void clear() {
+    surr = 0.f; hub = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dl[j] = 0.f;
+  }
+};
+
+
+// sigma-derived constants of the diagonal Gaussian into shared memory: [0,32) log sigma, [32,64) 1/var, [64,96) 2 var
+__device__ __forceinline__ void tc_ppo_stage_consts(const TcProblem& P, float* consts_s, int tid) {
+  if (P.epilogue == TC_EPI_PPO_ACTOR && tid < 32) {
+    float ls = 0.f, iv = 0.f, tv = 1.f;
+    if (tid < P.ppo.act_dim) {
+      const float sig = expf(__ldg(P.ppo.logstd + tid));
+      const float var = sig * sig;
+      ls = logf(sig); iv = 1.f / var; tv = 2.f * var;
+    }
+    consts_s[tid] = ls; consts_s[32 + tid] = iv; consts_s[64 + tid] = tv;
+  }
+}
+
+// Request the 32 x A action slab of this warp's rows (cp.async, zero-filled past the batch) and commit the group.
+__device__ __forceinline__ void tc_ppo_issue(const TcProblem& P, int m0, int warp, int lane, uint8_t* stage, bool valid) {
+  if (valid && P.epilogue == TC_EPI_PPO_ACTOR && ((warp - 2) >> 2) == 0) {
+    const int A = P.ppo.act_dim;
+    const int mq = m0 + (warp & 3) * 32;
+    const int rows = min(32, P.M - mq);
+    if (rows > 0) {
+      const int bytes = rows * A * 4;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(P.ppo.action + int64_t(mq) * A);
+      const uint32_t sbase = smem_u32(stage);
+      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int c = lane; c * 16 < bytes; c += 32) {
+          const uint32_t nb = uint32_t(min(16, bytes - c * 16));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + c * 16), "l"(src + c * 16), "r"(nb) : "memory");
+        }
+      } else {  // unaligned minibatch slice: plain loads
+        float* dst = reinterpret_cast<float*>(stage);
+        for (int i = lane; i < rows * A; i += 32) dst[i] = __ldg(P.ppo.action + int64_t(mq) * A + i);
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_ppo(const TcProblem& P, uint32_t tmem_acc, int m0, int warp, int lane,
+                                                uint64_t* tmem_full_bar, uint32_t full_parity, uint8_t* stage,
+                                                const float* bias_s, const float* consts_s, int groups_in_flight, PpoAcc& acc) {
+  const int q = warp & 3;
+  const int mq = m0 + q * 32, m = mq + lane;
+  const bool row_ok = m < P.M;
+  const bool worker = ((warp - 2) >> 2) == 0;  // the output columns (<= 32) live in the first column half
+  if (groups_in_flight > 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+  else asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // per-row scalars requested before the accumulator is awaited
+  float old_lp = 0.f, adv = 0.f, tgt = 0.f;
+  if (worker && row_ok) {
+    if (P.epilogue == TC_EPI_PPO_ACTOR) { old_lp = __ldg(P.ppo.old_logp + m); adv = __ldg(P.ppo.advantage + m); }
+    else tgt = __ldg(P.ppo.target + m);
+  }
+  mbar_wait(tmem_full_bar, full_parity);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncwarp();
+  if (!worker) return;
+  if (P.epilogue == TC_EPI_PPO_CRITIC) {
+    uint32_t v[16];
+    tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16), v);
+    if (row_ok) {
+      const float val = __uint_as_float(v[0]) + bias_s[0];
+      const float e = val - tgt;
+      const float ae = fabsf(e);
+      acc.hub += ae < 1.f ? 0.5f * e * e : ae - 0.5f;
+      const float dv = fminf(fmaxf(e, -1.f), 1.f) * P.ppo.inv_global_batch;
+      const int pitch = P.ppo.dz_pitch;
+      __nv_bfloat16* o = P.ppo.dz_out + int64_t(m) * pitch;
+      if (pitch == 8) {
+        const __nv_bfloat162 v0 = __floats2bfloat162_rn(dv, 0.f);
+        *reinterpret_cast<uint4*>(o) = make_uint4(*reinterpret_cast<const uint32_t*>(&v0), 0u, 0u, 0u);
+      } else {
+        for (int j = 0; j < pitch; ++j) o[j] = __float2bfloat16_rn(j == 0 ? dv : 0.f);
+      }
+    }
+    return;
+  }
+  // ---- actor ----
+  const int A = P.ppo.act_dim, pitch = P.ppo.dz_pitch;
+  const float* act_s = reinterpret_cast<const float*>(stage) + lane * A;                         // this row's action
+  __nv_bfloat16* dz_s = reinterpret_cast<__nv_bfloat16*>(stage + 32 * A * 4) + lane * pitch;   // this row's seeds
+  float z[32];
+  {
+    uint32_t v[16];
+    tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16), v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(v[j]);
+    if (A > 16) {
+      tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16) + 16u, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[16 + j] = __uint_as_float(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[16 + j] = 0.f;
+    }
+  }
+  const float scale = P.out_scale;
+  const bool ft = P.ppo.final_tanh != 0;
+  float lp = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < A) {
+      const float pre = z[j] + bias_s[j];
+      const float th = ft ? tanh_fast(pre) : pre;
+      const float mean = ft ? scale * th : pre;
+      const float d = act_s[j] - mean;
+      lp += -(d * d) / consts_s[64 + j] - consts_s[j] - kTcLogSqrt2Pi;
+      z[j] = d;  // keep (a - mean); tanh is recovered below as (a - d) / scale
+    }
+  }
+  float g_lp = 0.f;
+  if (row_ok) {
+    const float lo = 1.f - P.ppo.clip_eps, hi = 1.f + P.ppo.clip_eps;
+    const float ratio = expf(lp - old_lp);
+    const float s1 = ratio * adv, s2 = fminf(fmaxf(ratio, lo), hi) * adv;
+    const float w1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);
+    const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+    g_lp = -(w1 * adv + (1.f - w1) * adv * in_range) * P.ppo.inv_global_batch * ratio;
+    acc.surr += fminf(s1, s2);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < A) {
+      const float d = z[j];
+      const float dn = d * consts_s[32 + j];
+      float dmu = g_lp * dn;
+      if (ft) {
+        const float th = (act_s[j] - d) / scale;   // mean / scale
+        dmu *= scale * (1.f - th * th);
+      }
+      dz_s[j] = __float2bfloat16_rn(row_ok ? dmu : 0.f);
+      if (row_ok) acc.dl[j] += g_lp * (d * dn - 1.f);
+    } else if (j < pitch) {
+      dz_s[j] = __float2bfloat16_rn(0.f);
+    }
+  }
+  __syncwarp();
+  // coalesced store of the 32 x pitch bf16 seed slab (rows are adjacent in global memory)
+  const int rows = min(32, P.M - mq);
+  if (rows > 0) {
+    const int bytes = rows * pitch * 2;  // pitch % 8 == 0: whole 16-byte chunks
+    const uint32_t sbase = smem_u32(stage + 32 * A * 4);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(P.ppo.dz_out + int64_t(mq) * pitch);
+    for (int c = lane; c * 16 < bytes; c += 32) {
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(sbase + c * 16) : "memory");
+      *reinterpret_cast<uint4*>(dst + c * 16) = make_uint4(w0, w1, w2, w3);
+    }
+  }
+  __syncwarp();
+}
+
+// After the last tile: reduce the per-thread sums over the CTA (fixed order) and write this CTA's row of partials.
+// red_s: (TC_EPI_WARPS / 2) x 34 floats of shared memory.  Called by all epilogue warps.
+__device__ __forceinline__ void tc_ppo_finish(const TcProblem& P, int warp, int lane, float* red_s, const PpoAcc& acc) {
+  const int A = P.ppo.act_dim;
+  const bool worker = ((warp - 2) >> 2) == 0;
+  const int w = warp & 3;
+  if (worker) {
+    const float s = warp_sum(acc.surr), h = warp_sum(acc.hub);
+    if (lane == 0) { red_s[w * 34] = s; red_s[w * 34 + 1] = h; }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = warp_sum(j < A ? acc.dl[j] : 0.f);
+      if (lane == 0) red_s[w * 34 + 2 + j] = d;
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");  // epilogue warps only
+  const int t = (warp - 2) * 32 + lane;
+  if (t < 2 + A) {
+    float s = 0.f;
+    for (int k = 0; k < 4; ++k) s += red_s[k * 34 + t];
+    if (P.epilogue == TC_EPI_PPO_CRITIC && t != 1) s = 0.f;
+    if (P.epilogue == TC_EPI_PPO_ACTOR && t == 1) s = 0.f;
+    P.ppo.partials[int64_t(blockIdx.x) * (2 + A) + t] = s;
+  }
 }
 
 }  // namespace b200ppo

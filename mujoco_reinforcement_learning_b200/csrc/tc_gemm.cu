@@ -46,8 +46,10 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // BN floats
-  uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 1024;                        // TC_EPI_WARPS x 4 KB
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // BN floats (<= 256)
+  float* consts_s = bias_s + 256;                                                        // 96 floats (fused PPO epilogue)
+  float* red_s = bias_s + 352;                                                           // 4 x 34 floats
+  uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 2048;                        // TC_EPI_WARPS x 4 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   const bool has_k = kt_end > kt_begin;
 
   tc_stage_bias(P, n0, BN, bias_s, threadIdx.x, TC_THREADS);
+  tc_ppo_stage_consts(P, consts_s, threadIdx.x);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -136,7 +139,14 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
     }
   } else {  // ===== epilogue warps 2..9 =====
     if constexpr (BN <= 128) {
-      if (P.staged) {
+      if (P.epilogue >= TC_EPI_PPO_ACTOR) {
+        uint8_t* st = stage_area + (warp - 2) * TC_STAGE_BYTES;
+        PpoAcc acc;
+        acc.clear();
+        tc_ppo_issue(P, m0, warp, lane, st, true);
+        tc_epilogue_ppo<BN>(P, tmem_base, m0, warp, lane, tmem_full_bar, 0, st, bias_s, consts_s, 0, acc);
+        tc_ppo_finish(P, warp, lane, red_s, acc);
+      } else if (P.staged) {
         uint8_t* st = stage_area + (warp - 2) * TC_STAGE_BYTES;
         tc_issue_aux<BN>(P, m0, n0, warp, lane, st, true);
         tc_epilogue_staged<BN>(P, split, tmem_base, has_k, m0, n0, warp, lane, tmem_full_bar, 0, st, bias_s, 0);
@@ -229,7 +239,7 @@ int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B
 
 template <int BN>
 static int launch_bn(const TcGroup& g, cudaStream_t st) {
-  constexpr int smem = TcCfg<BN>::STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256 + 1024 + TC_EPI_WARPS * TC_STAGE_BYTES;
+  constexpr int smem = TcCfg<BN>::STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256 + 2048 + TC_EPI_WARPS * TC_STAGE_BYTES;
   static bool configured = false;
   if (!configured) {
     B2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -240,7 +250,8 @@ static int launch_bn(const TcGroup& g, cudaStream_t st) {
   return B200PPO_OK;
 }
 
-int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st) {
+int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st, int* grid_out) {
+  if (grid_out) *grid_out = g.total_tiles;
   if (g.total_tiles == 0) return B200PPO_OK;
   switch (bn) {
     case 64: return launch_bn<64>(g, st);

@@ -11,6 +11,23 @@ enum TcEpilogue : int {
   TC_EPI_FWD = 0,    // h = act(acc + bias[n]) -> bf16 (and optionally fp32)
   TC_EPI_DGRAD = 1,  // dz = acc * act'(aux[m,n]) -> bf16
   TC_EPI_STORE = 2,  // fp32 store of a split-K partial; column `bias_col` is routed to bias_grad[m]
+  // Output layers of the PPO update with the loss fused in (one accumulator row = one sample, all act_dim outputs of
+  // the row live in one thread): nothing but the gradient seeds and per-CTA loss partials leaves the kernel.
+  TC_EPI_PPO_ACTOR = 3,   // mean = [scale*tanh](acc + bias); log-prob, ratio, clipped surrogate; dz -> bf16; partial sums
+  TC_EPI_PPO_CRITIC = 4,  // v = acc + bias; Huber; dv -> bf16; partial sum
+};
+
+// Extra operands of the fused PPO epilogues (src/entities/algorithms/ppo.py:113-132).
+struct TcPpo {
+  const float* logstd;     // [A]
+  const float* action;     // [M, A]
+  const float* old_logp;   // [M]
+  const float* advantage;  // [M]
+  const float* target;     // [M]
+  __nv_bfloat16* dz_out;   // actor: [M, dz_pitch] ; critic: [M, dz_pitch] with dv in column 0
+  float* partials;         // [gridDim.x][2 + A]: (sum surrogate, sum huber, sum d loss / d logstd_j) per CTA
+  int dz_pitch, act_dim, final_tanh;
+  float clip_eps, inv_global_batch;
 };
 
 // activation codes of TC_EPI_FWD beyond B200PPO_ACT_TANH / B200PPO_ACT_RELU
@@ -37,7 +54,12 @@ struct TcProblem {
   int bias_col;  // -1: none
   float out_scale;
   int staged;  // epilogue goes through the shared-memory staging tile (set by tc_group_add)
+  TcPpo ppo;
 };
+
+// Fused PPO epilogue applies when a warp's action slab (32 x A floats) and bf16 seed slab (32 x pad8(A)) share its 4 KB
+// staging tile, i.e. A <= 21 (Humanoid 17, Ant 8, HalfCheetah 6, Hopper 3).
+inline bool tc_ppo_fits(int act_dim) { return act_dim >= 1 && act_dim * 128 + ((act_dim + 7) / 8 * 8) * 64 <= 4096; }
 
 constexpr int kMaxTcProblems = 6;
 
@@ -57,12 +79,12 @@ struct TcOperand {
 int tc_init();  // resolves cuTensorMapEncodeTiled; returns B200PPO_OK or an error
 // bn: N tile (64, 128 or 256).  Fills tensor maps (cached) and tile bookkeeping.
 int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B, int bn, int split_k);
-int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st);
+int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st, int* grid_out = nullptr);
 int tc_pick_bn(int64_t rows_total_tiles_m, int N);
 int tc_ctas_per_sm(int bn);
 // Persistent weights-stationary variant (tc_ws.cu) for forward / dgrad groups with many row tiles.
 bool tc_ws_applicable(int64_t total_tiles_m, int maxN, int maxK);
 int tc_ws_bn(int maxN, int maxK);
-int launch_tc_ws(const TcGroup& g, cudaStream_t st);  // resident CTAs per SM of the bn-wide kernel instance
+int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out = nullptr);  // resident CTAs per SM of the bn-wide kernel instance
 
 }  // namespace b200ppo

@@ -57,10 +57,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
   uint64_t* acc_full = a_empty + a_stages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // BN floats
-  uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 1024;                  // TC_EPI_WARPS x 4 KB
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // BN floats (<= 256)
+  float* consts_s = bias_s + 256;                                                    // 96 floats (fused PPO epilogue)
+  float* red_s = bias_s + 352;                                                       // 4 x 34 floats
+  uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 2048;                  // TC_EPI_WARPS x 2 x 4 KB
 
   tc_stage_bias(P, n0, BN, bias_s, threadIdx.x, TC_THREADS);
+  tc_ppo_stage_consts(P, consts_s, threadIdx.x);
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
     for (int s = 0; s < a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -121,6 +124,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
       // two staging tiles per warp: while tile t is finished and stored from one, the dgrad's activation slab of tile
       // t + ctas is already streaming into the other (cp.async), i.e. behind the MMAs of the next tile
       uint8_t* st[2] = {stage_area + (warp - 2) * 2 * TC_STAGE_BYTES, stage_area + (warp - 2) * 2 * TC_STAGE_BYTES + TC_STAGE_BYTES};
+      if (P.epilogue >= TC_EPI_PPO_ACTOR) {  // output layers with the PPO loss fused in
+        PpoAcc acc;
+        acc.clear();
+        tc_ppo_issue(P, cta_local * TC_BM, warp, lane, st[0], cta_local < tiles_m);
+        for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
+          const int buf = t & 1;
+          const int next = tile + ctas;
+          tc_ppo_issue(P, next * TC_BM, warp, lane, st[buf ^ 1], next < tiles_m);
+          tc_epilogue_ppo<BN>(P, tmem_base + uint32_t(buf * BN), tile * TC_BM, warp, lane, &acc_full[buf], uint32_t((t >> 1) & 1),
+                              st[buf], bias_s, consts_s, 1, acc);
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        tc_ppo_finish(P, warp, lane, red_s, acc);
+      } else {
       if (P.staged) tc_issue_aux<BN>(P, cta_local * TC_BM, n0, warp, lane, st[0], cta_local < tiles_m);
       for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
         const int buf = t & 1;
@@ -137,6 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
     } else {
       for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
         const int buf = t & 1;
@@ -156,7 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
 }
 
 constexpr int kWsMaxSmem = 227 * 1024;
-constexpr int kWsFixedSmem = 1024 + 512 + 1024 + 2 * TC_EPI_WARPS * TC_STAGE_BYTES;  // staging is double-buffered here  // alignment slack + barriers + epilogue staging
+constexpr int kWsFixedSmem = 1024 + 512 + 2048 + 2 * TC_EPI_WARPS * TC_STAGE_BYTES;  // staging is double-buffered here  // alignment slack + barriers + epilogue staging
 
 // N tile and A-ring depth for a group, or bn = 0 when the weights-stationary kernel does not apply.
 // N tile <= 128: each epilogue warp then owns 64 columns = ONE 128-byte staging row, so the dgrad's whole activation
@@ -205,7 +226,7 @@ static int launch_ws_bn(const WsGroup& g, int stages, int kb_max, int grid, cuda
 }
 
 // g: one or two forward / dgrad problems built with tc_group_add(..., bn = tc_ws_bn(maxN, maxK), split 1), K-major.
-int launch_tc_ws(const TcGroup& g, cudaStream_t st) {
+int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out) {
   B2_CHECK_ARG(g.count >= 1 && g.count <= 2, "weights-stationary launch takes one or two problems");
   int maxN = 0, maxK = 0;
   for (int i = 0; i < g.count; ++i) {
@@ -240,6 +261,7 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st) {
   w.cta_begin[w.n_slots] = std::max(begin, grid);
   const int kb_max = (maxK + TC_BK - 1) / TC_BK;
   const int total = w.cta_begin[w.n_slots];
+  if (grid_out) *grid_out = total;
   switch (bn) {
     case 64: return launch_ws_bn<64>(w, stages, kb_max, total, st);
     case 128: return launch_ws_bn<128>(w, stages, kb_max, total, st);
