@@ -367,7 +367,6 @@ static int alloc_bf16_workspaces(b200ppo_ctx* c) {
       }
       B2_TRY(dev_alloc(&bf.dZ[n][l], Bm * bf.pitchZ[n][l], true));
       B2_TRY(dev_alloc(&bf.W[n][l], int64_t(N.d.dims[l]) * bf.pitchW[n][l], true));
-      if (l >= 1) B2_TRY(dev_alloc(&bf.WT[n][l], int64_t(N.in_dim(l)) * bf.pitchZ[n][l], true));
       WeightCast& w = bf.casts.w[bf.casts.count++];
       w.src = nullptr;  // the parameter base is a per-call argument: filled in by cast_weights()
       w.dst = bf.W[n][l]; w.dst_t = bf.WT[n][l];
@@ -460,7 +459,7 @@ static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t
   auto& bf = ctx->bf;
   int maxL = 0;
   for (int n = 0; n < 2; ++n) maxL = std::max(maxL, ctx->net[n].d.n_layers);
-  // dgrads, deepest first: dZ_{l-1} = (dZ_l W_l) * act'(H_{l-1}),  B operand = W_l^T (K-major bf16 copy)
+  // dgrads, deepest first: dZ_{l-1} = (dZ_l W_l) * act'(H_{l-1}),  B operand = the bf16 copy of W_l read MN-major
   for (int s = 0; s < maxL; ++s) {
     TcGroup g{};
     int maxN = 0, nets_here = 0;
@@ -487,7 +486,7 @@ static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t
       p.out_bf16 = bf.dZ[n][l - 1]; p.ld_bf16 = bf.pitchZ[n][l - 1];
       p.bias_col = -1;
       TcOperand A{bf.dZ[n][l], bf.pitchZ[n][l], 0};
-      TcOperand Bop{bf.WT[n][l], bf.pitchZ[n][l], 0};
+      TcOperand Bop{bf.W[n][l], bf.pitchW[n][l], 1};  // W_l is [out = K][in = N]: an MN-major operand, no transposed copy
       B2_TRY(tc_group_add(g, p, A, Bop, bn, 1));
     }
     PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, ws ? launch_tc_ws(g, st) : launch_tc_group(g, bn, st));

@@ -447,7 +447,7 @@ __device__ __forceinline__ void tc_ppo_stage_consts(const TcProblem& P, float* c
 
 // Request the 32 x A action slab of this warp's rows (cp.async, zero-filled past the batch) and commit the group.
 __device__ __forceinline__ void tc_ppo_issue(const TcProblem& P, int m0, int warp, int lane, uint8_t* stage, bool valid) {
-  if (valid && P.epilogue == TC_EPI_PPO_ACTOR && ((warp - 2) >> 2) == 0) {
+  if (valid && P.epilogue == TC_EPI_PPO_ACTOR) {
     const int A = P.ppo.act_dim;
     const int mq = m0 + (warp & 3) * 32;
     const int rows = min(32, P.M - mq);
@@ -472,11 +472,14 @@ __device__ __forceinline__ void tc_ppo_issue(const TcProblem& P, int m0, int war
 template <int BN>
 __device__ __forceinline__ void tc_epilogue_ppo(const TcProblem& P, uint32_t tmem_acc, int m0, int warp, int lane,
                                                 uint64_t* tmem_full_bar, uint32_t full_parity, uint8_t* stage,
-                                                const float* bias_s, const float* consts_s, int groups_in_flight, PpoAcc& acc) {
+                                                const float* bias_s, const float* consts_s, int groups_in_flight, PpoAcc& acc,
+                                                bool worker) {
+  // worker: this warp processes the tile's rows of its TMEM lane quarter (the <= 32 output columns all sit in one
+  // thread).  Two warps share a lane quarter: the one-tile kernel lets the first work; the persistent kernel
+  // alternates tiles between the two warp groups.
   const int q = warp & 3;
   const int mq = m0 + q * 32, m = mq + lane;
   const bool row_ok = m < P.M;
-  const bool worker = ((warp - 2) >> 2) == 0;  // the output columns (<= 32) live in the first column half
   if (groups_in_flight > 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
   else asm volatile("cp.async.wait_group 0;" ::: "memory");
   // per-row scalars requested before the accumulator is awaited
@@ -585,11 +588,13 @@ __device__ __forceinline__ void tc_epilogue_ppo(const TcProblem& P, uint32_t tme
 }
 
 // After the last tile: reduce the per-thread sums over the CTA (fixed order) and write this CTA's row of partials.
-// red_s: (TC_EPI_WARPS / 2) x 34 floats of shared memory.  Called by all epilogue warps.
-__device__ __forceinline__ void tc_ppo_finish(const TcProblem& P, int warp, int lane, float* red_s, const PpoAcc& acc) {
+// red_s: TC_EPI_WARPS x 34 floats of shared memory.  Called by all epilogue warps.
+__device__ __forceinline__ void tc_ppo_finish(const TcProblem& P, int warp, int lane, float* red_s, const PpoAcc& acc,
+                                              bool all_warps_worked) {
   const int A = P.ppo.act_dim;
-  const bool worker = ((warp - 2) >> 2) == 0;
-  const int w = warp & 3;
+  const bool worker = all_warps_worked || ((warp - 2) >> 2) == 0;
+  const int w = all_warps_worked ? warp - 2 : (warp & 3);
+  const int n_rows = all_warps_worked ? TC_EPI_WARPS : 4;
   if (worker) {
     const float s = warp_sum(acc.surr), h = warp_sum(acc.hub);
     if (lane == 0) { red_s[w * 34] = s; red_s[w * 34 + 1] = h; }
@@ -603,7 +608,7 @@ __device__ __forceinline__ void tc_ppo_finish(const TcProblem& P, int warp, int 
   const int t = (warp - 2) * 32 + lane;
   if (t < 2 + A) {
     float s = 0.f;
-    for (int k = 0; k < 4; ++k) s += red_s[k * 34 + t];
+    for (int k = 0; k < n_rows; ++k) s += red_s[k * 34 + t];
     if (P.epilogue == TC_EPI_PPO_CRITIC && t != 1) s = 0.f;
     if (P.epilogue == TC_EPI_PPO_ACTOR && t == 1) s = 0.f;
     P.ppo.partials[int64_t(blockIdx.x) * (2 + A) + t] = s;

@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // BN floats (<= 256)
   float* consts_s = bias_s + 256;                                                        // 96 floats (fused PPO epilogue)
-  float* red_s = bias_s + 352;                                                           // 4 x 34 floats
-  uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 2048;                        // TC_EPI_WARPS x 4 KB
+  float* red_s = bias_s + 352;                                                           // 8 x 34 floats
+  uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 3072;                        // TC_EPI_WARPS x 4 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -143,9 +143,10 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
         uint8_t* st = stage_area + (warp - 2) * TC_STAGE_BYTES;
         PpoAcc acc;
         acc.clear();
-        tc_ppo_issue(P, m0, warp, lane, st, true);
-        tc_epilogue_ppo<BN>(P, tmem_base, m0, warp, lane, tmem_full_bar, 0, st, bias_s, consts_s, 0, acc);
-        tc_ppo_finish(P, warp, lane, red_s, acc);
+        const bool worker = ((warp - 2) >> 2) == 0;
+        tc_ppo_issue(P, m0, warp, lane, st, worker);
+        tc_epilogue_ppo<BN>(P, tmem_base, m0, warp, lane, tmem_full_bar, 0, st, bias_s, consts_s, 0, acc, worker);
+        tc_ppo_finish(P, warp, lane, red_s, acc, false);
       } else if (P.staged) {
         uint8_t* st = stage_area + (warp - 2) * TC_STAGE_BYTES;
         tc_issue_aux<BN>(P, m0, n0, warp, lane, st, true);
@@ -239,7 +240,7 @@ int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B
 
 template <int BN>
 static int launch_bn(const TcGroup& g, cudaStream_t st) {
-  constexpr int smem = TcCfg<BN>::STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256 + 2048 + TC_EPI_WARPS * TC_STAGE_BYTES;
+  constexpr int smem = TcCfg<BN>::STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256 + 3072 + TC_EPI_WARPS * TC_STAGE_BYTES;
   static bool configured = false;
   if (!configured) {
     B2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -59,15 +59,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // BN floats (<= 256)
   float* consts_s = bias_s + 256;                                                    // 96 floats (fused PPO epilogue)
-  float* red_s = bias_s + 352;                                                       // 4 x 34 floats
-  uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 2048;                  // TC_EPI_WARPS x 2 x 4 KB
+  float* red_s = bias_s + 352;                                                       // 8 x 34 floats
+  uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 3072;                  // TC_EPI_WARPS x 2 x 4 KB
 
   tc_stage_bias(P, n0, BN, bias_s, threadIdx.x, TC_THREADS);
   tc_ppo_stage_consts(P, consts_s, threadIdx.x);
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
     for (int s = 0; s < a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TC_EPI_WARPS); }
+    // fused PPO epilogue: the two warp groups alternate tiles, so only four warps release an accumulator
+    const uint32_t releasers = P.epilogue >= TC_EPI_PPO_ACTOR ? TC_EPI_WARPS / 2 : TC_EPI_WARPS;
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], releasers); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
@@ -81,7 +83,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       mbar_expect_tx(w_full, uint32_t(KB) * W_KB_BYTES);
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + size_t(kb) * W_KB_BYTES, &P.tmB, w_full, kb * TC_BK, n0);
+      if (!P.b_mn_major) {
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + size_t(kb) * W_KB_BYTES, &P.tmB, w_full, kb * TC_BK, n0);
+      } else {  // W given as [K][N] (the dgrad reads nn.Linear's [out, in] weight as is): 64-wide N atoms per k-block
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(sW + size_t(kb) * W_KB_BYTES + j * 64 * TC_BK * 2, &P.tmB, w_full, n0 + 64 * j, kb * TC_BK);
+      }
       int it = 0;
       for (int tile = cta_local; tile < tiles_m; tile += ctas) {
         for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -94,7 +103,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {  // ===== MMA issuer =====
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(TC_BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(P.b_mn_major != 0) << 16) | (uint32_t(BN >> 3) << 17) |
+                           (uint32_t(TC_BM >> 4) << 24);
+    const uint32_t b_lbo = P.b_mn_major ? TC_BK * 128 : 0, b_kstep = P.b_mn_major ? 2048 : 32;
     mbar_wait(w_full, 0);
     int it = 0, t = 0;
     for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
@@ -110,8 +121,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
           const uint32_t a_addr = smem_u32(sA + size_t(s) * TC_A_BYTES), b_addr = smem_u32(sW + size_t(kb) * W_KB_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(tmem_base + uint32_t(buf * BN), umma_desc(a_addr + k * 32, 0, 1024), umma_desc(b_addr + k * 32, 0, 1024), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_base + uint32_t(buf * BN), umma_desc(a_addr + k * 32, 0, 1024), umma_desc(b_addr + k * b_kstep, b_lbo, 1024),
+                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&a_empty[s]);
           if (kb == KB - 1) umma_commit(&acc_full[buf]);
         }
@@ -125,21 +136,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
       // t + ctas is already streaming into the other (cp.async), i.e. behind the MMAs of the next tile
       uint8_t* st[2] = {stage_area + (warp - 2) * 2 * TC_STAGE_BYTES, stage_area + (warp - 2) * 2 * TC_STAGE_BYTES + TC_STAGE_BYTES};
       if (P.epilogue >= TC_EPI_PPO_ACTOR) {  // output layers with the PPO loss fused in
+        // warp group g (warps 2-5 / 6-9) takes the tiles t with t % 2 == g: tile t lives in TMEM buffer t % 2, so each
+        // group always drains the same accumulator while the other group works on the next tile.
         PpoAcc acc;
         acc.clear();
-        tc_ppo_issue(P, cta_local * TC_BM, warp, lane, st[0], cta_local < tiles_m);
-        for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
-          const int buf = t & 1;
-          const int next = tile + ctas;
-          tc_ppo_issue(P, next * TC_BM, warp, lane, st[buf ^ 1], next < tiles_m);
-          tc_epilogue_ppo<BN>(P, tmem_base + uint32_t(buf * BN), tile * TC_BM, warp, lane, &acc_full[buf], uint32_t((t >> 1) & 1),
-                              st[buf], bias_s, consts_s, 1, acc);
+        const int grp_id = (warp - 2) >> 2;
+        const int step = 2 * ctas;
+        int tile = cta_local + grp_id * ctas, u = 0;  // u counts this group's tiles
+        tc_ppo_issue(P, tile * TC_BM, warp, lane, st[0], tile < tiles_m);
+        for (; tile < tiles_m; tile += step, ++u) {
+          const int next = tile + step;
+          tc_ppo_issue(P, next * TC_BM, warp, lane, st[(u & 1) ^ 1], next < tiles_m);
+          tc_epilogue_ppo<BN>(P, tmem_base + uint32_t(grp_id * BN), tile * TC_BM, warp, lane, &acc_full[grp_id], uint32_t(u & 1),
+                              st[u & 1], bias_s, consts_s, 1, acc, true);
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          if (lane == 0) mbar_arrive(&acc_empty[grp_id]);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        tc_ppo_finish(P, warp, lane, red_s, acc);
+        tc_ppo_finish(P, warp, lane, red_s, acc, true);
       } else {
       if (P.staged) tc_issue_aux<BN>(P, cta_local * TC_BM, n0, warp, lane, st[0], cta_local < tiles_m);
       for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
@@ -177,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
 }
 
 constexpr int kWsMaxSmem = 227 * 1024;
-constexpr int kWsFixedSmem = 1024 + 512 + 2048 + 2 * TC_EPI_WARPS * TC_STAGE_BYTES;  // staging is double-buffered here  // alignment slack + barriers + epilogue staging
+constexpr int kWsFixedSmem = 1024 + 512 + 3072 + 2 * TC_EPI_WARPS * TC_STAGE_BYTES;  // staging is double-buffered here  // alignment slack + barriers + epilogue staging
 
 // N tile and A-ring depth for a group, or bn = 0 when the weights-stationary kernel does not apply.
 // N tile <= 128: each epilogue warp then owns 64 columns = ONE 128-byte staging row, so the dgrad's whole activation
@@ -230,7 +245,7 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out) {
   B2_CHECK_ARG(g.count >= 1 && g.count <= 2, "weights-stationary launch takes one or two problems");
   int maxN = 0, maxK = 0;
   for (int i = 0; i < g.count; ++i) {
-    B2_CHECK_ARG(!g.p[i].a_mn_major && !g.p[i].b_mn_major && g.p[i].split_k == 1, "weights-stationary kernel: K-major, no split-K");
+    B2_CHECK_ARG(!g.p[i].a_mn_major && g.p[i].split_k == 1, "weights-stationary kernel: K-major A, no split-K");
     maxN = std::max(maxN, g.p[i].N);
     maxK = std::max(maxK, g.p[i].K);
   }
