@@ -200,7 +200,11 @@ def hbm_kernel_lines(pk):
     med, best = cuda_time(lambda: pkg.gather_minibatch(idx, obs, act, s, s, s, check=False), 10)
     by = (2 * (4 * OBS_DIM + 4 * ACT_DIM + 12) + 8) * m
     out["gather_epoch_524288"] = {"bytes": by, "ms": med, "GBps": by / 1e9 / (med * 1e-3), "frac": by / 1e9 / (med * 1e-3) / pk["hbm"]}
-    del obs, act, s, idx
+    ident = torch.arange(m, device=dev)
+    med2, _ = cuda_time(lambda: pkg.gather_minibatch(ident, obs, act, s, s, s, check=False), 10)
+    out["gather_epoch_524288_identity_idx"] = {"bytes": by, "ms": med2, "GBps": by / 1e9 / (med2 * 1e-3), "frac": by / 1e9 / (med2 * 1e-3) / pk["hbm"],
+                                               "note": "same kernel, idx = arange: isolates the cost of the random 1504-byte row reads"}
+    del obs, act, s, idx, ident
     # K5 on a 64M-parameter vector (1.79 GB) and on the real 329k-parameter set
     for n_par, key in ((64 * 1024 * 1024, "adam_64M"), (329251, "adam_329k")):
         p, g, mm, vv = (torch.randn(n_par, device=dev) for _ in range(4))
@@ -402,7 +406,13 @@ def run_b200(args, config):
     roofline = {"kernel": "gemm_group_kernel (actor+critic MLP forward/dgrad/wgrad, fp32 FFMA)" if args.precision == "fp32"
                 else "tcgen05 bf16 GEMMs (actor+critic MLP forward/dgrad/wgrad)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tensor_sustained"], "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
+                "frac": achieved / pk["tensor_sustained"],
+                # DRAM bytes of the six GEMM launches of ONE 32768-row minibatch (sum of dram__bytes_read+write over
+                # profiles/r01_ncu_tc_kernels_B32768.csv); the HBM floor of the update is 1584 B/sample = 52 MB: the
+                # excess is activations crossing HBM between the per-layer kernels
+                "traffic": 381.5e6 if (args.precision == "bf16" and B == 32768) else None,
+                "traffic_note": "bytes per minibatch over 6 GEMM launches (ncu, profiles/r01_ncu_tc_kernels_B32768.csv)",
+                "peak_source": pk["source"] + " bf16 sustained",
                 "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
                 "flops_per_sample": fl["total"], "launch_groups": sum(prof[k]["groups"] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad") if k in prof)}
 

@@ -10,6 +10,8 @@
 // Algorithmic bytes per sample: 2*(4*D + 4*A + 12) + 8  (SURVEY.md §8d).
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200ppo {
@@ -70,6 +72,62 @@ gather_minibatch_kernel(const int64_t* __restrict__ idx, int64_t count, int64_t 
     if (lane == 1 && adv != nullptr) adv_o[i] = __ldg(adv + s);
     if (lane == 2 && tgt != nullptr) tgt_o[i] = __ldg(tgt + s);
   }
+}
+
+
+// ---- TMA (bulk-copy) variant of the fp32 gather ----------------------------------------------------------------------
+// When an observation row is a multiple of 16 bytes (376 floats = 1504 B), each LANE drives its own row through the
+// copy engine: cp.async.bulk global -> its shared-memory slot (mbarrier completion), then cp.async.bulk slot -> global.
+// No registers hold row data, 32 rows are in flight per warp (48 KB), and the short leaves (action row, three
+// scalars) are copied by the same lane while its bulk load is in the air.  One warp per CTA, slots = 32 x row_bytes.
+__global__ void __launch_bounds__(32)
+gather_minibatch_tma_kernel(const int64_t* __restrict__ idx, int64_t count, int64_t n_rows, int64_t chunk, int64_t chunk_stride,
+                            int64_t chunk_offset, const float* __restrict__ obs, int obs_dim, const float* __restrict__ act,
+                            int act_dim, const float* __restrict__ logp, const float* __restrict__ adv,
+                            const float* __restrict__ tgt, float* __restrict__ obs_o, float* __restrict__ act_o,
+                            float* __restrict__ logp_o, float* __restrict__ adv_o, float* __restrict__ tgt_o, int32_t* err_flag) {
+  extern __shared__ __align__(128) uint8_t slots[];
+  __shared__ __align__(8) uint64_t bars[32];
+  const int lane = threadIdx.x;
+  const uint32_t row_bytes = uint32_t(obs_dim) * 4u;
+  const uint32_t slot = static_cast<uint32_t>(__cvta_generic_to_shared(slots)) + lane * row_bytes;
+  const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&bars[lane]));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  uint32_t phase = 0;
+  for (int64_t i = int64_t(blockIdx.x) * 32 + lane; i < count; i += int64_t(gridDim.x) * 32) {
+    const int64_t pos = (chunk == count) ? i + chunk_offset : (i / chunk) * chunk_stride + chunk_offset + i % chunk;
+    const int64_t s = resolve_index(idx, pos, n_rows, err_flag);
+    if (s < 0) continue;
+    // the previous bulk store of this lane must have finished READING the slot before it is refilled
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot),
+                 "l"(obs + s * obs_dim), "r"(row_bytes), "r"(bar)
+                 : "memory");
+    // short leaves while the row is in flight
+    if (act != nullptr)
+      for (int k = 0; k < act_dim; ++k) act_o[i * act_dim + k] = __ldg(act + s * act_dim + k);
+    if (logp != nullptr) logp_o[i] = __ldg(logp + s);
+    if (adv != nullptr) adv_o[i] = __ldg(adv + s);
+    if (tgt != nullptr) tgt_o[i] = __ldg(tgt + s);
+    uint32_t done;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(phase)
+          : "memory");
+    } while (!done);
+    phase ^= 1u;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(obs_o + i * obs_dim), "r"(slot), "r"(row_bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Same gather, observations emitted as bf16 rows of pitch `pitch` elements with a 1.0 in column obs_dim (the
@@ -141,6 +199,21 @@ int launch_gather_chunked(const int64_t* idx, int64_t count, int64_t n_rows, int
                           float* logp_o, float* adv_o, float* tgt_o, int32_t* err_flag, cudaStream_t st) {
   if (count == 0) return B200PPO_OK;
   const bool vec = (obs_dim % 4 == 0) && aligned16(obs) && aligned16(obs_o);
+  const size_t tma_smem = size_t(32) * obs_dim * 4;
+  if (vec && tma_smem <= 56 * 1024 && count >= 4096) {  // bulk-copy engine path (rows are whole 16-byte multiples)
+    static bool configured = false;
+    if (!configured) {
+      B2_CUDA(cudaFuncSetAttribute(gather_minibatch_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
+      configured = true;
+    }
+    const int per_sm = int(std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / std::max<size_t>(tma_smem, 1))));
+    int64_t blocks = std::min<int64_t>((count + 31) / 32, int64_t(num_sms()) * per_sm);
+    gather_minibatch_tma_kernel<<<unsigned(blocks), 32, tma_smem, st>>>(idx, count, n_rows, chunk, chunk_stride, chunk_offset, obs,
+                                                                        obs_dim, act, act_dim, logp, adv, tgt, obs_o, act_o, logp_o,
+                                                                        adv_o, tgt_o, err_flag);
+    B2_LAUNCH_CHECK();
+    return B200PPO_OK;
+  }
   dim3 block(256), grid(gather_grid(count, 8));
   if (vec)
     gather_minibatch_kernel<true><<<grid, block, 0, st>>>(idx, count, n_rows, chunk, chunk_stride, chunk_offset, obs, obs_dim, act, act_dim, logp, adv, tgt, obs_o, act_o, logp_o, adv_o, tgt_o, err_flag);

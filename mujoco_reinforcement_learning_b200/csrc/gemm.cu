@@ -104,7 +104,7 @@ __device__ __forceinline__ float apply_epilogue(float acc, int epi, float bias, 
 }
 
 template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+__global__ void __launch_bounds__((BM / TM) * (BN / TN), 2)  // two CTAs per SM: the second hides the first's load latency
 gemm_group_kernel(const __grid_constant__ GemmGroup grp) {
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int RG = TM / 4, CG = TN / 4;  // 4-wide row / column groups per thread
