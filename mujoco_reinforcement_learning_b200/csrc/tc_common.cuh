@@ -84,6 +84,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
 // MUFU.TANH: one instruction, max relative error ~2^-11 — below bf16's 2^-8 resolution of the stored activation
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -283,29 +284,31 @@ __device__ __forceinline__ void tc_issue_aux(const TcProblem& P, int m0, int n0,
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {  // packed MUFU tanh on two bf16 values
+  uint32_t y;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
+// bf16-output epilogue (hidden-layer forward and dgrad) through the warp's staging tile.  BN <= 128: the warp's
+// BN/2 columns are one group of <= 64 columns = one 128-byte staging row per accumulator row, and every index
+// computation below is a compile-time constant or hoisted out of the loops (the first version spent ~900 warp
+// instructions per tile here and was the limiter of the persistent kernel).
 template <int BN>
 __device__ __forceinline__ void tc_epilogue_staged(const TcProblem& P, int split, uint32_t tmem_acc, bool has_k, int m0, int n0,
                                                    int warp, int lane, uint64_t* tmem_full_bar, uint32_t full_parity,
                                                    uint8_t* stage, const float* bias_s, int aux_groups_in_flight) {
-  const int epi = P.epilogue, act = P.act, Mrows = P.M, Ncols = P.N;
-  __nv_bfloat16* __restrict__ outb = P.out_bf16;
-  float* __restrict__ outf = P.out_f32 != nullptr ? P.out_f32 + int64_t(split) * P.split_stride : nullptr;
-  float* __restrict__ bgrad = P.bias_grad != nullptr ? P.bias_grad + int64_t(split) * P.split_stride : nullptr;
-  const __nv_bfloat16* __restrict__ auxp = P.aux;
-  const int ld_bf16 = P.ld_bf16, ld_f32 = P.ld_f32, ld_aux = P.ld_aux, bias_col = P.bias_col;
-  const float out_scale = P.out_scale;
-  const int q = warp & 3;                 // TMEM lane quarter of this warp
-  const int mq = m0 + q * 32;             // first row of the warp's 32-row slab
-  const int m = mq + lane;
-  const bool f32_out = (epi == TC_EPI_STORE);
-  const int ncols_mat = f32_out ? (bias_col >= 0 ? bias_col : Ncols) : Ncols;  // columns stored through the staging tile
-  constexpr int WCOLS = BN / 2;           // columns per epilogue warp
+  static_assert(BN == 64 || BN == 128, "staged epilogue: BN <= 128");
+  constexpr int WCOLS = BN / 2, STEPS = WCOLS / 16, UPR = WCOLS / 8, RSTEP = 32 / UPR;
+  (void)split;
+  const int epi = P.epilogue, act = P.act;
+  const int q = warp & 3;
+  const int mq = m0 + q * 32;
   const int col0 = ((warp - 2) >> 2) * WCOLS;
-  const int GW = f32_out ? 32 : 64;       // columns per 128-byte staging row
   const uint32_t sbase = smem_u32(stage);
-
-  // dgrad: the activation tile was requested with cp.async by tc_issue_aux (this tile's group is the older one)
-  if (epi == TC_EPI_DGRAD) {
+  const uint32_t my_row = sbase + uint32_t(lane) * 128u;
+  const int sw = lane & 7;
+  if (epi == TC_EPI_DGRAD) {  // this tile's activation slab was requested with cp.async by tc_issue_aux
     if (aux_groups_in_flight > 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
@@ -313,101 +316,72 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcProblem& P, int split
     mbar_wait(tmem_full_bar, full_parity);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-#pragma unroll 1
-  for (int gc = 0; gc < WCOLS; gc += GW) {
-    const int gcols = (WCOLS - gc) < GW ? (WCOLS - gc) : GW;
-    const int nbg = n0 + col0 + gc;
-    __syncwarp();
-#pragma unroll 1
-    for (int s = 0; s < gcols / 16; ++s) {
-      uint32_t v[16];
-      if (has_k) {
-        tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(col0 + gc + s * 16), v);
-      } else {
+  __syncwarp();
+  const float* bs = bias_s + col0;
+  // (loading the whole 64-column slab with one tcgen05.ld.x64 and a single wait was measured: no gain, +70 registers)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0u;
+  for (int s = 0; s < STEPS; ++s) {
+    uint32_t v[16];
+    if (has_k) {
+      tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(col0 + s * 16), v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0u;
+    }
+    uint32_t o[8];
+    if (epi == TC_EPI_FWD) {
+      float z[16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 t = *reinterpret_cast<const float4*>(bs + s * 16 + u * 4);
+        z[u * 4] = __uint_as_float(v[u * 4]) + t.x; z[u * 4 + 1] = __uint_as_float(v[u * 4 + 1]) + t.y;
+        z[u * 4 + 2] = __uint_as_float(v[u * 4 + 2]) + t.z; z[u * 4 + 3] = __uint_as_float(v[u * 4 + 3]) + t.w;
       }
-      const int nb = nbg + s * 16;
-      float h[16];
-      if (epi == TC_EPI_FWD) {
+      if (act == B200PPO_ACT_TANH) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 t = *reinterpret_cast<const float4*>(bias_s + (nb - n0) + u * 4);
-          h[u * 4] = t.x; h[u * 4 + 1] = t.y; h[u * 4 + 2] = t.z; h[u * 4 + 3] = t.w;
-        }
-        if (act == B200PPO_ACT_TANH) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = tanh_fast(__uint_as_float(v[j]) + h[j]);
-        } else if (act == B200PPO_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = fmaxf(__uint_as_float(v[j]) + h[j], 0.f);
-        } else if (act == TC_ACT_TANH_SCALE) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = out_scale * tanh_fast(__uint_as_float(v[j]) + h[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = __uint_as_float(v[j]) + h[j];
-        }
-      } else if (epi == TC_EPI_DGRAD) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          uint32_t w0, w1, w2, w3;
-          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(sbase + stage_off(lane, s * 2 + u)) : "memory");
-          const uint32_t ww[4] = {w0, w1, w2, w3};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[t]);
-            h[u * 8 + t * 2] = __low2float(b2);
-            h[u * 8 + t * 2 + 1] = __high2float(b2);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float g = __uint_as_float(v[j]);
-          h[j] = act == B200PPO_ACT_TANH ? g * (1.f - h[j] * h[j]) : (h[j] > 0.f ? g : 0.f);
-        }
+        for (int j = 0; j < 8; ++j) o[j] = tanh_bf16x2(pack_bf16(z[2 * j], z[2 * j + 1]));
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) h[j] = __uint_as_float(v[j]);
-        if (bgrad != nullptr && bias_col >= nb && bias_col < nb + 16 && m < Mrows) {
-          float bg = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j == bias_col) bg = h[j];
-          bgrad[m] = bg;
-        }
+        for (int j = 0; j < 8; ++j) o[j] = pack_bf16(fmaxf(z[2 * j], 0.f), fmaxf(z[2 * j + 1], 0.f));
       }
-      if (f32_out) {
+    } else {  // TC_EPI_DGRAD: dz = acc * act'(h), h from the staged activation slab (this thread's row)
+      uint32_t w[8];
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(my_row + uint32_t(((2 * s) ^ sw) << 4)) : "memory");
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(my_row + uint32_t(((2 * s + 1) ^ sw) << 4)) : "memory");
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + stage_off(lane, s * 4 + u)), "r"(__float_as_uint(h[u * 4])),
-                       "r"(__float_as_uint(h[u * 4 + 1])), "r"(__float_as_uint(h[u * 4 + 2])), "r"(__float_as_uint(h[u * 4 + 3]))
-                       : "memory");
-      } else {
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + stage_off(lane, s * 2 + u)), "r"(pack_bf16(h[u * 8], h[u * 8 + 1])),
-                       "r"(pack_bf16(h[u * 8 + 2], h[u * 8 + 3])), "r"(pack_bf16(h[u * 8 + 4], h[u * 8 + 5])),
-                       "r"(pack_bf16(h[u * 8 + 6], h[u * 8 + 7]))
-                       : "memory");
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+        const float h0 = __low2float(b2), h1 = __high2float(b2);
+        const float g0 = __uint_as_float(v[2 * j]), g1 = __uint_as_float(v[2 * j + 1]);
+        if (act == B200PPO_ACT_TANH) o[j] = pack_bf16(g0 * (1.f - h0 * h0), g1 * (1.f - h1 * h1));
+        else o[j] = pack_bf16(h0 > 0.f ? g0 : 0.f, h1 > 0.f ? g1 : 0.f);
       }
     }
-    __syncwarp();
-    // staging -> global: 8 consecutive lanes write one full 128-byte line
-    const int upr = f32_out ? (gcols >> 2) : (gcols >> 3);
-    const int cpu = f32_out ? 4 : 8;  // columns per 16-byte unit
-    for (int idx = lane; idx < 32 * upr; idx += 32) {
-      const int row = idx / upr, unit = idx - row * upr;
-      const int col = nbg + unit * cpu;
-      if (mq + row < Mrows && col < ncols_mat) {
-        uint32_t w0, w1, w2, w3;
-        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(sbase + stage_off(row, unit)) : "memory");
-        if (f32_out) *reinterpret_cast<uint4*>(outf + int64_t(mq + row) * ld_f32 + col) = make_uint4(w0, w1, w2, w3);
-        else *reinterpret_cast<uint4*>(outb + int64_t(mq + row) * ld_bf16 + col) = make_uint4(w0, w1, w2, w3);
-      }
-    }
-    __syncwarp();
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s) ^ sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s + 1) ^ sw) << 4)), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
   }
+  __syncwarp();
+  // staging -> global: UPR consecutive lanes write one row's 16-byte units (a full 128-byte line when UPR == 8)
+  {
+    const int unit = lane % UPR, row0 = lane / UPR;
+    const int col = n0 + col0 + unit * 8;
+    const bool col_ok = col < P.N;
+    __nv_bfloat16* gp = P.out_bf16 + int64_t(mq + row0) * P.ld_bf16 + col;
+    const int64_t gstep = int64_t(RSTEP) * P.ld_bf16;
+    const int rows_left = P.M - mq - row0;  // this lane's rows are row0 + i*RSTEP
+#pragma unroll
+    for (int i = 0; i < UPR; ++i) {
+      const int row = row0 + i * RSTEP;
+      if (col_ok && i * RSTEP < rows_left) {
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                     : "r"(sbase + uint32_t(row * 128) + uint32_t((unit ^ (row & 7)) << 4)) : "memory");
+        *reinterpret_cast<uint4*>(gp) = make_uint4(w0, w1, w2, w3);
+      }
+      gp += gstep;
+    }
+  }
+  __syncwarp();
 }
 
 // Host-evaluated: may this problem use the staged epilogue (16-byte aligned rows and whole units inside the matrix)?
@@ -415,7 +389,8 @@ inline bool tc_can_stage(const TcProblem& p) {
   if (p.epilogue == TC_EPI_STORE) return false;  // measured: staging the fp32 split-K partials does not pay (58 vs 50 us)
   const bool out_ok = p.out_bf16 != nullptr && p.out_f32 == nullptr && p.ld_bf16 % 8 == 0 && p.N % 8 == 0 && aligned16(p.out_bf16);
   if (p.epilogue == TC_EPI_DGRAD) return out_ok && p.aux != nullptr && p.ld_aux % 8 == 0 && aligned16(p.aux);
-  return out_ok;
+  if (p.epilogue == TC_EPI_FWD) return out_ok && (p.act == B200PPO_ACT_TANH || p.act == B200PPO_ACT_RELU);
+  return false;
 }
 
 // ---- fused PPO-loss epilogues of the output layers ---------------------------------------------------------------------

@@ -24,6 +24,8 @@
 
 namespace b200ppo {
 
+extern long long* g_ws_trace;
+
 // smem ring depth: K loops are 1-6 tiles for forward/dgrad, so for BN <= 128 two 32 KB stages + the 32 KB epilogue
 // staging area let two CTAs share an SM (one CTA's epilogue overlaps the other's TMA/MMA main loop); the wide tiles
 // used by the long-K weight-gradient GEMM run one CTA per SM with a deeper ring.
@@ -318,7 +320,17 @@ extern "C" B2_EXPORT int b200ppo_debug_tc_gemm(const float* A, const float* B, f
   p.M = M; p.N = N; p.K = K;
   p.epilogue = TC_EPI_STORE;
   p.out_f32 = part; p.ld_f32 = N; p.split_stride = stride; p.bias_col = -1;
-  const bool ws = bn < 0;  // bn = -1: the persistent weights-stationary kernel
+  const bool ws = bn < 0;  // bn = -1: the persistent weights-stationary kernel; bn = -2: same, plus a clock64 timeline
+  long long* trace = nullptr;
+  if (bn == -2) {
+    p.epilogue = TC_EPI_FWD; p.act = B200PPO_ACT_TANH;  // the production forward epilogue, bf16 output
+    p.out_f32 = nullptr;
+    B2_CUDA(cudaMalloc(&p.out_bf16, size_t(M) * ((N + 7) / 8 * 8) * 2));
+    p.ld_bf16 = (N + 7) / 8 * 8;
+    B2_CUDA(cudaMalloc(&trace, 64 * 8 * sizeof(long long)));
+    B2_CUDA(cudaMemset(trace, 0, 64 * 8 * sizeof(long long)));
+    g_ws_trace = trace;
+  }
   if (ws) bn = tc_ws_bn(N, K);
   int rc = tc_group_add(g, p, TcOperand{Ab, a_pitch, a_mn_major}, TcOperand{Bb, b_pitch, b_mn_major}, bn, split_k);
   if (rc == B200PPO_OK) rc = ws ? launch_tc_ws(g, st) : launch_tc_group(g, bn, st);
@@ -327,6 +339,18 @@ extern "C" B2_EXPORT int b200ppo_debug_tc_gemm(const float* A, const float* B, f
     count_launch();
   }
   cudaStreamSynchronize(st);
+  if (trace != nullptr) {
+    long long h[64 * 8];
+    cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[0];
+    fprintf(stderr, "WS timeline of CTA 0 (cycles since first issue): tile | prod_first prod_last | mma_acc_free mma_kb0 mma_kbN | epi_start epi_end(w2) epi_end(slowest)\n");
+    for (int t = 0; t < 64 && h[t * 8] != 0; ++t)
+      fprintf(stderr, "  %2d | %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld %7lld\n", t, h[t * 8] - t0, h[t * 8 + 1] - t0, h[t * 8 + 2] - t0,
+              h[t * 8 + 3] - t0, h[t * 8 + 4] - t0, h[t * 8 + 5] - t0, h[t * 8 + 6] - t0, h[t * 8 + 7] - t0);
+    g_ws_trace = nullptr;
+    cudaFree(trace);
+    cudaFree(p.out_bf16);
+  }
   cudaFree(Ab); cudaFree(Bb); cudaFree(part);
   {
     std::lock_guard<std::mutex> lock(g_map_mutex);

@@ -24,7 +24,15 @@ struct WsGroup {
   int n_slots;
   int slot_prob[kWsMaxSlots], slot_n0[kWsMaxSlots];
   int cta_begin[kWsMaxSlots + 1];  // CTAs [cta_begin[i], cta_begin[i+1]) serve slot i
+  long long* trace;                // debug: clock64 timeline of CTA 0, [tile][8] (nullptr in production)
 };
+
+long long* g_ws_trace = nullptr;  // set by the debug entry point only
+
+#define WS_TRACE(tile_idx, slot_idx)                                                        \
+  do {                                                                                      \
+    if (grp.trace != nullptr && blockIdx.x == 0 && (tile_idx) < 64) grp.trace[(tile_idx) * 8 + (slot_idx)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -92,13 +100,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
             tma_load_2d(sW + size_t(kb) * W_KB_BYTES + j * 64 * TC_BK * 2, &P.tmB, w_full, n0 + 64 * j, kb * TC_BK);
       }
       int it = 0;
-      for (int tile = cta_local; tile < tiles_m; tile += ctas) {
+      int tt = 0;
+      for (int tile = cta_local; tile < tiles_m; tile += ctas, ++tt) {
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % a_stages;
           const uint32_t ph = (it / a_stages) & 1;
           mbar_wait(&a_empty[s], ph ^ 1);
+          if (kb == 0) WS_TRACE(tt, 0);
           mbar_expect_tx(&a_full[s], TC_A_BYTES);
           tma_load_2d(sA + size_t(s) * TC_A_BYTES, &P.tmA, &a_full[s], kb * TC_BK, tile * TC_BM);
+          if (kb == KB - 1) WS_TRACE(tt, 1);
         }
       }
     }
@@ -112,11 +123,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
       const int buf = t & 1;
       mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) WS_TRACE(t, 2);
       for (int kb = 0; kb < KB; ++kb, ++it) {
         const int s = it % a_stages;
         const uint32_t ph = (it / a_stages) & 1;
         mbar_wait(&a_full[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0 && kb == 0) WS_TRACE(t, 3);
+        if (lane == 0 && kb == KB - 1) WS_TRACE(t, 4);
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(sA + size_t(s) * TC_A_BYTES), b_addr = smem_u32(sW + size_t(kb) * W_KB_BYTES);
 #pragma unroll
@@ -161,9 +175,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
         const int buf = t & 1;
         if (P.staged) {
           const int next = tile + ctas;
+          if (warp == 2 && lane == 0) WS_TRACE(t, 5);
           tc_issue_aux<BN>(P, next * TC_BM, n0, warp, lane, st[buf ^ 1], next < tiles_m);
           tc_epilogue_staged<BN>(P, 0, tmem_base + uint32_t(buf * BN), true, tile * TC_BM, n0, warp, lane, &acc_full[buf],
                                  uint32_t((t >> 1) & 1), st[buf], bias_s, 1);
+          if (warp == 2 && lane == 0) WS_TRACE(t, 6);
+          if (lane == 0 && grp.trace != nullptr && blockIdx.x == 0 && t < 64)  // slowest epilogue warp of the tile
+            atomicMax(reinterpret_cast<unsigned long long*>(grp.trace) + t * 8 + 7, (unsigned long long)clock64());
         } else {
           tc_epilogue<BN>(P, 0, tmem_base + uint32_t(buf * BN), true, tile * TC_BM, n0, warp, lane, &acc_full[buf], uint32_t((t >> 1) & 1), bias_s);
         }
@@ -274,6 +292,7 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out) {
     begin += share;
   }
   w.cta_begin[w.n_slots] = std::max(begin, grid);
+  w.trace = g_ws_trace;
   const int kb_max = (maxK + TC_BK - 1) / TC_BK;
   const int total = w.cta_begin[w.n_slots];
   if (grid_out) *grid_out = total;
