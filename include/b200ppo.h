@@ -192,6 +192,19 @@ int b200ppo_update_host(b200ppo_ctx* ctx, float* params, float* exp_avg, float* 
                         b200ppo_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Observation normalisation feeding the policy.
+ * replaces: EnvironmentHelper.normalize_state/_normalize/get_state,
+ *           src/environments/humanoid/running_gym_sequential_vectorized.py:61-92.
+ *   obs        [N, obs_dim, window] fp32, or fp64 when obs_is_f64 (gym observations)
+ *   seg_bounds device int32 [n_segments + 1]: each range [b_s, b_{s+1}) of the observation vector is centred and
+ *              divided by its unbiased std (std == 0 -> 1) per env and per frame, in the input's precision;
+ *              normalize = 0 skips that and only casts / permutes (run.normalize_observations = False)
+ *   out        [N, window, obs_dim] fp32 (the permute(0, 2, 1) of get_state)
+ */
+int b200ppo_normalize_obs(const void* obs, int obs_is_f64, int64_t n_envs, int32_t obs_dim, int32_t window,
+                          const int32_t* seg_bounds, int32_t n_segments, int normalize, float* out, b200ppo_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Instrumentation (used by bench.py; no reference counterpart).
  * b200ppo_launch_count: CUDA kernels this library has launched in this process so far.
  * b200ppo_profile_begin/end: between the two calls every kernel group launched by b200ppo_train on this

@@ -2,7 +2,7 @@
 (`Actor`, `Critic`, `PPOAgent`, `PPO`, `generalized_advantage_estimate`) over hand-written sm_100a kernels."""
 from .config import (DynamicConfig, EnvironmentConfig, NetworkConfig, PPOConfig, Run, TrainingConfig)  # noqa: F401
 from .functional import (adam_step_, calculate_advantages, gather_minibatch, gather_rows,  # noqa: F401
-                         generalized_advantage_estimate)
+                         generalized_advantage_estimate, normalize_state)
 from .memory import RolloutMemory  # noqa: F401
 from .models import Actor, ActorCriticEngine, Critic, NetworkBlock, create_network  # noqa: F401
 from .agent import FusedAdam, PPOAgent  # noqa: F401

@@ -113,25 +113,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 1) {  // ===== MMA issuer =====
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(P.b_mn_major != 0) << 16) | (uint32_t(BN >> 3) << 17) |
-                           (uint32_t(TC_BM >> 4) << 24);
-    const uint32_t b_lbo = P.b_mn_major ? TC_BK * 128 : 0, b_kstep = P.b_mn_major ? 2048 : 32;
-    mbar_wait(w_full, 0);
-    int it = 0, t = 0;
-    for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
-      const int buf = t & 1;
-      mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) WS_TRACE(t, 2);
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % a_stages;
-        const uint32_t ph = (it / a_stages) & 1;
-        mbar_wait(&a_full[s], ph);
+  } else if (warp == 1) {  // ===== MMA issuer: ONE thread runs the whole loop (31 idle lanes would only add polling) =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(P.b_mn_major != 0) << 16) | (uint32_t(BN >> 3) << 17) |
+                             (uint32_t(TC_BM >> 4) << 24);
+      const uint32_t b_lbo = P.b_mn_major ? TC_BK * 128 : 0, b_kstep = P.b_mn_major ? 2048 : 32;
+      mbar_wait(w_full, 0);
+      int it = 0, t = 0;
+      for (int tile = cta_local; tile < tiles_m; tile += ctas, ++t) {
+        const int buf = t & 1;
+        mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0 && kb == 0) WS_TRACE(t, 3);
-        if (lane == 0 && kb == KB - 1) WS_TRACE(t, 4);
-        if (lane == 0) {
+        WS_TRACE(t, 2);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % a_stages;
+          const uint32_t ph = (it / a_stages) & 1;
+          mbar_wait(&a_full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (kb == 0) WS_TRACE(t, 3);
+          if (kb == KB - 1) WS_TRACE(t, 4);
           const uint32_t a_addr = smem_u32(sA + size_t(s) * TC_A_BYTES), b_addr = smem_u32(sW + size_t(kb) * W_KB_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
           umma_commit(&a_empty[s]);
           if (kb == KB - 1) umma_commit(&acc_full[buf]);
         }
-        __syncwarp();
       }
     }
   } else {  // ===== epilogue warps =====

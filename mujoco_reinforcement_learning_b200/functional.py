@@ -153,3 +153,30 @@ def adam_step_(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, beta1=0.9
                               param.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
                               _lib.stream_ptr()), "b200ppo_adam_step")
     return param
+
+
+# index ranges of the SymmetricHumanoid observation vector the reference normalises separately
+# (src/environments/humanoid/running_gym_sequential_vectorized.py:69-80); the last range ends at obs_dim
+HUMANOID_SEGMENTS = (0, 22, 45, 175, 253, 270)
+
+
+def normalize_state(observation: torch.Tensor, segments=HUMANOID_SEGMENTS, normalize: bool = True) -> torch.Tensor:
+    """`EnvironmentHelper.get_state` minus the environment (running_gym_sequential_vectorized.py:61-92): per-env,
+    per-frame normalisation of every index range of the observation, cast to fp32, permute to [N, window, obs].
+    `observation` is [N, obs_dim, window], float32 or float64 (gym), on the GPU."""
+    _lib.require_cuda(observation, "observation")
+    if observation.dtype not in (torch.float32, torch.float64) or observation.dim() != 3:
+        raise RuntimeError("observation must be a float32/float64 tensor shaped [N, obs_dim, window]")
+    lib = _lib.load()
+    obs = observation.contiguous()
+    n, d, w = obs.shape
+    bounds = [int(b) for b in segments if int(b) < d]
+    if not bounds or bounds[0] != 0:
+        bounds = [0] + bounds
+    bounds.append(d)
+    seg = torch.tensor(bounds, dtype=torch.int32, device=obs.device)
+    out = torch.empty((n, w, d), dtype=torch.float32, device=obs.device)
+    _lib.check(
+        lib.b200ppo_normalize_obs(_lib.ptr(obs), int(obs.dtype == torch.float64), n, d, w, _lib.ptr(seg), len(bounds) - 1,
+                                  int(bool(normalize)), _lib.ptr(out), _lib.stream_ptr()), "b200ppo_normalize_obs")
+    return out

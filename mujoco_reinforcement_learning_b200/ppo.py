@@ -30,9 +30,10 @@ class PPO:
 
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def rollout(self) -> RolloutMemory:
+    def rollout(self, noise: Optional[torch.Tensor] = None) -> RolloutMemory:
         """ppo.py:13-60 with pre-allocated [N, T, ...] device buffers written in place (no per-step
-        containers, no final concat) and one fused inference call per step for V(s), pi(s), log-prob."""
+        containers, no final concat) and one fused inference call per step for V(s), pi(s), log-prob.
+        `noise` ([T, N, act_dim] standard-normal draws) replaces the device RNG, for reproducible comparisons."""
         helper, run = self.environment_helper, self.run
         helper.reset()
         helper.reset_environment(test_phase=False)
@@ -52,7 +53,7 @@ class PPO:
         }
         for t in range(steps):
             current_state = next_state
-            action, logp, value = self.agent.act_fused(current_state)
+            action, logp, value = self.agent.act_fused(current_state, None if noise is None else noise[t].to(dev))
             helper.step(action)
             next_state = helper.get_state(test_phase=False).to(dev, torch.float32)
             buf["current_state"][:, t] = current_state

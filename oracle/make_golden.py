@@ -34,6 +34,7 @@ CASES = {
     "adv_norm": dict(kind="adv", N=5, T=64, seed=12, normalize_advantage=True, advantage_scaler=0.7),
     "adv_rnorm": dict(kind="adv", N=3, T=130, seed=13, normalize_rewards=True, advantage_scaler=1.3),
     "adv_f64": dict(kind="adv", N=4, T=50, seed=14, reward_f64=True),
+    "obsnorm": dict(kind="obsnorm", N=5, T=1, seed=31),
     "train_tanh64": dict(kind="train", D=17, A=6, hidden=[64, 64], act="Tanh", N=4, T=64, B=48, epochs=2, seed=21),
     "train_relu3": dict(kind="train", D=11, A=3, hidden=[32, 24, 16], act="ReLU", N=3, T=50, B=32, epochs=2,
                         seed=22),
@@ -96,7 +97,20 @@ def run_case(name: str):
                              reward_f64=spec.get("reward_f64", False))
     roll["current_state"] = roll["current_state"].reshape(N, T, D)  # window_length 1, flattened
     out = {}
-    if spec["kind"] == "adv":
+    if spec["kind"] == "obsnorm":
+        # EnvironmentHelper.normalize_state / _normalize run verbatim (running_gym_sequential_vectorized.py:61-82) on a
+        # stand-in `self`; the cast + permute of get_state (:89-91) follow, since get_state itself needs a live env.
+        import types
+        from environments.humanoid.running_gym_sequential_vectorized import EnvironmentHelper as RefHelper
+        g = torch.Generator().manual_seed(spec["seed"])
+        obs = torch.randn(spec["N"], 376, 5, generator=g, dtype=torch.float64) * 3.0 + 0.5
+        obs[2, 253:270, 1] = 0.25  # a constant segment: std == 0 -> 1
+        stand_in = types.SimpleNamespace()
+        stand_in._normalize = lambda x: RefHelper._normalize(stand_in, x)
+        normed = RefHelper.normalize_state(stand_in, obs.clone())
+        out["in_observation"] = obs.numpy()
+        out["state"] = normed.to(torch.float32).permute(0, 2, 1).contiguous().numpy()
+    elif spec["kind"] == "adv":
         mem = TensorDict({k: v.clone() for k, v in roll.items()}, batch_size=(N, T))
         algo = PPO(_Helper(run), agent=None)
         algo.calculate_advantages(mem)

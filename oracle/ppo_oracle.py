@@ -296,3 +296,49 @@ def synthetic_rollout(n_envs: int, steps: int, obs_dim: int, act_dim: int, seed:
         "terminated": terminated,
         "truncated": torch.zeros_like(terminated),
     }
+
+
+# ----------------------------------------------------------------------------------
+# Observation normalisation — src/environments/humanoid/running_gym_sequential_vectorized.py:61-92
+# ----------------------------------------------------------------------------------
+def normalize_state(observation: torch.Tensor, bounds=(0, 22, 45, 175, 253, 270), normalize: bool = True) -> torch.Tensor:
+    """observation [N, obs_dim, window] (float64 from gym) -> [N, window, obs_dim] float32."""
+    state = observation.clone()
+    if normalize:
+        edges = [b for b in bounds if b < state.shape[1]] + [state.shape[1]]
+        for b, e in zip(edges[:-1], edges[1:]):
+            seg = state[:, b:e]
+            seg = seg - seg.mean(dim=1).unsqueeze(1)      # :62
+            std = seg.std(dim=1).unsqueeze(1)             # :63 (unbiased)
+            std[std == 0] = 1                             # :64
+            state[:, b:e] = seg / std                     # :65
+    return state.to(torch.float32).permute(0, 2, 1)       # :89-91
+
+
+def rollout(agent: OracleAgent, helper, steps: int, noise: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """`PPO.rollout` — src/entities/algorithms/ppo.py:13-60 with the Normal draws supplied (`noise` [T, N, A]:
+    action = mean + std * noise is what `Normal.sample()` computes)."""
+    helper.reset()
+    helper.reset_environment(test_phase=False)
+    next_state = helper.get_state(test_phase=False)
+    items = {k: [] for k in ("current_state", "current_state_value", "next_state_value", "action", "action_log_prob",
+                             "reward", "terminated", "truncated")}
+    with torch.no_grad():
+        for t in range(steps):
+            current_state = torch.clone(next_state)
+            value = agent.get_state_value(current_state)
+            mean, std = agent.networks["actor"](current_state)
+            action = mean + std * noise[t]
+            logp = torch.distributions.Normal(mean, std).log_prob(action).sum(dim=1)
+            helper.step(action)
+            next_state = helper.get_state(test_phase=False)
+            next_value = agent.get_state_value(next_state)
+            items["current_state"].append(current_state.unsqueeze(1))
+            items["current_state_value"].append(value.unsqueeze(1))
+            items["next_state_value"].append(next_value.unsqueeze(1))
+            items["action"].append(action.unsqueeze(1))
+            items["action_log_prob"].append(logp.unsqueeze(1))
+            items["reward"].append(torch.tensor(helper.timestep.reward)[:, None].unsqueeze(1))
+            items["terminated"].append(torch.tensor(helper.timestep.terminated[:, None]))
+            items["truncated"].append(torch.tensor(helper.timestep.truncated[:, None]))
+    return {k: torch.cat(v, dim=1) for k, v in items.items()}

@@ -180,3 +180,10 @@ def test_adam_naive_matches_torch():
         pn, m, v = naive.adam_step_naive(pn, gr.double().numpy(), m, v, step, 3e-4)
     assert rel_err(p.detach() - p0, pn - p0.double().numpy()) < 1e-3  # the update itself (fp32 cancellation on p - p0)
     assert_close(p, pn, 1e-6, "params")
+
+
+def test_normalize_state_matches_reference():
+    g = load_golden("obsnorm")
+    out = O.normalize_state(torch.from_numpy(g["in_observation"]))
+    assert out.dtype == torch.float32 and tuple(out.shape) == g["state"].shape
+    assert np.array_equal(out.numpy(), g["state"])
