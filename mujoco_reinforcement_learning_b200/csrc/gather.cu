@@ -12,6 +12,8 @@
 
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200ppo {
@@ -200,7 +202,8 @@ int launch_gather_chunked(const int64_t* idx, int64_t count, int64_t n_rows, int
   if (count == 0) return B200PPO_OK;
   const bool vec = (obs_dim % 4 == 0) && aligned16(obs) && aligned16(obs_o);
   const size_t tma_smem = size_t(32) * obs_dim * 4;
-  if (vec && tma_smem <= 56 * 1024 && count >= 4096) {  // bulk-copy engine path (rows are whole 16-byte multiples)
+  static const char* mode = getenv("B200PPO_GATHER");  // profiles/gather_variants.py: "ldg" forces the load/store kernel
+  if (vec && tma_smem <= 56 * 1024 && count >= 4096 && !(mode != nullptr && mode[0] == 'l')) {  // bulk-copy engine path (rows are whole 16-byte multiples)
     static bool configured = false;
     if (!configured) {
       B2_CUDA(cudaFuncSetAttribute(gather_minibatch_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
