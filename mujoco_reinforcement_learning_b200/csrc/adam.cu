@@ -87,6 +87,7 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
                  AdamScalars s1, const __grid_constant__ CastTable ct, const __grid_constant__ LossCombine lc) {
   __shared__ float s_lc[64];
   __shared__ float s_scr[256];
+  pdl_wait_then_release();  // the gradient partials come from the kernel right before this one (common.cuh, PDL)
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
   const int64_t n4 = n >> 2;  // the flat buffer is padded to a multiple of 32 elements
@@ -203,8 +204,8 @@ int launch_adam_cast(float* params, const float* grads, int n_partials, int64_t 
     ct.dst[k] = w.dst; ct.dst_t[k] = w.dst_t;
     ct.in[k] = w.in; ct.pitch[k] = w.pitch; ct.pitch_t[k] = w.pitch_t;
   }
-  adam_cast_kernel<<<ew_grid(n / 4), 256, 0, st>>>(params, grads, n_partials, partial_stride, exp_avg, exp_avg_sq, n, seg_split,
-                                                  s0, s1, ct, lc);
+  B2_CUDA(launch_pdl(adam_cast_kernel, dim3(ew_grid(n / 4)), dim3(256), 0, st, params, grads, n_partials, partial_stride, exp_avg, exp_avg_sq, n, seg_split,
+                                                  s0, s1, ct, lc));
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }

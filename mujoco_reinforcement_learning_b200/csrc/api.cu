@@ -447,7 +447,8 @@ static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_b
       B2_TRY(tc_group_add(g, p, A, Bop, bn, 1));
     }
     int grid = 0;
-    PROF(ctx, B200PPO_PROF_GEMM_FWD, st, ws ? launch_tc_ws(g, st, &grid) : launch_tc_group(g, bn, st, &grid));
+    // layer 0 may directly follow the optimizer (its weights are then one kernel old): only deeper layers preload W
+    PROF(ctx, B200PPO_PROF_GEMM_FWD, st, ws ? launch_tc_ws(g, st, &grid, l > 0) : launch_tc_group(g, bn, st, &grid));
     if (fuse != nullptr && l == maxL - 1) fuse->loss_ctas = grid;
   }
   return B200PPO_OK;
@@ -489,7 +490,7 @@ static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t
       TcOperand Bop{bf.W[n][l], bf.pitchW[n][l], 1};  // W_l is [out = K][in = N]: an MN-major operand, no transposed copy
       B2_TRY(tc_group_add(g, p, A, Bop, bn, 1));
     }
-    PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, ws ? launch_tc_ws(g, st) : launch_tc_group(g, bn, st));
+    PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, ws ? launch_tc_ws(g, st, nullptr, true) : launch_tc_group(g, bn, st));
   }
   // every weight / bias gradient: dW_l = dZ_l^T [H_{l-1} | 1], both operands MN-major, split-K over the batch.
   // N tile: the width that wastes the least padded MMA work over all problems (N = in+1 is 257 / 377 for 256 / 376

@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <utility>
 
 #include "b200ppo.h"
 
@@ -51,6 +54,45 @@ inline int num_sms() {
       sms = 148;
   }
   return sms;
+}
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------------
+// The minibatch loop is a chain of short kernels (7 launches of 15-50 us at the bench shape, far less at small
+// minibatches), so launch latency and each kernel's set-up (barrier init, TMEM allocation, loading stationary weights)
+// are a visible share of the step.  Kernels of that chain are launched with the programmatic-serialization attribute:
+// a CTA of kernel n+1 may start as soon as every CTA of kernel n has passed pdl_wait_then_release(), i.e. while kernel
+// n is still draining, does its set-up, and blocks in griddepcontrol.wait until kernel n has completed and flushed.
+// Rules that keep this correct: (1) every kernel launched this way calls the wait before touching anything the
+// previous kernel wrote, and releases its dependents only AFTER its own wait — so when a CTA of kernel n+1 runs, kernel
+// n-1 and everything before it is complete; (2) before the wait a kernel may only READ data written two or more kernels
+// back (the stationary weights, except in the kernel right after the optimizer) and writes nothing global.
+inline bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("B200PPO_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// No-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_wait_then_release() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

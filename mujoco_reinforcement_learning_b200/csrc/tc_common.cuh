@@ -294,10 +294,15 @@ __device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {  // packed MUFU ta
 // BN/2 columns are one group of <= 64 columns = one 128-byte staging row per accumulator row, and every index
 // computation below is a compile-time constant or hoisted out of the loops (the first version spent ~900 warp
 // instructions per tile here and was the limiter of the persistent kernel).
-template <int BN>
+// TMA_OUT: the finished tile leaves through the copy engine (one cp.async.bulk.tensor store of the swizzled 32 x 64
+// tile per warp, tile 1024-byte aligned) instead of 8 LDS + 8 STG per lane; the caller guards the tile's reuse with
+// cp.async.bulk.wait_group.read.  Measured with profiles/mma_probe.cu: the LSU store path (32 B/clk/SM) serialises
+// behind the warps that issue it, the bulk store drains in the background.
+template <int BN, bool TMA_OUT = false>
 __device__ __forceinline__ void tc_epilogue_staged(const TcProblem& P, int split, uint32_t tmem_acc, bool has_k, int m0, int n0,
                                                    int warp, int lane, uint64_t* tmem_full_bar, uint32_t full_parity,
-                                                   uint8_t* stage, const float* bias_s, int aux_groups_in_flight) {
+                                                   uint8_t* stage, const float* bias_s, int aux_groups_in_flight,
+                                                   const CUtensorMap* tm_out = nullptr, long long* tr = nullptr) {
   static_assert(BN == 64 || BN == 128, "staged epilogue: BN <= 128");
   constexpr int WCOLS = BN / 2, STEPS = WCOLS / 16, UPR = WCOLS / 8, RSTEP = 32 / UPR;
   (void)split;
@@ -317,6 +322,7 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcProblem& P, int split
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   __syncwarp();
+  if (tr != nullptr) tr[0] = clock64();  // accumulator ready
   const float* bs = bias_s + col0;
   // (loading the whole 64-column slab with one tcgen05.ld.x64 and a single wait was measured: no gain, +70 registers)
 #pragma unroll
@@ -328,6 +334,7 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcProblem& P, int split
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0u;
     }
+    if (tr != nullptr && s < 4) tr[1 + s] = clock64();  // TMEM load of step s returned
     uint32_t o[8];
     if (epi == TC_EPI_FWD) {
       float z[16];
@@ -359,6 +366,18 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcProblem& P, int split
     }
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s) ^ sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s + 1) ^ sw) << 4)), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+  }
+  if (tr != nullptr) tr[5] = clock64();  // math + staging writes done
+  if constexpr (TMA_OUT) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy st.shared -> visible to the copy engine
+    __syncwarp();
+    if (lane == 0) {  // rows >= M and columns >= N are clipped by the tensor map
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm_out)),
+                   "r"(sbase), "r"(n0 + col0), "r"(mq)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    return;
   }
   __syncwarp();
   // staging -> global: UPR consecutive lanes write one row's 16-byte units (a full 128-byte line when UPR == 8)

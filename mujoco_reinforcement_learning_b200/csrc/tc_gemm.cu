@@ -16,6 +16,7 @@
 // Operands may be K-major or MN-major (UMMA descriptor major bits), so forward (X W^T), dgrad (dZ W via a
 // transposed bf16 weight copy) and wgrad (dZ^T X, both operands MN-major) share the kernel with no transposes
 // of activations.
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -70,8 +71,6 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   const int kt_end = min(total_kt, kt_begin + P.k_tiles_per_split);
   const bool has_k = kt_end > kt_begin;
 
-  tc_stage_bias(P, n0, BN, bias_s, threadIdx.x, TC_THREADS);
-  tc_ppo_stage_consts(P, consts_s, threadIdx.x);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -87,6 +86,12 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait_then_release();  // everything below reads what earlier kernels of the chain wrote
+  if (warp >= 2) {          // epilogue warps stage their constants (named barrier 1: the other two warps are already streaming)
+    tc_stage_bias(P, n0, BN, bias_s, threadIdx.x - 64, TC_THREADS - 64);
+    tc_ppo_stage_consts(P, consts_s, threadIdx.x - 64);
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS - 64) : "memory");
+  }
 
   if (warp == 0) {
     if (lane == 0 && has_k) {  // ===== TMA producer =====
@@ -187,7 +192,7 @@ int tc_init() {
   return B200PPO_OK;
 }
 
-static int make_map(CUtensorMap* out, const __nv_bfloat16* ptr, int64_t inner, int64_t outer, int64_t pitch, int box_inner,
+int tc_make_map(CUtensorMap* out, const __nv_bfloat16* ptr, int64_t inner, int64_t outer, int64_t pitch, int box_inner,
                     int box_outer) {
   B2_TRY(tc_init());
   auto key = std::make_tuple(static_cast<const void*>(ptr), inner, outer, pitch, box_inner, box_outer);
@@ -222,10 +227,10 @@ int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B
   B2_CHECK_ARG(g.count < kMaxTcProblems, "too many problems in one tensor-core group");
   p.a_mn_major = A.mn_major;
   p.b_mn_major = B.mn_major;
-  if (!A.mn_major) B2_TRY(make_map(&p.tmA, A.ptr, p.K, p.M, A.pitch, TC_BK, TC_BM));
-  else B2_TRY(make_map(&p.tmA, A.ptr, p.M, p.K, A.pitch, 64, TC_BK));
-  if (!B.mn_major) B2_TRY(make_map(&p.tmB, B.ptr, p.K, p.N, B.pitch, TC_BK, bn));
-  else B2_TRY(make_map(&p.tmB, B.ptr, p.N, p.K, B.pitch, 64, TC_BK));
+  if (!A.mn_major) B2_TRY(tc_make_map(&p.tmA, A.ptr, p.K, p.M, A.pitch, TC_BK, TC_BM));
+  else B2_TRY(tc_make_map(&p.tmA, A.ptr, p.M, p.K, A.pitch, 64, TC_BK));
+  if (!B.mn_major) B2_TRY(tc_make_map(&p.tmB, B.ptr, p.K, p.N, B.pitch, TC_BK, bn));
+  else B2_TRY(tc_make_map(&p.tmB, B.ptr, p.N, p.K, B.pitch, 64, TC_BK));
   const int total_kt = (p.K + TC_BK - 1) / TC_BK;
   if (split_k < 1) split_k = 1;
   if (split_k > total_kt) split_k = total_kt;
@@ -248,7 +253,7 @@ static int launch_bn(const TcGroup& g, cudaStream_t st) {
     B2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  tc_gemm_kernel<BN><<<g.total_tiles, TC_THREADS, smem, st>>>(g);
+  B2_CUDA(launch_pdl(tc_gemm_kernel<BN>, dim3(g.total_tiles), dim3(TC_THREADS), smem, st, g));
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }
@@ -290,6 +295,12 @@ __global__ void sum_splits_kernel(const float* __restrict__ part, int splits, in
   out[i] = s;
 }
 
+__global__ void bf16_rows_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int64_t rows, int64_t cols, int64_t pitch, float* __restrict__ dst) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  dst[i] = __bfloat162float(src[(i / cols) * pitch + i % cols]);
+}
+
 }  // namespace b200ppo
 
 using namespace b200ppo;
@@ -320,37 +331,53 @@ extern "C" B2_EXPORT int b200ppo_debug_tc_gemm(const float* A, const float* B, f
   p.M = M; p.N = N; p.K = K;
   p.epilogue = TC_EPI_STORE;
   p.out_f32 = part; p.ld_f32 = N; p.split_stride = stride; p.bias_col = -1;
-  const bool ws = bn < 0;  // bn = -1: the persistent weights-stationary kernel; bn = -2: same, plus a clock64 timeline
+  // bn = -1: the persistent weights-stationary kernel; bn = -2: its forward (tanh, bf16) epilogue plus a clock64 timeline;
+  // bn = -3: forward epilogue, C = float(tanh(A B^T) rounded to bf16) — the path the CTA-pair kernel takes for N > 128
+  const bool ws = bn < 0;
+  const bool fwd_check = bn == -3;
   long long* trace = nullptr;
-  if (bn == -2) {
+  if (bn == -2 || bn == -3) {
     p.epilogue = TC_EPI_FWD; p.act = B200PPO_ACT_TANH;  // the production forward epilogue, bf16 output
+    if (getenv("B200PPO_DEBUG_RELU") != nullptr) p.act = B200PPO_ACT_RELU;  // profiling: the epilogue without MUFU work
     p.out_f32 = nullptr;
     B2_CUDA(cudaMalloc(&p.out_bf16, size_t(M) * ((N + 7) / 8 * 8) * 2));
     p.ld_bf16 = (N + 7) / 8 * 8;
-    B2_CUDA(cudaMalloc(&trace, 64 * 8 * sizeof(long long)));
-    B2_CUDA(cudaMemset(trace, 0, 64 * 8 * sizeof(long long)));
-    g_ws_trace = trace;
+    if (bn == -2) {
+      B2_CUDA(cudaMalloc(&trace, 64 * 16 * sizeof(long long)));
+      B2_CUDA(cudaMemset(trace, 0, 64 * 16 * sizeof(long long)));
+      g_ws_trace = trace;
+    }
   }
   if (ws) bn = tc_ws_bn(N, K);
   int rc = tc_group_add(g, p, TcOperand{Ab, a_pitch, a_mn_major}, TcOperand{Bb, b_pitch, b_mn_major}, bn, split_k);
   if (rc == B200PPO_OK) rc = ws ? launch_tc_ws(g, st) : launch_tc_group(g, bn, st);
-  if (rc == B200PPO_OK) {
+  if (rc == B200PPO_OK && fwd_check) {
+    bf16_rows_to_f32_kernel<<<unsigned((mn + 255) / 256), 256, 0, st>>>(p.out_bf16, M, N, p.ld_bf16, C);
+    count_launch();
+  } else if (rc == B200PPO_OK) {
     sum_splits_kernel<<<unsigned((mn + 255) / 256), 256, 0, st>>>(part, g.p[0].split_k, stride, mn, C);
     count_launch();
   }
   cudaStreamSynchronize(st);
   if (trace != nullptr) {
-    long long h[64 * 8];
+    long long h[64 * 16];
     cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
     const long long t0 = h[0];
     fprintf(stderr, "WS timeline of CTA 0 (cycles since first issue): tile | prod_first prod_last | mma_acc_free mma_kb0 mma_kbN | epi_start epi_end(w2) epi_end(slowest)\n");
-    for (int t = 0; t < 64 && h[t * 8] != 0; ++t)
-      fprintf(stderr, "  %2d | %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld %7lld\n", t, h[t * 8] - t0, h[t * 8 + 1] - t0, h[t * 8 + 2] - t0,
-              h[t * 8 + 3] - t0, h[t * 8 + 4] - t0, h[t * 8 + 5] - t0, h[t * 8 + 6] - t0, h[t * 8 + 7] - t0);
+    for (int t = 0; t < 63 && h[t * 16] != 0; ++t) {
+      fprintf(stderr, "  %2d | %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld %7lld", t, h[t * 16] - t0, h[t * 16 + 1] - t0, h[t * 16 + 2] - t0,
+              h[t * 16 + 3] - t0, h[t * 16 + 4] - t0, h[t * 16 + 5] - t0, h[t * 16 + 6] - t0, h[t * 16 + 7] - t0);
+      // warp 2's epilogue phases: accumulator ready, the four TMEM loads returned, staging written
+      fprintf(stderr, " | %7lld %7lld %7lld %7lld %7lld %7lld\n", h[t * 16 + 8] - t0, h[t * 16 + 9] - t0, h[t * 16 + 10] - t0, h[t * 16 + 11] - t0,
+              h[t * 16 + 12] - t0, h[t * 16 + 13] - t0);
+    }
+    if (h[63 * 16] != 0)
+      fprintf(stderr, "  kernel entry %lld | set-up done %lld | W resident %lld | kernel end %lld\n", h[63 * 16] - t0, h[63 * 16 + 1] - t0,
+              h[63 * 16 + 2] - t0, h[63 * 16 + 3] - t0);
     g_ws_trace = nullptr;
     cudaFree(trace);
-    cudaFree(p.out_bf16);
   }
+  if (p.out_bf16 != nullptr) cudaFree(p.out_bf16);
   cudaFree(Ab); cudaFree(Bb); cudaFree(part);
   {
     std::lock_guard<std::mutex> lock(g_map_mutex);

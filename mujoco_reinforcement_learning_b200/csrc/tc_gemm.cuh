@@ -76,6 +76,8 @@ struct TcOperand {
   int mn_major;    // 0: array is [MN][K] (K contiguous); 1: array is [K][MN] (MN contiguous)
 };
 
+// 2-D bf16 tensor map with 128-byte swizzle over a [outer][pitch] array whose first `inner` columns are addressable (cached).
+int tc_make_map(CUtensorMap* out, const __nv_bfloat16* ptr, int64_t inner, int64_t outer, int64_t pitch, int box_inner, int box_outer);
 int tc_init();  // resolves cuTensorMapEncodeTiled; returns B200PPO_OK or an error
 // bn: N tile (64, 128 or 256).  Fills tensor maps (cached) and tile bookkeeping.
 int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B, int bn, int split_k);
@@ -85,6 +87,7 @@ int tc_ctas_per_sm(int bn);
 // Persistent weights-stationary variant (tc_ws.cu) for forward / dgrad groups with many row tiles.
 bool tc_ws_applicable(int64_t total_tiles_m, int maxN, int maxK);
 int tc_ws_bn(int maxN, int maxK);
-int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out = nullptr);  // resident CTAs per SM of the bn-wide kernel instance
+// w_early: the weights were last written two or more kernels back in the stream (never true right after the optimizer)
+int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out = nullptr, bool w_early = false);  // resident CTAs per SM of the bn-wide kernel instance
 
 }  // namespace b200ppo

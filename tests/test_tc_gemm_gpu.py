@@ -52,3 +52,29 @@ def test_tc_gemm_matches_torch(M, N, K, a_mn, b_mn, bn, split):
     err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
     assert torch.isfinite(C).all()
     assert err < 2e-5, f"scaled max error {err:.3e}"  # same bf16 operands, fp32 vs fp64 accumulation only
+
+
+FWD_CASES = [
+    # M, N, K — forward epilogue (tanh, bf16 bulk store); N > 128 takes the CTA-pair (cta_group::2) kernel
+    (40000, 256, 376),
+    (40000, 256, 256),
+    (32768, 256, 64),
+    (33000, 200, 130),    # ragged N and K, M not a multiple of 256
+    (40000, 128, 376),    # N <= 128: single-CTA kernel, bulk store
+    (513, 256, 256),      # fewer tiles than CTA pairs
+]
+
+
+@pytest.mark.parametrize("M,N,K", FWD_CASES)
+def test_ws_forward_epilogue_matches_torch(M, N, K):
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(M + N * 5 + K)
+    A = torch.randn((M, K), device=DEV, generator=g)
+    B = torch.randn((N, K), device=DEV, generator=g) / K ** 0.5
+    C = torch.full((M, N), float("nan"), device=DEV)
+    _lib.check(lib.b200ppo_debug_tc_gemm(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, 0, 0, -3, 1,
+                                         _lib.stream_ptr()), "debug_tc_gemm")
+    ref = torch.tanh(A.bfloat16().double() @ B.bfloat16().double().t())
+    assert torch.isfinite(C).all()
+    err = (C.double() - ref).abs().max().item()
+    assert err < 1e-2, f"max abs error {err:.3e}"  # bf16 output (2^-9 relative) + MUFU tanh (2^-11)
