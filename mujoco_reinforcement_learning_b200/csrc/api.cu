@@ -142,6 +142,8 @@ struct b200ppo_ctx {
     int pitchH[2][B200PPO_MAX_LAYERS] = {}, pitchZ[2][B200PPO_MAX_LAYERS] = {}, pitchW[2][B200PPO_MAX_LAYERS] = {};
     __nv_bfloat16* X = nullptr;      // [max_batch, pitchX] staged observations (grads-only entry point)
     __nv_bfloat16* sh_obs = nullptr; // [sh_cap, pitchX] shuffled observations of an epoch
+    __nv_bfloat16* obs_table = nullptr;  // [table_cap, pitchX] the whole rollout's observations as bf16 rows (+ ones-column)
+    int64_t table_cap = 0;
     int pitchX = 0;
     WeightCastGroup casts{};
   } bf;
@@ -736,7 +738,7 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   dev_free(c->err_flag);
   for (int n = 0; n < 2; ++n)
     for (int l = 0; l < B200PPO_MAX_LAYERS; ++l) { dev_free(c->bf.H[n][l]); dev_free(c->bf.dZ[n][l]); dev_free(c->bf.W[n][l]); dev_free(c->bf.WT[n][l]); }
-  dev_free(c->bf.X); dev_free(c->bf.sh_obs);
+  dev_free(c->bf.X); dev_free(c->bf.sh_obs); dev_free(c->bf.obs_table);
   dev_free(c->sh_obs); dev_free(c->sh_act); dev_free(c->sh_logp); dev_free(c->sh_adv); dev_free(c->sh_tgt);
   dev_free(c->host.obs); dev_free(c->host.act); dev_free(c->host.logp); dev_free(c->host.rew); dev_free(c->host.val);
   dev_free(c->host.nval); dev_free(c->host.adv); dev_free(c->host.tgt); dev_free(c->host.losses); dev_free(c->host.term);
@@ -883,9 +885,34 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
   const bool tc = ctx->precision == B200PPO_PREC_BF16;
   const int PX = ctx->bf.pitchX;
   if (tc) PROF(ctx, B200PPO_PROF_OTHER, st, cast_weights(ctx, params, st));
+  // Every epoch gathers nb*lb observation rows.  Converting on the fly reads 4D and writes 2*pitch bytes per row and
+  // epoch; converting the whole rollout ONCE and then gathering bf16 rows byte for byte (bulk-copy kernel) costs
+  // n_samples*(4D + 2*pitch) up front and 4*pitch per row and epoch.  Same bits either way.
+  bool table = false;
+  if (tc && PX % 8 == 0) {
+    const double direct = double(epochs) * double(nb * lb) * (4.0 * D + 2.0 * PX);
+    const double pre = double(n_samples) * (4.0 * D + 2.0 * PX) + double(epochs) * double(nb * lb) * 4.0 * PX;
+    table = pre < 0.9 * direct && nb * lb >= 4096;
+  }
+  if (table) {
+    if (n_samples > ctx->bf.table_cap) {
+      B2_CUDA(cudaDeviceSynchronize());
+      dev_free(ctx->bf.obs_table);
+      ctx->bf.table_cap = 0;
+      B2_TRY(dev_alloc(&ctx->bf.obs_table, n_samples * PX));
+      ctx->bf.table_cap = n_samples;
+    }
+    PROF(ctx, B200PPO_PROF_GATHER, st, launch_cast_rows_ones(obs, n_samples, D, ctx->bf.obs_table, PX, st));
+  }
   for (int e = 0; e < epochs; ++e) {
     // shuffled_memory = memory[idx] restricted to the rows this rank will consume
-    if (tc)
+    if (table)  // bf16 rows moved as PX/2 "floats" by the bulk-copy gather: a byte copy
+      PROF(ctx, B200PPO_PROF_GATHER, st,
+           launch_gather_chunked(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
+                                 reinterpret_cast<const float*>(ctx->bf.obs_table), PX / 2, action, A, old_logp, advantage, target,
+                                 reinterpret_cast<float*>(ctx->bf.sh_obs), ctx->sh_act, ctx->sh_logp, ctx->sh_adv, ctx->sh_tgt,
+                                 ctx->err_flag, st));
+    else if (tc)
       PROF(ctx, B200PPO_PROF_GATHER, st,
            launch_gather_chunked_bf16(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
                                       obs, D, action, A, old_logp, advantage, target, ctx->bf.sh_obs, PX, ctx->sh_act,

@@ -28,6 +28,25 @@ cast_rows_ones_kernel(const float* __restrict__ src, int64_t rows, int cols, __n
   }
 }
 
+// Vector path (cols and pitch multiples of 4, 16-byte aligned rows): one float4 in, four bf16 out per thread and step.
+__global__ void __launch_bounds__(256)
+cast_rows_ones_vec4_kernel(const float* __restrict__ src, int64_t rows, int cols, __nv_bfloat16* __restrict__ dst, int pitch) {
+  const int upr = pitch >> 2;  // 4-element units per output row
+  const int64_t total = rows * upr;
+  for (int64_t u = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; u < total; u += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = u / upr;
+    const int c = int(u - r * upr) << 2;
+    float4 v;
+    if (c < cols) v = ldg_stream4(src + r * cols + c);
+    else v = make_float4(c == cols ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 w;
+    w.x = *reinterpret_cast<const uint32_t*>(&lo);
+    w.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst + r * pitch + c) = w;
+  }
+}
+
 __global__ void __launch_bounds__(256) init_ones_column_kernel(__nv_bfloat16* __restrict__ dst, int64_t rows, int pitch, int col) {
   const int64_t total = rows * pitch;
   for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x)
@@ -45,6 +64,12 @@ int launch_cast_weights(const WeightCastGroup& g, cudaStream_t st) {
 
 int launch_cast_rows_ones(const float* src, int64_t rows, int cols, __nv_bfloat16* dst, int pitch, cudaStream_t st) {
   if (rows == 0) return B200PPO_OK;
+  if (cols % 4 == 0 && pitch % 4 == 0 && aligned16(src) && aligned16(dst)) {
+    const int64_t blocks = std::min<int64_t>((rows * (pitch / 4) + 255) / 256, 32 * num_sms());
+    cast_rows_ones_vec4_kernel<<<unsigned(blocks), 256, 0, st>>>(src, rows, cols, dst, pitch);
+    B2_LAUNCH_CHECK();
+    return B200PPO_OK;
+  }
   const int64_t blocks = std::min<int64_t>((rows * pitch + 255) / 256, 16 * num_sms());
   cast_rows_ones_kernel<<<unsigned(blocks), 256, 0, st>>>(src, rows, cols, dst, pitch);
   B2_LAUNCH_CHECK();

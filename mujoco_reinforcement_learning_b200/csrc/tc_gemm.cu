@@ -339,6 +339,13 @@ extern "C" B2_EXPORT int b200ppo_debug_tc_gemm(const float* A, const float* B, f
   if (bn == -2 || bn == -3) {
     p.epilogue = TC_EPI_FWD; p.act = B200PPO_ACT_TANH;  // the production forward epilogue, bf16 output
     if (getenv("B200PPO_DEBUG_RELU") != nullptr) p.act = B200PPO_ACT_RELU;  // profiling: the epilogue without MUFU work
+    if (getenv("B200PPO_DEBUG_DGRAD") != nullptr) {  // profiling: the dgrad epilogue (activation operand = the output buffer's twin)
+      p.epilogue = TC_EPI_DGRAD;
+      __nv_bfloat16* auxb = nullptr;
+      B2_CUDA(cudaMalloc(&auxb, size_t(M) * ((N + 7) / 8 * 8) * 2));
+      B2_CUDA(cudaMemset(auxb, 0x3c, size_t(M) * ((N + 7) / 8 * 8) * 2));
+      p.aux = auxb; p.ld_aux = (N + 7) / 8 * 8;
+    }
     p.out_f32 = nullptr;
     B2_CUDA(cudaMalloc(&p.out_bf16, size_t(M) * ((N + 7) / 8 * 8) * 2));
     p.ld_bf16 = (N + 7) / 8 * 8;
@@ -378,6 +385,7 @@ extern "C" B2_EXPORT int b200ppo_debug_tc_gemm(const float* A, const float* B, f
     cudaFree(trace);
   }
   if (p.out_bf16 != nullptr) cudaFree(p.out_bf16);
+  if (p.aux != nullptr) cudaFree(const_cast<__nv_bfloat16*>(p.aux));
   cudaFree(Ab); cudaFree(Bb); cudaFree(part);
   {
     std::lock_guard<std::mutex> lock(g_map_mutex);
