@@ -498,6 +498,29 @@ static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t
   // N tile: the width that wastes the least padded MMA work over all problems (N = in+1 is 257 / 377 for 256 / 376
   // inputs: 192-wide tiles cover both in two tiles where 128-wide ones need three); split-K: as many splits as fill
   // ONE wave of resident CTAs — one CTA more than a wave would double the kernel's duration.
+  static const char* wg_mode = getenv("B200PPO_WGRAD");  // profiling switch: "tile" keeps the one-tile kernel
+  const int n_problems = ctx->net[0].d.n_layers + ctx->net[1].d.n_layers;
+  if (B >= 2048 && n_problems <= kMaxTcProblems && !(wg_mode != nullptr && wg_mode[0] == 't')) {
+    // CTA pairs: 256 x 256 output blocks, bias gradient from a ones-tile MMA (tc_wgrad.cu)
+    TcGroup g{};
+    for (int n = 0; n < 2; ++n) {
+      const Net& N = ctx->net[n];
+      for (int l = 0; l < N.d.n_layers; ++l) {
+        TcProblem p{};
+        p.M = N.d.dims[l]; p.N = N.in_dim(l); p.K = int(B);
+        p.epilogue = TC_EPI_STORE;
+        p.out_f32 = gpart + N.w_off[l]; p.ld_f32 = N.in_dim(l); p.split_stride = ctx->n_params;
+        p.bias_grad = gpart + N.b_off[l]; p.bias_col = -1;
+        TcOperand A{bf.dZ[n][l], bf.pitchZ[n][l], 1};
+        TcOperand Bop{l == 0 ? xb : bf.H[n][l - 1], l == 0 ? bf.pitchX : bf.pitchH[n][l - 1], 1};
+        B2_TRY(tc_group_add(g, p, A, Bop, 128, 1));
+      }
+    }
+    int split = 1;
+    PROF(ctx, B200PPO_PROF_GEMM_WGRAD, st, launch_tc_wgrad2(g, ctx->max_split, st, &split));
+    if (split_out) *split_out = split;
+    return B200PPO_OK;
+  }
   int bn = 64;
   {
     int maxN = 0;

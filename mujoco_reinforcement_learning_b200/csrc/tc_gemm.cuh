@@ -90,4 +90,8 @@ int tc_ws_bn(int maxN, int maxK);
 // w_early: the weights were last written two or more kernels back in the stream (never true right after the optimizer)
 int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out = nullptr, bool w_early = false);  // resident CTAs per SM of the bn-wide kernel instance
 
+// CTA-pair weight-gradient kernel (tc_wgrad.cu): every problem MN-major x MN-major with fp32 split-K partials; N is the
+// layer's input width without a ones-column, the bias gradient comes from a second MMA against a tile of ones.
+int launch_tc_wgrad2(const TcGroup& g, int max_split, cudaStream_t st, int* split_out);
+
 }  // namespace b200ppo
