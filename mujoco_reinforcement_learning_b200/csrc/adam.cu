@@ -95,9 +95,22 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
   const bool lc_owner = lc.partials != nullptr && int64_t(blockIdx.x) == ((lc.logstd_off >> 2) / blockDim.x) % gridDim.x;
   if (lc_owner) combine_losses(lc, s_lc, s_scr);
   for (int64_t i = tid; i < n4; i += nthreads) {
+    // every load of this element is issued before the first use: the kernel is one L2 round trip deep, not n_partials
+    const float4 p0 = *reinterpret_cast<float4*>(params + 4 * i);
+    const float4 m0 = *reinterpret_cast<float4*>(exp_avg + 4 * i);
+    const float4 v0 = *reinterpret_cast<float4*>(exp_avg_sq + 4 * i);
     float4 g = *reinterpret_cast<const float4*>(grads + 4 * i);
-    for (int k = 1; k < n_partials; ++k) {
-      const float4 h = *reinterpret_cast<const float4*>(grads + k * partial_stride + 4 * i);
+    int k0 = 1;
+    for (; k0 + 3 < n_partials; k0 += 4) {  // partials are added in index order (deterministic)
+      const float4 h0 = *reinterpret_cast<const float4*>(grads + (k0 + 0) * partial_stride + 4 * i);
+      const float4 h1 = *reinterpret_cast<const float4*>(grads + (k0 + 1) * partial_stride + 4 * i);
+      const float4 h2 = *reinterpret_cast<const float4*>(grads + (k0 + 2) * partial_stride + 4 * i);
+      const float4 h3 = *reinterpret_cast<const float4*>(grads + (k0 + 3) * partial_stride + 4 * i);
+      g.x = (((g.x + h0.x) + h1.x) + h2.x) + h3.x; g.y = (((g.y + h0.y) + h1.y) + h2.y) + h3.y;
+      g.z = (((g.z + h0.z) + h1.z) + h2.z) + h3.z; g.w = (((g.w + h0.w) + h1.w) + h2.w) + h3.w;
+    }
+    for (; k0 < n_partials; ++k0) {
+      const float4 h = *reinterpret_cast<const float4*>(grads + k0 * partial_stride + 4 * i);
       g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
     }
     if (lc_owner && 4 * i + 3 >= lc.logstd_off && 4 * i < lc.logstd_off + lc.act_dim) {
@@ -107,9 +120,7 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
       if (r + 2 >= 0 && r + 2 < lc.act_dim) g.z = s_lc[2 + r + 2];
       if (r + 3 >= 0 && r + 3 < lc.act_dim) g.w = s_lc[2 + r + 3];
     }
-    float4 p = *reinterpret_cast<float4*>(params + 4 * i);
-    float4 m = *reinterpret_cast<float4*>(exp_avg + 4 * i);
-    float4 v = *reinterpret_cast<float4*>(exp_avg_sq + 4 * i);
+    float4 p = p0, m = m0, v = v0;
     const int64_t e = 4 * i;
     adam_update(p.x, g.x, m.x, v.x, e + 0 < seg_split ? s0 : s1);
     adam_update(p.y, g.y, m.y, v.y, e + 1 < seg_split ? s0 : s1);
@@ -124,7 +135,16 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
 #pragma unroll 1
     for (int c = 0; c < ct.count; ++c)
       if (e >= ct.begin[c] && e < ct.end[c]) k = c;
-    if (k >= 0) {
+    if (k >= 0 && ct.dst_t[k] == nullptr && (ct.in[k] & 3) == 0 && (ct.pitch[k] & 3) == 0 && e + 3 < ct.end[k]) {
+      // whole float4 inside one row (rows are multiples of 4 wide): one 32-bit division, one 8-byte store
+      const uint32_t in = uint32_t(ct.in[k]), rel = uint32_t(e - ct.begin[k]);
+      const uint32_t o = rel / in, c2 = rel - o * in;
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+      uint2 w;
+      w.x = *reinterpret_cast<const uint32_t*>(&lo);
+      w.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(ct.dst[k] + int64_t(o) * ct.pitch[k] + c2) = w;
+    } else if (k >= 0) {
       const float pv[4] = {p.x, p.y, p.z, p.w};
       const int in = ct.in[k];
       const int64_t rel = e - ct.begin[k];

@@ -343,6 +343,7 @@ static int backward_nets(b200ppo_ctx* ctx, const float* params, const float* x, 
 
 
 static inline int pad8(int x) { return (x + 7) / 8 * 8; }
+static inline int pad16(int x) { return (x + 15) / 16 * 16; }  // rows that start on 32-byte sectors (256-bit loads / stores)
 
 // bf16 operands of the tensor-core path.  Every Linear of both nets runs on tcgen05 (the 17- and 1-wide output
 // layers too: a mostly-empty 128x64 tile costs less than a latency-bound SIMT pass).
@@ -363,7 +364,7 @@ static int alloc_bf16_workspaces(b200ppo_ctx* c) {
       bf.pitchZ[n][l] = pad8(N.d.dims[l]);
       bf.pitchW[n][l] = pad8(N.in_dim(l));
       if (!last) {  // hidden activation with the ones-column the wgrad reads the bias gradient from
-        bf.pitchH[n][l] = pad8(N.d.dims[l] + 1);
+        bf.pitchH[n][l] = pad16(N.d.dims[l] + 1);
         B2_TRY(dev_alloc(&bf.H[n][l], Bm * bf.pitchH[n][l]));
         B2_TRY(launch_init_ones_column(bf.H[n][l], Bm, bf.pitchH[n][l], N.d.dims[l], nullptr));
       }

@@ -322,6 +322,30 @@ __device__ __forceinline__ void ws2_finish16(const uint32_t (&v)[16], const floa
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s + 1) ^ sw) << 4)), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
 }
 
+// 256-bit global accesses (one full 32-byte sector per thread): the dgrad epilogue of the pair kernel reads its
+// activation row and writes its result row straight from registers — no staging tile, so shared memory is left to the
+// operands (W half + a deep A ring) and the epilogue does not compete with the MMAs for shared-memory bandwidth.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// dz = acc * act'(h) for 16 columns of this thread's row; h: 16 bf16 activations (8 words)
+__device__ __forceinline__ void ws2_dgrad16(const uint32_t (&v)[16], const uint32_t (&h)[8], int act, uint32_t (&o)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float h0 = __uint_as_float(h[j] << 16), h1 = __uint_as_float(h[j] & 0xFFFF0000u);
+    const float g0 = __uint_as_float(v[2 * j]), g1 = __uint_as_float(v[2 * j + 1]);
+    if (act == B200PPO_ACT_TANH) o[j] = pack_bf16(g0 * (1.f - h0 * h0), g1 * (1.f - h1 * h1));
+    else o[j] = pack_bf16(h0 > 0.f ? g0 : 0.f, h1 > 0.f ? g1 : 0.f);
+  }
+}
+
 constexpr int WS2_EPI_WARPS = 16;  // four per TMEM lane quarter, one 64-column chunk each: MUFU.TANH (16/clk/SM) is the epilogue's
                                    // floor, and two lock-stepped warps per scheduler left it half idle
 constexpr int WS2_THREADS = (2 + WS2_EPI_WARPS) * 32;
@@ -458,6 +482,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS2_THREADS, 1) tc_w
     const int col0 = chunk * 64;
     const float* bs = bias_s + col0;
     int t = 0, tile_i = 0;
+    if (P.epilogue == TC_EPI_DGRAD) {  // direct: activation row in, result row out, 32 bytes per access (rows are 32-byte aligned)
+      const bool cols_ok = n0 + col0 + 64 <= P.N;
+      for (int tile = pair_local; tile < tiles2; tile += pairs, ++t) {
+        const int buf = t & 1;
+        const int m = tile * 2 * TC_BM + int(rank) * TC_BM + q * 32 + lane;
+        const bool row_ok = m < P.M;
+        const __nv_bfloat16* arow = P.aux + int64_t(row_ok ? m : 0) * P.ld_aux + n0 + col0;
+        __nv_bfloat16* orow = P.out_bf16 + int64_t(row_ok ? m : 0) * P.ld_bf16 + n0 + col0;
+        uint32_t ax[4][8];
+        if (cols_ok) {  // requested before the accumulator is awaited: the latency hides behind the MMAs
+#pragma unroll
+          for (int sidx = 0; sidx < 4; ++sidx) ldg256(arow + sidx * 16, ax[sidx]);
+        } else {
+#pragma unroll
+          for (int sidx = 0; sidx < 4; ++sidx)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = n0 + col0 + sidx * 16 + 2 * j;
+              const uint32_t lo = c < P.N ? uint32_t(__bfloat16_as_ushort(arow[sidx * 16 + 2 * j])) : 0u;
+              const uint32_t hi = c + 1 < P.N ? uint32_t(__bfloat16_as_ushort(arow[sidx * 16 + 2 * j + 1])) : 0u;
+              ax[sidx][j] = lo | (hi << 16);
+            }
+        }
+        const uint32_t tcol = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN + col0);
+        mbar_wait(&acc_full[buf], uint32_t((t >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        __syncwarp();
+        uint32_t va[16], vb[16], o[8];
+        auto emit = [&](int sidx) {
+          if (!row_ok) return;
+          if (cols_ok) {
+            stg256(orow + sidx * 16, o);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = n0 + col0 + sidx * 16 + 2 * j;
+              if (c < P.N) orow[sidx * 16 + 2 * j] = __ushort_as_bfloat16(uint16_t(o[j] & 0xFFFFu));
+              if (c + 1 < P.N) orow[sidx * 16 + 2 * j + 1] = __ushort_as_bfloat16(uint16_t(o[j] >> 16));
+            }
+          }
+        };
+        tmem_ld16_nowait(tcol, va);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld16_nowait(tcol + 16, vb);
+        ws2_dgrad16(va, ax[0], act, o); emit(0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld16_nowait(tcol + 32, va);
+        ws2_dgrad16(vb, ax[1], act, o); emit(1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld16_nowait(tcol + 48, vb);
+        ws2_dgrad16(va, ax[2], act, o); emit(2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty[buf]) : "memory");
+        ws2_dgrad16(vb, ax[3], act, o); emit(3);
+      }
+    } else
     for (int tile = pair_local; tile < tiles2; tile += pairs, ++t) {
       const int buf = t & 1;
       const int mq = tile * 2 * TC_BM + int(rank) * TC_BM + q * 32;
@@ -604,11 +686,17 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
   ws_plan(maxN, maxK, kind, &bn, &stages, &stage_tiles, tc_ws_bn(maxN, maxK));
   // CTA pairs with 256-wide MMAs for wide forward layers (every problem N > 128, operands built for 128-row boxes)
   static const char* pair_mode = getenv("B200PPO_WS_PAIR");  // profiling switch: "0" keeps the single-CTA kernel
-  bool pair = kind == 0 && bn == 128 && !(pair_mode != nullptr && pair_mode[0] == '0');
-  for (int i = 0; i < g.count; ++i) pair = pair && g.p[i].N > 128 && g.p[i].tiles_m >= 2;
+  bool pair = (kind == 0 || kind == 1) && bn == 128 && !(pair_mode != nullptr && pair_mode[0] == '0');
+  for (int i = 0; i < g.count; ++i) {
+    const TcProblem& q = g.p[i];
+    pair = pair && q.N > 128 && q.tiles_m >= 2;
+    if (kind == 1)  // every problem a dgrad whose rows start on 32-byte sectors (direct 256-bit epilogue)
+      pair = pair && q.epilogue == TC_EPI_DGRAD && q.out_bf16 != nullptr && q.aux != nullptr && q.ld_bf16 % 16 == 0 && q.ld_aux % 16 == 0 &&
+             (reinterpret_cast<uintptr_t>(q.out_bf16) & 31u) == 0 && (reinterpret_cast<uintptr_t>(q.aux) & 31u) == 0;
+  }
   const int pair_kb = (maxK + TC_BK - 1) / TC_BK;
   int pair_stages = 0;
-  const int pair_tiles = 1;  // one staging tile per epilogue warp: its bulk store has a whole row tile to drain
+  const int pair_tiles = kind == 1 ? 0 : 1;  // forward: one staging tile per epilogue warp (its bulk store has a whole row tile to drain)
   if (pair) {
     const int64_t avail = kWsMaxSmem - ws2_fixed_smem(pair_tiles) - int64_t(pair_kb) * 128 * TC_BK * 2;
     pair_stages = int(std::min<int64_t>(8, avail / TC_A_BYTES));
@@ -625,8 +713,10 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
     for (int i = 0; i < g.count; ++i) {
       const TcProblem& q = g.p[i];
       w.p[i] = q;
-      B2_TRY(tc_make_map(&w.tm_out[i], q.out_bf16, q.N, q.M, q.ld_bf16, 64, 32));
-      w.tma_out[i] = 1;
+      if (kind == 0) {
+        B2_TRY(tc_make_map(&w.tm_out[i], q.out_bf16, q.N, q.M, q.ld_bf16, 64, 32));
+        w.tma_out[i] = 1;
+      }
       for (int n0 = 0; n0 < q.N; n0 += 256) {
         w.slot_prob[w.n_slots] = i;
         w.slot_n0[w.n_slots] = n0;
