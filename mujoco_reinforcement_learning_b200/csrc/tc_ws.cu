@@ -302,7 +302,8 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
 }
 
 // 16 accumulator columns of this thread's row -> bias + activation -> bf16 -> two swizzled 16-byte units of the row
-__device__ __forceinline__ void ws2_finish16(const uint32_t (&v)[16], const float* bs, int act, uint32_t my_row, int sw, int s) {
+// 16 accumulator columns of this thread's row -> bias + activation -> 16 bf16 (8 words)
+__device__ __forceinline__ void ws2_act16(const uint32_t (&v)[16], const float* bs, int act, uint32_t (&o)[8]) {
   float z[16];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
@@ -310,7 +311,6 @@ __device__ __forceinline__ void ws2_finish16(const uint32_t (&v)[16], const floa
     z[u * 4] = __uint_as_float(v[u * 4]) + t.x; z[u * 4 + 1] = __uint_as_float(v[u * 4 + 1]) + t.y;
     z[u * 4 + 2] = __uint_as_float(v[u * 4 + 2]) + t.z; z[u * 4 + 3] = __uint_as_float(v[u * 4 + 3]) + t.w;
   }
-  uint32_t o[8];
   if (act == B200PPO_ACT_TANH) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = tanh_bf16x2(pack_bf16(z[2 * j], z[2 * j + 1]));
@@ -318,6 +318,11 @@ __device__ __forceinline__ void ws2_finish16(const uint32_t (&v)[16], const floa
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = pack_bf16(fmaxf(z[2 * j], 0.f), fmaxf(z[2 * j + 1], 0.f));
   }
+}
+// ... into two swizzled 16-byte units of the row's staging line
+__device__ __forceinline__ void ws2_finish16(const uint32_t (&v)[16], const float* bs, int act, uint32_t my_row, int sw, int s) {
+  uint32_t o[8];
+  ws2_act16(v, bs, act, o);
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s) ^ sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s + 1) ^ sw) << 4)), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
 }
@@ -539,6 +544,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS2_THREADS, 1) tc_w
         if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty[buf]) : "memory");
         ws2_dgrad16(vb, ax[3], act, o); emit(3);
       }
+    } else if (grp.tma_out[pidx] == 0) {  // forward, direct: 32-byte row segments from registers (rows 32-byte aligned, whole chunk < N)
+      for (int tile = pair_local; tile < tiles2; tile += pairs, ++t) {
+        const int buf = t & 1;
+        const int m = tile * 2 * TC_BM + int(rank) * TC_BM + q * 32 + lane;
+        const bool row_ok = m < P.M;
+        __nv_bfloat16* orow = P.out_bf16 + int64_t(row_ok ? m : 0) * P.ld_bf16 + n0 + col0;
+        const uint32_t tcol = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN + col0);
+        mbar_wait(&acc_full[buf], uint32_t((t >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        __syncwarp();
+        uint32_t va[16], vb[16], o[8];
+        tmem_ld16_nowait(tcol, va);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld16_nowait(tcol + 16, vb);
+        ws2_act16(va, bs, act, o);
+        if (row_ok) stg256(orow, o);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld16_nowait(tcol + 32, va);
+        ws2_act16(vb, bs + 16, act, o);
+        if (row_ok) stg256(orow + 16, o);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld16_nowait(tcol + 48, vb);
+        ws2_act16(va, bs + 32, act, o);
+        if (row_ok) stg256(orow + 32, o);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty[buf]) : "memory");
+        ws2_act16(vb, bs + 48, act, o);
+        if (row_ok) stg256(orow + 48, o);
+      }
     } else
     for (int tile = pair_local; tile < tiles2; tile += pairs, ++t) {
       const int buf = t & 1;
@@ -696,7 +732,13 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
   }
   const int pair_kb = (maxK + TC_BK - 1) / TC_BK;
   int pair_stages = 0;
-  const int pair_tiles = kind == 1 ? 0 : 1;  // forward: one staging tile per epilogue warp (its bulk store has a whole row tile to drain)
+  // forward epilogue: 256-bit stores straight from registers when every row segment is a whole, aligned 32-byte sector
+  // (measured 3% faster than staging + bulk store, and the staging tiles' shared memory goes to the A ring instead)
+  static const char* fwd_mode = getenv("B200PPO_WS_FWD");  // profiling switch: "tma" keeps the staged bulk-store epilogue
+  bool fwd_direct = kind == 0 && !(fwd_mode != nullptr && fwd_mode[0] == 't');
+  for (int i = 0; i < g.count; ++i)
+    fwd_direct = fwd_direct && g.p[i].N % 64 == 0 && g.p[i].ld_bf16 % 16 == 0 && (reinterpret_cast<uintptr_t>(g.p[i].out_bf16) & 31u) == 0;
+  const int pair_tiles = (kind == 1 || fwd_direct) ? 0 : 1;  // staged forward: one tile per epilogue warp (a whole row tile to drain)
   if (pair) {
     const int64_t avail = kWsMaxSmem - ws2_fixed_smem(pair_tiles) - int64_t(pair_kb) * 128 * TC_BK * 2;
     pair_stages = int(std::min<int64_t>(8, avail / TC_A_BYTES));
@@ -714,8 +756,8 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
       const TcProblem& q = g.p[i];
       w.p[i] = q;
       if (kind == 0) {
-        B2_TRY(tc_make_map(&w.tm_out[i], q.out_bf16, q.N, q.M, q.ld_bf16, 64, 32));
-        w.tma_out[i] = 1;
+        if (!fwd_direct) B2_TRY(tc_make_map(&w.tm_out[i], q.out_bf16, q.N, q.M, q.ld_bf16, 64, 32));
+        w.tma_out[i] = fwd_direct ? 0 : 1;
       }
       for (int n0 = 0; n0 < q.N; n0 += 256) {
         w.slot_prob[w.n_slots] = i;
