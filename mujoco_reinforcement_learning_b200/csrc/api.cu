@@ -123,8 +123,11 @@ struct b200ppo_ctx {
   float* scratch = nullptr;     // [8] losses / entropy scratch
   int32_t* err_flag = nullptr;
   // shuffled-epoch buffers (train)
+  // two sets (rows [0, sh_cap) and [sh_cap, 2 sh_cap)): epoch e+1 is gathered on a side stream while epoch e trains
   float *sh_obs = nullptr, *sh_act = nullptr, *sh_logp = nullptr, *sh_adv = nullptr, *sh_tgt = nullptr;
   int64_t sh_cap = 0;
+  cudaStream_t gather_stream = nullptr;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
   // device staging of the host entry point
   struct {
     float *obs = nullptr, *act = nullptr, *logp = nullptr, *rew = nullptr, *val = nullptr, *nval = nullptr;
@@ -682,13 +685,21 @@ static int ensure_shuffle_capacity(b200ppo_ctx* ctx, int64_t rows) {
   dev_free(ctx->bf.sh_obs);
   ctx->sh_cap = 0;
   const int D = ctx->net[0].d.in_dim, A = ctx->net[0].out_dim();
-  if (ctx->precision == B200PPO_PREC_BF16) B2_TRY(dev_alloc(&ctx->bf.sh_obs, rows * ctx->bf.pitchX));
-  else B2_TRY(dev_alloc(&ctx->sh_obs, rows * D));
-  B2_TRY(dev_alloc(&ctx->sh_act, rows * A));
-  B2_TRY(dev_alloc(&ctx->sh_logp, rows));
-  B2_TRY(dev_alloc(&ctx->sh_adv, rows));
-  B2_TRY(dev_alloc(&ctx->sh_tgt, rows));
+  if (ctx->precision == B200PPO_PREC_BF16) B2_TRY(dev_alloc(&ctx->bf.sh_obs, 2 * rows * ctx->bf.pitchX));
+  else B2_TRY(dev_alloc(&ctx->sh_obs, 2 * rows * D));
+  B2_TRY(dev_alloc(&ctx->sh_act, 2 * rows * A));
+  B2_TRY(dev_alloc(&ctx->sh_logp, 2 * rows));
+  B2_TRY(dev_alloc(&ctx->sh_adv, 2 * rows));
+  B2_TRY(dev_alloc(&ctx->sh_tgt, 2 * rows));
   ctx->sh_cap = rows;
+  if (ctx->gather_stream == nullptr) {
+    B2_CUDA(cudaStreamCreateWithFlags(&ctx->gather_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      B2_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+      B2_CUDA(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+    }
+    B2_CUDA(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+  }
   return B200PPO_OK;
 }
 
@@ -767,6 +778,11 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   dev_free(c->host.obs); dev_free(c->host.act); dev_free(c->host.logp); dev_free(c->host.rew); dev_free(c->host.val);
   dev_free(c->host.nval); dev_free(c->host.adv); dev_free(c->host.tgt); dev_free(c->host.losses); dev_free(c->host.term);
   dev_free(c->host.perms);
+  if (c->gather_stream) {
+    cudaStreamDestroy(c->gather_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_ready[i]); cudaEventDestroy(c->ev_free[i]); }
+    cudaEventDestroy(c->ev_start);
+  }
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   delete c;
 }
@@ -928,26 +944,48 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
     }
     PROF(ctx, B200PPO_PROF_GATHER, st, launch_cast_rows_ones(obs, n_samples, D, ctx->bf.obs_table, PX, st));
   }
-  for (int e = 0; e < epochs; ++e) {
-    // shuffled_memory = memory[idx] restricted to the rows this rank will consume
+  // shuffled_memory = memory[idx] restricted to the rows this rank will consume (ppo.py:103-106).  The permutations are
+  // known up front, so the gather of epoch e + 1 runs on a side stream into the other buffer set while epoch e trains:
+  // the update kernels are latency-bound and leave HBM idle, the copy engine work hides behind them.
+  const bool overlap = epochs > 1 && !ctx->prof.on;
+  const int64_t cap = ctx->sh_cap;
+  auto gather_epoch = [&](int e, int set, cudaStream_t gs) -> int {
+    const int64_t o = int64_t(set) * cap;
+    const int64_t* idx = perms + int64_t(e) * n_samples;
     if (table)  // bf16 rows moved as PX/2 "floats" by the bulk-copy gather: a byte copy
-      PROF(ctx, B200PPO_PROF_GATHER, st,
-           launch_gather_chunked(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
-                                 reinterpret_cast<const float*>(ctx->bf.obs_table), PX / 2, action, A, old_logp, advantage, target,
-                                 reinterpret_cast<float*>(ctx->bf.sh_obs), ctx->sh_act, ctx->sh_logp, ctx->sh_adv, ctx->sh_tgt,
-                                 ctx->err_flag, st));
-    else if (tc)
-      PROF(ctx, B200PPO_PROF_GATHER, st,
-           launch_gather_chunked_bf16(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
-                                      obs, D, action, A, old_logp, advantage, target, ctx->bf.sh_obs, PX, ctx->sh_act,
-                                      ctx->sh_logp, ctx->sh_adv, ctx->sh_tgt, ctx->err_flag, st));
-    else
-      PROF(ctx, B200PPO_PROF_GATHER, st,
-           launch_gather_chunked(perms + int64_t(e) * n_samples, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
-                                 obs, D, action, A, old_logp, advantage, target, ctx->sh_obs, ctx->sh_act, ctx->sh_logp,
-                                 ctx->sh_adv, ctx->sh_tgt, ctx->err_flag, st));
+      return launch_gather_chunked(idx, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
+                                   reinterpret_cast<const float*>(ctx->bf.obs_table), PX / 2, action, A, old_logp, advantage, target,
+                                   reinterpret_cast<float*>(ctx->bf.sh_obs + o * PX), ctx->sh_act + o * A, ctx->sh_logp + o,
+                                   ctx->sh_adv + o, ctx->sh_tgt + o, ctx->err_flag, gs);
+    if (tc)
+      return launch_gather_chunked_bf16(idx, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb, obs, D, action, A, old_logp,
+                                        advantage, target, ctx->bf.sh_obs + o * PX, PX, ctx->sh_act + o * A, ctx->sh_logp + o,
+                                        ctx->sh_adv + o, ctx->sh_tgt + o, ctx->err_flag, gs);
+    return launch_gather_chunked(idx, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb, obs, D, action, A, old_logp, advantage,
+                                 target, ctx->sh_obs + o * D, ctx->sh_act + o * A, ctx->sh_logp + o, ctx->sh_adv + o, ctx->sh_tgt + o,
+                                 ctx->err_flag, gs);
+  };
+  if (overlap) {
+    B2_CUDA(cudaEventRecord(ctx->ev_start, st));  // the rollout (and the bf16 table) are complete on the caller's stream
+    B2_CUDA(cudaStreamWaitEvent(ctx->gather_stream, ctx->ev_start, 0));
+    B2_TRY(gather_epoch(0, 0, ctx->gather_stream));
+    B2_CUDA(cudaEventRecord(ctx->ev_ready[0], ctx->gather_stream));
+  }
+  for (int e = 0; e < epochs; ++e) {
+    const int set = overlap ? (e & 1) : 0;
+    if (overlap) {
+      if (e + 1 < epochs) {
+        if (e >= 1) B2_CUDA(cudaStreamWaitEvent(ctx->gather_stream, ctx->ev_free[(e + 1) & 1], 0));  // epoch e-1 is done with that set
+        B2_TRY(gather_epoch(e + 1, (e + 1) & 1, ctx->gather_stream));
+        B2_CUDA(cudaEventRecord(ctx->ev_ready[(e + 1) & 1], ctx->gather_stream));
+      }
+      B2_CUDA(cudaStreamWaitEvent(st, ctx->ev_ready[set], 0));
+    } else {
+      PROF(ctx, B200PPO_PROF_GATHER, st, gather_epoch(e, 0, st));
+    }
+    const int64_t so = int64_t(set) * cap;
     for (int64_t i = 0; i < nb; ++i) {
-      const int64_t r0 = i * lb;
+      const int64_t r0 = so + i * lb;
       float* loss_slot = losses_out ? losses_out + (int64_t(e) * nb + i) * 2 : ctx->scratch;
       int split = 1, loss_ctas = 0;
       ++step;
@@ -994,6 +1032,7 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
         B2_LAUNCH_CHECK();
       }
     }
+    if (overlap) B2_CUDA(cudaEventRecord(ctx->ev_free[set], st));
   }
   *adam_step_io = step;
   return B200PPO_OK;

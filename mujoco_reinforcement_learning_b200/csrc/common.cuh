@@ -132,8 +132,16 @@ __device__ __forceinline__ float combine_partials(const float* partials, unsigne
   if (c < width && part < PARTS) {
     const unsigned per = (n_cta + PARTS - 1) / PARTS;
     const unsigned k0 = part * per, k1 = min(n_cta, k0 + per);
-#pragma unroll 4
-    for (unsigned k = k0; k < k1; ++k) s += __ldcg(partials + size_t(k) * width + c);
+    // 16 independent L2 loads in flight per thread: the owner block sits on the optimizer kernel's critical path
+    unsigned k = k0;
+    for (; k + 16 <= k1; k += 16) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __ldcg(partials + size_t(k + j) * width + c);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s += v[j];
+    }
+    for (; k < k1; ++k) s += __ldcg(partials + size_t(k) * width + c);
   }
   s_scratch[tid] = s;
   __syncthreads();
