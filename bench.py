@@ -400,7 +400,13 @@ def run_b200(args, config):
         if k in prof and prof[k]["ms"] > 0:
             prof[k]["TFLOPs"] = fl[key] * lb_rows / (prof[k]["ms"] * 1e-3) / 1e12
     if "gather" in prof and prof["gather"]["ms"] > 0:
-        by = (2 * (4 * OBS_DIM + 4 * ACT_DIM + 12) + 8) * (E * nb * B)
+        if args.precision == "bf16":
+            # one fp32 -> bf16 conversion of the whole rollout (rows of PX = 384 bf16), then per epoch a byte gather of bf16
+            # rows plus the fp32 leaves and the int64 index
+            PX = (OBS_DIM + 1 + 7) // 8 * 8
+            by = M_local * (4 * OBS_DIM + 2 * PX) + (2 * (2 * PX + 4 * ACT_DIM + 12) + 8) * (E * nb * B)
+        else:
+            by = (2 * (4 * OBS_DIM + 4 * ACT_DIM + 12) + 8) * (E * nb * B)
         prof["gather"]["GBps"] = by / 1e9 / (prof["gather"]["ms"] * 1e-3)
         prof["gather"]["frac_hbm"] = prof["gather"]["GBps"] / pk["hbm"]
     roofline = {"kernel": "gemm_group_kernel (actor+critic MLP forward/dgrad/wgrad, fp32 FFMA)" if args.precision == "fp32"
@@ -410,7 +416,7 @@ def run_b200(args, config):
                 # DRAM bytes of the six GEMM launches of ONE 32768-row minibatch (sum of dram__bytes_read+write over
                 # profiles/r01_ncu_tc_kernels_B32768.csv); the HBM floor of the update is 1584 B/sample = 52 MB: the
                 # excess is activations crossing HBM between the per-layer kernels
-                "traffic": 381.5e6 if (args.precision == "bf16" and B == 32768) else None,
+                "traffic": 389.6e6 if (args.precision == "bf16" and B == 32768) else None,
                 "traffic_note": "bytes per minibatch over 6 GEMM launches (ncu, profiles/r01_ncu_tc_kernels_B32768.csv)",
                 "peak_source": pk["source"] + " bf16 sustained",
                 "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
