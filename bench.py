@@ -377,6 +377,39 @@ def run_b200(args, config):
                "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": dt / args.steps * 1e3,
                "api": "b200ppo_update_host (C ABI, pinned host buffers)"}
 
+    else:
+        # N > 1: the public Python API per rank — pinned host slab -> device, GAE, slab all-gather (NCCL), global-permutation
+        # update with the per-minibatch all-reduce, losses back on the host; barrier + max over ranks like `value`
+        pin = {k: v.pin_memory() for k, v in host.items()}
+        pin_perms = [p.pin_memory() for p in perms_host]
+
+        def step_host(i):
+            dd = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
+            mem = pkg.RolloutMemory(dd, (n_envs, T))
+            algo.calculate_advantages(mem)
+            fields = D.all_gather_fields({
+                "current_state": mem["current_state"].reshape(M_local, OBS_DIM), "action": mem["action"].reshape(M_local, ACT_DIM),
+                "action_log_prob": mem["action_log_prob"].reshape(M_local), "advantage": mem["advantage"].reshape(M_local),
+                "current_state_value_target": mem["current_state_value_target"].reshape(M_local)})
+            out = eng.train(fields["current_state"], fields["action"], fields["action_log_prob"], fields["advantage"],
+                            fields["current_state_value_target"], pin_perms[i].to(dev, non_blocking=True), GB, hp)
+            return out.cpu()
+
+        step_host(0)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            loss_host = step_host(args.warmup + k)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        h2d = sum(v.numel() * v.element_size() for v in host.values()) + perms_host[0].numel() * 8
+        e2e = {"value": args.steps * samples_per_step / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": dt / args.steps * 1e3,
+               "api": "PPO.calculate_advantages + distributed.all_gather_fields + ActorCriticEngine.train per rank, pinned host slabs "
+                      "(bytes are per rank)"}
+
     # ---- per-kernel-class device time of one step (CUDA events on the launching stream) ----------------------
     _lib.check(lib.b200ppo_profile_begin(eng._ctx))
     ga, gb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

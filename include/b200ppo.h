@@ -239,6 +239,12 @@ int b200ppo_debug_tc_gemm(const float* A, const float* B, float* C, int32_t M, i
 int b200ppo_comm_unique_id(uint8_t id_out[128]);
 int b200ppo_comm_init(b200ppo_ctx* ctx, const uint8_t unique_id[128], int32_t rank, int32_t world_size);
 int b200ppo_comm_world(const b200ppo_ctx* ctx, int32_t* rank, int32_t* world_size);
+/* Optional, after b200ppo_comm_init, bf16 path, world_size <= 8 on one NVLink/NVSwitch node: replace the per-minibatch
+ * ncclAllReduce by an exchange over peer-mapped memory fused into the optimizer kernel.  Every rank exports the
+ * 64-byte cudaIpcMemHandle of its exchange buffer, the caller all-gathers the handles (rank order) and hands the
+ * world_size x 64 bytes to every rank.  Same result on every rank; ranks sum in rank order. */
+int b200ppo_p2p_export(b200ppo_ctx* ctx, uint8_t handle_out[64]);
+int b200ppo_p2p_import(b200ppo_ctx* ctx, const uint8_t* handles, int32_t world_size);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,8 @@ SIGNATURES = {
     "b200ppo_comm_unique_id": (c_i32, [c_ptr]),
     "b200ppo_comm_init": (c_i32, [c_ptr, c_ptr, c_i32, c_i32]),
     "b200ppo_comm_world": (c_i32, [c_ptr, C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "b200ppo_p2p_export": (c_i32, [c_ptr, c_ptr]),
+    "b200ppo_p2p_import": (c_i32, [c_ptr, c_ptr, c_i32]),
 }
 
 

@@ -81,13 +81,54 @@ __device__ __forceinline__ void combine_losses(const LossCombine& lc, float* s_l
   __syncthreads();
 }
 
+// Flag exchange of the peer-memory all-reduce: tell every peer that this rank's buffer of exchange `seq` is complete
+// (the kernel that wrote it finished before this one started), then wait until every peer has said the same.
+__device__ __forceinline__ void peer_exchange_barrier(const PeerSrc& ps) {
+  const int q = threadIdx.x;
+  if (q < ps.world && q != ps.rank) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ps.flags_peer[q] + ps.rank), "r"(ps.seq) : "memory");
+    }
+    const long long t0 = clock64();
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ps.flags_local + q) : "memory");
+      if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer died; flag the error instead of hanging the GPU
+        if (ps.err != nullptr) *ps.err = 3;
+        break;
+      }
+    } while (int(v - ps.seq) < 0);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float4 ld_peer4(const float* p) {  // peer memory: never through a stale L1 line
+  float4 r;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
 __global__ void __launch_bounds__(256)
 adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, int n_partials, int64_t partial_stride,
                  float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t n, int64_t seg_split, AdamScalars s0,
-                 AdamScalars s1, const __grid_constant__ CastTable ct, const __grid_constant__ LossCombine lc) {
+                 AdamScalars s1, const __grid_constant__ CastTable ct, const __grid_constant__ LossCombine lc,
+                 const __grid_constant__ PeerSrc ps) {
   __shared__ float s_lc[64];
   __shared__ float s_scr[256];
   pdl_wait_then_release();  // the gradient partials come from the kernel right before this one (common.cuh, PDL)
+  if (ps.world > 0) {
+    peer_exchange_barrier(ps);
+    if (blockIdx.x == 0 && threadIdx.x < 2 && ps.losses_out != nullptr) {
+      float l = 0.f;
+      for (int r = 0; r < ps.world; ++r) {
+        float t;
+        asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(t) : "l"(ps.src[r] + n + threadIdx.x) : "memory");
+        l += t;
+      }
+      ps.losses_out[threadIdx.x] = l;
+    }
+  }
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
   const int64_t n4 = n >> 2;  // the flat buffer is padded to a multiple of 32 elements
@@ -99,8 +140,20 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
     const float4 p0 = *reinterpret_cast<float4*>(params + 4 * i);
     const float4 m0 = *reinterpret_cast<float4*>(exp_avg + 4 * i);
     const float4 v0 = *reinterpret_cast<float4*>(exp_avg_sq + 4 * i);
-    float4 g = *reinterpret_cast<const float4*>(grads + 4 * i);
-    int k0 = 1;
+    float4 g;
+    if (ps.world > 0) {  // every rank's buffer, all loads in flight, summed in rank order
+      float4 h[kMaxPeers];
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r)
+        if (r < ps.world) h[r] = ld_peer4(ps.src[r] + 4 * i);
+      g = h[0];
+#pragma unroll
+      for (int r = 1; r < kMaxPeers; ++r)
+        if (r < ps.world) { g.x += h[r].x; g.y += h[r].y; g.z += h[r].z; g.w += h[r].w; }
+    } else {
+      g = *reinterpret_cast<const float4*>(grads + 4 * i);
+    }
+    int k0 = ps.world > 0 ? n_partials : 1;
     for (; k0 + 3 < n_partials; k0 += 4) {  // partials are added in index order (deterministic)
       const float4 h0 = *reinterpret_cast<const float4*>(grads + (k0 + 0) * partial_stride + 4 * i);
       const float4 h1 = *reinterpret_cast<const float4*>(grads + (k0 + 1) * partial_stride + 4 * i);
@@ -210,8 +263,9 @@ int launch_adam(float* params, const float* grads, int n_partials, int64_t parti
 
 int launch_adam_cast(float* params, const float* grads, int n_partials, int64_t partial_stride, float* exp_avg,
                      float* exp_avg_sq, int64_t n, int64_t seg_split, const AdamScalars& s0, const AdamScalars& s1,
-                     const WeightCastGroup& casts, const LossCombine& lc, cudaStream_t st) {
+                     const WeightCastGroup& casts, const LossCombine& lc, cudaStream_t st, const PeerSrc* peers) {
   if (n == 0) return B200PPO_OK;
+  const PeerSrc no_peers{};
   B2_CHECK_ARG(lc.partials == nullptr || (lc.act_dim + 2 <= 64 && lc.logstd_off % 4 == 0), "loss combine: act_dim <= 62");
   B2_CHECK_ARG(n % 4 == 0, "fused Adam + cast expects the padded flat parameter buffer");
   CastTable ct{};
@@ -225,7 +279,7 @@ int launch_adam_cast(float* params, const float* grads, int n_partials, int64_t 
     ct.in[k] = w.in; ct.pitch[k] = w.pitch; ct.pitch_t[k] = w.pitch_t;
   }
   B2_CUDA(launch_pdl(adam_cast_kernel, dim3(ew_grid(n / 4)), dim3(256), 0, st, params, grads, n_partials, partial_stride, exp_avg, exp_avg_sq, n, seg_split,
-                                                  s0, s1, ct, lc));
+                                                  s0, s1, ct, lc, peers ? *peers : no_peers));
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }

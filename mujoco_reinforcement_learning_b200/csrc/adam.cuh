@@ -30,12 +30,27 @@ struct LossCombine {
   float* losses_out = nullptr;      // [2]
 };
 
+// Multi-GPU without a library collective: every rank leaves its reduced gradient (+ trailing loss sums) in a buffer
+// that its peers have mapped (cudaIpc over NVLink / NVSwitch), raises a flag in every peer's flag array, and the
+// optimizer kernel itself waits for the G flags and sums the G buffers in rank order (identical bits on every rank)
+// while applying Adam — the all-reduce, its launch and the separate reduction pass disappear from the critical path.
+constexpr int kMaxPeers = 8;
+struct PeerSrc {
+  const float* src[kMaxPeers] = {};      // rank-ordered; src[rank] is the local buffer
+  unsigned* flags_peer[kMaxPeers] = {};  // every rank's flag array [kMaxPeers] (slot q is written by rank q)
+  unsigned* flags_local = nullptr;
+  int world = 0, rank = 0;
+  unsigned seq = 0;                      // value the flags must reach for this exchange
+  int32_t* err = nullptr;                // set to 3 when a peer does not show up within ~2 s
+  float* losses_out = nullptr;           // [2] = sum over ranks of src[p][n + {0, 1}]
+};
+
 // Same update, and in the same pass the bf16 shadow copies of the hidden/output weight matrices that the tensor-core
 // GEMMs read (W and W^T, see cast.cuh) are re-emitted from the freshly updated fp32 master values: no separate cast
 // launch, no second read of the parameters.  `casts.w[k].src` must point into `params`.
 int launch_adam_cast(float* params, const float* grads, int n_partials, int64_t partial_stride, float* exp_avg,
                      float* exp_avg_sq, int64_t n, int64_t seg_split, const AdamScalars& s0, const AdamScalars& s1,
-                     const WeightCastGroup& casts, const LossCombine& lc, cudaStream_t st);
+                     const WeightCastGroup& casts, const LossCombine& lc, cudaStream_t st, const PeerSrc* peers = nullptr);
 
 int launch_reduce_partials(const float* grads, int n_partials, int64_t partial_stride, int64_t n, float* out,
                            cudaStream_t st, const LossCombine* lc = nullptr);

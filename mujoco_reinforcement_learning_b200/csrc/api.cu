@@ -126,6 +126,13 @@ struct b200ppo_ctx {
   // two sets (rows [0, sh_cap) and [sh_cap, 2 sh_cap)): epoch e+1 is gathered on a side stream while epoch e trains
   float *sh_obs = nullptr, *sh_act = nullptr, *sh_logp = nullptr, *sh_adv = nullptr, *sh_tgt = nullptr;
   int64_t sh_cap = 0;
+  // peer-memory gradient exchange (multi-GPU, see adam.cuh PeerSrc): two buffers of xstride floats + a flag array, one
+  // allocation so that one cudaIpc handle covers it
+  float* xbuf = nullptr;
+  int64_t xstride = 0;
+  float* peer_x[kMaxPeers] = {};
+  bool p2p = false;
+  unsigned p2p_seq = 0;
   cudaStream_t gather_stream = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
   // device staging of the host entry point
@@ -778,6 +785,9 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   dev_free(c->host.obs); dev_free(c->host.act); dev_free(c->host.logp); dev_free(c->host.rew); dev_free(c->host.val);
   dev_free(c->host.nval); dev_free(c->host.adv); dev_free(c->host.tgt); dev_free(c->host.losses); dev_free(c->host.term);
   dev_free(c->host.perms);
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (c->peer_x[r] != nullptr && c->peer_x[r] != c->xbuf) cudaIpcCloseMemHandle(c->peer_x[r]);
+  dev_free(c->xbuf);
   if (c->gather_stream) {
     cudaStreamDestroy(c->gather_stream);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_ready[i]); cudaEventDestroy(c->ev_free[i]); }
@@ -1004,6 +1014,28 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
           PROF(ctx, B200PPO_PROF_ADAM, st,
                launch_adam(params, ctx->gpart, split, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa,
                            sc, nullptr, st));
+      } else if (ctx->p2p && tc) {
+        // peer-memory exchange fused into the optimizer kernel: reduce the split-K partials into this rank's exchange
+        // buffer, then Adam waits for the peers' flags and sums the G buffers in rank order (adam.cu)
+        const unsigned seq = ++ctx->p2p_seq;
+        const int64_t xo = int64_t(seq & 1) * ctx->xstride;
+        float* xb = ctx->xbuf + xo;
+        float* red_losses = xb + ctx->n_params;
+        B2_TRY(minibatch_fwd_bwd(ctx, params, nullptr, ctx->bf.sh_obs + r0 * PX, ctx->sh_act + r0 * A, ctx->sh_logp + r0,
+                                 ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp, red_losses, &split, &loss_ctas, st));
+        const LossCombine lc = make_loss_combine(ctx, params, loss_ctas, lb, hp, red_losses);
+        PROF(ctx, B200PPO_PROF_OTHER, st, launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, xb, st, &lc));
+        PeerSrc ps{};
+        ps.world = ctx->world; ps.rank = ctx->rank; ps.seq = seq; ps.err = ctx->err_flag; ps.losses_out = loss_slot;
+        unsigned* flags0 = reinterpret_cast<unsigned*>(ctx->xbuf + 2 * ctx->xstride);
+        ps.flags_local = flags0;
+        for (int r = 0; r < ctx->world; ++r) {
+          ps.src[r] = ctx->peer_x[r] + xo;
+          ps.flags_peer[r] = reinterpret_cast<unsigned*>(ctx->peer_x[r] + 2 * ctx->xstride);
+        }
+        PROF(ctx, B200PPO_PROF_ADAM, st,
+             launch_adam_cast(params, xb, 1, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa, sc,
+                              cast_group(ctx, params), LossCombine{}, st, &ps));
       } else {
         float* red_losses = ctx->grad_flat + ctx->n_params;
         B2_TRY(minibatch_fwd_bwd(ctx, params, tc ? nullptr : ctx->sh_obs + r0 * D, tc ? ctx->bf.sh_obs + r0 * PX : nullptr,
@@ -1148,6 +1180,40 @@ extern "C" B2_EXPORT int b200ppo_comm_init(b200ppo_ctx* ctx, const uint8_t uniqu
     return B200PPO_ENCCL;
   }
   ctx->comm = comm; ctx->rank = rank; ctx->world = world_size;
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_p2p_export(b200ppo_ctx* ctx, uint8_t handle_out[64]) {
+  B2_CHECK_ARG(ctx && handle_out, "b200ppo_p2p_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (ctx->xbuf == nullptr) {
+    ctx->xstride = (ctx->n_params + 4 + 31) / 32 * 32;
+    B2_TRY(dev_alloc(&ctx->xbuf, 2 * ctx->xstride + 64, true));  // + the flag array (kMaxPeers words, padded)
+    B2_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  B2_CUDA(cudaIpcGetMemHandle(&h, ctx->xbuf));
+  memcpy(handle_out, &h, 64);
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_p2p_import(b200ppo_ctx* ctx, const uint8_t* handles, int32_t world_size) {
+  B2_CHECK_ARG(ctx && handles, "b200ppo_p2p_import: null pointer");
+  B2_CHECK_ARG(ctx->xbuf != nullptr, "b200ppo_p2p_import: call b200ppo_p2p_export first");
+  B2_CHECK_ARG(world_size == ctx->world && world_size >= 2 && world_size <= kMaxPeers,
+               "b200ppo_p2p_import: world size %d does not match the communicator (%d) or exceeds %d", world_size, ctx->world, kMaxPeers);
+  for (int r = 0; r < world_size; ++r) {
+    if (r == ctx->rank) {
+      ctx->peer_x[r] = ctx->xbuf;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * r, 64);
+    void* ptr = nullptr;
+    B2_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_x[r] = static_cast<float*>(ptr);
+  }
+  ctx->p2p = true;
   return B200PPO_OK;
 }
 

@@ -9,6 +9,7 @@ partials) is summed with one NCCL all-reduce per minibatch inside `b200ppo_train
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict
 
 import torch
@@ -42,6 +43,21 @@ def init_engine_comm(engine, group=None) -> None:
     with torch.cuda.device(engine.device):
         _lib.check(lib.b200ppo_comm_init(engine._ctx, ident, rank, world), "b200ppo_comm_init")
     engine.rank, engine.world = rank, world
+    engine.p2p = False
+    # gradient exchange over peer-mapped memory fused into the optimizer kernel (bf16 path, one NVSwitch node)
+    if (backend == "nccl" and 2 <= world <= 8 and os.environ.get("B200PPO_P2P", "1") != "0"
+            and getattr(engine, "precision", None) == _lib.PREC_BF16):
+        handle = (C.c_uint8 * 64)()
+        with torch.cuda.device(engine.device):
+            _lib.check(lib.b200ppo_p2p_export(engine._ctx, handle), "b200ppo_p2p_export")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=engine.device)
+        everyone = torch.empty(world * 64, dtype=torch.uint8, device=engine.device)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        handles = (C.c_uint8 * (world * 64))(*everyone.cpu().tolist())
+        with torch.cuda.device(engine.device):
+            _lib.check(lib.b200ppo_p2p_import(engine._ctx, handles, world), "b200ppo_p2p_import")
+        dist.barrier(group=group)  # nobody starts an exchange before every rank has mapped its peers
+        engine.p2p = True
 
 
 def all_gather_fields(fields: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:

@@ -65,7 +65,7 @@ def main():
     ref = p_d.clone()
     dist.broadcast(ref, src=0)
     same = torch.equal(ref, p_d)
-    print(f"rank {rank}/{world} [{precision}]: param err {err_p:.2e} loss err {err_l:.2e} replicas identical {same}", flush=True)
+    print(f"rank {rank}/{world} [{precision}] exchange {'p2p' if agent.engine.p2p else 'nccl'}: param err {err_p:.2e} loss err {err_l:.2e} replicas identical {same}", flush=True)
     ok = err_p <= tol and err_l <= max(tol, 1e-5) and same and agent.engine.adam_step == agent1.engine.adam_step
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
