@@ -213,17 +213,46 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
   }
 }
 
-// Sum partials only (used before the NCCL all-reduce and by the grads-only entry point).
+// Sum partials only (used before the gradient exchange between ranks and by the grads-only entry point).
+// float4 per thread, partials added in index order with four loads in flight (n is padded to a multiple of 4 by the
+// callers that pass aligned buffers; the scalar loop covers everything else).
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ grads, int n_partials, int64_t partial_stride, int64_t n,
-                       float* __restrict__ out, const __grid_constant__ LossCombine lc) {
+                       float* __restrict__ out, const __grid_constant__ LossCombine lc, int vec4) {
   __shared__ float s_lc[64];
   __shared__ float s_scr[256];
+  pdl_wait_then_release();
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
-  const bool lc_owner = lc.partials != nullptr && int64_t(blockIdx.x) == (lc.logstd_off / blockDim.x) % gridDim.x;
+  const int64_t n4 = vec4 ? (n >> 2) : 0;
+  const bool lc_owner = lc.partials != nullptr && int64_t(blockIdx.x) == (vec4 ? ((lc.logstd_off >> 2) / blockDim.x) % gridDim.x
+                                                                               : (lc.logstd_off / blockDim.x) % gridDim.x);
   if (lc_owner) combine_losses(lc, s_lc, s_scr);
-  for (int64_t e = tid; e < n; e += nthreads) {
+  for (int64_t i = tid; i < n4; i += nthreads) {
+    float4 g = *reinterpret_cast<const float4*>(grads + 4 * i);
+    int k0 = 1;
+    for (; k0 + 3 < n_partials; k0 += 4) {
+      const float4 h0 = *reinterpret_cast<const float4*>(grads + (k0 + 0) * partial_stride + 4 * i);
+      const float4 h1 = *reinterpret_cast<const float4*>(grads + (k0 + 1) * partial_stride + 4 * i);
+      const float4 h2 = *reinterpret_cast<const float4*>(grads + (k0 + 2) * partial_stride + 4 * i);
+      const float4 h3 = *reinterpret_cast<const float4*>(grads + (k0 + 3) * partial_stride + 4 * i);
+      g.x = (((g.x + h0.x) + h1.x) + h2.x) + h3.x; g.y = (((g.y + h0.y) + h1.y) + h2.y) + h3.y;
+      g.z = (((g.z + h0.z) + h1.z) + h2.z) + h3.z; g.w = (((g.w + h0.w) + h1.w) + h2.w) + h3.w;
+    }
+    for (; k0 < n_partials; ++k0) {
+      const float4 h = *reinterpret_cast<const float4*>(grads + k0 * partial_stride + 4 * i);
+      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+    }
+    if (lc_owner && 4 * i + 3 >= lc.logstd_off && 4 * i < lc.logstd_off + lc.act_dim) {
+      const int64_t r = 4 * i - lc.logstd_off;
+      if (r + 0 >= 0 && r + 0 < lc.act_dim) g.x = s_lc[2 + r + 0];
+      if (r + 1 >= 0 && r + 1 < lc.act_dim) g.y = s_lc[2 + r + 1];
+      if (r + 2 >= 0 && r + 2 < lc.act_dim) g.z = s_lc[2 + r + 2];
+      if (r + 3 >= 0 && r + 3 < lc.act_dim) g.w = s_lc[2 + r + 3];
+    }
+    *reinterpret_cast<float4*>(out + 4 * i) = g;
+  }
+  for (int64_t e = 4 * n4 + tid; e < n; e += nthreads) {
     float g = grads[e];
     for (int k = 1; k < n_partials; ++k) g += grads[k * partial_stride + e];
     if (lc_owner && e >= lc.logstd_off && e < lc.logstd_off + lc.act_dim) g = s_lc[2 + (e - lc.logstd_off)];
@@ -288,7 +317,9 @@ int launch_reduce_partials(const float* grads, int n_partials, int64_t partial_s
                            cudaStream_t st, const LossCombine* lc) {
   if (n == 0) return B200PPO_OK;
   const LossCombine none{};
-  reduce_partials_kernel<<<ew_grid(n), 256, 0, st>>>(grads, n_partials, partial_stride, n, out, lc ? *lc : none);
+  const int vec4 = (n % 4 == 0 && partial_stride % 4 == 0 && aligned16(grads) && aligned16(out) && (lc == nullptr || lc->logstd_off % 4 == 0)) ? 1 : 0;
+  B2_CUDA(launch_pdl(reduce_partials_kernel, dim3(ew_grid(vec4 ? n / 4 : n)), dim3(256), 0, st, grads, n_partials, partial_stride, n, out,
+                     lc ? *lc : none, vec4));
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }
