@@ -312,7 +312,7 @@ def run_b200(args, config):
                   "action_log_prob": mem["action_log_prob"].reshape(M_local), "advantage": mem["advantage"].reshape(M_local),
                   "current_state_value_target": mem["current_state_value_target"].reshape(M_local)}
         if world > 1:
-            fields = D.all_gather_fields(fields)
+            fields = D.share_rollout(eng, fields)
         return eng.train(fields["current_state"], fields["action"], fields["action_log_prob"], fields["advantage"],
                          fields["current_state_value_target"], perms_dev[i], GB, hp)
 
@@ -387,7 +387,7 @@ def run_b200(args, config):
             dd = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
             mem = pkg.RolloutMemory(dd, (n_envs, T))
             algo.calculate_advantages(mem)
-            fields = D.all_gather_fields({
+            fields = D.share_rollout(eng, {
                 "current_state": mem["current_state"].reshape(M_local, OBS_DIM), "action": mem["action"].reshape(M_local, ACT_DIM),
                 "action_log_prob": mem["action_log_prob"].reshape(M_local), "advantage": mem["advantage"].reshape(M_local),
                 "current_state_value_target": mem["current_state_value_target"].reshape(M_local)})

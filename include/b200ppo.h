@@ -245,6 +245,19 @@ int b200ppo_comm_world(const b200ppo_ctx* ctx, int32_t* rank, int32_t* world_siz
  * world_size x 64 bytes to every rank.  Same result on every rank; ranks sum in rank order. */
 int b200ppo_p2p_export(b200ppo_ctx* ctx, uint8_t handle_out[64]);
 int b200ppo_p2p_import(b200ppo_ctx* ctx, const uint8_t* handles, int32_t world_size);
+/* Optional (same conditions): share the rollout's observations between ranks without an all-gather.  Every rank keeps
+ * its own env slab as a bf16 table (rows of in_dim values + the ones-column) that its peers map over NVLink;
+ * b200ppo_train(obs = NULL, n_samples = world_size * rows_local) then gathers the rows of the GLOBAL permutation
+ * straight from the owners' tables with the copy engine, on a side stream behind the previous epoch's kernels.
+ * replaces: nothing in the reference (single process); it stands in for gathering `memory['current_state']` of
+ * src/entities/algorithms/ppo.py:104 when that tensor is spread over ranks.
+ * export (re)allocates the table for rows_local rows and returns its cudaIpcMemHandle; import takes the handles of all
+ * ranks (rank order); fill converts the rank's fp32 slab [rows_local, in_dim] on `stream`.  The caller orders fill
+ * before every peer's train (e.g. the all-gather of the small leaves on the same stream) and the next fill after every
+ * peer's train (any collective). */
+int b200ppo_table_export(b200ppo_ctx* ctx, int64_t rows_local, uint8_t handle_out[64]);
+int b200ppo_table_import(b200ppo_ctx* ctx, const uint8_t* handles, int32_t world_size, int64_t rows_local);
+int b200ppo_table_fill(b200ppo_ctx* ctx, const float* obs_local, int64_t rows_local, b200ppo_stream stream);
 
 #ifdef __cplusplus
 }

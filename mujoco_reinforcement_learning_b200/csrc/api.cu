@@ -132,6 +132,10 @@ struct b200ppo_ctx {
   int64_t xstride = 0;
   float* peer_x[kMaxPeers] = {};
   bool p2p = false;
+  // rollout observations shared across ranks as bf16 tables (each rank converts its own slab; peers map it)
+  __nv_bfloat16* peer_table[kMaxPeers] = {};
+  int64_t shared_rows = 0;   // rows of every rank's table; 0 = tables not shared
+  bool shared_filled = false;
   unsigned p2p_seq = 0;
   cudaStream_t gather_stream = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
@@ -714,6 +718,10 @@ int launch_gather_chunked(const int64_t* idx, int64_t count, int64_t n_rows, int
                           int64_t chunk_offset, const float* obs, int obs_dim, const float* act, int act_dim,
                           const float* logp, const float* adv, const float* tgt, float* obs_o, float* act_o,
                           float* logp_o, float* adv_o, float* tgt_o, int32_t* err_flag, cudaStream_t st);
+int launch_gather_parts(const int64_t* idx, int64_t count, int64_t n_rows, int64_t chunk, int64_t chunk_stride, int64_t chunk_offset,
+                        const float* const* obs_parts, int n_parts, int64_t rows_per_part, int row_floats, const float* act,
+                        int act_dim, const float* logp, const float* adv, const float* tgt, float* obs_o, float* act_o,
+                        float* logp_o, float* adv_o, float* tgt_o, int32_t* err_flag, cudaStream_t st);
 int launch_gather_chunked_bf16(const int64_t* idx, int64_t count, int64_t n_rows, int64_t chunk, int64_t chunk_stride,
                                int64_t chunk_offset, const float* obs, int obs_dim, const float* act, int act_dim,
                                const float* logp, const float* adv, const float* tgt, __nv_bfloat16* obs_o, int pitch,
@@ -785,8 +793,10 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   dev_free(c->host.obs); dev_free(c->host.act); dev_free(c->host.logp); dev_free(c->host.rew); dev_free(c->host.val);
   dev_free(c->host.nval); dev_free(c->host.adv); dev_free(c->host.tgt); dev_free(c->host.losses); dev_free(c->host.term);
   dev_free(c->host.perms);
-  for (int r = 0; r < kMaxPeers; ++r)
+  for (int r = 0; r < kMaxPeers; ++r) {
     if (c->peer_x[r] != nullptr && c->peer_x[r] != c->xbuf) cudaIpcCloseMemHandle(c->peer_x[r]);
+    if (c->peer_table[r] != nullptr && c->peer_table[r] != c->bf.obs_table) cudaIpcCloseMemHandle(c->peer_table[r]);
+  }
   dev_free(c->xbuf);
   if (c->gather_stream) {
     cudaStreamDestroy(c->gather_stream);
@@ -918,9 +928,12 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
                              const float* advantage, const float* target, int64_t n_samples, const int64_t* perms,
                              int32_t epochs, int64_t batch, int64_t max_minibatches_per_epoch,
                              const b200ppo_hparams* hp, float* losses_out, b200ppo_stream stream) {
-  B2_CHECK_ARG(ctx && params && exp_avg && exp_avg_sq && adam_step_io && obs && action && old_logp && advantage &&
-                   target && perms && hp,
+  B2_CHECK_ARG(ctx && params && exp_avg && exp_avg_sq && adam_step_io && action && old_logp && advantage && target && perms && hp,
                "b200ppo_train: null pointer");
+  const bool shared_obs = obs == nullptr;  // observations come from the ranks' shared bf16 tables (b200ppo_table_*)
+  B2_CHECK_ARG(!shared_obs || (ctx->shared_rows > 0 && ctx->shared_filled && ctx->precision == B200PPO_PREC_BF16 &&
+                               n_samples == ctx->shared_rows * ctx->world),
+               "b200ppo_train: obs == NULL needs filled shared observation tables covering n_samples = world x rows");
   B2_CHECK_ARG(epochs >= 0 && batch > 0 && n_samples >= 0, "b200ppo_train: bad sizes");
   B2_CHECK_ARG(batch % ctx->world == 0, "b200ppo_train: batch %lld not divisible by world size %d", (long long)batch, ctx->world);
   const int64_t lb = batch / ctx->world;  // rows of each minibatch owned by this rank
@@ -939,7 +952,7 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
   // epoch; converting the whole rollout ONCE and then gathering bf16 rows byte for byte (bulk-copy kernel) costs
   // n_samples*(4D + 2*pitch) up front and 4*pitch per row and epoch.  Same bits either way.
   bool table = false;
-  if (tc && PX % 8 == 0) {
+  if (tc && PX % 8 == 0 && !shared_obs) {
     const double direct = double(epochs) * double(nb * lb) * (4.0 * D + 2.0 * PX);
     const double pre = double(n_samples) * (4.0 * D + 2.0 * PX) + double(epochs) * double(nb * lb) * 4.0 * PX;
     table = pre < 0.9 * direct && nb * lb >= 4096;
@@ -962,6 +975,13 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
   auto gather_epoch = [&](int e, int set, cudaStream_t gs) -> int {
     const int64_t o = int64_t(set) * cap;
     const int64_t* idx = perms + int64_t(e) * n_samples;
+    if (shared_obs) {  // rows pulled from every rank's table over NVLink by the copy engine
+      const float* parts[kMaxPeers];
+      for (int r = 0; r < ctx->world; ++r) parts[r] = reinterpret_cast<const float*>(ctx->peer_table[r]);
+      return launch_gather_parts(idx, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb, parts, ctx->world, ctx->shared_rows, PX / 2,
+                                 action, A, old_logp, advantage, target, reinterpret_cast<float*>(ctx->bf.sh_obs + o * PX),
+                                 ctx->sh_act + o * A, ctx->sh_logp + o, ctx->sh_adv + o, ctx->sh_tgt + o, ctx->err_flag, gs);
+    }
     if (table)  // bf16 rows moved as PX/2 "floats" by the bulk-copy gather: a byte copy
       return launch_gather_chunked(idx, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
                                    reinterpret_cast<const float*>(ctx->bf.obs_table), PX / 2, action, A, old_logp, advantage, target,
@@ -1214,6 +1234,58 @@ extern "C" B2_EXPORT int b200ppo_p2p_import(b200ppo_ctx* ctx, const uint8_t* han
     ctx->peer_x[r] = static_cast<float*>(ptr);
   }
   ctx->p2p = true;
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_table_export(b200ppo_ctx* ctx, int64_t rows_local, uint8_t handle_out[64]) {
+  B2_CHECK_ARG(ctx && handle_out && rows_local > 0, "b200ppo_table_export: bad argument");
+  B2_CHECK_ARG(ctx->precision == B200PPO_PREC_BF16 && ctx->bf.pitchX % 8 == 0, "b200ppo_table_export: bf16 contexts only");
+  if (rows_local > ctx->bf.table_cap || ctx->shared_rows != rows_local) {
+    B2_CUDA(cudaDeviceSynchronize());
+    for (int r = 0; r < kMaxPeers; ++r) {
+      if (ctx->peer_table[r] != nullptr && ctx->peer_table[r] != ctx->bf.obs_table) cudaIpcCloseMemHandle(ctx->peer_table[r]);
+      ctx->peer_table[r] = nullptr;
+    }
+    if (rows_local > ctx->bf.table_cap) {
+      dev_free(ctx->bf.obs_table);
+      ctx->bf.table_cap = 0;
+      B2_TRY(dev_alloc(&ctx->bf.obs_table, rows_local * ctx->bf.pitchX));
+      ctx->bf.table_cap = rows_local;
+    }
+  }
+  ctx->shared_rows = 0;  // until b200ppo_table_import
+  ctx->shared_filled = false;
+  cudaIpcMemHandle_t h;
+  B2_CUDA(cudaIpcGetMemHandle(&h, ctx->bf.obs_table));
+  memcpy(handle_out, &h, 64);
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_table_import(b200ppo_ctx* ctx, const uint8_t* handles, int32_t world_size, int64_t rows_local) {
+  B2_CHECK_ARG(ctx && handles && rows_local > 0 && rows_local <= ctx->bf.table_cap, "b200ppo_table_import: bad argument");
+  B2_CHECK_ARG(world_size == ctx->world && world_size >= 2 && world_size <= kMaxPeers, "b200ppo_table_import: world size mismatch");
+  for (int r = 0; r < world_size; ++r) {
+    if (r == ctx->rank) {
+      ctx->peer_table[r] = ctx->bf.obs_table;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * r, 64);
+    void* ptr = nullptr;
+    B2_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_table[r] = static_cast<__nv_bfloat16*>(ptr);
+  }
+  ctx->shared_rows = rows_local;
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_table_fill(b200ppo_ctx* ctx, const float* obs_local, int64_t rows_local, b200ppo_stream stream) {
+  B2_CHECK_ARG(ctx && obs_local, "b200ppo_table_fill: null pointer");
+  B2_CHECK_ARG(ctx->shared_rows > 0 && rows_local == ctx->shared_rows, "b200ppo_table_fill: tables are shared for %lld rows per rank",
+               (long long)ctx->shared_rows);
+  B2_TRY(launch_cast_rows_ones(obs_local, rows_local, ctx->net[0].d.in_dim, ctx->bf.obs_table, ctx->bf.pitchX,
+                               static_cast<cudaStream_t>(stream)));
+  ctx->shared_filled = true;
   return B200PPO_OK;
 }
 

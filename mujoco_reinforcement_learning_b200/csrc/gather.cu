@@ -77,6 +77,14 @@ gather_minibatch_kernel(const int64_t* __restrict__ idx, int64_t count, int64_t 
 }
 
 
+// The observation rows may live in several arrays of equal length (multi-GPU: every rank's slab of the rollout, its own
+// and its peers' mapped over NVLink) — row s is row s % rows_per_part of part s / rows_per_part.
+struct ObsParts {
+  const float* part[8];
+  int64_t rows_per_part;
+  int count;  // 0: one array (`obs`)
+};
+
 // ---- TMA (bulk-copy) variant of the fp32 gather ----------------------------------------------------------------------
 // When an observation row is a multiple of 16 bytes (376 floats = 1504 B), each LANE drives its own row through the
 // copy engine: cp.async.bulk global -> its shared-memory slot (mbarrier completion), then cp.async.bulk slot -> global.
@@ -87,7 +95,8 @@ gather_minibatch_tma_kernel(const int64_t* __restrict__ idx, int64_t count, int6
                             int64_t chunk_offset, const float* __restrict__ obs, int obs_dim, const float* __restrict__ act,
                             int act_dim, const float* __restrict__ logp, const float* __restrict__ adv,
                             const float* __restrict__ tgt, float* __restrict__ obs_o, float* __restrict__ act_o,
-                            float* __restrict__ logp_o, float* __restrict__ adv_o, float* __restrict__ tgt_o, int32_t* err_flag) {
+                            float* __restrict__ logp_o, float* __restrict__ adv_o, float* __restrict__ tgt_o, int32_t* err_flag,
+                            const ObsParts parts) {
   extern __shared__ __align__(128) uint8_t slots[];
   __shared__ __align__(8) uint64_t bars[32];
   const int lane = threadIdx.x;
@@ -105,8 +114,15 @@ gather_minibatch_tma_kernel(const int64_t* __restrict__ idx, int64_t count, int6
     // the previous bulk store of this lane must have finished READING the slot before it is refilled
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot),
-                 "l"(obs + s * obs_dim), "r"(row_bytes), "r"(bar)
+    const float* src;
+    if (parts.count > 0) {
+      const int64_t pi = s / parts.rows_per_part;
+      src = parts.part[pi] + (s - pi * parts.rows_per_part) * obs_dim;
+    } else {
+      src = obs + s * obs_dim;
+    }
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot), "l"(src),
+                 "r"(row_bytes), "r"(bar)
                  : "memory");
     // short leaves while the row is in flight
     if (act != nullptr)
@@ -213,7 +229,7 @@ int launch_gather_chunked(const int64_t* idx, int64_t count, int64_t n_rows, int
     int64_t blocks = std::min<int64_t>((count + 31) / 32, int64_t(num_sms()) * per_sm);
     gather_minibatch_tma_kernel<<<unsigned(blocks), 32, tma_smem, st>>>(idx, count, n_rows, chunk, chunk_stride, chunk_offset, obs,
                                                                         obs_dim, act, act_dim, logp, adv, tgt, obs_o, act_o, logp_o,
-                                                                        adv_o, tgt_o, err_flag);
+                                                                        adv_o, tgt_o, err_flag, ObsParts{});
     B2_LAUNCH_CHECK();
     return B200PPO_OK;
   }
@@ -222,6 +238,37 @@ int launch_gather_chunked(const int64_t* idx, int64_t count, int64_t n_rows, int
     gather_minibatch_kernel<true><<<grid, block, 0, st>>>(idx, count, n_rows, chunk, chunk_stride, chunk_offset, obs, obs_dim, act, act_dim, logp, adv, tgt, obs_o, act_o, logp_o, adv_o, tgt_o, err_flag);
   else
     gather_minibatch_kernel<false><<<grid, block, 0, st>>>(idx, count, n_rows, chunk, chunk_stride, chunk_offset, obs, obs_dim, act, act_dim, logp, adv, tgt, obs_o, act_o, logp_o, adv_o, tgt_o, err_flag);
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
+
+// Bulk-copy gather whose observation rows come from `n_parts` arrays of `rows_per_part` rows each (row_floats floats per
+// row, a multiple of 4, every array 16-byte aligned).
+int launch_gather_parts(const int64_t* idx, int64_t count, int64_t n_rows, int64_t chunk, int64_t chunk_stride, int64_t chunk_offset,
+                        const float* const* obs_parts, int n_parts, int64_t rows_per_part, int row_floats, const float* act,
+                        int act_dim, const float* logp, const float* adv, const float* tgt, float* obs_o, float* act_o,
+                        float* logp_o, float* adv_o, float* tgt_o, int32_t* err_flag, cudaStream_t st) {
+  if (count == 0) return B200PPO_OK;
+  B2_CHECK_ARG(n_parts >= 1 && n_parts <= 8 && rows_per_part > 0 && n_rows <= rows_per_part * n_parts, "gather: bad parts");
+  const size_t tma_smem = size_t(32) * row_floats * 4;
+  B2_CHECK_ARG(row_floats % 4 == 0 && tma_smem <= 56 * 1024 && aligned16(obs_o), "gather from parts: rows must be 16-byte multiples <= 1792 bytes");
+  ObsParts parts{};
+  parts.count = n_parts;
+  parts.rows_per_part = rows_per_part;
+  for (int i = 0; i < n_parts; ++i) {
+    B2_CHECK_ARG(obs_parts[i] != nullptr && aligned16(obs_parts[i]), "gather from parts: null or misaligned part");
+    parts.part[i] = obs_parts[i];
+  }
+  static bool configured = false;
+  if (!configured) {
+    B2_CUDA(cudaFuncSetAttribute(gather_minibatch_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
+    configured = true;
+  }
+  const int per_sm = int(std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / std::max<size_t>(tma_smem, 1))));
+  int64_t blocks = std::min<int64_t>((count + 31) / 32, int64_t(num_sms()) * per_sm);
+  gather_minibatch_tma_kernel<<<unsigned(blocks), 32, tma_smem, st>>>(idx, count, n_rows, chunk, chunk_stride, chunk_offset, nullptr,
+                                                                      row_floats, act, act_dim, logp, adv, tgt, obs_o, act_o, logp_o,
+                                                                      adv_o, tgt_o, err_flag, parts);
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }

@@ -70,3 +70,42 @@ def all_gather_fields(fields: Dict[str, torch.Tensor], group=None) -> Dict[str, 
         dist.all_gather_into_tensor(full, v, group=group)
         out[k] = full
     return out
+
+
+def share_rollout(engine, fields: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
+    """Make this rank's slab of the rollout available to every rank for the global-permutation update.
+
+    With the peer-memory path (`engine.p2p`): the observations (95 % of the bytes) are NOT all-gathered — every rank
+    converts its slab into a bf16 table that its peers have mapped, and `engine.train(None, ...)` pulls the rows of the
+    global permutation from the owners over NVLink, on a side stream behind the previous epoch's kernels.  Only the small
+    leaves (action, log-prob, advantage, target) are all-gathered.  Returns the fields for `engine.train`, with
+    `current_state` = None.  Without it: `all_gather_fields`.
+    """
+    if not getattr(engine, "p2p", False):
+        return all_gather_fields(fields, group)
+    world = dist.get_world_size(group)
+    lib = _lib.load()
+    obs = _lib.require_cuda(fields["current_state"], "current_state", torch.float32).contiguous()
+    rows = obs.shape[0]
+    obs = obs.reshape(rows, -1)
+    # every peer has finished gathering from the tables of the previous rollout once this collective completes
+    token = torch.zeros(1, device=obs.device)
+    dist.all_reduce(token, group=group)
+    if getattr(engine, "_shared_rows", 0) != rows:
+        handle = (C.c_uint8 * 64)()
+        with torch.cuda.device(engine.device):
+            _lib.check(lib.b200ppo_table_export(engine._ctx, rows, handle), "b200ppo_table_export")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=engine.device)
+        everyone = torch.empty(world * 64, dtype=torch.uint8, device=engine.device)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        handles = (C.c_uint8 * (world * 64))(*everyone.cpu().tolist())
+        with torch.cuda.device(engine.device):
+            _lib.check(lib.b200ppo_table_import(engine._ctx, handles, world, rows), "b200ppo_table_import")
+        engine._shared_rows = rows
+    with torch.cuda.device(engine.device):
+        _lib.check(lib.b200ppo_table_fill(engine._ctx, _lib.ptr(obs), rows, _lib.stream_ptr()), "b200ppo_table_fill")
+    # the all-gather of the small leaves follows the fill in stream order on every rank: when it completes here, every
+    # rank's table is complete
+    out = all_gather_fields({k: v for k, v in fields.items() if k != "current_state"}, group)
+    out["current_state"] = None
+    return out

@@ -340,11 +340,14 @@ class ActorCriticEngine:
               max_minibatches_per_epoch: int = 0) -> torch.Tensor:
         """`PPO.train` inner loops (ppo.py:101-140) in one native call.  Returns device losses [epochs*nb, 2]."""
         self.ensure_bound()
-        M = obs.shape[0]
         f = lambda t, n: _lib.require_cuda(t, n, torch.float32).contiguous()
-        obs = f(obs, "current_state").reshape(M, -1)
-        if obs.shape[1] != self.obs_dim:
-            raise RuntimeError(f"expected {self.obs_dim} observation features, got {obs.shape[1]}")
+        if obs is None:  # observations live in the ranks' shared bf16 tables (distributed.share_rollout)
+            M = action.shape[0]
+        else:
+            M = obs.shape[0]
+            obs = f(obs, "current_state").reshape(M, -1)
+            if obs.shape[1] != self.obs_dim:
+                raise RuntimeError(f"expected {self.obs_dim} observation features, got {obs.shape[1]}")
         action, old_logp = f(action, "action").reshape(M, -1), f(old_logp, "action_log_prob").reshape(M)
         advantage, target = f(advantage, "advantage").reshape(M), f(target, "current_state_value_target").reshape(M)
         perms = _lib.require_cuda(perms, "perms", torch.int64).contiguous().reshape(-1, M)
@@ -352,10 +355,10 @@ class ActorCriticEngine:
         nb = M // int(batch)
         if max_minibatches_per_epoch > 0:
             nb = min(nb, max_minibatches_per_epoch)
-        losses = torch.zeros((epochs * nb, 2), dtype=torch.float32, device=obs.device)
+        losses = torch.zeros((epochs * nb, 2), dtype=torch.float32, device=action.device)
         step = C.c_int64(self.adam_step)
         _lib.check(self.lib.b200ppo_train(self._ctx, _lib.ptr(self.flat), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
-                                          C.byref(step), _lib.ptr(obs), _lib.ptr(action), _lib.ptr(old_logp),
+                                          C.byref(step), _lib.ptr(obs) if obs is not None else None, _lib.ptr(action), _lib.ptr(old_logp),
                                           _lib.ptr(advantage), _lib.ptr(target), M, _lib.ptr(perms), epochs, int(batch),
                                           int(max_minibatches_per_epoch), C.byref(hp), _lib.ptr(losses),
                                           _lib.stream_ptr()), "b200ppo_train")

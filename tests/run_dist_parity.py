@@ -46,6 +46,10 @@ def main():
     gathered = D.all_gather_fields(mine)
     for k, v in full.items():
         assert torch.equal(gathered[k].cpu(), v.reshape(M, -1)), f"all-gather order broken for {k}"
+    shared = D.share_rollout(agent.engine, mine)  # peer-memory path: observations stay with their owners (bf16 tables)
+    if agent.engine.p2p:
+        assert shared["current_state"] is None
+        gathered = shared
     hp = agent.engine.hparams(1e-4, 1e-4, 0.1, 1e-4)
     losses_d = agent.engine.train(gathered["current_state"], gathered["action"], gathered["action_log_prob"].reshape(M),
                                   gathered["advantage"].reshape(M), gathered["current_state_value_target"].reshape(M),
