@@ -40,6 +40,10 @@ CASES = {
                         seed=22),
     "train_tanh96": dict(kind="train", D=27, A=8, hidden=[96, 80], act="Tanh", N=8, T=32, B=64, epochs=1, seed=23,
                          out_max=2.0),
+    # Soft Actor-Critic update step: two consecutive SoftActorCritic.train calls on a replay memory
+    "sac_tanh32": dict(kind="sac", D=7, W=2, A=3, hidden=[32, 24], act="Tanh", N=6, T=40, B=64, seed=41, calls=2),
+    "sac_relu48": dict(kind="sac", D=5, W=2, A=4, hidden=[48, 48], act="ReLU", N=4, T=50, B=96, seed=42, calls=2,
+                       out_max=2.0, lr=3e-4),
 }
 
 
@@ -56,7 +60,7 @@ def _build_run(spec, tmpdir):
                     entropy_eps=spec.get("ent", 1e-4), advantage_scaler=spec.get("advantage_scaler", 1.0),
                     normalize_advantage=spec.get("normalize_advantage", False), critic_coeffiecient=1.0),
         F.SACConfig(1.0, 0.99, 0.05, 0.005, 999, 1, False),
-        F.EnvironmentConfig(maximum_timesteps=spec["T"], num_envs=spec["N"], window_length=1),
+        F.EnvironmentConfig(maximum_timesteps=spec["T"], num_envs=spec["N"], window_length=spec.get("W", 1)),
         F.AgentConfig(sub_action_count=1),
         F.NetworkConfig(input_shape=spec.get("D", 4), output_shape=spec.get("A", 2),
                         output_max_value=spec.get("out_max", 1.0), activation_class=act_cls,
@@ -110,6 +114,63 @@ def run_case(name: str):
         normed = RefHelper.normalize_state(stand_in, obs.clone())
         out["in_observation"] = obs.numpy()
         out["state"] = normed.to(torch.float32).permute(0, 2, 1).contiguous().numpy()
+    elif spec["kind"] == "sac":
+        # SoftActorCritic.train runs verbatim (soft_actor_critic.py:33-118) with the agent's two module-level names
+        # re-pointed at the MLP classes models.linear.actor.Actor / models.linear.q_network.QNetwork (as committed it binds
+        # the Transformer variants).  torch.randperm and the standard-normal draws inside Normal.rsample are recorded.
+        import torch.distributions.normal as normal_mod
+        import entities.agents.soft_actor_critic_agent as sac_agent_mod
+        from models.linear.actor import Actor as LinearActor
+        from models.linear.q_network import QNetwork as LinearQ
+        from oracle.sac_oracle import synthetic_replay
+        sac_agent_mod.Actor = LinearActor
+        sac_agent_mod.QNetwork = LinearQ
+        agent = sac_agent_mod.SoftActorCriticAgent()
+        from entities.algorithms.soft_actor_critic import SoftActorCritic
+        algo = SoftActorCritic(_Helper(run), agent)  # hard_update(target, online) happens here
+        for k, v in agent.networks.state_dict().items():
+            out["init/" + k] = v.detach().clone().numpy()
+        W = spec["W"]
+        replay = synthetic_replay(N, T, (W, D), A, seed=2000 + spec["seed"])
+        for k, v in replay.items():
+            out["mem/" + k] = v.numpy()
+        perms, eps = [], []
+        real_randperm, real_std_normal = torch.randperm, normal_mod._standard_normal
+
+        def recording_randperm(*a, **k):
+            p = real_randperm(*a, **k)
+            perms.append(p.clone())
+            return p
+
+        def recording_std_normal(*a, **k):
+            e = real_std_normal(*a, **k)
+            eps.append(e.clone())
+            return e
+
+        torch.randperm = recording_randperm
+        normal_mod._standard_normal = recording_std_normal
+        losses = []
+        try:
+            for call in range(spec["calls"]):
+                mem = TensorDict({k: v.clone() for k, v in replay.items()}, batch_size=(N, T))
+                losses.append(list(algo.train(mem, call)))
+        finally:
+            torch.randperm = real_randperm
+            normal_mod._standard_normal = real_std_normal
+        out["perms"] = torch.stack(perms).numpy()
+        out["eps"] = torch.stack(eps).numpy()            # [2 * calls, B, A]: (next-state draw, policy draw) per call
+        out["losses"] = np.array(losses, dtype=np.float64)
+        for k, v in agent.networks.state_dict().items():
+            out["final/" + k] = v.detach().clone().numpy()
+        for oname in ("actor", "online_critic"):
+            sd = agent.optimizers[oname].state_dict()
+            for pid, st in sd["state"].items():
+                out[f"opt/{oname}/{pid}/exp_avg"] = st["exp_avg"].numpy()
+                out[f"opt/{oname}/{pid}/exp_avg_sq"] = st["exp_avg_sq"].numpy()
+        out["cfg"] = np.array([spec["B"], spec.get("lr", 1e-4), 0.99, 0.05, 0.005, 1, 1.0, spec.get("out_max", 1.0), spec["W"]],
+                              dtype=np.float64)  # batch, lr, gamma, alpha, tau, target_update_interval, max_grad_norm, out_max, window
+        out["hidden"] = np.array(spec["hidden"], dtype=np.int64)
+        out["activation"] = np.array(spec["act"].lower())
     elif spec["kind"] == "adv":
         mem = TensorDict({k: v.clone() for k, v in roll.items()}, batch_size=(N, T))
         algo = PPO(_Helper(run), agent=None)

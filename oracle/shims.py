@@ -7,7 +7,8 @@ installable here.  This module registers the smallest stand-ins that make
 unmodified:
 
  * `tensordict.TensorDict` — dict of tensors sharing leading batch dims, with exactly the
-   operations ppo.py touches (`[]` by key / index tensor / slice, `[]=`, `len`, `view(-1)`).
+   operations ppo.py and soft_actor_critic.py touch (`[]` by key / index tensor / slice, `[]=`, `len`,
+   `view(-1)`, `torch.clone`).
  * `torchrl.objectives.value.functional.generalized_advantage_estimate` — the restatement in
    `oracle/ppo_oracle.py` (torchrl's source is not available: parity unpinned for it).
  * `mlflow`, `mediapy`, `gymnasium(.core)` — import-time placeholders, never called on the path.
@@ -46,6 +47,14 @@ class TensorDict:
         assert isinstance(key, str)
         assert value.shape[:len(self.batch_size)] == self.batch_size, (key, value.shape, self.batch_size)
         self._d[key] = value
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        # `torch.clone(memory)` — soft_actor_critic.py:40
+        if func is torch.clone:
+            td = args[0]
+            return TensorDict({k: v.clone() for k, v in td._d.items()}, batch_size=td.batch_size)
+        return NotImplemented
 
     def view(self, *shape):
         assert shape == (-1,)
