@@ -230,6 +230,10 @@ int b200ppo_profile_end(b200ppo_ctx* ctx, double ms_out[B200PPO_PROF_CLASSES], i
 int b200ppo_debug_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t a_mn_major,
                           int32_t b_mn_major, int32_t bn, int32_t split_k, b200ppo_stream stream);
 
+/* Polyak averaging, in place: target[i] = target[i] * (1 - tau) + source[i] * tau over flat fp32 buffers.
+ * replaces: soft_update, src/entities/algorithms/soft_actor_critic.py:12-14 (the SAC update step). */
+int b200ppo_polyak_update(float* target, const float* source, int64_t n, double tau, b200ppo_stream stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The update is data-parallel over samples: every rank computes the
  * gradient of its slice of each minibatch, gradients are summed over ranks (NCCL all-reduce over

@@ -34,6 +34,18 @@ class PPOConfig:
 
 
 @dataclass
+class SACConfig:
+    """src/entities/features.py:91-98."""
+    max_grad_norm: float = 1.0   # dead field: SoftActorCritic.train clips with ppo_config.max_grad_norm (:67, :84)
+    gamma: float = 0.99
+    alpha: float = 0.05
+    tau: float = 0.005
+    memory_capacity: int = 999
+    target_update_interval: int = 1
+    automatic_entropy_tuning: bool = False
+
+
+@dataclass
 class EnvironmentConfig:
     maximum_timesteps: int = 500
     num_envs: int = 5
@@ -69,6 +81,7 @@ class DynamicConfig:
 class Run:
     training_config: TrainingConfig = field(default_factory=TrainingConfig)
     ppo_config: PPOConfig = field(default_factory=PPOConfig)
+    sac_config: SACConfig = field(default_factory=SACConfig)
     environment_config: EnvironmentConfig = field(default_factory=EnvironmentConfig)
     network_config: NetworkConfig = field(default_factory=NetworkConfig)
     dynamic_config: DynamicConfig = field(default_factory=DynamicConfig)

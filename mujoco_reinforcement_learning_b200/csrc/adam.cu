@@ -324,9 +324,39 @@ int launch_reduce_partials(const float* grads, int n_partials, int64_t partial_s
   return B200PPO_OK;
 }
 
+// Polyak averaging of a flat parameter buffer: target = target * (1 - tau) + source * tau.
+// replaces: soft_update (src/entities/algorithms/soft_actor_critic.py:12-14), one launch for every tensor of both
+// Q networks.  The two products and the sum are rounded separately, like the three ATen ops of the reference.
+// Algorithmic bytes: 12 per parameter.
+__global__ void __launch_bounds__(256)
+polyak_kernel(float* __restrict__ target, const float* __restrict__ source, int64_t n, float one_minus_tau, float tau) {
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(source)) & 15u) == 0 ? (n >> 2) : 0;
+  for (int64_t i = tid; i < n4; i += nthreads) {
+    float4 t = ldg_stream4(target + 4 * i);
+    const float4 s = ldg_stream4(source + 4 * i);
+    t.x = __fadd_rn(__fmul_rn(t.x, one_minus_tau), __fmul_rn(s.x, tau));
+    t.y = __fadd_rn(__fmul_rn(t.y, one_minus_tau), __fmul_rn(s.y, tau));
+    t.z = __fadd_rn(__fmul_rn(t.z, one_minus_tau), __fmul_rn(s.z, tau));
+    t.w = __fadd_rn(__fmul_rn(t.w, one_minus_tau), __fmul_rn(s.w, tau));
+    stg_stream4(target + 4 * i, t);
+  }
+  for (int64_t e = 4 * n4 + tid; e < n; e += nthreads)
+    target[e] = __fadd_rn(__fmul_rn(target[e], one_minus_tau), __fmul_rn(source[e], tau));
+}
+
 }  // namespace b200ppo
 
 using namespace b200ppo;
+
+extern "C" B2_EXPORT int b200ppo_polyak_update(float* target, const float* source, int64_t n, double tau, b200ppo_stream stream) {
+  B2_CHECK_ARG(target && source && n >= 0, "b200ppo_polyak_update: bad argument");
+  if (n == 0) return B200PPO_OK;
+  polyak_kernel<<<ew_grid((n + 3) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(target, source, n, float(1.0 - tau), float(tau));
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
 
 extern "C" B2_EXPORT int b200ppo_adam_step(float* params, const float* grads, int32_t n_partials, int64_t partial_stride,
                                  float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,

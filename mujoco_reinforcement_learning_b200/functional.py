@@ -155,6 +155,21 @@ def adam_step_(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, beta1=0.9
     return param
 
 
+def polyak_update_(target: torch.Tensor, source: torch.Tensor, tau: float) -> torch.Tensor:
+    """In-place `target = target * (1 - tau) + source * tau` on flat contiguous fp32 CUDA tensors
+    (`soft_update`, soft_actor_critic.py:12-14, for every tensor of a network at once)."""
+    lib = _lib.load()
+    for name, t in (("target", target), ("source", source)):
+        _lib.require_cuda(t, name, torch.float32)
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} must be contiguous")
+    if target.numel() != source.numel():
+        raise RuntimeError("target and source must have the same number of elements")
+    _lib.check(lib.b200ppo_polyak_update(_lib.ptr(target), _lib.ptr(source), target.numel(), float(tau), _lib.stream_ptr()),
+               "b200ppo_polyak_update")
+    return target
+
+
 # index ranges of the SymmetricHumanoid observation vector the reference normalises separately
 # (src/environments/humanoid/running_gym_sequential_vectorized.py:69-80); the last range ends at obs_dim
 HUMANOID_SEGMENTS = (0, 22, 45, 175, 253, 270)
