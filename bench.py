@@ -217,6 +217,48 @@ def hbm_kernel_lines(pk):
         else:
             out[key]["note"] = "L2-resident (9.2 MB): launch/latency bound"
         del p, g, mm, vv
+    # SURVEY 8f rank 4 (SAC update step): the Polyak average as an HBM kernel (12 B/param) and one SoftActorCritic.train call
+    n_par = 64 * 1024 * 1024
+    tgt, src = torch.randn(n_par, device=dev), torch.randn(n_par, device=dev)
+    med, best = cuda_time(lambda: pkg.polyak_update_(tgt, src, 0.005), 10)
+    out["polyak_64M"] = {"bytes": 12 * n_par, "ms": med, "GBps": 12 * n_par / 1e9 / (med * 1e-3), "frac": 12 * n_par / 1e9 / (med * 1e-3) / pk["hbm"]}
+    del tgt, src
+    prev_run = pkg.Run.instance()
+    sac_B, sac_obs = 4096, 188  # two-frame window of 188 features = the 376 inputs of the PPO bench; 256x256 tanh MLPs
+    run_sac = pkg.Run(training_config=pkg.TrainingConfig(learning_rate=1e-4, batch_size=sac_B), environment_config=pkg.EnvironmentConfig(window_length=2),
+                      network_config=pkg.NetworkConfig(input_shape=sac_obs, output_shape=ACT_DIM, linear_hidden_shapes=HIDDEN), device=str(dev))
+    torch.manual_seed(0)
+    sac_agent = pkg.SoftActorCriticAgent(run_sac)
+    sac = pkg.SoftActorCritic(type("H", (), {"run": run_sac})(), sac_agent)
+    n_env, n_t = 256, 256
+    replay = {"current_state": torch.randn(n_env, n_t, 2, sac_obs, device=dev), "next_state": torch.randn(n_env, n_t, 2, sac_obs, device=dev),
+              "action": torch.randn(n_env, n_t, ACT_DIM, device=dev), "reward": torch.randn(n_env, n_t, 1, device=dev),
+              "is_alive": torch.rand(n_env, n_t, 1, device=dev) > 0.05}
+    idx_host = torch.randperm(n_env * n_t)
+    counter = [0]
+
+    def sac_step():
+        sac.train(replay, counter[0], idx=idx_host)
+        counter[0] += 1
+    med, best = cuda_time(sac_step, 10)
+    out["sac_update_B4096"] = {"ms": med, "samples_per_s": sac_B / (med * 1e-3), "replay_rows": n_env * n_t,
+                               "note": "one SoftActorCritic.train call (fp32 kernels): gather, TD target, twin-Q step, policy step through dQ/da, Polyak"}
+    # the same call through the CPU oracle port (reference's torch CPU ops), all host threads, three calls
+    from oracle import sac_oracle as SO
+    torch.set_num_threads(os.cpu_count() or 1)
+    ocfg = SO.SacConfig(state_dim=2 * sac_obs, act_dim=ACT_DIM, hidden=HIDDEN, batch_size=sac_B)
+    oagent = SO.OracleSacAgent(ocfg)
+    oflat = {k: v.reshape(n_env * n_t, *v.shape[2:]).cpu() for k, v in replay.items()}
+    eps_host = torch.randn(2, sac_B, ACT_DIM)
+    SO.sac_train_step(oagent, oflat, idx_host, eps_host[0], eps_host[1], 0)
+    t0 = time.perf_counter()
+    for c in range(3):
+        SO.sac_train_step(oagent, oflat, idx_host, eps_host[0], eps_host[1], c + 1)
+    cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+    out["sac_update_B4096"]["cpu_port_ms"] = cpu_ms
+    out["sac_update_B4096"]["cpu_cores"] = os.cpu_count() or 1
+    del replay, sac, sac_agent, oagent, oflat
+    pkg.Run._instance = prev_run
     torch.cuda.empty_cache()
     return out
 
