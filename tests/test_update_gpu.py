@@ -301,3 +301,35 @@ def test_bf16_train_vs_oracle(shape):
         for pid, st in opt.state_dict()["state"].items():
             assert_close_l2(st["exp_avg"], ref_state[pid]["exp_avg"], mom_tol, f"bf16 {oname}/{pid}/exp_avg")
             assert float(st["step"]) == float(ref_state[pid]["step"])
+
+
+def test_checkpoint_files_move_between_implementations(tmp_path):
+    """`Agent.save` / `load` (agent.py:47-72): the files written by the CUDA agent load into stock torch modules and
+    `torch.optim.Adam` (the reference's side), and back into a fresh CUDA agent, without loss."""
+    oracle, agent, run = make_pair(11, 3, [32, 24], [32, 24], "tanh", batch=64, epochs=1, n_envs=4, steps=32, seed=3, max_batch=128)
+    run.experiment_path = str(tmp_path)
+    roll = O.synthetic_rollout(4, 32, 11, 3, seed=5)
+    adv, tgt = O.calculate_advantages(roll["reward"], roll["current_state_value"], roll["next_state_value"], roll["terminated"], 0.99, 0.98)
+    memory = pkg.RolloutMemory({"current_state": roll["current_state"].to(DEV), "action": roll["action"].to(DEV),
+                                "action_log_prob": (torch.randn(4, 32) * 0.1 - 4).to(DEV), "advantage": adv.to(DEV),
+                                "current_state_value_target": tgt.to(DEV)}, (4, 32))
+    pkg.PPO(type("H", (), {"run": run})(), agent).train(memory, perms=torch.randperm(128)[None])
+    agent.save()
+    d = tmp_path / "networks" / "0"
+    assert sorted(p.name for p in d.iterdir()) == ["networks.pth", "optimizer_actor.pth", "optimizer_critic.pth"]
+    # reference side: same key names, same Adam state layout
+    sd = torch.load(d / "networks.pth", map_location="cpu")
+    assert list(sd.keys()) == list(oracle.networks.state_dict().keys())
+    oracle.networks.load_state_dict(sd)
+    for name in ("actor", "critic"):
+        osd = torch.load(d / f"optimizer_{name}.pth", map_location="cpu")
+        oracle.optimizers[name].load_state_dict(osd)
+        assert all(float(st["step"]) == 2.0 for st in oracle.optimizers[name].state_dict()["state"].values())
+    # back into a fresh CUDA agent
+    _, agent2, run2 = make_pair(11, 3, [32, 24], [32, 24], "tanh", batch=64, epochs=1, n_envs=4, steps=32, seed=99, max_batch=128)
+    run2.experiment_path = str(tmp_path)
+    agent2.load()
+    assert torch.equal(agent2.engine.flat, agent.engine.flat)
+    assert torch.equal(agent2.engine.exp_avg, agent.engine.exp_avg) and torch.equal(agent2.engine.exp_avg_sq, agent.engine.exp_avg_sq)
+    assert agent2.engine.adam_step == agent.engine.adam_step == 2
+    assert agent2.engine.params_are_bound()
