@@ -90,7 +90,13 @@ __global__ void __launch_bounds__(128)
 gae_scan_kernel(const RewT* __restrict__ reward, const float* __restrict__ value,
                 const float* __restrict__ next_value, const uint8_t* __restrict__ term,
                 const uint8_t* __restrict__ done, int64_t n_envs, int T, float gamma, float disc, float scaler,
-                float* __restrict__ adv, float* __restrict__ tgt) {
+                float* __restrict__ adv, float* __restrict__ tgt, int row_in_smem) {
+  // NORM_ADV with row_in_smem: the warp keeps its row of both outputs (2 x T floats) in shared memory until the
+  // row statistics are known, so every output element is written to global memory exactly once (22 B per element
+  // like the plain scan) instead of written, re-read twice and re-written.
+  extern __shared__ __align__(16) float gae_rows[];
+  float* row_a = gae_rows + size_t(threadIdx.x >> 5) * 2 * size_t((T + 3) & ~3);
+  float* row_t = row_a + ((T + 3) & ~3);
   const int lane = threadIdx.x & 31;
   const int64_t env = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (env >= n_envs) return;
@@ -158,7 +164,10 @@ gae_scan_kernel(const RewT* __restrict__ reward, const float* __restrict__ value
     }
     carry = __shfl_sync(0xffffffffu, x, 0);
     if (valid) {
-      if constexpr (VEC == 4) {
+      if (NORM_ADV && row_in_smem) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { row_a[t0 + i] = a_out[i]; row_t[t0 + i] = t_out[i]; }
+      } else if constexpr (VEC == 4) {
         stg_stream4(adv + row + t0, make_float4(a_out[0], a_out[1], a_out[2], a_out[3]));
         stg_stream4(tgt + row + t0, make_float4(t_out[0], t_out[1], t_out[2], t_out[3]));
       } else {
@@ -176,6 +185,32 @@ gae_scan_kernel(const RewT* __restrict__ reward, const float* __restrict__ value
   if constexpr (NORM_ADV) {  // ppo.py:81-88: both outputs, per env over time, unbiased std, no epsilon
     const float mean_a = warp_sum(sum_a) / float(T), mean_t = warp_sum(sum_t) / float(T);
     float qa = 0.f, qt = 0.f;
+    if (row_in_smem) {  // every lane touches only the shared-memory elements it wrote itself
+      for (int t = lane * VEC; t < T; t += TILE) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          float ca = row_a[t + i] - mean_a, ct = row_t[t + i] - mean_t;
+          qa += ca * ca; qt += ct * ct;
+        }
+      }
+      const float sa = sqrtf(warp_sum(qa) / float(T - 1)), stt = sqrtf(warp_sum(qt) / float(T - 1));
+      for (int t = lane * VEC; t < T; t += TILE) {
+        float a4[VEC], t4[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          a4[i] = __fmul_rn(__fdiv_rn(row_a[t + i] - mean_a, sa), scaler);
+          t4[i] = __fmul_rn(__fdiv_rn(row_t[t + i] - mean_t, stt), scaler);
+        }
+        if constexpr (VEC == 4) {
+          stg_stream4(adv + row + t, make_float4(a4[0], a4[1], a4[2], a4[3]));
+          stg_stream4(tgt + row + t, make_float4(t4[0], t4[1], t4[2], t4[3]));
+        } else {
+          adv[row + t] = a4[0];
+          tgt[row + t] = t4[0];
+        }
+      }
+      return;
+    }
     // every lane re-reads exactly the elements it wrote itself
     for (int t = lane * VEC; t < T; t += TILE) {
 #pragma unroll
@@ -202,7 +237,15 @@ static int launch_gae(const void* reward, const float* value, const float* next_
   const int warps = 4;
   dim3 grid((unsigned)((N + warps - 1) / warps)), block(warps * 32);
   const RewT* r = static_cast<const RewT*>(reward);
-#define GAE_GO(NR, NA) gae_scan_kernel<RewT, AccT, VEC, NR, NA><<<grid, block, 0, st>>>(r, value, next_value, term, done, N, T, gamma, disc, scaler, adv, tgt)
+  // rows of both outputs stay in shared memory while their statistics are computed when 4 warps x 2 x T floats fit
+  const size_t row_bytes = size_t(warps) * 2 * size_t((T + 3) & ~3) * sizeof(float);
+  const int in_smem = (na && row_bytes <= 96 * 1024) ? 1 : 0;
+  const size_t smem = in_smem ? row_bytes : 0;
+  if (smem > 48 * 1024) {
+    if (nr) B2_CUDA(cudaFuncSetAttribute(gae_scan_kernel<RewT, AccT, VEC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    else B2_CUDA(cudaFuncSetAttribute(gae_scan_kernel<RewT, AccT, VEC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  }
+#define GAE_GO(NR, NA) gae_scan_kernel<RewT, AccT, VEC, NR, NA><<<grid, block, smem, st>>>(r, value, next_value, term, done, N, T, gamma, disc, scaler, adv, tgt, in_smem)
   if (nr && na) GAE_GO(true, true);
   else if (nr) GAE_GO(true, false);
   else if (na) GAE_GO(false, true);
