@@ -463,11 +463,85 @@ __device__ __forceinline__ void tc_ppo_issue(const TcProblem& P, int m0, int war
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// One row of the actor's fused loss epilogue: log-prob of the stored action, ratio, clipped surrogate, gradient seeds
+// (ppo.py:113-120 and its autograd), NC = act_dim rounded up to a multiple of 8 (columns >= act_dim are masked).
+template <int NC>
+__device__ __forceinline__ void tc_ppo_actor_row(const TcProblem& P, uint32_t tmem_acc, int q, bool row_ok, float old_lp, float adv,
+                                                 const float* act_s, __nv_bfloat16* dz_s, const float* bias_s, const float* consts_s,
+                                                 PpoAcc& acc) {
+  const int A = P.ppo.act_dim, pitch = P.ppo.dz_pitch;
+  float z[NC];
+  {
+    uint32_t v[16];
+    tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16), v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < NC) z[j] = __uint_as_float(v[j]);
+    if constexpr (NC > 16) {
+      tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16) + 16u, v);
+#pragma unroll
+      for (int j = 0; j < NC - 16; ++j) z[16 + j] = __uint_as_float(v[j]);
+    }
+  }
+  const float scale = P.out_scale, inv_scale = 1.f / P.out_scale;
+  const bool ft = P.ppo.final_tanh != 0;
+  float lp = 0.f;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    if (j < A) {
+      const float pre = z[j] + bias_s[j];
+      const float th = ft ? tanh_fast(pre) : pre;
+      const float mean = ft ? scale * th : pre;
+      const float d = act_s[j] - mean;
+      lp += -(d * d) * (0.5f * consts_s[32 + j]) - consts_s[j] - kTcLogSqrt2Pi;  // -(a-mu)^2 / (2 var) - log sigma - log sqrt(2 pi)
+      z[j] = d;  // keep (a - mean); tanh is recovered below as (a - d) / scale
+    }
+  }
+  float g_lp = 0.f;
+  if (row_ok) {
+    const float lo = 1.f - P.ppo.clip_eps, hi = 1.f + P.ppo.clip_eps;
+    const float ratio = expf(lp - old_lp);
+    const float s1 = ratio * adv, s2 = fminf(fmaxf(ratio, lo), hi) * adv;
+    const float w1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);
+    const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+    g_lp = -(w1 * adv + (1.f - w1) * adv * in_range) * P.ppo.inv_global_batch * ratio;
+    acc.surr += fminf(s1, s2);
+  }
+  uint32_t packed[NC / 2];
+#pragma unroll
+  for (int j = 0; j < NC; j += 2) {
+    float dm[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int jj = j + u;
+      dm[u] = 0.f;
+      if (jj < A) {
+        const float d = z[jj];
+        const float dn = d * consts_s[32 + jj];
+        float dmu = g_lp * dn;
+        if (ft) {
+          const float th = (act_s[jj] - d) * inv_scale;  // mean / scale
+          dmu *= scale * (1.f - th * th);
+        }
+        dm[u] = row_ok ? dmu : 0.f;
+        if (row_ok) acc.dl[jj] += g_lp * (d * dn - 1.f);
+      }
+    }
+    packed[j >> 1] = pack_bf16(dm[0], dm[1]);
+  }
+  // this row's seeds: pitch % 8 == 0 bf16 values, zero beyond act_dim
+  uint32_t* dzw = reinterpret_cast<uint32_t*>(dz_s);
+#pragma unroll
+  for (int w = 0; w < NC / 2; ++w)
+    if (2 * w < pitch) dzw[w] = packed[w];
+  for (int w = NC / 2; 2 * w < pitch; ++w) dzw[w] = 0u;
+}
+
 template <int BN>
 __device__ __forceinline__ void tc_epilogue_ppo(const TcProblem& P, uint32_t tmem_acc, int m0, int warp, int lane,
                                                 uint64_t* tmem_full_bar, uint32_t full_parity, uint8_t* stage,
                                                 const float* bias_s, const float* consts_s, int groups_in_flight, PpoAcc& acc,
-                                                bool worker) {
+                                                bool worker, long long* tr = nullptr) {
   // worker: this warp processes the tile's rows of its TMEM lane quarter (the <= 32 output columns all sit in one
   // thread).  Two warps share a lane quarter: the one-tile kernel lets the first work; the persistent kernel
   // alternates tiles between the two warp groups.
@@ -476,6 +550,7 @@ __device__ __forceinline__ void tc_epilogue_ppo(const TcProblem& P, uint32_t tme
   const bool row_ok = m < P.M;
   if (groups_in_flight > 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
   else asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (tr != nullptr) tr[0] = clock64();  // action slab landed
   // per-row scalars requested before the accumulator is awaited
   float old_lp = 0.f, adv = 0.f, tgt = 0.f;
   if (worker && row_ok) {
@@ -485,6 +560,7 @@ __device__ __forceinline__ void tc_epilogue_ppo(const TcProblem& P, uint32_t tme
   mbar_wait(tmem_full_bar, full_parity);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncwarp();
+  if (tr != nullptr) tr[1] = clock64();  // accumulator ready
   if (!worker) return;
   if (P.epilogue == TC_EPI_PPO_CRITIC) {
     uint32_t v[16];
@@ -507,65 +583,20 @@ __device__ __forceinline__ void tc_epilogue_ppo(const TcProblem& P, uint32_t tme
     return;
   }
   // ---- actor ----
+  // The per-row math below ran ~3500 instructions per row (clock64 timeline: 10-12 k cycles per tile, THE limiter of
+  // this launch): all 32 possible action columns were unrolled with predicates and every column paid two IEEE divisions.
+  // Now the column loop is unrolled to the next multiple of 8 of act_dim and the divisions are multiplications by the
+  // reciprocals staged in shared memory (the bf16 path's 2e-2 tolerance; the fp32 path keeps true divisions).
   const int A = P.ppo.act_dim, pitch = P.ppo.dz_pitch;
   const float* act_s = reinterpret_cast<const float*>(stage) + lane * A;                         // this row's action
   __nv_bfloat16* dz_s = reinterpret_cast<__nv_bfloat16*>(stage + 32 * A * 4) + lane * pitch;   // this row's seeds
-  float z[32];
-  {
-    uint32_t v[16];
-    tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16), v);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(v[j]);
-    if (A > 16) {
-      tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16) + 16u, v);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) z[16 + j] = __uint_as_float(v[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) z[16 + j] = 0.f;
-    }
-  }
-  const float scale = P.out_scale;
-  const bool ft = P.ppo.final_tanh != 0;
-  float lp = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (j < A) {
-      const float pre = z[j] + bias_s[j];
-      const float th = ft ? tanh_fast(pre) : pre;
-      const float mean = ft ? scale * th : pre;
-      const float d = act_s[j] - mean;
-      lp += -(d * d) / consts_s[64 + j] - consts_s[j] - kTcLogSqrt2Pi;
-      z[j] = d;  // keep (a - mean); tanh is recovered below as (a - d) / scale
-    }
-  }
-  float g_lp = 0.f;
-  if (row_ok) {
-    const float lo = 1.f - P.ppo.clip_eps, hi = 1.f + P.ppo.clip_eps;
-    const float ratio = expf(lp - old_lp);
-    const float s1 = ratio * adv, s2 = fminf(fmaxf(ratio, lo), hi) * adv;
-    const float w1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);
-    const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
-    g_lp = -(w1 * adv + (1.f - w1) * adv * in_range) * P.ppo.inv_global_batch * ratio;
-    acc.surr += fminf(s1, s2);
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (j < A) {
-      const float d = z[j];
-      const float dn = d * consts_s[32 + j];
-      float dmu = g_lp * dn;
-      if (ft) {
-        const float th = (act_s[j] - d) / scale;   // mean / scale
-        dmu *= scale * (1.f - th * th);
-      }
-      dz_s[j] = __float2bfloat16_rn(row_ok ? dmu : 0.f);
-      if (row_ok) acc.dl[j] += g_lp * (d * dn - 1.f);
-    } else if (j < pitch) {
-      dz_s[j] = __float2bfloat16_rn(0.f);
-    }
-  }
+  const int nch = (A + 7) >> 3;
+  if (nch <= 1) tc_ppo_actor_row<8>(P, tmem_acc, q, row_ok, old_lp, adv, act_s, dz_s, bias_s, consts_s, acc);
+  else if (nch == 2) tc_ppo_actor_row<16>(P, tmem_acc, q, row_ok, old_lp, adv, act_s, dz_s, bias_s, consts_s, acc);
+  else if (nch == 3) tc_ppo_actor_row<24>(P, tmem_acc, q, row_ok, old_lp, adv, act_s, dz_s, bias_s, consts_s, acc);
+  else tc_ppo_actor_row<32>(P, tmem_acc, q, row_ok, old_lp, adv, act_s, dz_s, bias_s, consts_s, acc);
   __syncwarp();
+  if (tr != nullptr) tr[2] = clock64();  // row math done
   // coalesced store of the 32 x pitch bf16 seed slab (rows are adjacent in global memory)
   const int rows = min(32, P.M - mq);
   if (rows > 0) {

@@ -174,8 +174,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
         for (; tile < tiles_m; tile += step, ++u) {
           const int next = tile + step;
           tc_ppo_issue(P, next * TC_BM, warp, lane, st[(u & 1) ^ 1], next < tiles_m);
+          if ((warp & 3) == 2 && lane == 0) WS_TRACE(2 * u + grp_id, 5);
           tc_epilogue_ppo<BN>(P, tmem_base + uint32_t(grp_id * BN), tile * TC_BM, warp, lane, &acc_full[grp_id], uint32_t(u & 1),
-                              st[u & 1], bias_s, consts_s, 1, acc, true);
+                              st[u & 1], bias_s, consts_s, 1, acc, true,
+                              (grp.trace != nullptr && blockIdx.x == 0 && (warp & 3) == 2 && lane == 0 && 2 * u + grp_id < 63)
+                                  ? grp.trace + (2 * u + grp_id) * 16 + 8 : nullptr);
+          if ((warp & 3) == 2 && lane == 0) WS_TRACE(2 * u + grp_id, 6);
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[grp_id]);
@@ -826,6 +830,28 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
   const int kb_max = (maxK + TC_BK - 1) / TC_BK;
   const int total = w.cta_begin[w.n_slots];
   if (grid_out) *grid_out = total;
+  // profiling aid: B200PPO_WS_TRACE=ppo prints the clock64 timeline of CTA 0 of the 20th fused-loss output-layer launch
+  static const char* trace_mode = getenv("B200PPO_WS_TRACE");
+  if (trace_mode != nullptr && trace_mode[0] == 'p' && bn == 64 && g.p[0].epilogue >= TC_EPI_PPO_ACTOR) {
+    static int calls = 0;
+    if (++calls == 20) {
+      long long* tr = nullptr;
+      B2_CUDA(cudaMalloc(&tr, 64 * 16 * sizeof(long long)));
+      B2_CUDA(cudaMemset(tr, 0, 64 * 16 * sizeof(long long)));
+      w.trace = tr;
+      const int rc = launch_ws_bn<64>(w, stages, kb_max, total, st);
+      cudaStreamSynchronize(st);
+      long long h[64 * 16];
+      cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost);
+      const long long t0 = h[0];
+      fprintf(stderr, "fused-loss output layer, CTA 0: tile | prod_first prod_last | mma_acc_free mma_kb0 mma_kbN | epi_start epi_end\n");
+      for (int t = 0; t < 16 && h[t * 16] != 0; ++t)
+        fprintf(stderr, "  %2d | %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld | slab %7lld acc %7lld math %7lld\n", t, h[t * 16] - t0, h[t * 16 + 1] - t0, h[t * 16 + 2] - t0,
+                h[t * 16 + 3] - t0, h[t * 16 + 4] - t0, h[t * 16 + 5] - t0, h[t * 16 + 6] - t0, h[t * 16 + 8] - t0, h[t * 16 + 9] - t0, h[t * 16 + 10] - t0);
+      cudaFree(tr);
+      return rc;
+    }
+  }
   switch (bn) {
     case 64: return launch_ws_bn<64>(w, stages, kb_max, total, st);
     case 128: return launch_ws_bn<128>(w, stages, kb_max, total, st);
