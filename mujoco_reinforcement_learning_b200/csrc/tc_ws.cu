@@ -855,8 +855,9 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
   switch (bn) {
     case 64: return launch_ws_bn<64>(w, stages, kb_max, total, st);
     case 128: return launch_ws_bn<128>(w, stages, kb_max, total, st);
-    default: return launch_ws_bn<256>(w, stages, kb_max, total, st);
   }
+  set_error("weights-stationary kernel: unsupported N tile %d", bn);
+  return B200PPO_EINVAL;
 }
 
 }  // namespace b200ppo
