@@ -333,9 +333,21 @@ extern "C" B2_EXPORT int b200ppo_debug_tc_gemm(const float* A, const float* B, f
   p.out_f32 = part; p.ld_f32 = N; p.split_stride = stride; p.bias_col = -1;
   // bn = -1: the persistent weights-stationary kernel; bn = -2: its forward (tanh, bf16) epilogue plus a clock64 timeline;
   // bn = -3: forward epilogue, C = float(tanh(A B^T) rounded to bf16) — the path the CTA-pair kernel takes for N > 128
+  // bn = -4: dgrad epilogue, C on entry holds the activation operand h; C = float(bf16(A B^T * (1 - bf16(h)^2)))
   const bool ws = bn < 0;
-  const bool fwd_check = bn == -3;
+  const bool fwd_check = bn == -3 || bn == -4;
   long long* trace = nullptr;
+  if (bn == -4) {
+    p.epilogue = TC_EPI_DGRAD; p.act = B200PPO_ACT_TANH;
+    p.out_f32 = nullptr;
+    const int64_t ld = (N + 7) / 8 * 8;
+    __nv_bfloat16* auxb = nullptr;
+    B2_CUDA(cudaMalloc(&p.out_bf16, size_t(M) * ld * 2));
+    B2_CUDA(cudaMalloc(&auxb, size_t(M) * ld * 2));
+    cast_pad_bf16_kernel<<<unsigned((int64_t(M) * ld + 255) / 256), 256, 0, st>>>(C, M, N, ld, auxb);
+    B2_LAUNCH_CHECK();
+    p.ld_bf16 = int(ld); p.aux = auxb; p.ld_aux = int(ld);
+  }
   if (bn == -2 || bn == -3) {
     p.epilogue = TC_EPI_FWD; p.act = B200PPO_ACT_TANH;  // the production forward epilogue, bf16 output
     if (getenv("B200PPO_DEBUG_RELU") != nullptr) p.act = B200PPO_ACT_RELU;  // profiling: the epilogue without MUFU work

@@ -78,3 +78,31 @@ def test_ws_forward_epilogue_matches_torch(M, N, K):
     assert torch.isfinite(C).all()
     err = (C.double() - ref).abs().max().item()
     assert err < 1e-2, f"max abs error {err:.3e}"  # bf16 output (2^-9 relative) + MUFU tanh (2^-11)
+
+
+DGRAD_CASES = [
+    # M, N, K, b_mn — dgrad epilogue dz = (A B^T) * (1 - h^2); N > 128 with 32-byte row pitch takes the CTA-pair kernel
+    (40000, 256, 256, 1),   # the production layer-2 dgrad: W read MN-major ([out, in] as stored)
+    (40000, 256, 17, 1),    # output-layer dgrad: K = act_dim
+    (33000, 208, 96, 0),    # last 64-column chunk ragged (208 = 3*64 + 16): element-wise tail of the direct epilogue
+    (33000, 200, 64, 0),    # row pitch not a multiple of 16: single-CTA kernel
+    (700, 256, 256, 1),     # fewer row tiles than CTA pairs, ragged M
+]
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", DGRAD_CASES)
+def test_ws_dgrad_epilogue_matches_torch(M, N, K, b_mn):
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(M + N * 11 + K)
+    A = torch.randn((M, K), device=DEV, generator=g)
+    B = torch.randn((K, N) if b_mn else (N, K), device=DEV, generator=g) / K ** 0.5
+    h = torch.tanh(torch.randn((M, N), device=DEV, generator=g))
+    C = h.clone()
+    _lib.check(lib.b200ppo_debug_tc_gemm(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, 0, b_mn, -4, 1,
+                                         _lib.stream_ptr()), "debug_tc_gemm")
+    Bm = B.bfloat16().double().t() if b_mn else B.bfloat16().double()
+    hb = h.bfloat16().double()
+    ref = (A.bfloat16().double() @ Bm.t()) * (1.0 - hb * hb)
+    assert torch.isfinite(C).all()
+    err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 6e-3, f"scaled max error {err:.3e}"  # bf16 output rounding (2^-9 relative)
