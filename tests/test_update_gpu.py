@@ -262,7 +262,9 @@ def test_bf16_minibatch_losses_and_gradients_vs_oracle(name):
                                    dict(D=376, A=17, H=[256, 256], N=64, T=64, B=4096, act="relu"),
                                    dict(D=376, A=17, H=[256, 256], N=16, T=64, B=500),
                                    dict(D=27, A=8, H=[256, 256], N=32, T=32, B=256),
-                                   dict(D=11, A=3, H=[64, 64], N=16, T=256, B=1024)])
+                                   dict(D=11, A=3, H=[64, 64], N=16, T=256, B=1024),
+                                   # the bench minibatch: CTA-pair forward / dgrad / wgrad kernels, fused-loss output layer
+                                   dict(D=376, A=17, H=[256, 256], N=256, T=128, B=32768)])
 def test_bf16_train_vs_oracle(shape):
     D, A, H, N, T, B = (shape[k] for k in "DAHNTB")
     oracle, agent, run = make_pair(D, A, H, H, shape.get("act", "tanh"), batch=B, epochs=1, n_envs=N, steps=T, seed=4,
