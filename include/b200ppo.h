@@ -248,9 +248,12 @@ int b200ppo_comm_world(const b200ppo_ctx* ctx, int32_t* rank, int32_t* world_siz
 /* Optional, after b200ppo_comm_init, bf16 path, world_size <= 8 on one NVLink/NVSwitch node: replace the per-minibatch
  * ncclAllReduce by an exchange over peer-mapped memory fused into the optimizer kernel.  Every rank exports the
  * 64-byte cudaIpcMemHandle of its exchange buffer, the caller all-gathers the handles (rank order) and hands the
- * world_size x 64 bytes to every rank.  Same result on every rank; ranks sum in rank order. */
+ * world_size x 64 bytes to every rank, then b200ppo_p2p_enable(ctx, 1) on every rank.  Same result on every rank; ranks
+ * sum in rank order. */
 int b200ppo_p2p_export(b200ppo_ctx* ctx, uint8_t handle_out[64]);
 int b200ppo_p2p_import(b200ppo_ctx* ctx, const uint8_t* handles, int32_t world_size);
+/* Switch the exchange on once EVERY rank has imported successfully (the caller agrees on that with a collective), or off. */
+int b200ppo_p2p_enable(b200ppo_ctx* ctx, int32_t on);
 /* Optional (same conditions): share the rollout's observations between ranks without an all-gather.  Every rank keeps
  * its own env slab as a bf16 table (rows of in_dim values + the ones-column) that its peers map over NVLink;
  * b200ppo_train(obs = NULL, n_samples = world_size * rows_local) then gathers the rows of the GLOBAL permutation

@@ -1233,7 +1233,16 @@ extern "C" B2_EXPORT int b200ppo_p2p_import(b200ppo_ctx* ctx, const uint8_t* han
     B2_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->peer_x[r] = static_cast<float*>(ptr);
   }
-  ctx->p2p = true;
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_p2p_enable(b200ppo_ctx* ctx, int32_t on) {
+  B2_CHECK_ARG(ctx, "b200ppo_p2p_enable: null context");
+  if (on) {
+    B2_CHECK_ARG(ctx->xbuf != nullptr && ctx->world >= 2, "b200ppo_p2p_enable: export / import the exchange buffers first");
+    for (int r = 0; r < ctx->world; ++r) B2_CHECK_ARG(ctx->peer_x[r] != nullptr, "b200ppo_p2p_enable: rank %d is not mapped", r);
+  }
+  ctx->p2p = on != 0;
   return B200PPO_OK;
 }
 

@@ -47,17 +47,31 @@ def init_engine_comm(engine, group=None) -> None:
     # gradient exchange over peer-mapped memory fused into the optimizer kernel (bf16 path, one NVSwitch node)
     if (backend == "nccl" and 2 <= world <= 8 and os.environ.get("B200PPO_P2P", "1") != "0"
             and getattr(engine, "precision", None) == _lib.PREC_BF16):
+        # every collective below is executed by every rank whatever happens locally; the exchange is switched on only if
+        # all ranks mapped all peers (cudaIpc needs peer access between the devices), otherwise everyone keeps NCCL
         handle = (C.c_uint8 * 64)()
-        with torch.cuda.device(engine.device):
-            _lib.check(lib.b200ppo_p2p_export(engine._ctx, handle), "b200ppo_p2p_export")
+        ok = True
+        try:
+            with torch.cuda.device(engine.device):
+                _lib.check(lib.b200ppo_p2p_export(engine._ctx, handle), "b200ppo_p2p_export")
+        except RuntimeError:
+            ok = False
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=engine.device)
         everyone = torch.empty(world * 64, dtype=torch.uint8, device=engine.device)
         dist.all_gather_into_tensor(everyone, mine, group=group)
-        handles = (C.c_uint8 * (world * 64))(*everyone.cpu().tolist())
-        with torch.cuda.device(engine.device):
-            _lib.check(lib.b200ppo_p2p_import(engine._ctx, handles, world), "b200ppo_p2p_import")
-        dist.barrier(group=group)  # nobody starts an exchange before every rank has mapped its peers
-        engine.p2p = True
+        if ok:
+            try:
+                handles = (C.c_uint8 * (world * 64))(*everyone.cpu().tolist())
+                with torch.cuda.device(engine.device):
+                    _lib.check(lib.b200ppo_p2p_import(engine._ctx, handles, world), "b200ppo_p2p_import")
+            except RuntimeError:
+                ok = False
+        agreed = torch.tensor([1 if ok else 0], dtype=torch.int32, device=engine.device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=group)  # also: nobody starts an exchange before every rank has mapped its peers
+        if int(agreed.item()) == 1:
+            with torch.cuda.device(engine.device):
+                _lib.check(lib.b200ppo_p2p_enable(engine._ctx, 1), "b200ppo_p2p_enable")
+            engine.p2p = True
 
 
 def all_gather_fields(fields: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
@@ -81,7 +95,7 @@ def share_rollout(engine, fields: Dict[str, torch.Tensor], group=None) -> Dict[s
     leaves (action, log-prob, advantage, target) are all-gathered.  Returns the fields for `engine.train`, with
     `current_state` = None.  Without it: `all_gather_fields`.
     """
-    if not getattr(engine, "p2p", False):
+    if not getattr(engine, "p2p", False) or getattr(engine, "_tables_ok", None) is False:
         return all_gather_fields(fields, group)
     world = dist.get_world_size(group)
     lib = _lib.load()
@@ -92,15 +106,29 @@ def share_rollout(engine, fields: Dict[str, torch.Tensor], group=None) -> Dict[s
     token = torch.zeros(1, device=obs.device)
     dist.all_reduce(token, group=group)
     if getattr(engine, "_shared_rows", 0) != rows:
+        # (re)map the tables; every rank runs every collective, and the tables are used only if all ranks mapped all peers
         handle = (C.c_uint8 * 64)()
-        with torch.cuda.device(engine.device):
-            _lib.check(lib.b200ppo_table_export(engine._ctx, rows, handle), "b200ppo_table_export")
+        ok = True
+        try:
+            with torch.cuda.device(engine.device):
+                _lib.check(lib.b200ppo_table_export(engine._ctx, rows, handle), "b200ppo_table_export")
+        except RuntimeError:
+            ok = False
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=engine.device)
         everyone = torch.empty(world * 64, dtype=torch.uint8, device=engine.device)
         dist.all_gather_into_tensor(everyone, mine, group=group)
-        handles = (C.c_uint8 * (world * 64))(*everyone.cpu().tolist())
-        with torch.cuda.device(engine.device):
-            _lib.check(lib.b200ppo_table_import(engine._ctx, handles, world, rows), "b200ppo_table_import")
+        if ok:
+            try:
+                handles = (C.c_uint8 * (world * 64))(*everyone.cpu().tolist())
+                with torch.cuda.device(engine.device):
+                    _lib.check(lib.b200ppo_table_import(engine._ctx, handles, world, rows), "b200ppo_table_import")
+            except RuntimeError:
+                ok = False
+        agreed = torch.tensor([1 if ok else 0], dtype=torch.int32, device=engine.device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=group)
+        engine._tables_ok = int(agreed.item()) == 1
+        if not engine._tables_ok:
+            return all_gather_fields(fields, group)
         engine._shared_rows = rows
     with torch.cuda.device(engine.device):
         _lib.check(lib.b200ppo_table_fill(engine._ctx, _lib.ptr(obs), rows, _lib.stream_ptr()), "b200ppo_table_fill")
