@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));  // power of two
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer + offset (not an integer round trip): the compiler keeps the shared address space and emits LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + TC_STAGES * B_BYTES);

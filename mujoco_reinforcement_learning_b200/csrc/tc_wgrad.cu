@@ -74,7 +74,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_wg
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t BIAS_COL = 256;  // TMEM column of the 32-wide bias accumulator
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer + offset (not an integer round trip): the compiler keeps the shared address space and emits LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;
   uint8_t* ones = smem + WG2_STAGES * WG2_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + WG2_ONES_BYTES);

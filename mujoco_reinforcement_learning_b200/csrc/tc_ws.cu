@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
   constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   constexpr int W_KB_BYTES = BN * TC_BK * 2;  // one 64-wide k-block of W
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer + offset (not an integer round trip): the compiler keeps the shared address space and emits LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int slot = 0;
 #pragma unroll 1
@@ -365,7 +366,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS2_THREADS, 1) tc_w
   constexpr uint32_t TMEM_COLS = 512;
   constexpr int W_KB_BYTES = BNL * TC_BK * 2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer + offset (not an integer round trip): the compiler keeps the shared address space and emits LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   if (grp.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) grp.trace[63 * 16] = clock64();  // kernel entry
