@@ -109,6 +109,9 @@ __device__ __forceinline__ float4 ld_peer4(const float* p) {  // peer memory: ne
   return r;
 }
 
+// PEERS: the gradient is the rank-ordered sum of every rank's exchange buffer (multi-GPU); kept out of the single-GPU
+// instantiation, whose register count (64) sets its occupancy.
+template <bool PEERS>
 __global__ void __launch_bounds__(256)
 adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, int n_partials, int64_t partial_stride,
                  float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t n, int64_t seg_split, AdamScalars s0,
@@ -117,7 +120,7 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
   __shared__ float s_lc[64];
   __shared__ float s_scr[256];
   pdl_wait_then_release();  // the gradient partials come from the kernel right before this one (common.cuh, PDL)
-  if (ps.world > 0) {
+  if constexpr (PEERS) {
     peer_exchange_barrier(ps);
     if (blockIdx.x == 0 && threadIdx.x < 2 && ps.losses_out != nullptr) {
       float l = 0.f;
@@ -141,7 +144,7 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
     const float4 m0 = *reinterpret_cast<float4*>(exp_avg + 4 * i);
     const float4 v0 = *reinterpret_cast<float4*>(exp_avg_sq + 4 * i);
     float4 g;
-    if (ps.world > 0) {  // every rank's buffer, all loads in flight, summed in rank order
+    if constexpr (PEERS) {  // every rank's buffer, all loads in flight, summed in rank order
       float4 h[kMaxPeers];
 #pragma unroll
       for (int r = 0; r < kMaxPeers; ++r)
@@ -153,7 +156,7 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
     } else {
       g = *reinterpret_cast<const float4*>(grads + 4 * i);
     }
-    int k0 = ps.world > 0 ? n_partials : 1;
+    int k0 = PEERS ? n_partials : 1;
     for (; k0 + 3 < n_partials; k0 += 4) {  // partials are added in index order (deterministic)
       const float4 h0 = *reinterpret_cast<const float4*>(grads + (k0 + 0) * partial_stride + 4 * i);
       const float4 h1 = *reinterpret_cast<const float4*>(grads + (k0 + 1) * partial_stride + 4 * i);
@@ -307,8 +310,12 @@ int launch_adam_cast(float* params, const float* grads, int n_partials, int64_t 
     ct.dst[k] = w.dst; ct.dst_t[k] = w.dst_t;
     ct.in[k] = w.in; ct.pitch[k] = w.pitch; ct.pitch_t[k] = w.pitch_t;
   }
-  B2_CUDA(launch_pdl(adam_cast_kernel, dim3(ew_grid(n / 4)), dim3(256), 0, st, params, grads, n_partials, partial_stride, exp_avg, exp_avg_sq, n, seg_split,
-                                                  s0, s1, ct, lc, peers ? *peers : no_peers));
+  if (peers != nullptr && peers->world > 0)
+    B2_CUDA(launch_pdl(adam_cast_kernel<true>, dim3(ew_grid(n / 4)), dim3(256), 0, st, params, grads, n_partials, partial_stride, exp_avg,
+                       exp_avg_sq, n, seg_split, s0, s1, ct, lc, *peers));
+  else
+    B2_CUDA(launch_pdl(adam_cast_kernel<false>, dim3(ew_grid(n / 4)), dim3(256), 0, st, params, grads, n_partials, partial_stride, exp_avg,
+                       exp_avg_sq, n, seg_split, s0, s1, ct, lc, no_peers));
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }
