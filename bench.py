@@ -309,6 +309,9 @@ def run_b200(args, config):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # one rank per GPU on a multi-socket host: run (and pin host buffers) on the CPUs local to this rank's GPU
+        from mujoco_reinforcement_learning_b200.distributed import bind_host_to_gpu
+        config["host_affinity"] = "gpu-local cpus" if bind_host_to_gpu(dev) else "unchanged"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()

@@ -26,6 +26,34 @@ def rank_rows(minibatch_index: int, global_batch: int, world: int, rank: int) ->
     return range(start, start + lb)
 
 
+def bind_host_to_gpu(device) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to `device` (its NUMA node), restricted to the CPUs
+    the process is already allowed on.  Called once per rank BEFORE the pinned host buffers are allocated: with eight
+    ranks on a two-socket host a slab pinned on the far socket crosses the inter-socket link on every host->device copy.
+    Returns False (and changes nothing) when NVML is unavailable or fewer than four local CPUs are allowed."""
+    try:
+        import pynvml
+        dev = torch.device(device)
+        props = torch.cuda.get_device_properties(dev)
+        bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        pynvml.nvmlInit()
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, ((os.cpu_count() or 1) + 63) // 64)
+        finally:
+            pynvml.nvmlShutdown()
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        both = local & allowed
+        if len(both) < 4:  # nothing local is allowed (or too little to hold the launch, NCCL proxy and runtime threads)
+            return False
+        if both != allowed:
+            os.sched_setaffinity(0, both)
+        return True
+    except Exception:  # affinity is an optimisation: never a reason to fail a run
+        return False
+
+
 def init_engine_comm(engine, group=None) -> None:
     """Create the engine's NCCL communicator: rank 0 makes the unique id, torch.distributed carries it."""
     if not dist.is_initialized():
