@@ -66,6 +66,21 @@ def _gloo_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def test_bind_host_to_gpu_never_fails_and_stays_inside_the_allowed_cpus():
+    """The NUMA binding is an optimisation: without a GPU / NVML it reports False and leaves the affinity alone;
+    with one it may only narrow the allowed set."""
+    before = os.sched_getaffinity(0)
+    try:
+        ok = D.bind_host_to_gpu("cuda:0")
+        after = os.sched_getaffinity(0)
+        assert isinstance(ok, bool)
+        assert after <= before and len(after) >= 1
+        if not ok:
+            assert after == before
+    finally:
+        os.sched_setaffinity(0, before)
+
+
 def test_gloo_world2_allgather_and_gradient_sum():
     world = 2
     mgr = mp.Manager()
