@@ -305,6 +305,43 @@ def test_bf16_train_vs_oracle(shape):
             assert float(st["step"]) == float(ref_state[pid]["step"])
 
 
+@pytest.mark.parametrize("shape", [dict(D=376, A=17, H=[256, 256], B=32768, act="tanh"),
+                                   dict(D=376, A=17, H=[256, 256], B=40000 - 7, act="relu"),   # ragged last row tile
+                                   dict(D=27, A=8, H=[256, 256], B=40960, act="tanh"),
+                                   dict(D=64, A=3, H=[128, 64], B=40960, act="tanh")])
+def test_bf16_output_dgrad_in_the_loss_epilogue_matches_the_separate_launch(shape, monkeypatch):
+    """B200PPO_FUSE_OUT_DGRAD=1: the output layers' dgrad (dZ2 = (dZout W_out) * act'(H2)) is computed inside the
+    fused-loss epilogue of the weights-stationary kernel instead of by its own launch.  Same seeds, same bf16 weights,
+    fp32 accumulation in a different order: gradients agree with the separate-launch path far inside the bf16
+    tolerance, and with the oracle to the usual 2e-2."""
+    D, A, H, B = (shape[k] for k in "DAHB")
+    oracle, agent, run = make_pair(D, A, H, H, shape["act"], batch=B, epochs=1, n_envs=1, steps=B, seed=11, max_batch=B,
+                                   precision="bf16")
+    g = torch.Generator().manual_seed(5)
+    obs, act = torch.randn(B, D, generator=g), torch.randn(B, A, generator=g)
+    adv, tgt = torch.randn(B, 1, generator=g), torch.randn(B, 1, generator=g)
+    with torch.no_grad():
+        mean, std = oracle.networks["actor"](obs)
+        old_lp = torch.distributions.Normal(mean, std).log_prob(act).sum(1) + 0.02 * torch.randn(B, generator=g)
+    eng = agent.engine
+    hp = eng.hparams(1e-4, 1e-4, oracle.cfg.clip_epsilon, oracle.cfg.entropy_eps)
+    args = [t.to(DEV) for t in (obs, act, old_lp, adv, tgt)]
+    monkeypatch.setenv("B200PPO_FUSE_OUT_DGRAD", "0")
+    losses0, grads0 = eng.minibatch_grads(*args, hp)
+    losses0, grads0 = losses0.clone(), grads0.clone()
+    monkeypatch.setenv("B200PPO_FUSE_OUT_DGRAD", "1")
+    losses1, grads1 = eng.minibatch_grads(*args, hp)
+    torch.cuda.synchronize()
+    assert torch.equal(losses0, losses1)
+    n0 = eng.grads_by_name(grads0, agent.networks.named_parameters())
+    n1 = eng.grads_by_name(grads1, agent.networks.named_parameters())
+    for k in n0:
+        assert_close_l2(n1[k], n0[k].cpu(), 2e-3, f"fused vs separate dgrad: {k}")
+    al, cl, grads_ref, _, _ = O.minibatch_grads(oracle, obs, act, old_lp, adv, tgt)
+    for k, ref in grads_ref.items():
+        assert_close_l2(n1[k], ref, RTOL_BF16 if shape["act"] == "tanh" else 5e-2, f"fused dgrad vs oracle: {k}")
+
+
 def test_checkpoint_files_move_between_implementations(tmp_path):
     """`Agent.save` / `load` (agent.py:47-72): the files written by the CUDA agent load into stock torch modules and
     `torch.optim.Adam` (the reference's side), and back into a fresh CUDA agent, without loss."""
