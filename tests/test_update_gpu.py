@@ -332,7 +332,8 @@ def test_bf16_output_dgrad_in_the_loss_epilogue_matches_the_separate_launch(shap
     monkeypatch.setenv("B200PPO_FUSE_OUT_DGRAD", "1")
     losses1, grads1 = eng.minibatch_grads(*args, hp)
     torch.cuda.synchronize()
-    assert torch.equal(losses0, losses1)
+    # same per-row terms; the CTAs' partial sums are combined in a different order (the fused launch shares its CTAs out by cost)
+    assert torch.allclose(losses0, losses1, rtol=1e-5, atol=1e-6)
     n0 = eng.grads_by_name(grads0, agent.networks.named_parameters())
     n1 = eng.grads_by_name(grads1, agent.networks.named_parameters())
     for k in n0:
