@@ -1,6 +1,6 @@
 """Turn raw captures in gpurun_out/ (ncu launch lists, .ncu-rep) into the tracked summaries under profiles/.
 
-    python profiles/summarize.py launches <gpurun_out/x_launches.csv> <profiles/out.md>
+    python profiles/summarize.py launches <gpurun_out/x_launches.csv> <profiles/out.md> [exclude-regex]
     python profiles/summarize.py rep <gpurun_out/x.ncu-rep> <profiles/out.csv>
 """
 import collections
@@ -17,7 +17,8 @@ KEYS = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct"]
 
 
-def launches(src, dst):
+def launches(src, dst, exclude=None):
+    import re
     lines = [l for l in open(src) if not l.startswith("==")]
     tot, cnt = collections.defaultdict(float), collections.Counter()
     for row in csv.DictReader(io.StringIO("".join(lines))):
@@ -26,11 +27,16 @@ def launches(src, dst):
         v = float(row["Metric Value"].replace(",", ""))
         v = {"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(row["Metric Unit"], v)
         k = row["Kernel Name"].split("(")[0]
+        if exclude and re.search(exclude, k):
+            continue
         tot[k] += v
         cnt[k] += 1
     s = sum(tot.values())
     with open(dst, "w") as f:
-        f.write(f"source: {src} (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised: compare shares)\n\n")
+        f.write(f"source: {src} (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised: compare shares)\n")
+        if exclude:
+            f.write(f"launches matching /{exclude}/ left out\n")
+        f.write("\n")
         f.write("| kernel | launches | total ms | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(tot.items(), key=lambda x: -x[1]):
             f.write(f"| `{k}` | {cnt[k]} | {v / 1e3:.3f} | {v / cnt[k]:.2f} | {v / s:.1%} |\n")
@@ -53,4 +59,4 @@ def rep(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "rep": rep}[sys.argv[1]](*sys.argv[2:])
