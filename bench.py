@@ -392,7 +392,9 @@ def run_b200(args, config):
 
     # ---- e2e through the C ABI with host buffers (single GPU: the host entry point is per-rank) --------------
     e2e = None
-    if world == 1:
+    if args.no_e2e:
+        pass
+    elif world == 1:
         pin = {k: v.pin_memory() for k, v in host.items()}
         pin_perms = [p.pin_memory() for p in perms_host]
         loss_host = torch.empty((E * nb, 2), dtype=torch.float32).pin_memory()
@@ -566,6 +568,7 @@ def main():
     ap.add_argument("--no-kernels", action="store_true", help="skip the HBM-kernel roofline mini-benchmarks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--no-variants", action="store_true", help="skip the secondary (precision, minibatch) settings")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer end-to-end measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

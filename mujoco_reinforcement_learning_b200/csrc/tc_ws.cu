@@ -10,6 +10,7 @@
 //   warp 1      MMA issuer (one lane): tcgen05.mma M=128, N=BN, K=16, commit -> frees the A stage / publishes the tile
 //   warps 2-9   epilogue (shared with tc_gemm.cu): tcgen05.ld, bias + MUFU tanh | act' multiply, bf16/fp32 stores
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -916,9 +917,16 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
   }
   // CTAs are shared out by row tiles — weighted by the epilogue's cost per tile when the output-layer dgrad rides in the
   // fused-loss epilogue: the actor's rows then carry act_dim FMAs per hidden unit on top of the loss math, the critic's one
+  static const char* cost_mode = getenv("B200PPO_FUSE_COST");  // profiling switch: "<actor>,<critic>" relative cost per row tile
+  int cost_actor = 0, cost_critic = 0;
+  if (cost_mode != nullptr && sscanf(cost_mode, "%d,%d", &cost_actor, &cost_critic) == 2 && cost_actor >= 1 && cost_critic >= 1) {
+  } else {
+    cost_actor = cost_critic = 0;
+  }
   auto tile_cost = [&](int i) -> int64_t {
     const TcProblem& q = g.p[i];
     if (q.ppo.dgrad_out == nullptr) return 1;
+    if (cost_actor > 0) return q.epilogue == TC_EPI_PPO_ACTOR ? cost_actor : cost_critic;
     return q.epilogue == TC_EPI_PPO_ACTOR ? 3 + (q.ppo.act_dim + 3) / 4 : 2;
   };
   int64_t work = 0, tiles_total = 0;  // (weighted) row tiles summed over slots

@@ -14,6 +14,10 @@ timeout 300 $SHORT > $OUT/${TAG}_bench_sep.json 2> $OUT/${TAG}_bench.err
 echo bench_sep_rc=$?
 B200PPO_FUSE_OUT_DGRAD=1 timeout 300 $SHORT > $OUT/${TAG}_bench_fused.json 2>> $OUT/${TAG}_bench.err
 echo bench_fused_rc=$?
+for COST in 5,2 12,2 1,1; do
+  B200PPO_FUSE_OUT_DGRAD=1 B200PPO_FUSE_COST=$COST timeout 300 $SHORT --no-e2e > $OUT/${TAG}_bench_fused_cost_${COST/,/_}.json 2>> $OUT/${TAG}_bench.err
+  echo bench_fused_cost_${COST}_rc=$?
+done
 B200PPO_FUSE_OUT_DGRAD=1 timeout 300 python -m pytest tests/test_update_gpu.py tests/test_distributed.py -m gpu -q -k "bf16" > $OUT/${TAG}_tests_bf16_fused_env.log 2>&1
 echo tests_bf16_env_rc=$?
 tail -3 $OUT/${TAG}_tests_bf16_fused_env.log
