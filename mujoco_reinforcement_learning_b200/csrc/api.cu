@@ -478,6 +478,7 @@ static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_b
           p.ppo.h = bf.H[n][l - 1]; p.ppo.h_pitch = bf.pitchH[n][l - 1];
           p.ppo.w_bf16 = bf.W[n][l]; p.ppo.w_pitch = bf.pitchW[n][l];
           p.ppo.hidden = N.in_dim(l); p.ppo.hidden_act = N.d.activation;
+          p.ppo.dgrad_nseeds = N.d.dims[l];
           fuse->dgrad_fused = true;
         }
       } else if (last) {

@@ -35,6 +35,7 @@ struct TcPpo {
   const __nv_bfloat16* h;        // [M, h_pitch] last hidden activation (this GEMM's A operand), rows 32-byte aligned
   const __nv_bfloat16* w_bf16;   // [N, w_pitch] bf16 copy of the output layer's weight (this GEMM's B operand)
   int dgrad_pitch, h_pitch, w_pitch, hidden, hidden_act;
+  int dgrad_nseeds;              // rows of w_bf16 = seeds per sample (act_dim for the actor, 1 for the critic)
 };
 
 // activation codes of TC_EPI_FWD beyond B200PPO_ACT_TANH / B200PPO_ACT_RELU

@@ -32,8 +32,10 @@ struct WsGroup {
   int tma_out[2];                  // the problem's epilogue leaves through tm_out
   int stage_tiles;                 // 4 KB staging tiles per epilogue warp (2, or 3 when a dgrad's weights leave room)
   int w_early;                     // the stationary weights were written >= 2 kernels back: load them before the PDL wait
-  int w32_bytes;                   // FUSE: shared memory behind the staging tiles for the fp32 copy of the output layer's weight
+  int w32_bytes;                   // FUSE: shared memory behind the staging tiles for the fp32 copy of the output layer's weight,
+                                   // followed by kWsSeedBytes of per-warp fp32 seed scratch
 };
+constexpr int kWsSeedBytes = 8 * 32 * 24 * 4;  // eight epilogue warps x 32 rows x up to 24 seeds
 
 long long* g_ws_trace = nullptr;  // set by the debug entry point only
 
@@ -71,81 +73,114 @@ __device__ __forceinline__ void ws2_dgrad16(const uint32_t (&v)[16], const uint3
 }
 
 // ---- output-layer dgrad inside the fused-loss epilogue (TcPpo::dgrad_out) --------------------------------------------------
-// dz_prev[m, c] = (sum_j seed[j] * W[j, c]) * act'(h[m, c]): one row per thread, like the loss math that produced the
-// seeds.  w32: fp32 copy of the layer's bf16 weight, [n_seeds][hidden] in shared memory — every lane reads the same
-// address (broadcast).  16 columns = one 256-bit access of the activation row and one of the result row; the next
-// activation segment is requested one step ahead.  CUDA cores, not a second MMA: n_seeds <= 32 FMAs per element is
-// less than the epilogue's own row math per tile, and nothing new has to be synchronised.
-template <int NS>
-__device__ __forceinline__ void ws_out_dgrad_row(const TcPpo& pp, int n_seeds, const float (&seed)[NS], int m, bool row_ok,
-                                                 const float* w32) {
+// dz_prev[m, c] = (sum_j seed[m, j] * W[j, c]) * act'(h[m, c]) for the 32 rows of this warp's TMEM lane quarter.
+// The rows' seeds go through a per-warp fp32 scratch in shared memory, so the work can be laid out for memory instead
+// of for the accumulator: a LANE owns four hidden columns (their weights stay in registers for the whole row tile), the
+// warp walks the rows, every global access of a row is one contiguous 256-byte piece (a first version with one row per
+// thread issued 32 separate sectors per instruction and cost more than the launch it replaced).  The seeds of a row
+// are broadcast loads; the products run on packed fp32 FMAs (FFMA2).  CUDA cores, not a second MMA: nothing new has
+// to be synchronised beyond a __syncwarp.
+__device__ __forceinline__ void ffma2_bcast(float& c0, float& c1, float a0, float a1, float b) {  // (c0, c1) += (a0, a1) * b
+  uint64_t A, B, C;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(C) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(C) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(C));
+}
+__device__ __forceinline__ uint2 ldg64_stream(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+// NSP: seeds per row in the scratch (n_seeds rounded up to a multiple of 4, the padding holds zeros).
+template <int NSP>
+__device__ __forceinline__ void ws_out_dgrad_cols(const TcPpo& pp, int mq, int M, int lane, const float* seed_s, const float* w32) {
   const int Hd = pp.hidden, act = pp.hidden_act;
-  const __nv_bfloat16* hrow = pp.h + int64_t(row_ok ? m : 0) * pp.h_pitch;
-  __nv_bfloat16* orow = pp.dgrad_out + int64_t(row_ok ? m : 0) * pp.dgrad_pitch;
-  uint32_t hcur[8], hnext[8];
-  ldg256(hrow, hcur);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) hnext[k] = 0u;
+  const int rows = min(32, M - mq);  // the same for every lane
+  if (rows <= 0) return;
+  const int n_rows_w = pp.dgrad_nseeds;
 #pragma unroll 1
-  for (int c0 = 0; c0 < Hd; c0 += 16) {
-    if (c0 + 16 < Hd) ldg256(hrow + c0 + 16, hnext);
-    float acc[16];
+  for (int c0 = 0; c0 < Hd; c0 += 128) {
+    const int c = c0 + 4 * lane;
+    const bool col_ok = c < Hd;  // hidden % 4 == 0: a lane's four columns are all inside or all outside
+    float w[NSP][4];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    for (int j = 0; j < NSP; ++j) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < n_rows_w && col_ok) t = *reinterpret_cast<const float4*>(w32 + j * Hd + c);
+      w[j][0] = t.x; w[j][1] = t.y; w[j][2] = t.z; w[j][3] = t.w;
+    }
+    const __nv_bfloat16* hp = pp.h + int64_t(mq) * pp.h_pitch + (col_ok ? c : 0);
+    __nv_bfloat16* op = pp.dgrad_out + int64_t(mq) * pp.dgrad_pitch + (col_ok ? c : 0);
+#pragma unroll 1
+    for (int r0 = 0; r0 < rows; r0 += 4) {
+      uint2 hv[4];
 #pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      if (j < n_seeds) {
-        const float4* wp = reinterpret_cast<const float4*>(w32 + j * Hd + c0);
-        const float sj = seed[j];
+      for (int u = 0; u < 4; ++u) {  // four rows' activations in flight before the first product
+        hv[u] = make_uint2(0u, 0u);
+        if (r0 + u < rows) hv[u] = ldg64_stream(hp + int64_t(r0 + u) * pp.h_pitch);
+      }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 w = wp[u];
-          acc[4 * u] = fmaf(sj, w.x, acc[4 * u]);
-          acc[4 * u + 1] = fmaf(sj, w.y, acc[4 * u + 1]);
-          acc[4 * u + 2] = fmaf(sj, w.z, acc[4 * u + 2]);
-          acc[4 * u + 3] = fmaf(sj, w.w, acc[4 * u + 3]);
+      for (int u = 0; u < 4; ++u) {
+        if (r0 + u < rows) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          const float4* sp = reinterpret_cast<const float4*>(seed_s + (r0 + u) * NSP);
+#pragma unroll
+          for (int jj = 0; jj < NSP / 4; ++jj) {
+            const float4 sv = sp[jj];  // every lane reads the same address: broadcast
+            ffma2_bcast(a0, a1, w[4 * jj][0], w[4 * jj][1], sv.x);         ffma2_bcast(a2, a3, w[4 * jj][2], w[4 * jj][3], sv.x);
+            ffma2_bcast(a0, a1, w[4 * jj + 1][0], w[4 * jj + 1][1], sv.y); ffma2_bcast(a2, a3, w[4 * jj + 1][2], w[4 * jj + 1][3], sv.y);
+            ffma2_bcast(a0, a1, w[4 * jj + 2][0], w[4 * jj + 2][1], sv.z); ffma2_bcast(a2, a3, w[4 * jj + 2][2], w[4 * jj + 2][3], sv.z);
+            ffma2_bcast(a0, a1, w[4 * jj + 3][0], w[4 * jj + 3][1], sv.w); ffma2_bcast(a2, a3, w[4 * jj + 3][2], w[4 * jj + 3][3], sv.w);
+          }
+          const float h0 = __uint_as_float(hv[u].x << 16), h1 = __uint_as_float(hv[u].x & 0xFFFF0000u);
+          const float h2 = __uint_as_float(hv[u].y << 16), h3 = __uint_as_float(hv[u].y & 0xFFFF0000u);
+          uint2 o;
+          if (act == B200PPO_ACT_TANH) {
+            o.x = pack_bf16(a0 * (1.f - h0 * h0), a1 * (1.f - h1 * h1));
+            o.y = pack_bf16(a2 * (1.f - h2 * h2), a3 * (1.f - h3 * h3));
+          } else {
+            o.x = pack_bf16(h0 > 0.f ? a0 : 0.f, h1 > 0.f ? a1 : 0.f);
+            o.y = pack_bf16(h2 > 0.f ? a2 : 0.f, h3 > 0.f ? a3 : 0.f);
+          }
+          if (col_ok) *reinterpret_cast<uint2*>(op + int64_t(r0 + u) * pp.dgrad_pitch) = o;
         }
       }
     }
-    uint32_t v[16], o[8];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(acc[k]);
-    ws2_dgrad16(v, hcur, act, o);
-    if (row_ok) stg256(orow + c0, o);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) hcur[k] = hnext[k];
   }
 }
 
-// This thread's row of the tile: the actor's seeds are read back from the warp's staging slab (bf16, as stored for the
-// weight-gradient kernel), the critic's single seed arrives in a register.
+// seed_s: this warp's scratch, 32 rows x nsp floats.  The actor's seeds are read back from the warp's staging slab (bf16,
+// as stored for the weight-gradient kernel), each lane converting its own row; the critic's single seed arrives in a register.
 __device__ __forceinline__ void ws_out_dgrad(const TcProblem& P, int m0, int warp, int lane, const uint8_t* stage, const float* w32,
-                                             float critic_seed) {
-  const int m = m0 + (warp & 3) * 32 + lane;
-  const bool row_ok = m < P.M;
+                                             float* seed_s, float critic_seed) {
+  const int mq = m0 + (warp & 3) * 32;
+  const int nsp = (P.ppo.dgrad_nseeds + 3) & ~3;
+  __syncwarp();  // the previous tile's rows have been consumed by every lane
   if (P.epilogue == TC_EPI_PPO_CRITIC) {
-    const float seed[1] = {critic_seed};
-    ws_out_dgrad_row<1>(P.ppo, 1, seed, m, row_ok, w32);
-    return;
-  }
-  const int A = P.ppo.act_dim, pitch = P.ppo.dz_pitch;
-  const uint32_t* dzw = reinterpret_cast<const uint32_t*>(stage + 32 * A * 4) + lane * (pitch >> 1);
-  auto run = [&](auto nc_tag) {
-    constexpr int NC = decltype(nc_tag)::value;
-    float seed[NC];
-#pragma unroll
-    for (int w = 0; w < NC / 2; ++w) {
-      const uint32_t x = 2 * w < pitch ? dzw[w] : 0u;
-      seed[2 * w] = __uint_as_float(x << 16);
-      seed[2 * w + 1] = __uint_as_float(x & 0xFFFF0000u);
+    *reinterpret_cast<float4*>(seed_s + lane * 4) = make_float4(critic_seed, 0.f, 0.f, 0.f);
+  } else {
+    const int pitch = P.ppo.dz_pitch;  // bf16 seeds per row in the slab, a multiple of 8, zero beyond act_dim
+    const uint32_t* dzw = reinterpret_cast<const uint32_t*>(stage + 32 * P.ppo.act_dim * 4) + lane * (pitch >> 1);
+    float* dst = seed_s + lane * nsp;
+    for (int k = 0; k < nsp; k += 4) {
+      const uint32_t x0 = k < pitch ? dzw[k >> 1] : 0u, x1 = k + 2 < pitch ? dzw[(k >> 1) + 1] : 0u;
+      *reinterpret_cast<float4*>(dst + k) = make_float4(__uint_as_float(x0 << 16), __uint_as_float(x0 & 0xFFFF0000u),
+                                                        __uint_as_float(x1 << 16), __uint_as_float(x1 & 0xFFFF0000u));
     }
-    ws_out_dgrad_row<NC>(P.ppo, A, seed, m, row_ok, w32);
-  };
-  const int nch = (A + 7) >> 3;
-  if (nch <= 1) run(std::integral_constant<int, 8>{});
-  else if (nch == 2) run(std::integral_constant<int, 16>{});
-  else if (nch == 3) run(std::integral_constant<int, 24>{});
-  else run(std::integral_constant<int, 32>{});
+  }
+  __syncwarp();
+  switch (nsp) {
+    case 4: ws_out_dgrad_cols<4>(P.ppo, mq, P.M, lane, seed_s, w32); break;
+    case 8: ws_out_dgrad_cols<8>(P.ppo, mq, P.M, lane, seed_s, w32); break;
+    case 12: ws_out_dgrad_cols<12>(P.ppo, mq, P.M, lane, seed_s, w32); break;
+    case 16: ws_out_dgrad_cols<16>(P.ppo, mq, P.M, lane, seed_s, w32); break;
+    case 20: ws_out_dgrad_cols<20>(P.ppo, mq, P.M, lane, seed_s, w32); break;
+    case 24: ws_out_dgrad_cols<24>(P.ppo, mq, P.M, lane, seed_s, w32); break;
+    default: break;  // launch_tc_ws refuses wider output layers
+  }
 }
 
 template <int BN, bool FUSE = false>
@@ -302,7 +337,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[grp_id]);
           if constexpr (FUSE) {  // the accumulator is already back with the MMA warp: the dgrad only needs the seeds
-            if (P.ppo.dgrad_out != nullptr) ws_out_dgrad(P, tile * TC_BM, warp, lane, st[u & 1], w32_s, critic_seed);
+            if (P.ppo.dgrad_out != nullptr)
+              ws_out_dgrad(P, tile * TC_BM, warp, lane, st[u & 1], w32_s, w32_s + (grp.w32_bytes >> 2) + (warp - 2) * 32 * 24, critic_seed);
           }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -790,9 +826,9 @@ bool tc_ws_applicable(int64_t total_tiles_m, int maxN, int maxK) {
 bool tc_ws_out_dgrad_fits(int n_out, int hidden) {
   int bn, st, tl;
   ws_plan(n_out, hidden, 2, &bn, &st, &tl);
-  if (bn != 64 || n_out < 1 || n_out > 32 || hidden < 16 || hidden % 16 != 0) return false;
+  if (bn != 64 || n_out < 1 || n_out > 24 || hidden < 16 || hidden % 16 != 0) return false;
   const int kb = (hidden + TC_BK - 1) / TC_BK;
-  const int64_t avail = kWsMaxSmem - ws_fixed_smem(tl) - int64_t(kb) * bn * TC_BK * 2 - (int64_t(n_out) * hidden * 4 + 15) / 16 * 16;
+  const int64_t avail = kWsMaxSmem - ws_fixed_smem(tl) - int64_t(kb) * bn * TC_BK * 2 - (int64_t(n_out) * hidden * 4 + 15) / 16 * 16 - kWsSeedBytes;
   return avail / TC_A_BYTES >= 3;
 }
 
@@ -804,7 +840,7 @@ int tc_ws_bn(int maxN, int maxK) {
 
 template <int BN, bool FUSE = false>
 static int launch_ws_bn(const WsGroup& g, int stages, int kb_max, int grid, cudaStream_t st) {
-  const int smem = kb_max * BN * TC_BK * 2 + stages * TC_A_BYTES + ws_fixed_smem(g.stage_tiles) + (FUSE ? g.w32_bytes : 0);
+  const int smem = kb_max * BN * TC_BK * 2 + stages * TC_A_BYTES + ws_fixed_smem(g.stage_tiles) + (FUSE ? g.w32_bytes + kWsSeedBytes : 0);
   static int configured = 0;
   if (configured < smem) {
     B2_CUDA(cudaFuncSetAttribute(tc_ws_kernel<BN, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -962,7 +998,10 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
     B2_CHECK_ARG(bn == 64, "fused output-layer dgrad: only with the 64-wide weights-stationary kernel");
     for (int i = 0; i < g.count; ++i)
       B2_CHECK_ARG(g.p[i].epilogue >= TC_EPI_PPO_ACTOR && g.p[i].ppo.dgrad_out != nullptr, "fused output-layer dgrad: every problem of the launch must carry it");
-    const int64_t avail = kWsMaxSmem - ws_fixed_smem(stage_tiles) - int64_t(kb_max) * bn * TC_BK * 2 - w.w32_bytes;
+    for (int i = 0; i < g.count; ++i)
+      B2_CHECK_ARG(g.p[i].ppo.dgrad_nseeds >= 1 && g.p[i].ppo.dgrad_nseeds <= 24 && g.p[i].ppo.dgrad_nseeds == g.p[i].N && g.p[i].ppo.hidden % 4 == 0,
+                   "fused output-layer dgrad: 1..24 outputs, hidden width a multiple of 4");
+    const int64_t avail = kWsMaxSmem - ws_fixed_smem(stage_tiles) - int64_t(kb_max) * bn * TC_BK * 2 - w.w32_bytes - kWsSeedBytes;
     stages = int(std::min<int64_t>(stages, avail / TC_A_BYTES));
     B2_CHECK_ARG(stages >= 3, "fused output-layer dgrad: weight copy does not fit in shared memory");
   }

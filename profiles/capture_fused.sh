@@ -14,7 +14,7 @@ timeout 300 $SHORT > $OUT/${TAG}_bench_sep.json 2> $OUT/${TAG}_bench.err
 echo bench_sep_rc=$?
 B200PPO_FUSE_OUT_DGRAD=1 timeout 300 $SHORT > $OUT/${TAG}_bench_fused.json 2>> $OUT/${TAG}_bench.err
 echo bench_fused_rc=$?
-for COST in 5,2 12,2 1,1; do
+for COST in 3,1 2,1 6,1; do
   B200PPO_FUSE_OUT_DGRAD=1 B200PPO_FUSE_COST=$COST timeout 300 $SHORT --no-e2e > $OUT/${TAG}_bench_fused_cost_${COST/,/_}.json 2>> $OUT/${TAG}_bench.err
   echo bench_fused_cost_${COST}_rc=$?
 done

