@@ -413,29 +413,7 @@ struct PpoFuse {
   const float *action, *old_logp, *advantage, *target;
   const b200ppo_hparams* hp;
   int loss_ctas;  // out: CTAs that wrote a row of loss partials
-  bool dgrad_fused = false;  // out: the output layers' dgrad ran inside the loss epilogue (bf.dZ[n][L-2] is filled)
 };
-
-// Output-layer dgrad inside the fused-loss epilogue (tc_ws.cu, TcPpo::dgrad_out): both nets of equal depth, last hidden
-// layers of the same width, rows of the activation / gradient buffers on 32-byte sectors.
-// B200PPO_FUSE_OUT_DGRAD=1 switches it on (off by default until it has been measured on the GPU).
-static bool out_dgrad_fusable(const b200ppo_ctx* ctx) {
-  const char* mode = getenv("B200PPO_FUSE_OUT_DGRAD");  // read per call: the parity test flips it inside one process
-  if (mode == nullptr || mode[0] != '1') return false;
-  const auto& bf = ctx->bf;
-  const int L = ctx->net[0].d.n_layers;
-  if (L < 2 || ctx->net[1].d.n_layers != L) return false;
-  const int hidden = ctx->net[0].in_dim(L - 1);
-  int n_out = 0;
-  for (int n = 0; n < 2; ++n) {
-    const Net& N = ctx->net[n];
-    if (N.in_dim(L - 1) != hidden || (N.d.activation != B200PPO_ACT_TANH && N.d.activation != B200PPO_ACT_RELU)) return false;
-    if (bf.pitchZ[n][L - 2] % 16 != 0 || bf.pitchH[n][L - 2] % 16 != 0) return false;
-    if ((reinterpret_cast<uintptr_t>(bf.dZ[n][L - 2]) & 31u) != 0 || (reinterpret_cast<uintptr_t>(bf.H[n][L - 2]) & 31u) != 0) return false;
-    n_out = std::max(n_out, N.d.dims[L - 1]);
-  }
-  return tc_ws_out_dgrad_fits(n_out, hidden);
-}
 
 static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_bfloat16* xb, int64_t B,
                              float* const outs[2], cudaStream_t st, PpoFuse* fuse = nullptr) {
@@ -473,14 +451,6 @@ static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_b
         p.ppo.final_tanh = N.d.final_tanh;
         p.ppo.clip_eps = float(fuse->hp->clip_epsilon);
         p.ppo.inv_global_batch = 1.f / float(B * ctx->world);
-        if (ws && out_dgrad_fusable(ctx)) {
-          p.ppo.dgrad_out = bf.dZ[n][l - 1]; p.ppo.dgrad_pitch = bf.pitchZ[n][l - 1];
-          p.ppo.h = bf.H[n][l - 1]; p.ppo.h_pitch = bf.pitchH[n][l - 1];
-          p.ppo.w_bf16 = bf.W[n][l]; p.ppo.w_pitch = bf.pitchW[n][l];
-          p.ppo.hidden = N.in_dim(l); p.ppo.hidden_act = N.d.activation;
-          p.ppo.dgrad_nseeds = N.d.dims[l];
-          fuse->dgrad_fused = true;
-        }
       } else if (last) {
         p.act = N.d.final_tanh ? TC_ACT_TANH_SCALE : TC_ACT_NONE;
         p.out_scale = N.d.out_scale;
@@ -503,12 +473,12 @@ static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_b
 
 // backward of both nets on the tensor cores.  bf.dZ[n][L-1] (dL/dz of the output layers, bf16) is filled on entry.
 static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t B, float* gpart, int* split_out,
-                              cudaStream_t st, bool out_dgrad_done = false) {
+                              cudaStream_t st) {
   auto& bf = ctx->bf;
   int maxL = 0;
   for (int n = 0; n < 2; ++n) maxL = std::max(maxL, ctx->net[n].d.n_layers);
   // dgrads, deepest first: dZ_{l-1} = (dZ_l W_l) * act'(H_{l-1}),  B operand = the bf16 copy of W_l read MN-major
-  for (int s = out_dgrad_done ? 1 : 0; s < maxL; ++s) {  // out_dgrad_done: dZ_{L-2} came out of the fused-loss epilogue
+  for (int s = 0; s < maxL; ++s) {
     TcGroup g{};
     int maxN = 0, nets_here = 0;
     for (int n = 0; n < 2; ++n) {
@@ -660,7 +630,7 @@ static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float*
       PpoFuse fuse{action, old_logp, adv, tgt, hp, 0};
       B2_TRY(forward_nets_bf16(ctx, params, obs_b, B, outs, st, &fuse));
       *loss_ctas_out = fuse.loss_ctas;
-      return backward_nets_bf16(ctx, obs_b, B, ctx->gpart, split_out, st, fuse.dgrad_fused);
+      return backward_nets_bf16(ctx, obs_b, B, ctx->gpart, split_out, st);
     }
     B2_TRY(forward_nets_bf16(ctx, params, obs_b, B, outs, st));
     LossArgs la{};

@@ -541,7 +541,7 @@ template <int BN>
 __device__ __forceinline__ void tc_epilogue_ppo(const TcProblem& P, uint32_t tmem_acc, int m0, int warp, int lane,
                                                 uint64_t* tmem_full_bar, uint32_t full_parity, uint8_t* stage,
                                                 const float* bias_s, const float* consts_s, int groups_in_flight, PpoAcc& acc,
-                                                bool worker, long long* tr = nullptr, float* critic_seed = nullptr) {
+                                                bool worker, long long* tr = nullptr) {
   // worker: this warp processes the tile's rows of its TMEM lane quarter (the <= 32 output columns all sit in one
   // thread).  Two warps share a lane quarter: the one-tile kernel lets the first work; the persistent kernel
   // alternates tiles between the two warp groups.
@@ -565,14 +565,12 @@ __device__ __forceinline__ void tc_epilogue_ppo(const TcProblem& P, uint32_t tme
   if (P.epilogue == TC_EPI_PPO_CRITIC) {
     uint32_t v[16];
     tmem_ld16(tmem_acc + (uint32_t(q * 32) << 16), v);
-    if (critic_seed != nullptr) *critic_seed = 0.f;
     if (row_ok) {
       const float val = __uint_as_float(v[0]) + bias_s[0];
       const float e = val - tgt;
       const float ae = fabsf(e);
       acc.hub += ae < 1.f ? 0.5f * e * e : ae - 0.5f;
       const float dv = fminf(fmaxf(e, -1.f), 1.f) * P.ppo.inv_global_batch;
-      if (critic_seed != nullptr) *critic_seed = __bfloat162float(__float2bfloat16_rn(dv));  // the value the wgrad reads
       const int pitch = P.ppo.dz_pitch;
       __nv_bfloat16* o = P.ppo.dz_out + int64_t(m) * pitch;
       if (pitch == 8) {

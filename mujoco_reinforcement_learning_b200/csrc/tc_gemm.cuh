@@ -28,14 +28,6 @@ struct TcPpo {
   float* partials;         // [gridDim.x][2 + A]: (sum surrogate, sum huber, sum d loss / d logstd_j) per CTA
   int dz_pitch, act_dim, final_tanh;
   float clip_eps, inv_global_batch;
-  // Optional (weights-stationary kernel only, nullptr = off): the output layer's dgrad in the same epilogue,
-  // dgrad_out[m, c] = (sum_j dz[m, j] * W[j, c]) * act'(h[m, c]) for c < hidden — the seeds of a row never leave the
-  // thread that computed them, so the separate dgrad launch over the same rows disappears (ppo.py:121,134 autograd).
-  __nv_bfloat16* dgrad_out;      // [M, dgrad_pitch] bf16, rows 32-byte aligned
-  const __nv_bfloat16* h;        // [M, h_pitch] last hidden activation (this GEMM's A operand), rows 32-byte aligned
-  const __nv_bfloat16* w_bf16;   // [N, w_pitch] bf16 copy of the output layer's weight (this GEMM's B operand)
-  int dgrad_pitch, h_pitch, w_pitch, hidden, hidden_act;
-  int dgrad_nseeds;              // rows of w_bf16 = seeds per sample (act_dim for the actor, 1 for the critic)
 };
 
 // activation codes of TC_EPI_FWD beyond B200PPO_ACT_TANH / B200PPO_ACT_RELU
@@ -95,7 +87,6 @@ int tc_ctas_per_sm(int bn);
 // Persistent weights-stationary variant (tc_ws.cu) for forward / dgrad groups with many row tiles.
 bool tc_ws_applicable(int64_t total_tiles_m, int maxN, int maxK);
 int tc_ws_bn(int maxN, int maxK);
-bool tc_ws_out_dgrad_fits(int n_out, int hidden);  // TcPpo::dgrad_out usable for these output / hidden widths
 // w_early: the weights were last written two or more kernels back in the stream (never true right after the optimizer)
 int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out = nullptr, bool w_early = false);  // resident CTAs per SM of the bn-wide kernel instance
 

@@ -10,9 +10,7 @@
 //   warp 1      MMA issuer (one lane): tcgen05.mma M=128, N=BN, K=16, commit -> frees the A stage / publishes the tile
 //   warps 2-9   epilogue (shared with tc_gemm.cu): tcgen05.ld, bias + MUFU tanh | act' multiply, bf16/fp32 stores
 #include <algorithm>
-#include <cstdio>
 #include <cstdlib>
-#include <type_traits>
 
 #include "tc_common.cuh"
 
@@ -32,10 +30,7 @@ struct WsGroup {
   int tma_out[2];                  // the problem's epilogue leaves through tm_out
   int stage_tiles;                 // 4 KB staging tiles per epilogue warp (2, or 3 when a dgrad's weights leave room)
   int w_early;                     // the stationary weights were written >= 2 kernels back: load them before the PDL wait
-  int w32_bytes;                   // FUSE: shared memory behind the staging tiles for the fp32 copy of the output layer's weight,
-                                   // followed by kWsSeedBytes of per-warp fp32 seed scratch
 };
-constexpr int kWsSeedBytes = 8 * 32 * 24 * 4;  // eight epilogue warps x 32 rows x up to 24 seeds
 
 long long* g_ws_trace = nullptr;  // set by the debug entry point only
 
@@ -48,142 +43,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// 256-bit global accesses (one full 32-byte sector per thread): the dgrad epilogue of the pair kernel reads its
-// activation row and writes its result row straight from registers — no staging tile, so shared memory is left to the
-// operands (W half + a deep A ring) and the epilogue does not compete with the MMAs for shared-memory bandwidth.
-__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
-               "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-// dz = acc * act'(h) for 16 columns of this thread's row; h: 16 bf16 activations (8 words)
-__device__ __forceinline__ void ws2_dgrad16(const uint32_t (&v)[16], const uint32_t (&h)[8], int act, uint32_t (&o)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float h0 = __uint_as_float(h[j] << 16), h1 = __uint_as_float(h[j] & 0xFFFF0000u);
-    const float g0 = __uint_as_float(v[2 * j]), g1 = __uint_as_float(v[2 * j + 1]);
-    if (act == B200PPO_ACT_TANH) o[j] = pack_bf16(g0 * (1.f - h0 * h0), g1 * (1.f - h1 * h1));
-    else o[j] = pack_bf16(h0 > 0.f ? g0 : 0.f, h1 > 0.f ? g1 : 0.f);
-  }
-}
-
-// ---- output-layer dgrad inside the fused-loss epilogue (TcPpo::dgrad_out) --------------------------------------------------
-// dz_prev[m, c] = (sum_j seed[m, j] * W[j, c]) * act'(h[m, c]) for the 32 rows of this warp's TMEM lane quarter.
-// The rows' seeds go through a per-warp fp32 scratch in shared memory, so the work can be laid out for memory instead
-// of for the accumulator: a LANE owns four hidden columns (their weights stay in registers for the whole row tile), the
-// warp walks the rows, every global access of a row is one contiguous 256-byte piece (a first version with one row per
-// thread issued 32 separate sectors per instruction and cost more than the launch it replaced).  The seeds of a row
-// are broadcast loads; the products run on packed fp32 FMAs (FFMA2).  CUDA cores, not a second MMA: nothing new has
-// to be synchronised beyond a __syncwarp.
-__device__ __forceinline__ void ffma2_bcast(float& c0, float& c1, float a0, float a1, float b) {  // (c0, c1) += (a0, a1) * b
-  uint64_t A, B, C;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(C) : "f"(c0), "f"(c1));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(C) : "l"(A), "l"(B));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(C));
-}
-__device__ __forceinline__ uint2 ldg64_stream(const void* p) {
-  uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  return r;
-}
-
-// NSP: seeds per row in the scratch (n_seeds rounded up to a multiple of 4, the padding holds zeros).
-template <int NSP>
-__device__ __forceinline__ void ws_out_dgrad_cols(const TcPpo& pp, int mq, int M, int lane, const float* seed_s, const float* w32) {
-  const int Hd = pp.hidden, act = pp.hidden_act;
-  const int rows = min(32, M - mq);  // the same for every lane
-  if (rows <= 0) return;
-  const int n_rows_w = pp.dgrad_nseeds;
-#pragma unroll 1
-  for (int c0 = 0; c0 < Hd; c0 += 128) {
-    const int c = c0 + 4 * lane;
-    const bool col_ok = c < Hd;  // hidden % 4 == 0: a lane's four columns are all inside or all outside
-    float w[NSP][4];
-#pragma unroll
-    for (int j = 0; j < NSP; ++j) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < n_rows_w && col_ok) t = *reinterpret_cast<const float4*>(w32 + j * Hd + c);
-      w[j][0] = t.x; w[j][1] = t.y; w[j][2] = t.z; w[j][3] = t.w;
-    }
-    const __nv_bfloat16* hp = pp.h + int64_t(mq) * pp.h_pitch + (col_ok ? c : 0);
-    __nv_bfloat16* op = pp.dgrad_out + int64_t(mq) * pp.dgrad_pitch + (col_ok ? c : 0);
-#pragma unroll 1
-    for (int r0 = 0; r0 < rows; r0 += 4) {
-      uint2 hv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {  // four rows' activations in flight before the first product
-        hv[u] = make_uint2(0u, 0u);
-        if (r0 + u < rows) hv[u] = ldg64_stream(hp + int64_t(r0 + u) * pp.h_pitch);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (r0 + u < rows) {
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-          const float4* sp = reinterpret_cast<const float4*>(seed_s + (r0 + u) * NSP);
-#pragma unroll
-          for (int jj = 0; jj < NSP / 4; ++jj) {
-            const float4 sv = sp[jj];  // every lane reads the same address: broadcast
-            ffma2_bcast(a0, a1, w[4 * jj][0], w[4 * jj][1], sv.x);         ffma2_bcast(a2, a3, w[4 * jj][2], w[4 * jj][3], sv.x);
-            ffma2_bcast(a0, a1, w[4 * jj + 1][0], w[4 * jj + 1][1], sv.y); ffma2_bcast(a2, a3, w[4 * jj + 1][2], w[4 * jj + 1][3], sv.y);
-            ffma2_bcast(a0, a1, w[4 * jj + 2][0], w[4 * jj + 2][1], sv.z); ffma2_bcast(a2, a3, w[4 * jj + 2][2], w[4 * jj + 2][3], sv.z);
-            ffma2_bcast(a0, a1, w[4 * jj + 3][0], w[4 * jj + 3][1], sv.w); ffma2_bcast(a2, a3, w[4 * jj + 3][2], w[4 * jj + 3][3], sv.w);
-          }
-          const float h0 = __uint_as_float(hv[u].x << 16), h1 = __uint_as_float(hv[u].x & 0xFFFF0000u);
-          const float h2 = __uint_as_float(hv[u].y << 16), h3 = __uint_as_float(hv[u].y & 0xFFFF0000u);
-          uint2 o;
-          if (act == B200PPO_ACT_TANH) {
-            o.x = pack_bf16(a0 * (1.f - h0 * h0), a1 * (1.f - h1 * h1));
-            o.y = pack_bf16(a2 * (1.f - h2 * h2), a3 * (1.f - h3 * h3));
-          } else {
-            o.x = pack_bf16(h0 > 0.f ? a0 : 0.f, h1 > 0.f ? a1 : 0.f);
-            o.y = pack_bf16(h2 > 0.f ? a2 : 0.f, h3 > 0.f ? a3 : 0.f);
-          }
-          if (col_ok) *reinterpret_cast<uint2*>(op + int64_t(r0 + u) * pp.dgrad_pitch) = o;
-        }
-      }
-    }
-  }
-}
-
-// seed_s: this warp's scratch, 32 rows x nsp floats.  The actor's seeds are read back from the warp's staging slab (bf16,
-// as stored for the weight-gradient kernel), each lane converting its own row; the critic's single seed arrives in a register.
-__device__ __forceinline__ void ws_out_dgrad(const TcProblem& P, int m0, int warp, int lane, const uint8_t* stage, const float* w32,
-                                             float* seed_s, float critic_seed) {
-  const int mq = m0 + (warp & 3) * 32;
-  const int nsp = (P.ppo.dgrad_nseeds + 3) & ~3;
-  __syncwarp();  // the previous tile's rows have been consumed by every lane
-  if (P.epilogue == TC_EPI_PPO_CRITIC) {
-    *reinterpret_cast<float4*>(seed_s + lane * 4) = make_float4(critic_seed, 0.f, 0.f, 0.f);
-  } else {
-    const int pitch = P.ppo.dz_pitch;  // bf16 seeds per row in the slab, a multiple of 8, zero beyond act_dim
-    const uint32_t* dzw = reinterpret_cast<const uint32_t*>(stage + 32 * P.ppo.act_dim * 4) + lane * (pitch >> 1);
-    float* dst = seed_s + lane * nsp;
-    for (int k = 0; k < nsp; k += 4) {
-      const uint32_t x0 = k < pitch ? dzw[k >> 1] : 0u, x1 = k + 2 < pitch ? dzw[(k >> 1) + 1] : 0u;
-      *reinterpret_cast<float4*>(dst + k) = make_float4(__uint_as_float(x0 << 16), __uint_as_float(x0 & 0xFFFF0000u),
-                                                        __uint_as_float(x1 << 16), __uint_as_float(x1 & 0xFFFF0000u));
-    }
-  }
-  __syncwarp();
-  switch (nsp) {
-    case 4: ws_out_dgrad_cols<4>(P.ppo, mq, P.M, lane, seed_s, w32); break;
-    case 8: ws_out_dgrad_cols<8>(P.ppo, mq, P.M, lane, seed_s, w32); break;
-    case 12: ws_out_dgrad_cols<12>(P.ppo, mq, P.M, lane, seed_s, w32); break;
-    case 16: ws_out_dgrad_cols<16>(P.ppo, mq, P.M, lane, seed_s, w32); break;
-    case 20: ws_out_dgrad_cols<20>(P.ppo, mq, P.M, lane, seed_s, w32); break;
-    case 24: ws_out_dgrad_cols<24>(P.ppo, mq, P.M, lane, seed_s, w32); break;
-    default: break;  // launch_tc_ws refuses wider output layers
-  }
-}
-
-template <int BN, bool FUSE = false>
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_constant__ WsGroup grp, int a_stages) {
   constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   constexpr int W_KB_BYTES = BN * TC_BK * 2;  // one 64-wide k-block of W
@@ -215,7 +75,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
   float* consts_s = bias_s + 256;                                                    // 96 floats (fused PPO epilogue)
   float* red_s = bias_s + 352;                                                       // 8 x 34 floats
   uint8_t* stage_area = reinterpret_cast<uint8_t*>(bars) + 4096;  // TC_EPI_WARPS x stage_tiles x 4 KB, 1024-byte aligned (swizzle atoms)
-  float* w32_s = reinterpret_cast<float*>(stage_area + size_t(TC_EPI_WARPS) * grp.stage_tiles * TC_STAGE_BYTES);  // FUSE only
 
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
@@ -249,15 +108,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
   if (warp >= 2) {  // epilogue warps stage their constants (named barrier 1: the other two warps are already streaming)
     tc_stage_bias(P, n0, BN, bias_s, threadIdx.x - 64, TC_THREADS - 64);
     tc_ppo_stage_consts(P, consts_s, threadIdx.x - 64);
-    if constexpr (FUSE) {
-      if (P.ppo.dgrad_out != nullptr) {  // fp32 copy of the bf16 weight the MMA reads, row-major [N][hidden]
-        const int Hd = P.ppo.hidden, total = P.N * Hd;
-        for (int i = int(threadIdx.x) - 64; i < total; i += TC_THREADS - 64) {
-          const int j = i / Hd, c = i - j * Hd;
-          w32_s[i] = __bfloat162float(P.ppo.w_bf16[int64_t(j) * P.ppo.w_pitch + c]);
-        }
-      }
-    }
     asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS - 64) : "memory");
   }
 
@@ -326,20 +176,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ws_kernel(const __grid_const
           const int next = tile + step;
           tc_ppo_issue(P, next * TC_BM, warp, lane, st[(u & 1) ^ 1], next < tiles_m);
           if ((warp & 3) == 2 && lane == 0) WS_TRACE(2 * u + grp_id, 5);
-          float critic_seed = 0.f;
           tc_epilogue_ppo<BN>(P, tmem_base + uint32_t(grp_id * BN), tile * TC_BM, warp, lane, &acc_full[grp_id], uint32_t(u & 1),
                               st[u & 1], bias_s, consts_s, 1, acc, true,
                               (grp.trace != nullptr && blockIdx.x == 0 && (warp & 3) == 2 && lane == 0 && 2 * u + grp_id < 63)
-                                  ? grp.trace + (2 * u + grp_id) * 16 + 8 : nullptr,
-                              &critic_seed);
+                                  ? grp.trace + (2 * u + grp_id) * 16 + 8 : nullptr);
           if ((warp & 3) == 2 && lane == 0) WS_TRACE(2 * u + grp_id, 6);
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[grp_id]);
-          if constexpr (FUSE) {  // the accumulator is already back with the MMA warp: the dgrad only needs the seeds
-            if (P.ppo.dgrad_out != nullptr)
-              ws_out_dgrad(P, tile * TC_BM, warp, lane, st[u & 1], w32_s, w32_s + (grp.w32_bytes >> 2) + (warp - 2) * 32 * 24, critic_seed);
-          }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         tc_ppo_finish(P, warp, lane, red_s, acc, true);
@@ -486,6 +330,30 @@ __device__ __forceinline__ void ws2_finish16(const uint32_t (&v)[16], const floa
   ws2_act16(v, bs, act, o);
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s) ^ sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s + 1) ^ sw) << 4)), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
+
+// 256-bit global accesses (one full 32-byte sector per thread): the dgrad epilogue of the pair kernel reads its
+// activation row and writes its result row straight from registers — no staging tile, so shared memory is left to the
+// operands (W half + a deep A ring) and the epilogue does not compete with the MMAs for shared-memory bandwidth.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// dz = acc * act'(h) for 16 columns of this thread's row; h: 16 bf16 activations (8 words)
+__device__ __forceinline__ void ws2_dgrad16(const uint32_t (&v)[16], const uint32_t (&h)[8], int act, uint32_t (&o)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float h0 = __uint_as_float(h[j] << 16), h1 = __uint_as_float(h[j] & 0xFFFF0000u);
+    const float g0 = __uint_as_float(v[2 * j]), g1 = __uint_as_float(v[2 * j + 1]);
+    if (act == B200PPO_ACT_TANH) o[j] = pack_bf16(g0 * (1.f - h0 * h0), g1 * (1.f - h1 * h1));
+    else o[j] = pack_bf16(h0 > 0.f ? g0 : 0.f, h1 > 0.f ? g1 : 0.f);
+  }
 }
 
 constexpr int WS2_EPI_WARPS = 16;  // four per TMEM lane quarter, one 64-column chunk each: MUFU.TANH (16/clk/SM) is the epilogue's
@@ -821,32 +689,21 @@ bool tc_ws_applicable(int64_t total_tiles_m, int maxN, int maxK) {
   return bn != 0 && total_tiles_m >= 2ll * num_sms();
 }
 
-// May the output layers' dgrad ride in the fused-loss epilogue (TcPpo::dgrad_out)?  n_out: widest output layer of the
-// launch, hidden: width of the last hidden layer (= K of the launch).  Mirrors the shared-memory budget of launch_tc_ws.
-bool tc_ws_out_dgrad_fits(int n_out, int hidden) {
-  int bn, st, tl;
-  ws_plan(n_out, hidden, 2, &bn, &st, &tl);
-  if (bn != 64 || n_out < 1 || n_out > 24 || hidden < 16 || hidden % 16 != 0) return false;
-  const int kb = (hidden + TC_BK - 1) / TC_BK;
-  const int64_t avail = kWsMaxSmem - ws_fixed_smem(tl) - int64_t(kb) * bn * TC_BK * 2 - (int64_t(n_out) * hidden * 4 + 15) / 16 * 16 - kWsSeedBytes;
-  return avail / TC_A_BYTES >= 3;
-}
-
 int tc_ws_bn(int maxN, int maxK) {
   int bn, st, tl;
   ws_plan(maxN, maxK, 2, &bn, &st, &tl);
   return bn;
 }
 
-template <int BN, bool FUSE = false>
+template <int BN>
 static int launch_ws_bn(const WsGroup& g, int stages, int kb_max, int grid, cudaStream_t st) {
-  const int smem = kb_max * BN * TC_BK * 2 + stages * TC_A_BYTES + ws_fixed_smem(g.stage_tiles) + (FUSE ? g.w32_bytes + kWsSeedBytes : 0);
+  const int smem = kb_max * BN * TC_BK * 2 + stages * TC_A_BYTES + ws_fixed_smem(g.stage_tiles);
   static int configured = 0;
   if (configured < smem) {
-    B2_CUDA(cudaFuncSetAttribute(tc_ws_kernel<BN, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B2_CUDA(cudaFuncSetAttribute(tc_ws_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  B2_CUDA(launch_pdl(tc_ws_kernel<BN, FUSE>, dim3(grid), dim3(TC_THREADS), smem, st, g, stages));
+  B2_CUDA(launch_pdl(tc_ws_kernel<BN>, dim3(grid), dim3(TC_THREADS), smem, st, g, stages));
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }
@@ -951,36 +808,21 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
       w.tma_out[i] = 1;
     }
   }
-  // CTAs are shared out by row tiles — weighted by the epilogue's cost per tile when the output-layer dgrad rides in the
-  // fused-loss epilogue: the actor's rows then carry act_dim FMAs per hidden unit on top of the loss math, the critic's one
-  static const char* cost_mode = getenv("B200PPO_FUSE_COST");  // profiling switch: "<actor>,<critic>" relative cost per row tile
-  int cost_actor = 0, cost_critic = 0;
-  if (cost_mode != nullptr && sscanf(cost_mode, "%d,%d", &cost_actor, &cost_critic) == 2 && cost_actor >= 1 && cost_critic >= 1) {
-  } else {
-    cost_actor = cost_critic = 0;
-  }
-  auto tile_cost = [&](int i) -> int64_t {
-    const TcProblem& q = g.p[i];
-    if (q.ppo.dgrad_out == nullptr) return 1;
-    if (cost_actor > 0) return q.epilogue == TC_EPI_PPO_ACTOR ? cost_actor : cost_critic;
-    return q.epilogue == TC_EPI_PPO_ACTOR ? 3 + (q.ppo.act_dim + 3) / 4 : 2;
-  };
-  int64_t work = 0, tiles_total = 0;  // (weighted) row tiles summed over slots
+  int64_t work = 0;  // row tiles summed over slots
   for (int i = 0; i < g.count; ++i) {
     w.p[i] = g.p[i];
     for (int n0 = 0; n0 < g.p[i].N; n0 += bn) {
       w.slot_prob[w.n_slots] = i;
       w.slot_n0[w.n_slots] = n0;
       ++w.n_slots;
-      work += g.p[i].tiles_m * tile_cost(i);
-      tiles_total += g.p[i].tiles_m;
+      work += g.p[i].tiles_m;
     }
   }
-  const int grid = int(std::min<int64_t>(num_sms(), tiles_total));
+  const int grid = int(std::min<int64_t>(num_sms(), work));
   int begin = 0;
   for (int sidx = 0; sidx < w.n_slots; ++sidx) {
     w.cta_begin[sidx] = begin;
-    const int64_t tiles = g.p[w.slot_prob[sidx]].tiles_m * tile_cost(w.slot_prob[sidx]);
+    const int64_t tiles = g.p[w.slot_prob[sidx]].tiles_m;
     int share = (sidx == w.n_slots - 1) ? grid - begin : int((int64_t(grid) * tiles + work / 2) / work);
     if (share < 1) share = 1;
     begin += share;
@@ -990,21 +832,6 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
   const int kb_max = (maxK + TC_BK - 1) / TC_BK;
   const int total = w.cta_begin[w.n_slots];
   if (grid_out) *grid_out = total;
-  // output-layer dgrad in the fused-loss epilogue: the fp32 copy of the weight sits behind the staging tiles, the A ring
-  // gives up the stages it displaces
-  for (int i = 0; i < g.count; ++i)
-    if (g.p[i].ppo.dgrad_out != nullptr) w.w32_bytes = std::max(w.w32_bytes, (g.p[i].N * g.p[i].ppo.hidden * 4 + 15) / 16 * 16);
-  if (w.w32_bytes > 0) {
-    B2_CHECK_ARG(bn == 64, "fused output-layer dgrad: only with the 64-wide weights-stationary kernel");
-    for (int i = 0; i < g.count; ++i)
-      B2_CHECK_ARG(g.p[i].epilogue >= TC_EPI_PPO_ACTOR && g.p[i].ppo.dgrad_out != nullptr, "fused output-layer dgrad: every problem of the launch must carry it");
-    for (int i = 0; i < g.count; ++i)
-      B2_CHECK_ARG(g.p[i].ppo.dgrad_nseeds >= 1 && g.p[i].ppo.dgrad_nseeds <= 24 && g.p[i].ppo.dgrad_nseeds == g.p[i].N && g.p[i].ppo.hidden % 4 == 0,
-                   "fused output-layer dgrad: 1..24 outputs, hidden width a multiple of 4");
-    const int64_t avail = kWsMaxSmem - ws_fixed_smem(stage_tiles) - int64_t(kb_max) * bn * TC_BK * 2 - w.w32_bytes - kWsSeedBytes;
-    stages = int(std::min<int64_t>(stages, avail / TC_A_BYTES));
-    B2_CHECK_ARG(stages >= 3, "fused output-layer dgrad: weight copy does not fit in shared memory");
-  }
   // profiling aid: B200PPO_WS_TRACE=ppo prints the clock64 timeline of CTA 0 of the 20th fused-loss output-layer launch
   static const char* trace_mode = getenv("B200PPO_WS_TRACE");
   if (trace_mode != nullptr && trace_mode[0] == 'p' && bn == 64 && g.p[0].epilogue >= TC_EPI_PPO_ACTOR) {
@@ -1027,7 +854,6 @@ int launch_tc_ws(const TcGroup& g, cudaStream_t st, int* grid_out, bool w_early)
       return rc;
     }
   }
-  if (w.w32_bytes > 0) return launch_ws_bn<64, true>(w, stages, kb_max, total, st);
   switch (bn) {
     case 64: return launch_ws_bn<64>(w, stages, kb_max, total, st);
     case 128: return launch_ws_bn<128>(w, stages, kb_max, total, st);
