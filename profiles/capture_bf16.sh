@@ -21,6 +21,5 @@ K="python profiles/kernels.py update --precision bf16 --batch 32768"
 $K > $OUT/${TAG}_k_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k 'regex:tc_|adam_cast' -s 7 -c 7 -f -o $OUT/${TAG}_tc $K > $OUT/${TAG}_k_ncu.log 2>&1
 echo tc_rc=$?
-# informational: a minibatch whose activations stay in the 126 MB L2 between forward, dgrad and wgrad
-timeout 300 $SHORT --minibatch 16384 > $OUT/${TAG}_bench_mb16384.json 2>> $OUT/${TAG}_bench.err
-echo mb16384_rc=$?
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $OUT/${TAG}_smoke.log 2>&1
+echo smoke_rc=$?
