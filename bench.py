@@ -542,7 +542,7 @@ def run_b200(args, config):
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernel_classes": prof,
             "final_losses": final_losses, "samples_per_step": samples_per_step, "variants": variants}
     if rank == 0:
-        if not args.no_kernels:
+        if world == 1 and not args.no_kernels:  # per-kernel roofline lines belong to the N=1 run (the other ranks would only wait)
             line["hbm_kernels"] = hbm_kernel_lines(pk)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
