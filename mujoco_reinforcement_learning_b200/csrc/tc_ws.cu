@@ -488,7 +488,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS2_THREADS, 1) tc_w
     uint8_t* st_base = stage_area + (warp - 2) * ntiles * TC_STAGE_BYTES;
     const CUtensorMap* tm_out = &grp.tm_out[pidx];
     const int act = P.act;
-    const uint32_t leader_empty[2] = {mapa_u32(smem_u32(&acc_empty[0]), 0), mapa_u32(smem_u32(&acc_empty[1]), 0)};
+    // two scalars and a select, not an array indexed by `buf`: the array lived in local memory (an LDL in front of every arrive)
+    const uint32_t leader_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0), leader_empty1 = mapa_u32(smem_u32(&acc_empty[1]), 0);
     const int sw = lane & 7;
     const int col0 = chunk * 64;
     const float* bs = bias_s + col0;
@@ -547,7 +548,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS2_THREADS, 1) tc_w
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty[buf]) : "memory");
+        if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(buf ? leader_empty1 : leader_empty0) : "memory");
         ws2_dgrad16(vb, ax[3], act, o); emit(3);
       }
     } else if (grp.tma_out[pidx] == 0) {  // forward, direct: 32-byte row segments from registers (rows 32-byte aligned, whole chunk < N)
@@ -577,7 +578,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS2_THREADS, 1) tc_w
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty[buf]) : "memory");
+        if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(buf ? leader_empty1 : leader_empty0) : "memory");
         ws2_act16(vb, bs + 48, act, o);
         if (row_ok) stg256(orow + 48, o);
       }
@@ -615,7 +616,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS2_THREADS, 1) tc_w
       // last quarter of the math
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty[buf]) : "memory");
+      if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(buf ? leader_empty1 : leader_empty0) : "memory");
       ws2_finish16(vb, bs + 48, act, my_row, sw, 3);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
