@@ -438,8 +438,10 @@ def run_b200(args, config):
                 "current_state": mem["current_state"].reshape(M_local, OBS_DIM), "action": mem["action"].reshape(M_local, ACT_DIM),
                 "action_log_prob": mem["action_log_prob"].reshape(M_local), "advantage": mem["advantage"].reshape(M_local),
                 "current_state_value_target": mem["current_state_value_target"].reshape(M_local)})
+            # every rank holds the same global permutations on its host and uploads only the slots it consumes
+            my_perms = D.slice_perms_for_rank(pin_perms[i], GB, world, rank, dev)
             out = eng.train(fields["current_state"], fields["action"], fields["action_log_prob"], fields["advantage"],
-                            fields["current_state_value_target"], pin_perms[i].to(dev, non_blocking=True), GB, hp)
+                            fields["current_state_value_target"], my_perms, GB, hp, rank_sliced_perms=True)
             return out.cpu()
 
         step_host(0)
@@ -451,11 +453,11 @@ def run_b200(args, config):
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
-        h2d = sum(v.numel() * v.element_size() for v in host.values()) + perms_host[0].numel() * 8
+        h2d = sum(v.numel() * v.element_size() for v in host.values()) + perms_host[0].numel() * 8 // world
         e2e = {"value": args.steps * samples_per_step / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": dt / args.steps * 1e3,
-               "api": "PPO.calculate_advantages + distributed.all_gather_fields + ActorCriticEngine.train per rank, pinned host slabs "
-                      "(bytes are per rank)"}
+               "api": "PPO.calculate_advantages + distributed.share_rollout + ActorCriticEngine.train per rank, pinned host slabs, "
+                      "rank-sliced permutations (bytes are per rank)"}
 
     # ---- per-kernel-class device time of one step (CUDA events on the launching stream) ----------------------
     _lib.check(lib.b200ppo_profile_begin(eng._ctx))

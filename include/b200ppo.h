@@ -245,6 +245,12 @@ int b200ppo_polyak_update(float* target, const float* source, int64_t n, double 
 int b200ppo_comm_unique_id(uint8_t id_out[128]);
 int b200ppo_comm_init(b200ppo_ctx* ctx, const uint8_t unique_id[128], int32_t rank, int32_t world_size);
 int b200ppo_comm_world(const b200ppo_ctx* ctx, int32_t* rank, int32_t* world_size);
+/* Layout of the `perms` argument of b200ppo_train on this rank.  0 (default): the global permutations,
+ * [epochs][n_samples].  1: only the slots this rank consumes, [epochs][floor(n_samples / batch)][batch / world_size] —
+ * slot (e, i, j) = global slot e * n_samples + i * batch + rank * (batch / world_size) + j (the rows of
+ * `distributed.rank_rows`) — so that a rank uploads 1 / world_size of the index bytes.  The result is identical.
+ * replaces: nothing in the reference (its `torch.randperm`, ppo.py:103, is consumed whole by one process). */
+int b200ppo_set_perm_layout(b200ppo_ctx* ctx, int32_t rank_slices);
 /* Optional, after b200ppo_comm_init, bf16 path, world_size <= 8 on one NVLink/NVSwitch node: replace the per-minibatch
  * ncclAllReduce by an exchange over peer-mapped memory fused into the optimizer kernel.  Every rank exports the
  * 64-byte cudaIpcMemHandle of its exchange buffer, the caller all-gathers the handles (rank order) and hands the

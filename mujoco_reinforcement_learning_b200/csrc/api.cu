@@ -136,6 +136,7 @@ struct b200ppo_ctx {
   __nv_bfloat16* peer_table[kMaxPeers] = {};
   int64_t shared_rows = 0;   // rows of every rank's table; 0 = tables not shared
   bool shared_filled = false;
+  bool perm_rank_slices = false;  // b200ppo_set_perm_layout: `perms` holds only this rank's slots
   unsigned p2p_seq = 0;
   cudaStream_t gather_stream = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
@@ -974,24 +975,27 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
   const int64_t cap = ctx->sh_cap;
   auto gather_epoch = [&](int e, int set, cudaStream_t gs) -> int {
     const int64_t o = int64_t(set) * cap;
-    const int64_t* idx = perms + int64_t(e) * n_samples;
+    // global permutations: rank r's rows of minibatch i sit at slots i * batch + r * lb ...; rank slices: at i * lb ...
+    const bool sliced = ctx->perm_rank_slices;
+    const int64_t* idx = perms + int64_t(e) * (sliced ? (n_samples / batch) * lb : n_samples);
+    const int64_t cstride = sliced ? lb : batch, coff = sliced ? 0 : int64_t(ctx->rank) * lb;
     if (shared_obs) {  // rows pulled from every rank's table over NVLink by the copy engine
       const float* parts[kMaxPeers];
       for (int r = 0; r < ctx->world; ++r) parts[r] = reinterpret_cast<const float*>(ctx->peer_table[r]);
-      return launch_gather_parts(idx, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb, parts, ctx->world, ctx->shared_rows, PX / 2,
+      return launch_gather_parts(idx, nb * lb, n_samples, lb, cstride, coff, parts, ctx->world, ctx->shared_rows, PX / 2,
                                  action, A, old_logp, advantage, target, reinterpret_cast<float*>(ctx->bf.sh_obs + o * PX),
                                  ctx->sh_act + o * A, ctx->sh_logp + o, ctx->sh_adv + o, ctx->sh_tgt + o, ctx->err_flag, gs);
     }
     if (table)  // bf16 rows moved as PX/2 "floats" by the bulk-copy gather: a byte copy
-      return launch_gather_chunked(idx, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb,
+      return launch_gather_chunked(idx, nb * lb, n_samples, lb, cstride, coff,
                                    reinterpret_cast<const float*>(ctx->bf.obs_table), PX / 2, action, A, old_logp, advantage, target,
                                    reinterpret_cast<float*>(ctx->bf.sh_obs + o * PX), ctx->sh_act + o * A, ctx->sh_logp + o,
                                    ctx->sh_adv + o, ctx->sh_tgt + o, ctx->err_flag, gs);
     if (tc)
-      return launch_gather_chunked_bf16(idx, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb, obs, D, action, A, old_logp,
+      return launch_gather_chunked_bf16(idx, nb * lb, n_samples, lb, cstride, coff, obs, D, action, A, old_logp,
                                         advantage, target, ctx->bf.sh_obs + o * PX, PX, ctx->sh_act + o * A, ctx->sh_logp + o,
                                         ctx->sh_adv + o, ctx->sh_tgt + o, ctx->err_flag, gs);
-    return launch_gather_chunked(idx, nb * lb, n_samples, lb, batch, int64_t(ctx->rank) * lb, obs, D, action, A, old_logp, advantage,
+    return launch_gather_chunked(idx, nb * lb, n_samples, lb, cstride, coff, obs, D, action, A, old_logp, advantage,
                                  target, ctx->sh_obs + o * D, ctx->sh_act + o * A, ctx->sh_logp + o, ctx->sh_adv + o, ctx->sh_tgt + o,
                                  ctx->err_flag, gs);
   };
@@ -1098,6 +1102,7 @@ extern "C" B2_EXPORT int b200ppo_update_host(b200ppo_ctx* ctx, float* params, fl
                                    int normalize_advantage, double advantage_scaler, const int64_t* perms_host,
                                    int32_t epochs, int64_t batch, int64_t max_minibatches_per_epoch,
                                    const b200ppo_hparams* hp, float* losses_host, b200ppo_stream stream) {
+  B2_CHECK_ARG(ctx == nullptr || !ctx->perm_rank_slices, "b200ppo_update_host: takes the global permutations (b200ppo_set_perm_layout(ctx, 0))");
   B2_CHECK_ARG(ctx && obs_host && action_host && old_logp_host && reward_host && value_host && next_value_host &&
                    terminated_host && perms_host && hp,
                "b200ppo_update_host: null pointer");
@@ -1233,6 +1238,12 @@ extern "C" B2_EXPORT int b200ppo_p2p_import(b200ppo_ctx* ctx, const uint8_t* han
     B2_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->peer_x[r] = static_cast<float*>(ptr);
   }
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_set_perm_layout(b200ppo_ctx* ctx, int32_t rank_slices) {
+  B2_CHECK_ARG(ctx, "b200ppo_set_perm_layout: null context");
+  ctx->perm_rank_slices = rank_slices != 0;
   return B200PPO_OK;
 }
 

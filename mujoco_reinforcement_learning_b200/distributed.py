@@ -26,6 +26,24 @@ def rank_rows(minibatch_index: int, global_batch: int, world: int, rank: int) ->
     return range(start, start + lb)
 
 
+def slice_perms_for_rank(perms: torch.Tensor, global_batch: int, world: int, rank: int, device=None) -> torch.Tensor:
+    """The permutation slots rank `rank` consumes, [epochs, M // global_batch, global_batch // world], from the global
+    permutations [epochs, M] (`rank_rows` of every minibatch; the dropped tail is left behind).  With `perms` in pinned
+    host memory and a CUDA `device` every (epoch, minibatch) piece is one contiguous asynchronous copy on the current
+    stream, so a rank uploads 1 / world of the index bytes and the host never touches them
+    (`engine.train(..., rank_sliced_perms=True)` consumes the result)."""
+    perms = perms.reshape(perms.shape[0], -1) if perms.dim() > 1 else perms.reshape(1, -1)
+    epochs, M = perms.shape
+    lb = global_batch // world
+    nb = M // global_batch
+    src = perms[:, :nb * global_batch].reshape(epochs, nb, world, lb)[:, :, rank]
+    out = torch.empty((epochs, nb, lb), dtype=perms.dtype, device=device if device is not None else perms.device)
+    for e in range(epochs):
+        for i in range(nb):
+            out[e, i].copy_(src[e, i], non_blocking=True)
+    return out
+
+
 def bind_host_to_gpu(device) -> bool:
     """Pin the calling process to the CPUs NVML reports as local to `device` (its NUMA node), restricted to the CPUs
     the process is already allowed on.  Called once per rank BEFORE the pinned host buffers are allocated: with eight

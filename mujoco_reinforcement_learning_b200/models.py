@@ -337,8 +337,10 @@ class ActorCriticEngine:
         return {n: grads[off[id(p)]:off[id(p)] + p.numel()].view(p.shape) for n, p in named_parameters}
 
     def train(self, obs, action, old_logp, advantage, target, perms, batch: int, hp: _lib.HParams,
-              max_minibatches_per_epoch: int = 0) -> torch.Tensor:
-        """`PPO.train` inner loops (ppo.py:101-140) in one native call.  Returns device losses [epochs*nb, 2]."""
+              max_minibatches_per_epoch: int = 0, rank_sliced_perms: bool = False) -> torch.Tensor:
+        """`PPO.train` inner loops (ppo.py:101-140) in one native call.  Returns device losses [epochs*nb, 2].
+        rank_sliced_perms: `perms` is [epochs, M // batch, batch // world] — only the permutation slots this rank
+        consumes (`distributed.slice_perms_for_rank`) instead of the global [epochs, M]."""
         self.ensure_bound()
         f = lambda t, n: _lib.require_cuda(t, n, torch.float32).contiguous()
         if obs is None:  # observations live in the ranks' shared bf16 tables (distributed.share_rollout)
@@ -350,17 +352,29 @@ class ActorCriticEngine:
                 raise RuntimeError(f"expected {self.obs_dim} observation features, got {obs.shape[1]}")
         action, old_logp = f(action, "action").reshape(M, -1), f(old_logp, "action_log_prob").reshape(M)
         advantage, target = f(advantage, "advantage").reshape(M), f(target, "current_state_value_target").reshape(M)
-        perms = _lib.require_cuda(perms, "perms", torch.int64).contiguous().reshape(-1, M)
+        perms = _lib.require_cuda(perms, "perms", torch.int64).contiguous()
+        if rank_sliced_perms:
+            per_epoch = (M // int(batch)) * (int(batch) // max(int(getattr(self, "world", 1)), 1))
+            if per_epoch == 0 or perms.numel() % per_epoch != 0:
+                raise RuntimeError(f"rank-sliced perms must hold a multiple of {per_epoch} indices, got {perms.numel()}")
+            perms = perms.reshape(-1, per_epoch)
+        else:
+            perms = perms.reshape(-1, M)
         epochs = perms.shape[0]
         nb = M // int(batch)
         if max_minibatches_per_epoch > 0:
             nb = min(nb, max_minibatches_per_epoch)
         losses = torch.zeros((epochs * nb, 2), dtype=torch.float32, device=action.device)
         step = C.c_int64(self.adam_step)
-        _lib.check(self.lib.b200ppo_train(self._ctx, _lib.ptr(self.flat), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
-                                          C.byref(step), _lib.ptr(obs) if obs is not None else None, _lib.ptr(action), _lib.ptr(old_logp),
-                                          _lib.ptr(advantage), _lib.ptr(target), M, _lib.ptr(perms), epochs, int(batch),
-                                          int(max_minibatches_per_epoch), C.byref(hp), _lib.ptr(losses),
-                                          _lib.stream_ptr()), "b200ppo_train")
+        _lib.check(self.lib.b200ppo_set_perm_layout(self._ctx, 1 if rank_sliced_perms else 0), "b200ppo_set_perm_layout")
+        try:
+            _lib.check(self.lib.b200ppo_train(self._ctx, _lib.ptr(self.flat), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                              C.byref(step), _lib.ptr(obs) if obs is not None else None, _lib.ptr(action), _lib.ptr(old_logp),
+                                              _lib.ptr(advantage), _lib.ptr(target), M, _lib.ptr(perms), epochs, int(batch),
+                                              int(max_minibatches_per_epoch), C.byref(hp), _lib.ptr(losses),
+                                              _lib.stream_ptr()), "b200ppo_train")
+        finally:
+            if rank_sliced_perms:
+                _lib.check(self.lib.b200ppo_set_perm_layout(self._ctx, 0), "b200ppo_set_perm_layout")
         self.adam_step = int(step.value)
         return losses

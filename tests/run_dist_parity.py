@@ -51,10 +51,24 @@ def main():
         assert shared["current_state"] is None
         gathered = shared
     hp = agent.engine.hparams(1e-4, 1e-4, 0.1, 1e-4)
+    init_flat = agent.engine.flat.clone()
     losses_d = agent.engine.train(gathered["current_state"], gathered["action"], gathered["action_log_prob"].reshape(M),
                                   gathered["advantage"].reshape(M), gathered["current_state_value_target"].reshape(M),
                                   perms.to(dev), GB, hp)
     torch.cuda.synchronize()
+    # the same update again from the same initial state, every rank uploading only the permutation slots it consumes
+    p_first, l_first = agent.engine.flat.clone(), losses_d.clone()
+    agent.engine.flat.copy_(init_flat)
+    agent.engine.exp_avg.zero_()
+    agent.engine.exp_avg_sq.zero_()
+    agent.engine.adam_step = 0
+    my_perms = D.slice_perms_for_rank(perms.pin_memory(), GB, world, rank, dev)
+    assert my_perms.shape == (2, M // GB, GB // world)
+    losses_s = agent.engine.train(gathered["current_state"], gathered["action"], gathered["action_log_prob"].reshape(M),
+                                  gathered["advantage"].reshape(M), gathered["current_state_value_target"].reshape(M),
+                                  my_perms, GB, hp, rank_sliced_perms=True)
+    torch.cuda.synchronize()
+    sliced_same = torch.equal(agent.engine.flat, p_first) and torch.equal(losses_s, l_first)
     # single GPU reference on this rank: same global minibatch, world = 1
     run1, agent1 = make_agent()
     f = {k: v.reshape(M, -1).to(dev) for k, v in full.items()}
@@ -69,8 +83,8 @@ def main():
     ref = p_d.clone()
     dist.broadcast(ref, src=0)
     same = torch.equal(ref, p_d)
-    print(f"rank {rank}/{world} [{precision}] exchange {'p2p' if agent.engine.p2p else 'nccl'}: param err {err_p:.2e} loss err {err_l:.2e} replicas identical {same}", flush=True)
-    ok = err_p <= tol and err_l <= max(tol, 1e-5) and same and agent.engine.adam_step == agent1.engine.adam_step
+    print(f"rank {rank}/{world} [{precision}] exchange {'p2p' if agent.engine.p2p else 'nccl'}: param err {err_p:.2e} loss err {err_l:.2e} replicas identical {same} rank-sliced perms identical {sliced_same}", flush=True)
+    ok = err_p <= tol and err_l <= max(tol, 1e-5) and same and sliced_same and agent.engine.adam_step == agent1.engine.adam_step
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.barrier()

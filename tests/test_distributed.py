@@ -66,6 +66,24 @@ def _gloo_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def test_slice_perms_for_rank_is_rank_rows_of_every_minibatch():
+    """The rank-sliced permutation layout of `b200ppo_set_perm_layout(ctx, 1)`: slot (e, i, j) of rank r is global slot
+    i * batch + r * (batch / world) + j of epoch e; the tail beyond floor(M / batch) minibatches is left behind."""
+    M, GB, world, E = 1000, 96, 4, 3
+    g = torch.Generator().manual_seed(3)
+    perms = torch.stack([torch.randperm(M, generator=g) for _ in range(E)])
+    seen = [[] for _ in range(E)]
+    for r in range(world):
+        sl = D.slice_perms_for_rank(perms, GB, world, r)
+        assert sl.shape == (E, M // GB, GB // world) and sl.dtype == torch.int64
+        for e in range(E):
+            for i in range(M // GB):
+                assert torch.equal(sl[e, i], perms[e][list(D.rank_rows(i, GB, world, r))])
+            seen[e].append(sl[e].reshape(-1))
+    for e in range(E):  # the ranks' slices together are exactly the kept part of the permutation
+        assert torch.equal(torch.cat(seen[e]).sort().values, perms[e][:(M // GB) * GB].sort().values)
+
+
 def test_bind_host_to_gpu_never_fails_and_stays_inside_the_allowed_cpus():
     """The NUMA binding is an optimisation: without a GPU / NVML it reports False and leaves the affinity alone;
     with one it may only narrow the allowed set."""
