@@ -232,6 +232,11 @@ int b200ppo_profile_end(b200ppo_ctx* ctx, double ms_out[B200PPO_PROF_CLASSES], i
 int b200ppo_debug_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t a_mn_major,
                           int32_t b_mn_major, int32_t bn, int32_t split_k, b200ppo_stream stream);
 
+/* Test hook: the bf16 intermediates the last bf16 minibatch left in the context, as fp32 [rows][dims[layer]].
+ * kind 0: hidden activation H_layer (layer < n_layers - 1); kind 1: dL/dz of `layer` (the seeds for the output layer). */
+int b200ppo_debug_activations(b200ppo_ctx* ctx, int32_t net, int32_t kind, int32_t layer, int64_t rows, float* out,
+                              b200ppo_stream stream);
+
 /* Polyak averaging, in place: target[i] = target[i] * (1 - tau) + source[i] * tau over flat fp32 buffers.
  * replaces: soft_update, src/entities/algorithms/soft_actor_critic.py:12-14 (the SAC update step). */
 int b200ppo_polyak_update(float* target, const float* source, int64_t n, double tau, b200ppo_stream stream);

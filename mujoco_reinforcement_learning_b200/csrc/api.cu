@@ -16,6 +16,7 @@
 #include "gemm.cuh"
 #include "heads.cuh"
 #include "ppo_loss.cuh"
+#include "tc_chain.cuh"
 #include "tc_gemm.cuh"
 
 namespace b200ppo {
@@ -474,12 +475,13 @@ static int forward_nets_bf16(b200ppo_ctx* ctx, const float* params, const __nv_b
 
 // backward of both nets on the tensor cores.  bf.dZ[n][L-1] (dL/dz of the output layers, bf16) is filled on entry.
 static int backward_nets_bf16(b200ppo_ctx* ctx, const __nv_bfloat16* xb, int64_t B, float* gpart, int* split_out,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool skip_dgrad = false) {
   auto& bf = ctx->bf;
   int maxL = 0;
   for (int n = 0; n < 2; ++n) maxL = std::max(maxL, ctx->net[n].d.n_layers);
   // dgrads, deepest first: dZ_{l-1} = (dZ_l W_l) * act'(H_{l-1}),  B operand = the bf16 copy of W_l read MN-major
-  for (int s = 0; s < maxL; ++s) {
+  // (skip_dgrad: the fused chain kernel already left every dZ_l in place)
+  for (int s = 0; s < (skip_dgrad ? 0 : maxL); ++s) {
     TcGroup g{};
     int maxN = 0, nets_here = 0;
     for (int n = 0; n < 2; ++n) {
@@ -596,6 +598,65 @@ static int check_batch(const b200ppo_ctx* ctx, int64_t B, const char* who) {
   return B200PPO_OK;
 }
 
+// The fused chain kernel (tc_chain.cu) takes the minibatch when both nets are in -> 256 -> 256 -> out with the same
+// activation (the Humanoid / Ant shapes of BASELINE.json); other shapes keep the per-layer launches.
+static bool chain_applicable(const b200ppo_ctx* ctx) {
+  static const char* mode = getenv("B200PPO_CHAIN");  // profiling switch: "0" keeps the per-layer launches
+  if (mode != nullptr && mode[0] == '0') return false;
+  const Net& a = ctx->net[0];
+  const Net& c = ctx->net[1];
+  if (a.d.n_layers != 3 || c.d.n_layers != 3 || a.d.activation != c.d.activation || c.d.final_tanh) return false;
+  if (!tc_chain_shape_ok(a.d.in_dim, a.d.dims[0], a.d.dims[1], a.out_dim())) return false;
+  if (!tc_chain_shape_ok(c.d.in_dim, c.d.dims[0], c.d.dims[1], c.out_dim())) return false;
+  const auto& bf = ctx->bf;
+  for (int n = 0; n < 2; ++n) {
+    for (int l = 0; l < 2; ++l)
+      if (bf.pitchH[n][l] % 16 != 0 || bf.pitchZ[n][l] % 16 != 0) return false;
+    if (bf.pitchZ[n][2] % 8 != 0 || bf.pitchZ[n][2] > 32) return false;
+  }
+  return int64_t(num_sms()) + 8 <= ctx->loss_partial_rows;
+}
+
+static int launch_chain(b200ppo_ctx* ctx, const float* params, const __nv_bfloat16* xb, int64_t B, const float* action,
+                        const float* old_logp, const float* adv, const float* tgt, const b200ppo_hparams* hp, int* loss_ctas,
+                        cudaStream_t st) {
+  auto& bf = ctx->bf;
+  ChainArgs a{};
+  const int D = ctx->net[0].d.in_dim;
+  B2_TRY(tc_make_map(&a.x, xb, D, B, bf.pitchX, TC_CHAIN_BK, 128));
+  for (int n = 0; n < 2; ++n) {
+    const Net& N = ctx->net[n];
+    ChainNet& c = a.net[n];
+    const int out = N.out_dim();
+    B2_TRY(tc_make_map(&c.w1, bf.W[n][0], D, kChainHidden, bf.pitchW[n][0], TC_CHAIN_BK, 128));
+    B2_TRY(tc_make_map(&c.w2k, bf.W[n][1], kChainHidden, kChainHidden, bf.pitchW[n][1], TC_CHAIN_BK, 128));
+    B2_TRY(tc_make_map(&c.w2m, bf.W[n][1], kChainHidden, kChainHidden, bf.pitchW[n][1], 64, TC_CHAIN_BK));
+    B2_TRY(tc_make_map(&c.w3k, bf.W[n][2], kChainHidden, out, bf.pitchW[n][2], TC_CHAIN_BK, n ? 8 : 16));
+    B2_TRY(tc_make_map(&c.w3m, bf.W[n][2], kChainHidden, out, bf.pitchW[n][2], 64, n ? 16 : 32));
+    B2_TRY(tc_make_map(&c.sH1, bf.H[n][0], kChainHidden, B, bf.pitchH[n][0], 64, 32));
+    B2_TRY(tc_make_map(&c.sH2, bf.H[n][1], kChainHidden, B, bf.pitchH[n][1], 64, 32));
+    B2_TRY(tc_make_map(&c.sZ1, bf.dZ[n][0], kChainHidden, B, bf.pitchZ[n][0], 64, 32));
+    B2_TRY(tc_make_map(&c.sZ2, bf.dZ[n][1], kChainHidden, B, bf.pitchZ[n][1], 64, 32));
+    c.b1 = params + N.b_off[0]; c.b2 = params + N.b_off[1]; c.b3 = params + N.b_off[2];
+    c.H1 = bf.H[n][0]; c.H2 = bf.H[n][1]; c.dZ1 = bf.dZ[n][0]; c.dZ2 = bf.dZ[n][1]; c.dZ3 = bf.dZ[n][2];
+    c.pH1 = bf.pitchH[n][0]; c.pH2 = bf.pitchH[n][1]; c.pZ1 = bf.pitchZ[n][0]; c.pZ2 = bf.pitchZ[n][1]; c.pZ3 = bf.pitchZ[n][2];
+  }
+  a.ppo.logstd = params + ctx->logstd_off;
+  a.ppo.action = action; a.ppo.old_logp = old_logp; a.ppo.advantage = adv; a.ppo.target = tgt;
+  a.ppo.partials = ctx->loss_partials;
+  a.ppo.act_dim = ctx->net[0].out_dim();
+  a.ppo.final_tanh = ctx->net[0].d.final_tanh;
+  a.ppo.clip_eps = float(hp->clip_epsilon);
+  a.ppo.inv_global_batch = 1.f / float(B * ctx->world);
+  a.out_scale = ctx->net[0].d.out_scale;
+  a.M = int(B);
+  a.KB1 = (D + TC_CHAIN_BK - 1) / TC_CHAIN_BK;
+  a.act = ctx->net[0].d.activation;
+  a.tiles2 = int((B + 255) / 256);
+  a.trace = g_chain_trace;
+  return launch_tc_chain(a, st, loss_ctas);
+}
+
 // forward + losses + backward of one minibatch; gradients left as split-K partials in ctx->gpart.
 static void fill_loss_args(const b200ppo_ctx* ctx, LossArgs& la, const float* params, const float* mean, const float* value,
                            const float* action, const float* old_logp, const float* adv, const float* tgt, int64_t B,
@@ -625,6 +686,12 @@ static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float*
   const int La = Na.d.n_layers, Lc = Nc.d.n_layers;
   if (ctx->precision == B200PPO_PREC_BF16) {
     // tcgen05 everywhere: forward (L launches; PPO loss fused into the output layers' epilogue), dgrads (L-1), wgrads (1)
+    if (chain_applicable(ctx)) {  // one launch: forward, losses, dgrads (tc_chain.cu); then the weight gradients
+      int grid = 0;
+      PROF(ctx, B200PPO_PROF_GEMM_FWD, st, launch_chain(ctx, params, obs_b, B, action, old_logp, adv, tgt, hp, &grid, st));
+      *loss_ctas_out = grid;
+      return backward_nets_bf16(ctx, obs_b, B, ctx->gpart, split_out, st, true);
+    }
     const bool same_depth = La == Lc;  // both output layers in the same launch
     if (same_depth && tc_ppo_fits(Na.out_dim()) && Na.out_dim() <= 32 &&
         int64_t(2 * ((B + 127) / 128) + 8) <= ctx->loss_partial_rows) {
@@ -1157,6 +1224,28 @@ extern "C" B2_EXPORT int b200ppo_update_host(b200ppo_ctx* ctx, float* params, fl
 
 // ---- instrumentation -----------------------------------------------------------------------------------
 extern "C" B2_EXPORT int64_t b200ppo_launch_count(void) { return g_launches.load(); }
+
+namespace b200ppo {
+__global__ void bf16_rows_to_f32(const __nv_bfloat16* __restrict__ src, int64_t rows, int cols, int pitch, float* __restrict__ dst) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < rows * cols) dst[i] = __bfloat162float(src[(i / cols) * pitch + i % cols]);
+}
+}  // namespace b200ppo
+
+extern "C" B2_EXPORT int b200ppo_debug_activations(b200ppo_ctx* ctx, int32_t net, int32_t kind, int32_t layer, int64_t rows,
+                                                   float* out, b200ppo_stream stream) {
+  B2_CHECK_ARG(ctx && out && (net == 0 || net == 1) && (kind == 0 || kind == 1), "b200ppo_debug_activations: bad argument");
+  B2_CHECK_ARG(ctx->precision == B200PPO_PREC_BF16, "b200ppo_debug_activations: bf16 contexts only");
+  const Net& N = ctx->net[net];
+  B2_CHECK_ARG(layer >= 0 && layer < N.d.n_layers - (kind == 0 ? 1 : 0) && rows > 0 && rows <= ctx->max_batch,
+               "b200ppo_debug_activations: layer / rows out of range");
+  const __nv_bfloat16* src = kind == 0 ? ctx->bf.H[net][layer] : ctx->bf.dZ[net][layer];
+  const int pitch = kind == 0 ? ctx->bf.pitchH[net][layer] : ctx->bf.pitchZ[net][layer];
+  const int cols = N.d.dims[layer];
+  bf16_rows_to_f32<<<unsigned((rows * cols + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, cols, pitch, out);
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
 
 extern "C" B2_EXPORT int b200ppo_profile_begin(b200ppo_ctx* ctx) {
   B2_CHECK_ARG(ctx, "b200ppo_profile_begin: null context");

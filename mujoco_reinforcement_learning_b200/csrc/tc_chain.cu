@@ -1,0 +1,661 @@
+// One launch for the whole per-minibatch op chain of PPO.train up to the weight gradients: forward of both MLPs,
+// log-prob / ratio / clipped surrogate / Huber losses with their gradient seeds, and the dgrad chain back to dZ1.
+//
+// replaces: ppo.py:110-134 as far as it is row-local — actor(obs), critic(obs) (network_block_creator.py:74-86,
+//           linear/actor.py:25-30, critic.py:22-25), Normal.log_prob, the two losses (ppo.py:113-132) and the
+//           activation-gradient half of their autograd backward.  Weight gradients (a reduction over rows) stay in
+//           tc_wgrad.cu, the optimizer in adam.cu.
+//
+// Why: as separate launches (tc_ws.cu) every activation crossed HBM twice and every launch paid ~10 us of fill/drain
+// for ~10 us of row tiles.  Here a CTA PAIR (cta_group::2) owns a 256-row tile (128 rows per CTA) and walks it through
+// ten MMA steps; the epilogue of a step writes its bf16 result STRAIGHT INTO SHARED MEMORY in the K-major 128-byte
+// swizzled layout the next step's tcgen05.mma reads as its A operand (and once to HBM for the weight-gradient kernel):
+//
+//   step  MMA (M = 256, accumulators ping-pong between two 256-column TMEM buffers)      epilogue (16 warps / CTA)
+//   0 L1a  X   . W1a^T  K = in   N = 256   -> buf0     H1a = act(acc + b1a)      -> smem HA, global
+//   1 L1c  X   . W1c^T                     -> buf1     H1c                       -> smem HC (aliases X), global
+//   2 L2a  H1a . W2a^T  K = 256            -> buf0     H2a                       -> smem HA (over H1a), global
+//   3 L2c  H1c . W2c^T                     -> buf1     H2c                       -> smem HC, global
+//   4 L3a  H2a . W3a^T  N = 32             -> buf0     log-prob, ratio, surrogate, seeds dz3a -> smem, global
+//   5 L3c  H2c . W3c^T  N = 16             -> buf1     Huber, seed dv            -> smem, global
+//   6 D3a  dz3a . W3a   K = 32  N = 256    -> buf0     dZ2a = acc * act'(H2a)    in place in HA, global
+//   7 D3c  dv   . W3c   K = 16             -> buf1     dZ2c                      in place in HC, global
+//   8 D2a  dZ2a . W2a   K = 256            -> buf0     dZ1a = acc * act'(H1a from L2) -> global
+//   9 D2c  dZ2c . W2c                      -> buf1     dZ1c                      -> global
+//
+// Actor and critic alternate, so while the epilogue warps finish step s the tensor pipe already runs step s + 1 of the
+// other network; step s + 2 (same network) needs exactly what the epilogue of step s produces (its A operand and its
+// drained accumulator), which is ONE mbarrier per TMEM buffer.  The weights (640 KB + 256 KB for the dgrads) do not fit
+// next to the tiles, so they stream from L2 through a 4-stage ring of 16 KB per CTA (each CTA holds half of N; the pair
+// halves the L2->SM weight traffic per row) in exactly the order the MMAs consume them.
+//   warp 0 (both CTAs)  TMA producer: X k-blocks + the weight stream; bytes counted on the LEADER's mbarriers
+//   warp 1 (leader)     MMA issuer: tcgen05.mma.cta_group::2; tcgen05.commit multicast frees ring stages / publishes accumulators
+//   warps 2-17 (both)   epilogue: warp = (TMEM lane quarter, 64-column chunk = one k-block of the next A operand)
+#include <algorithm>
+#include <cstdlib>
+
+#include "tc_chain.cuh"
+#include "tc_common.cuh"
+
+namespace b200ppo {
+
+constexpr int CH_EPI_WARPS = 16;
+constexpr int CH_THREADS = (2 + CH_EPI_WARPS) * 32;
+constexpr int CH_SLOT = 16384;  // one k-block of a 128-row operand tile: 128 rows x 128 B
+constexpr int CH_NSLOT = 14;
+constexpr int CH_RING = 4;
+// slot map: X k-blocks 0-5 | actor tile 6-9 | weight ring 10-13; the critic tile aliases X 2-5 (free once L1c has
+// read X), the output-layer seeds alias X 0-1
+constexpr int CH_X0 = 0, CH_HA0 = 6, CH_RING0 = 10, CH_HC0 = 2, CH_DZ3A = 0, CH_DZ3C = 1;
+constexpr int CH_MISC = 2048;
+constexpr int CH_SMEM = 1024 + CH_NSLOT * CH_SLOT + CH_MISC;  // = 227 KB
+static_assert(CH_SMEM <= 227 * 1024, "chain kernel shared memory");
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // arrivals come from the peer CTA too
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+__device__ __forceinline__ void ch_bias16(const float* __restrict__ b, float (&o)[16]) {  // warp-uniform address: one L1 wavefront each
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(b) + u);
+    o[4 * u] = t.x; o[4 * u + 1] = t.y; o[4 * u + 2] = t.z; o[4 * u + 3] = t.w;
+  }
+}
+// 16 accumulator columns + bias -> activation -> 16 bf16 (8 words)
+__device__ __forceinline__ void ch_act16(const uint32_t (&v)[16], const float (&b)[16], int act, uint32_t (&o)[8]) {
+  if (act == B200PPO_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = tanh_bf16x2(pack_bf16(__uint_as_float(v[2 * j]) + b[2 * j], __uint_as_float(v[2 * j + 1]) + b[2 * j + 1]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = pack_bf16(fmaxf(__uint_as_float(v[2 * j]) + b[2 * j], 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + b[2 * j + 1], 0.f));
+  }
+}
+// 16 bf16 of this thread's row <-> the two swizzled 16-byte units (2s, 2s+1) of its 128-byte tile row
+__device__ __forceinline__ void ch_sts16(uint32_t srow, uint32_t sw, int s, const uint32_t (&o)[8]) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + (((2 * s) ^ sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + (((2 * s + 1) ^ sw) << 4)), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
+__device__ __forceinline__ void ch_lds16(uint32_t srow, uint32_t sw, int s, uint32_t (&h)[8]) {
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(srow + (((2 * s) ^ sw) << 4)) : "memory");
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(h[4]), "=r"(h[5]), "=r"(h[6]), "=r"(h[7]) : "r"(srow + (((2 * s + 1) ^ sw) << 4)) : "memory");
+}
+
+// Hidden-layer forward epilogue of this warp's 32 rows x 64 columns: TMEM -> bias + activation -> bf16 -> the next A
+// operand in shared memory (the caller then bulk-stores the same 4 KB sub-tile to global memory).  TMEM loads run one
+// 16-column slab ahead of the math and the bias one slab ahead of its use: the kernel leaves next to no L1, so a bias
+// load is an L2 round trip that must not sit between an accumulator slab and its math.  b0: bias of the first slab,
+// requested by the caller before it waited for the accumulator.
+__device__ __forceinline__ void ch_epi_forward(uint32_t tcol, const float* __restrict__ bias, float (&b0)[16], int act, uint32_t srow, uint32_t sw) {
+  uint32_t va[16], vb[16], o[8];
+  float b1[16];
+  tmem_ld16_nowait(tcol, va);
+  ch_bias16(bias + 16, b1);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 16, vb);
+  ch_act16(va, b0, act, o); ch_sts16(srow, sw, 0, o);
+  ch_bias16(bias + 32, b0);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 32, va);
+  ch_act16(vb, b1, act, o); ch_sts16(srow, sw, 1, o);
+  ch_bias16(bias + 48, b1);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 48, vb);
+  ch_act16(va, b0, act, o); ch_sts16(srow, sw, 2, o);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  ch_act16(vb, b1, act, o); ch_sts16(srow, sw, 3, o);
+}
+
+// dgrad epilogue, activation in shared memory (the tile this thread wrote two steps earlier): dZ = acc * act'(h),
+// written back IN PLACE — it is the next step's A operand and the source of the bulk store to global memory.
+__device__ __forceinline__ void ch_epi_dgrad_smem(uint32_t tcol, int act, uint32_t srow, uint32_t sw) {
+  uint32_t va[16], vb[16], h[8], o[8];
+  tmem_ld16_nowait(tcol, va);
+  ch_lds16(srow, sw, 0, h);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 16, vb);
+  ws2_dgrad16(va, h, act, o); ch_sts16(srow, sw, 0, o);
+  ch_lds16(srow, sw, 1, h);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 32, va);
+  ws2_dgrad16(vb, h, act, o); ch_sts16(srow, sw, 1, o);
+  ch_lds16(srow, sw, 2, h);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 48, vb);
+  ws2_dgrad16(va, h, act, o); ch_sts16(srow, sw, 2, o);
+  ch_lds16(srow, sw, 3, h);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  ws2_dgrad16(vb, h, act, o); ch_sts16(srow, sw, 3, o);
+}
+
+// dgrad epilogue of the first hidden layer: its activation was overwritten in shared memory by the second layer's, so
+// the row comes back from global memory (an L2 hit), requested by the caller BEFORE the accumulator is awaited.  The
+// result is no A operand; it is staged in the (now idle) actor tile only so that it leaves through the bulk store.
+__device__ __forceinline__ void ch_epi_dgrad_glob(uint32_t tcol, int act, const uint32_t (&ax)[4][8], uint32_t srow, uint32_t sw) {
+  uint32_t va[16], vb[16], o[8];
+  tmem_ld16_nowait(tcol, va);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 16, vb);
+  ws2_dgrad16(va, ax[0], act, o); ch_sts16(srow, sw, 0, o);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 32, va);
+  ws2_dgrad16(vb, ax[1], act, o); ch_sts16(srow, sw, 1, o);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 48, vb);
+  ws2_dgrad16(va, ax[2], act, o); ch_sts16(srow, sw, 2, o);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  ws2_dgrad16(vb, ax[3], act, o); ch_sts16(srow, sw, 3, o);
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Sum over the warp's 32 rows of eight per-row values at once: three exchange stages halve the number of values a lane
+// carries (8 -> 4 -> 2 -> 1), two plain stages finish; 9 shuffles instead of 40.  Returns the total of column
+// ch_red8_col(lane) in every lane.
+__device__ __forceinline__ int ch_red8_col(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+__device__ __forceinline__ float ch_red8(const float (&v)[8], int lane) {
+  float w[4], x[2];
+  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h16 ? v[4 + i] : v[i], send = h16 ? v[i] : v[4 + i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = h8 ? w[2 + i] : w[i], send = h8 ? w[i] : w[2 + i];
+    x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float y = (h4 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, h4 ? x[0] : x[1], 4);
+  y += __shfl_xor_sync(0xffffffffu, y, 2);
+  y += __shfl_xor_sync(0xffffffffu, y, 1);
+  return y;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_constant__ ChainArgs a) {
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr int H = kChainHidden;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* misc = smem + CH_NSLOT * CH_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint64_t* ring_full = bars;        // [4]  leader: both CTAs' TMA bytes
+  uint64_t* ring_empty = bars + 4;   // [4]  commit multicast
+  uint64_t* x_full = bars + 8;       // [6]  leader
+  uint64_t* x_free = bars + 14;      // [2]  slots 0-1 (after D3c), slots 2-5 (after D2c); commit multicast
+  uint64_t* acc_full = bars + 16;    // [2]  commit multicast
+  uint64_t* epi_done = bars + 18;    // [2]  leader: 2 x 16 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* b3_s = reinterpret_cast<float*>(misc + 192);     // [0,32) actor output bias, [32] critic output bias
+  float* consts_s = reinterpret_cast<float*>(misc + 384); // [0,32) log sigma, [32,64) 1/var
+  float* red_s = reinterpret_cast<float*>(misc + 768);    // [4][34] running loss sums of the four loss warps
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_local = int(blockIdx.x) >> 1, pairs = int(gridDim.x) >> 1;
+  const int KB1 = a.KB1, tiles2 = a.tiles2;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 18; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&epi_done[0], 2 * CH_EPI_WARPS);
+    mbar_init(&epi_done[1], 2 * CH_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait_then_release();  // the weights were re-cast by the optimizer kernel right before this one
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      uint32_t it = 0, cur_bar = 0;
+      auto ring_acquire = [&](uint32_t bytes) -> uint8_t* {
+        const uint32_t s = it & (CH_RING - 1), ph = (it / CH_RING) & 1;
+        mbar_wait(&ring_empty[s], ph ^ 1);
+        if (rank == 0) mbar_expect_tx(&ring_full[s], 2u * bytes);
+        cur_bar = mapa_u32(smem_u32(&ring_full[s]), 0);
+        ++it;
+        return smem + (CH_RING0 + s) * CH_SLOT;
+      };
+      int ti = 0;
+      for (int tile = pair_local; tile < tiles2; tile += pairs, ++ti) {
+        const int m0 = tile * 256 + int(rank) * 128;
+        const uint32_t xph = uint32_t(ti & 1);
+        for (int n = 0; n < 2; ++n)
+          for (int kb = 0; kb < KB1; ++kb) {
+            if (n == 0) {
+              if (kb == 0) mbar_wait(&x_free[0], xph ^ 1);
+              if (kb == 2) mbar_wait(&x_free[1], xph ^ 1);
+              if (rank == 0) mbar_expect_tx(&x_full[kb], 2u * CH_SLOT);
+              tma_load_2d_pair(smem + (CH_X0 + kb) * CH_SLOT, &a.x, mapa_u32(smem_u32(&x_full[kb]), 0), kb * TC_BK, m0);
+            }
+            uint8_t* dst = ring_acquire(CH_SLOT);
+            tma_load_2d_pair(dst, &a.net[n].w1, cur_bar, kb * TC_BK, int(rank) * 128);
+          }
+        for (int n = 0; n < 2; ++n)
+          for (int kb = 0; kb < H / TC_BK; ++kb) {
+            uint8_t* dst = ring_acquire(CH_SLOT);
+            tma_load_2d_pair(dst, &a.net[n].w2k, cur_bar, kb * TC_BK, int(rank) * 128);
+          }
+        {  // output layers, K-major: 16 (actor) / 8 (critic) rows of W3 per CTA, all four k-blocks in one stage
+          uint8_t* dst = ring_acquire(4 * 2048);
+          for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(dst + kb * 2048, &a.net[0].w3k, cur_bar, kb * TC_BK, int(rank) * 16);
+          dst = ring_acquire(4 * 1024);
+          for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(dst + kb * 1024, &a.net[1].w3k, cur_bar, kb * TC_BK, int(rank) * 8);
+        }
+        {  // dgrad through the output layers: W3 as [K = out][N = hidden], this CTA's 128 hidden columns as two 64-wide atoms
+          uint8_t* dst = ring_acquire(2 * 4096);
+          for (int j = 0; j < 2; ++j) tma_load_2d_pair(dst + j * 4096, &a.net[0].w3m, cur_bar, int(rank) * 128 + 64 * j, 0);
+          dst = ring_acquire(2 * 2048);
+          for (int j = 0; j < 2; ++j) tma_load_2d_pair(dst + j * 2048, &a.net[1].w3m, cur_bar, int(rank) * 128 + 64 * j, 0);
+        }
+        for (int n = 0; n < 2; ++n)
+          for (int kb = 0; kb < H / TC_BK; ++kb) {
+            uint8_t* dst = ring_acquire(CH_SLOT);
+            for (int j = 0; j < 2; ++j) tma_load_2d_pair(dst + j * 8192, &a.net[n].w2m, cur_bar, int(rank) * 128 + 64 * j, kb * TC_BK);
+          }
+      }
+      // every commit the leader multicast to this CTA has landed before the CTA may exit
+      for (int i = 0; i < CH_RING; ++i, ++it) mbar_wait(&ring_empty[it & (CH_RING - 1)], ((it / CH_RING) & 1) ^ 1);
+      if (ti > 0) {
+        mbar_wait(&x_free[0], uint32_t((ti - 1) & 1));
+        mbar_wait(&x_free[1], uint32_t((ti - 1) & 1));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {  // ===== MMA issuer of the pair =====
+      constexpr uint32_t ID_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(256 >> 4) << 24);  // D fp32, A/B bf16, M = 256
+      constexpr uint32_t ID_N256 = ID_BASE | (uint32_t(256 >> 3) << 17);
+      constexpr uint32_t ID_N256_BMN = ID_N256 | (1u << 16);
+      constexpr uint32_t ID_N32 = ID_BASE | (uint32_t(32 >> 3) << 17), ID_N16 = ID_BASE | (uint32_t(16 >> 3) << 17);
+      uint32_t it = 0, g = 0;
+      auto step_begin = [&]() -> uint32_t {  // the epilogue of step g - 2 has drained this accumulator and written this step's A operand
+        mbar_wait_cluster(&epi_done[g & 1], ((g >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (a.trace != nullptr && blockIdx.x == 0 && g < 60) a.trace[g * 8 + 0] = clock64();
+        return tmem_base + (g & 1) * 256u;
+      };
+      auto step_end = [&]() {
+        umma2_commit(&acc_full[g & 1]);
+        if (a.trace != nullptr && blockIdx.x == 0 && g < 60) a.trace[g * 8 + 1] = clock64();
+        ++g;
+      };
+      auto ring_wait = [&]() -> uint32_t {
+        const uint32_t s = it & (CH_RING - 1), ph = (it / CH_RING) & 1;
+        mbar_wait(&ring_full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        return smem_base + (CH_RING0 + s) * CH_SLOT;
+      };
+      auto ring_release = [&]() {
+        umma2_commit(&ring_empty[it & (CH_RING - 1)]);
+        ++it;
+      };
+      int ti = 0;
+      for (int tile = pair_local; tile < tiles2; tile += pairs, ++ti) {
+        for (int n = 0; n < 2; ++n) {  // steps 0, 1: first hidden layer
+          const uint32_t d = step_begin();
+          for (int kb = 0; kb < KB1; ++kb) {
+            if (n == 0) {
+              mbar_wait(&x_full[kb], uint32_t(ti & 1));
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const uint32_t b = ring_wait(), aa = smem_base + (CH_X0 + kb) * CH_SLOT;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(b + k * 32, 0, 1024), ID_N256, (kb > 0 || k > 0) ? 1u : 0u);
+            ring_release();
+          }
+          step_end();
+        }
+        for (int n = 0; n < 2; ++n) {  // steps 2, 3: second hidden layer
+          const uint32_t d = step_begin();
+          for (int kb = 0; kb < H / TC_BK; ++kb) {
+            const uint32_t b = ring_wait(), aa = smem_base + ((n ? CH_HC0 : CH_HA0) + kb) * CH_SLOT;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(b + k * 32, 0, 1024), ID_N256, (kb > 0 || k > 0) ? 1u : 0u);
+            ring_release();
+          }
+          step_end();
+        }
+        for (int n = 0; n < 2; ++n) {  // steps 4, 5: output layers (N = 32 / 16)
+          const uint32_t d = step_begin();
+          const uint32_t b = ring_wait();
+          for (int kb = 0; kb < H / TC_BK; ++kb) {
+            const uint32_t aa = smem_base + ((n ? CH_HC0 : CH_HA0) + kb) * CH_SLOT, bb = b + kb * (n ? 1024 : 2048);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(bb + k * 32, 0, 1024), n ? ID_N16 : ID_N32, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ring_release();
+          step_end();
+        }
+        for (int n = 0; n < 2; ++n) {  // steps 6, 7: dgrad through the output layers (K = 32 / 16)
+          const uint32_t d = step_begin();
+          const uint32_t b = ring_wait(), aa = smem_base + (n ? CH_DZ3C : CH_DZ3A) * CH_SLOT;
+          const int nk = n ? 1 : 2;
+          for (int k = 0; k < nk; ++k)
+            umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(b + k * 2048, n ? 2048 : 4096, 1024), ID_N256_BMN, k > 0 ? 1u : 0u);
+          ring_release();
+          if (n == 1) umma2_commit(&x_free[0]);  // the seed tiles (X slots 0-1) have been read
+          step_end();
+        }
+        for (int n = 0; n < 2; ++n) {  // steps 8, 9: dgrad through the second hidden layer
+          const uint32_t d = step_begin();
+          for (int kb = 0; kb < H / TC_BK; ++kb) {
+            const uint32_t b = ring_wait(), aa = smem_base + ((n ? CH_HC0 : CH_HA0) + kb) * CH_SLOT;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(b + k * 2048, 8192, 1024), ID_N256_BMN, (kb > 0 || k > 0) ? 1u : 0u);
+            ring_release();
+          }
+          if (n == 1) umma2_commit(&x_free[1]);  // the critic tile (X slots 2-5) has been read
+          step_end();
+        }
+      }
+    }
+  } else {  // ===== epilogue warps =====
+    const int q = warp & 3, chunk = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t sw = uint32_t(lane & 7);
+    const int act = a.act;
+    const int A = a.ppo.act_dim;
+    {  // constants of the output layers (written by the optimizer before this kernel: after the PDL wait)
+      const int t = threadIdx.x - 64;
+      if (t < 32) {
+        b3_s[t] = t < A ? __ldg(a.net[0].b3 + t) : 0.f;
+        float ls = 0.f, iv = 0.f;
+        if (t < A) {
+          const float sig = expf(__ldg(a.ppo.logstd + t));
+          ls = logf(sig); iv = 1.f / (sig * sig);
+        }
+        consts_s[t] = ls; consts_s[32 + t] = iv;
+      } else if (t == 32) {
+        b3_s[32] = __ldg(a.net[1].b3);
+      }
+      for (int i = t; i < 4 * 34; i += CH_EPI_WARPS * 32) red_s[i] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_WARPS * 32) : "memory");
+    }
+    const uint32_t lead_done0 = mapa_u32(smem_u32(&epi_done[0]), 0), lead_done1 = mapa_u32(smem_u32(&epi_done[1]), 0);
+    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
+    // this warp's 32 x 64 sub-tile (4 KB, one swizzle-atom column of a k-block) of the actor / critic tile, and this thread's row in it
+    const uint32_t sub_a = smem_base + (CH_HA0 + chunk) * CH_SLOT + uint32_t(q) * 4096u;
+    const uint32_t sub_c = smem_base + (CH_HC0 + chunk) * CH_SLOT + uint32_t(q) * 4096u;
+    const uint32_t row_a = sub_a + uint32_t(lane) * 128u, row_c = sub_c + uint32_t(lane) * 128u;
+    const uint32_t row_z3a = smem_base + CH_DZ3A * CH_SLOT + uint32_t(r) * 128u;
+    const uint32_t row_z3c = smem_base + CH_DZ3C * CH_SLOT + uint32_t(r) * 128u;
+    float* red_row = red_s + q * 34;
+    uint32_t g = 0;
+    auto acc_wait = [&]() {
+      mbar_wait(&acc_full[g & 1], (g >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 2] = clock64();
+    };
+    // End of a step for this warp: its shared-memory writes become visible to the async proxy (the tensor core's
+    // operand reads and the bulk store), the sub-tile it wrote leaves for global memory through the copy engine (one
+    // elected lane; rows past the batch are clipped by the tensor map), and the issuer learns that this warp has drained
+    // the accumulator and written its part of the next A operand.
+    auto step_done = [&](const CUtensorMap* store_map, uint32_t sub, int row0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"((g & 1) ? lead_done1 : lead_done0) : "memory");
+        if (store_map != nullptr) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(store_map)),
+                       "r"(sub), "r"(chunk * 64), "r"(row0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (a.trace != nullptr && blockIdx.x == 0 && g < 60)
+          atomicMax(reinterpret_cast<unsigned long long*>(a.trace) + g * 8 + 3, (unsigned long long)clock64());
+      }
+      ++g;
+    };
+    // before this warp overwrites a sub-tile: the bulk store that last read it has drained it (every store of this warp
+    // is older than anything it overwrites by at least one step, so this rarely waits)
+    auto stores_drained = [&]() {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    };
+    for (int tile = pair_local; tile < tiles2; tile += pairs) {
+      const int row0 = tile * 256 + int(rank) * 128 + q * 32;  // first global row of this warp's sub-tile
+      const int64_t m = int64_t(row0) + lane;
+      const bool row_ok = m < a.M;
+      const int64_t mm = row_ok ? m : 0;
+      for (int n = 0; n < 2; ++n) {  // steps 0, 1
+        const ChainNet& N = a.net[n];
+        float b0[16];
+        ch_bias16(N.b1 + chunk * 64, b0);
+        acc_wait();
+        stores_drained();
+        ch_epi_forward(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), N.b1 + chunk * 64, b0, act, n ? row_c : row_a, sw);
+        step_done(&N.sH1, n ? sub_c : sub_a, row0);
+      }
+      for (int n = 0; n < 2; ++n) {  // steps 2, 3
+        const ChainNet& N = a.net[n];
+        float b0[16];
+        ch_bias16(N.b2 + chunk * 64, b0);
+        acc_wait();
+        stores_drained();
+        ch_epi_forward(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), N.b2 + chunk * 64, b0, act, n ? row_c : row_a, sw);
+        step_done(&N.sH2, n ? sub_c : sub_a, row0);
+      }
+      // step 4: actor output layer + loss.  A row's columns are split over the four warps of its TMEM lane quarter
+      // (8 action columns each): partial log-probs meet in a 16-byte unit of the seed tile's row that the seeds do
+      // not use, then every warp finishes its own columns' seeds — one 16-byte unit of the K-major seed tile each.
+      {
+        const int j0 = chunk * 8;
+        float av[8];
+        const float* ap = a.ppo.action + mm * A + j0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] = (row_ok && j0 + i < A) ? __ldg(ap + i) : 0.f;
+        const float old_lp = row_ok ? __ldg(a.ppo.old_logp + mm) : 0.f, adv = row_ok ? __ldg(a.ppo.advantage + mm) : 0.f;
+        const float tgt = (chunk == 0 && row_ok) ? __ldg(a.ppo.target + mm) : 0.f;  // for step 5
+        acc_wait();
+        const float scale = a.out_scale;
+        const bool ft = a.ppo.final_tanh != 0;
+        float d[8], th[8];
+        float lp = 0.f;
+        if (j0 < A) {
+          uint32_t v[8];
+          tmem_ld8(lane_base + uint32_t(j0), v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = j0 + i;
+            d[i] = 0.f; th[i] = 0.f;
+            if (j < A) {
+              const float pre = __uint_as_float(v[i]) + b3_s[j];
+              th[i] = ft ? tanh_fast(pre) : pre;
+              const float mean = ft ? scale * th[i] : pre;
+              d[i] = av[i] - mean;
+              lp += -(d[i] * d[i]) * (0.5f * consts_s[32 + j]) - consts_s[j] - kTcLogSqrt2Pi;
+            }
+          }
+        }
+        const uint32_t lp_unit = row_z3a + ((4u ^ sw) << 4);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lp_unit + uint32_t(chunk) * 4u), "f"(lp) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");  // the four warps of this lane quarter
+        float l0, l1, l2, l3;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(l0), "=f"(l1), "=f"(l2), "=f"(l3) : "r"(lp_unit) : "memory");
+        const float lp_row = ((l0 + l1) + l2) + l3;  // same order in all four warps
+        float g_lp = 0.f, surr = 0.f;
+        if (row_ok) {
+          const float lo = 1.f - a.ppo.clip_eps, hi = 1.f + a.ppo.clip_eps;
+          const float ratio = expf(lp_row - old_lp);
+          const float s1 = ratio * adv, s2 = fminf(fmaxf(ratio, lo), hi) * adv;
+          const float w1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);
+          const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+          g_lp = -(w1 * adv + (1.f - w1) * adv * in_range) * a.ppo.inv_global_batch * ratio;
+          surr = fminf(s1, s2);
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          float dm[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int j = j0 + i + u;
+            dm[u] = 0.f;
+            if (j < A) {
+              const float dn = d[i + u] * consts_s[32 + j];
+              float dmu = g_lp * dn;
+              if (ft) dmu *= scale * (1.f - th[i + u] * th[i + u]);
+              dm[u] = dmu;                                      // g_lp = 0 for rows past the batch
+              d[i + u] = g_lp * (d[i + u] * dn - 1.f);          // this row's d loss / d logstd_j
+            }
+          }
+          pk[i >> 1] = pack_bf16(dm[0], dm[1]);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_z3a + ((uint32_t(chunk) ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        if (row_ok && j0 < a.net[0].pZ3)
+          *reinterpret_cast<uint4*>(a.net[0].dZ3 + mm * a.net[0].pZ3 + j0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (j0 < A) {  // warp-uniform
+          const float tot = ch_red8(d, lane);
+          const int col = j0 + ch_red8_col(lane);
+          if ((lane & 3) == 0 && col < A) red_row[2 + col] += tot;
+        }
+        if (chunk == 0) {
+          const float ssum = warp_sum(surr);
+          if (lane == 0) red_row[0] += ssum;
+        }
+        step_done(nullptr, 0, 0);
+        // step 5: critic output + Huber loss (one value per row: the chunk-0 warps; the others only keep step)
+        acc_wait();
+        if (chunk == 0) {
+          uint32_t v[8];
+          tmem_ld8(lane_base + 256u, v);
+          float dv = 0.f, hub = 0.f;
+          if (row_ok) {
+            const float e = __uint_as_float(v[0]) + b3_s[32] - tgt;
+            const float ae = fabsf(e);
+            hub = ae < 1.f ? 0.5f * e * e : ae - 0.5f;
+            dv = fminf(fmaxf(e, -1.f), 1.f) * a.ppo.inv_global_batch;
+          }
+          const uint32_t w0 = pack_bf16(dv, 0.f);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_z3c + ((0u ^ sw) << 4)), "r"(w0), "r"(0u), "r"(0u), "r"(0u) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_z3c + ((1u ^ sw) << 4)), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+          if (row_ok) {
+            const int pitch = a.net[1].pZ3;
+            uint4* gp = reinterpret_cast<uint4*>(a.net[1].dZ3 + mm * pitch);
+            gp[0] = make_uint4(w0, 0u, 0u, 0u);
+            for (int c = 1; 8 * c < pitch; ++c) gp[c] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          const float hs = warp_sum(hub);
+          if (lane == 0) red_row[1] += hs;
+        }
+        step_done(nullptr, 0, 0);
+      }
+      for (int n = 0; n < 2; ++n) {  // steps 6, 7
+        const ChainNet& N = a.net[n];
+        acc_wait();
+        stores_drained();
+        ch_epi_dgrad_smem(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), act, n ? row_c : row_a, sw);
+        step_done(&N.sZ2, n ? sub_c : sub_a, row0);
+      }
+      for (int n = 0; n < 2; ++n) {  // steps 8, 9
+        const ChainNet& N = a.net[n];
+        // H1 left through the copy engine in step n: complete (not merely read) before it is loaded back
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+        __syncwarp();
+        uint32_t ax[4][8];
+        const __nv_bfloat16* hrow = N.H1 + mm * N.pH1 + chunk * 64;
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(ax[s][0]), "=r"(ax[s][1]), "=r"(ax[s][2]), "=r"(ax[s][3]), "=r"(ax[s][4]), "=r"(ax[s][5]), "=r"(ax[s][6]), "=r"(ax[s][7])
+                       : "l"(hrow + s * 16)
+                       : "memory");
+        acc_wait();
+        ch_epi_dgrad_glob(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), act, ax, row_a, sw);  // both nets stage in the actor tile
+        step_done(&N.sZ1, sub_a, row0);
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // this CTA's row of loss partials: (sum surrogate, sum huber, sum d loss / d logstd_j)
+    asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_WARPS * 32) : "memory");
+    const int t = threadIdx.x - 64;
+    if (t < 2 + A) a.ppo.partials[int64_t(blockIdx.x) * (2 + A) + t] = red_s[t] + red_s[34 + t] + red_s[68 + t] + red_s[102 + t];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be reading this CTA's operands / arriving on its barriers
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+long long* g_chain_trace = nullptr;
+
+bool tc_chain_shape_ok(int in_dim, int h1, int h2, int out_dim) {
+  return in_dim >= 1 && in_dim <= kChainMaxIn && h1 == kChainHidden && h2 == kChainHidden && out_dim >= 1 && out_dim <= 32;
+}
+
+int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out) {
+  B2_CHECK_ARG(a.M > 0 && a.KB1 >= 1 && a.KB1 <= 6 && a.tiles2 == (a.M + 255) / 256, "chain kernel: bad shape");
+  static bool configured = false;
+  if (!configured) {
+    B2_CUDA(cudaFuncSetAttribute(tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    configured = true;
+  }
+  const int pairs = std::min(num_sms() / 2, a.tiles2);
+  if (grid_out) *grid_out = 2 * pairs;
+  // profiling aid: B200PPO_CHAIN_TRACE=<n> prints the clock64 timeline of pair 0 of the n-th launch (cycles since its
+  // first step): when the issuer got its operands, when it had issued the step, when the epilogue saw the accumulator
+  // and when the slowest epilogue warp of the leader was done with it
+  static const char* trace_env = getenv("B200PPO_CHAIN_TRACE");
+  static int calls = 0;
+  if (trace_env != nullptr && ++calls == atoi(trace_env)) {
+    long long* tr = nullptr;
+    B2_CUDA(cudaMalloc(&tr, 60 * 8 * sizeof(long long)));
+    B2_CUDA(cudaMemset(tr, 0, 60 * 8 * sizeof(long long)));
+    ChainArgs b = a;
+    b.trace = tr;
+    B2_CUDA(launch_pdl(tc_chain_kernel, dim3(2 * pairs), dim3(CH_THREADS), CH_SMEM, st, b));
+    B2_LAUNCH_CHECK();
+    B2_CUDA(cudaStreamSynchronize(st));
+    long long h[60 * 8];
+    B2_CUDA(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(tr);
+    static const char* names[10] = {"L1a", "L1c", "L2a", "L2c", "L3a", "L3c", "D3a", "D3c", "D2a", "D2c"};
+    fprintf(stderr, "chain kernel, pair 0 (M = %d, %d pairs): step | operands ready, issued | accumulator seen, epilogue done\n", a.M, pairs);
+    for (int g = 0; g < 60 && h[g * 8] != 0; ++g)
+      fprintf(stderr, "  %2d %s | %7lld %7lld | %7lld %7lld\n", g, names[g % 10], h[g * 8] - h[0], h[g * 8 + 1] - h[0], h[g * 8 + 2] - h[0],
+              h[g * 8 + 3] - h[0]);
+    return B200PPO_OK;
+  }
+  B2_CUDA(launch_pdl(tc_chain_kernel, dim3(2 * pairs), dim3(CH_THREADS), CH_SMEM, st, a));
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
+
+}  // namespace b200ppo

@@ -640,4 +640,102 @@ __device__ __forceinline__ void tc_ppo_finish(const TcProblem& P, int warp, int 
   }
 }
 
+// ---- CTA-pair (cta_group::2) building blocks shared by tc_ws.cu and tc_chain.cu ---------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are counted on an mbarrier of the pair's leader CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(uint16_t(3))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// 16 accumulator columns of this thread's row -> bias + activation -> bf16 -> two swizzled 16-byte units of the row
+// 16 accumulator columns of this thread's row -> bias + activation -> 16 bf16 (8 words)
+__device__ __forceinline__ void ws2_act16(const uint32_t (&v)[16], const float* bs, int act, uint32_t (&o)[8]) {
+  float z[16];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float4 t = *reinterpret_cast<const float4*>(bs + u * 4);
+    z[u * 4] = __uint_as_float(v[u * 4]) + t.x; z[u * 4 + 1] = __uint_as_float(v[u * 4 + 1]) + t.y;
+    z[u * 4 + 2] = __uint_as_float(v[u * 4 + 2]) + t.z; z[u * 4 + 3] = __uint_as_float(v[u * 4 + 3]) + t.w;
+  }
+  if (act == B200PPO_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = tanh_bf16x2(pack_bf16(z[2 * j], z[2 * j + 1]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = pack_bf16(fmaxf(z[2 * j], 0.f), fmaxf(z[2 * j + 1], 0.f));
+  }
+}
+// ... into two swizzled 16-byte units of the row's staging line
+__device__ __forceinline__ void ws2_finish16(const uint32_t (&v)[16], const float* bs, int act, uint32_t my_row, int sw, int s) {
+  uint32_t o[8];
+  ws2_act16(v, bs, act, o);
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s) ^ sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + uint32_t(((2 * s + 1) ^ sw) << 4)), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
+
+// 256-bit global accesses (one full 32-byte sector per thread): the dgrad epilogue of the pair kernel reads its
+// activation row and writes its result row straight from registers — no staging tile, so shared memory is left to the
+// operands (W half + a deep A ring) and the epilogue does not compete with the MMAs for shared-memory bandwidth.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// dz = acc * act'(h) for 16 columns of this thread's row; h: 16 bf16 activations (8 words)
+__device__ __forceinline__ void ws2_dgrad16(const uint32_t (&v)[16], const uint32_t (&h)[8], int act, uint32_t (&o)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float h0 = __uint_as_float(h[j] << 16), h1 = __uint_as_float(h[j] & 0xFFFF0000u);
+    const float g0 = __uint_as_float(v[2 * j]), g1 = __uint_as_float(v[2 * j + 1]);
+    if (act == B200PPO_ACT_TANH) o[j] = pack_bf16(g0 * (1.f - h0 * h0), g1 * (1.f - h1 * h1));
+    else o[j] = pack_bf16(h0 > 0.f ? g0 : 0.f, h1 > 0.f ? g1 : 0.f);
+  }
+}
+
 }  // namespace b200ppo

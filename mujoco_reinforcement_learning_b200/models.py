@@ -331,6 +331,14 @@ class ActorCriticEngine:
                    "b200ppo_minibatch_grads")
         return losses, grads
 
+    def debug_activations(self, net: int, kind: int, layer: int, rows: int) -> torch.Tensor:
+        """Test hook: bf16 intermediates of the last bf16 minibatch as fp32 (kind 0: H_layer, kind 1: dL/dz_layer)."""
+        dims = (self.actor.actor if net == 0 else self.critic.network).dims
+        out = torch.empty(rows, dims[layer], dtype=torch.float32, device=self.flat.device)
+        _lib.check(self.lib.b200ppo_debug_activations(self._ctx, net, kind, layer, rows, _lib.ptr(out), _lib.stream_ptr()),
+                   "b200ppo_debug_activations")
+        return out
+
     def grads_by_name(self, grads: torch.Tensor, named_parameters):
         """Split a flat gradient into {name: tensor} for an iterable of (name, parameter)."""
         off = {id(p): o for p, o in self.slots}
