@@ -43,10 +43,16 @@ constexpr int CH_EPI_WARPS = 16;
 constexpr int CH_THREADS = (2 + CH_EPI_WARPS) * 32;
 constexpr int CH_SLOT = 16384;  // one k-block of a 128-row operand tile: 128 rows x 128 B
 constexpr int CH_NSLOT = 14;
-constexpr int CH_RING = 4;
-// slot map: X k-blocks 0-5 | actor tile 6-9 | weight ring 10-13; the critic tile aliases X 2-5 (free once L1c has
-// read X), the output-layer seeds alias X 0-1
-constexpr int CH_X0 = 0, CH_HA0 = 6, CH_RING0 = 10, CH_HC0 = 2, CH_DZ3A = 0, CH_DZ3C = 1;
+constexpr int CH_RING = 3;
+// slot map: X k-blocks 0-5 | actor tile 6-9 | weight ring 10-12 | aux 13; the critic tile aliases X 2-5 (free once
+// L1c has read X), the output-layer seeds alias X 0-1
+constexpr int CH_X0 = 0, CH_HA0 = 6, CH_RING0 = 10, CH_AUX = 13, CH_HC0 = 2, CH_DZ3A = 0, CH_DZ3C = 1;
+// aux slot: the hidden-layer biases (the kernel leaves next to no L1: a bias load from global memory is an L2 round
+// trip in front of every accumulator slab) and the tile's loss operands, bulk-copied by the producer a tile ahead
+constexpr int CH_AUX_BIAS = 0;        // [net][layer][256] fp32
+constexpr int CH_AUX_ACT = 4096;      // [128][act_dim] fp32, act_dim <= kChainStageAct
+constexpr int CH_AUX_ROW = 14336;     // old_logp[128], advantage[128], target[128]
+constexpr int kChainStageAct = 20;
 constexpr int CH_MISC = 2048;
 constexpr int CH_SMEM = 1024 + CH_NSLOT * CH_SLOT + CH_MISC;  // = 227 KB
 static_assert(CH_SMEM <= 227 * 1024, "chain kernel shared memory");
@@ -63,6 +69,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+
+// plain bulk copy global -> this CTA's shared memory, bytes counted on a local mbarrier (16-byte granules)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
 }
 
 __device__ __forceinline__ void ch_bias16(const float* __restrict__ b, float (&o)[16]) {  // warp-uniform address: one L1 wavefront each
@@ -93,29 +106,34 @@ __device__ __forceinline__ void ch_lds16(uint32_t srow, uint32_t sw, int s, uint
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(h[4]), "=r"(h[5]), "=r"(h[6]), "=r"(h[7]) : "r"(srow + (((2 * s + 1) ^ sw) << 4)) : "memory");
 }
 
-// Hidden-layer forward epilogue of this warp's 32 rows x 64 columns: TMEM -> bias + activation -> bf16 -> the next A
-// operand in shared memory (the caller then bulk-stores the same 4 KB sub-tile to global memory).  TMEM loads run one
-// 16-column slab ahead of the math and the bias one slab ahead of its use: the kernel leaves next to no L1, so a bias
-// load is an L2 round trip that must not sit between an accumulator slab and its math.  b0: bias of the first slab,
-// requested by the caller before it waited for the accumulator.
-__device__ __forceinline__ void ch_epi_forward(uint32_t tcol, const float* __restrict__ bias, float (&b0)[16], int act, uint32_t srow, uint32_t sw) {
+__device__ __forceinline__ void ch_lds_bias16(uint32_t saddr, float (&b)[16]) {  // broadcast reads: every lane the same 64 bytes
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b[4 * u]), "=f"(b[4 * u + 1]), "=f"(b[4 * u + 2]), "=f"(b[4 * u + 3]) : "r"(saddr + 16u * u) : "memory");
+}
+
+// Hidden-layer forward epilogue of this warp's 32 rows x 64 columns: TMEM -> bias (shared memory) + activation -> bf16
+// -> the next A operand in shared memory (the caller then bulk-stores the same 4 KB sub-tile to global memory).  TMEM
+// loads run one 16-column slab ahead of the math.
+__device__ __forceinline__ void ch_epi_forward(uint32_t tcol, uint32_t bias_s, int act, uint32_t srow, uint32_t sw) {
   uint32_t va[16], vb[16], o[8];
-  float b1[16];
+  float b[16];
   tmem_ld16_nowait(tcol, va);
-  ch_bias16(bias + 16, b1);
+  ch_lds_bias16(bias_s, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   tmem_ld16_nowait(tcol + 16, vb);
-  ch_act16(va, b0, act, o); ch_sts16(srow, sw, 0, o);
-  ch_bias16(bias + 32, b0);
+  ch_act16(va, b, act, o); ch_sts16(srow, sw, 0, o);
+  ch_lds_bias16(bias_s + 64, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   tmem_ld16_nowait(tcol + 32, va);
-  ch_act16(vb, b1, act, o); ch_sts16(srow, sw, 1, o);
-  ch_bias16(bias + 48, b1);
+  ch_act16(vb, b, act, o); ch_sts16(srow, sw, 1, o);
+  ch_lds_bias16(bias_s + 128, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   tmem_ld16_nowait(tcol + 48, vb);
-  ch_act16(va, b0, act, o); ch_sts16(srow, sw, 2, o);
+  ch_act16(va, b, act, o); ch_sts16(srow, sw, 2, o);
+  ch_lds_bias16(bias_s + 192, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  ch_act16(vb, b1, act, o); ch_sts16(srow, sw, 3, o);
+  ch_act16(vb, b, act, o); ch_sts16(srow, sw, 3, o);
 }
 
 // dgrad epilogue, activation in shared memory (the tile this thread wrote two steps earlier): dZ = acc * act'(h),
@@ -142,21 +160,25 @@ __device__ __forceinline__ void ch_epi_dgrad_smem(uint32_t tcol, int act, uint32
 
 // dgrad epilogue of the first hidden layer: its activation was overwritten in shared memory by the second layer's, so
 // the row comes back from global memory (an L2 hit), requested by the caller BEFORE the accumulator is awaited.  The
-// result is no A operand; it is staged in the (now idle) actor tile only so that it leaves through the bulk store.
-__device__ __forceinline__ void ch_epi_dgrad_glob(uint32_t tcol, int act, const uint32_t (&ax)[4][8], uint32_t srow, uint32_t sw) {
+// result is no A operand: it goes straight from registers to global memory, one 32-byte sector per access.
+__device__ __forceinline__ void ch_epi_dgrad_glob(uint32_t tcol, int act, const uint32_t (&ax)[4][8], __nv_bfloat16* grow, bool row_ok) {
   uint32_t va[16], vb[16], o[8];
   tmem_ld16_nowait(tcol, va);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   tmem_ld16_nowait(tcol + 16, vb);
-  ws2_dgrad16(va, ax[0], act, o); ch_sts16(srow, sw, 0, o);
+  ws2_dgrad16(va, ax[0], act, o);
+  if (row_ok) stg256(grow, o);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   tmem_ld16_nowait(tcol + 32, va);
-  ws2_dgrad16(vb, ax[1], act, o); ch_sts16(srow, sw, 1, o);
+  ws2_dgrad16(vb, ax[1], act, o);
+  if (row_ok) stg256(grow + 16, o);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   tmem_ld16_nowait(tcol + 48, vb);
-  ws2_dgrad16(va, ax[2], act, o); ch_sts16(srow, sw, 2, o);
+  ws2_dgrad16(va, ax[2], act, o);
+  if (row_ok) stg256(grow + 32, o);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  ws2_dgrad16(vb, ax[3], act, o); ch_sts16(srow, sw, 3, o);
+  ws2_dgrad16(vb, ax[3], act, o);
+  if (row_ok) stg256(grow + 48, o);
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
@@ -203,7 +225,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
   uint64_t* x_free = bars + 14;      // [2]  slots 0-1 (after D3c), slots 2-5 (after D2c); commit multicast
   uint64_t* acc_full = bars + 16;    // [2]  commit multicast
   uint64_t* epi_done = bars + 18;    // [2]  leader: 2 x 16 epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* aux_full = bars + 20;    // [1]  this CTA's loss operands of the current tile have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
   float* b3_s = reinterpret_cast<float*>(misc + 192);     // [0,32) actor output bias, [32] critic output bias
   float* consts_s = reinterpret_cast<float*>(misc + 384); // [0,32) log sigma, [32,64) 1/var
   float* red_s = reinterpret_cast<float*>(misc + 768);    // [4][34] running loss sums of the four loss warps
@@ -216,6 +239,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 18; ++i) mbar_init(&bars[i], 1);
+    mbar_init(aux_full, 1);
     mbar_init(&epi_done[0], 2 * CH_EPI_WARPS);
     mbar_init(&epi_done[1], 2 * CH_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -232,15 +256,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      uint32_t it = 0, cur_bar = 0;
+      uint32_t rs = 0, rph = 0, cur_bar = 0;  // ring stage and its phase bit
       auto ring_acquire = [&](uint32_t bytes) -> uint8_t* {
-        const uint32_t s = it & (CH_RING - 1), ph = (it / CH_RING) & 1;
-        mbar_wait(&ring_empty[s], ph ^ 1);
-        if (rank == 0) mbar_expect_tx(&ring_full[s], 2u * bytes);
-        cur_bar = mapa_u32(smem_u32(&ring_full[s]), 0);
-        ++it;
-        return smem + (CH_RING0 + s) * CH_SLOT;
+        mbar_wait(&ring_empty[rs], rph ^ 1);
+        if (rank == 0) mbar_expect_tx(&ring_full[rs], 2u * bytes);
+        cur_bar = mapa_u32(smem_u32(&ring_full[rs]), 0);
+        uint8_t* dst = smem + (CH_RING0 + rs) * CH_SLOT;
+        if (++rs == CH_RING) { rs = 0; rph ^= 1; }
+        return dst;
       };
+      const int A = a.ppo.act_dim;
       int ti = 0;
       for (int tile = pair_local; tile < tiles2; tile += pairs, ++ti) {
         const int m0 = tile * 256 + int(rank) * 128;
@@ -248,7 +273,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
         for (int n = 0; n < 2; ++n)
           for (int kb = 0; kb < KB1; ++kb) {
             if (n == 0) {
-              if (kb == 0) mbar_wait(&x_free[0], xph ^ 1);
+              if (kb == 0) {
+                mbar_wait(&x_free[0], xph ^ 1);  // ... which also says that the previous tile's loss steps are over
+                if (a.stage_loss && m0 + 128 <= a.M) {  // this CTA's loss operands (whole tiles only: 16-byte granules)
+                  uint8_t* aux = smem + CH_AUX * CH_SLOT;
+                  mbar_expect_tx(aux_full, uint32_t(128 * A * 4 + 3 * 512));
+                  bulk_load(aux + CH_AUX_ACT, a.ppo.action + int64_t(m0) * A, uint32_t(128 * A * 4), aux_full);
+                  bulk_load(aux + CH_AUX_ROW, a.ppo.old_logp + m0, 512u, aux_full);
+                  bulk_load(aux + CH_AUX_ROW + 512, a.ppo.advantage + m0, 512u, aux_full);
+                  bulk_load(aux + CH_AUX_ROW + 1024, a.ppo.target + m0, 512u, aux_full);
+                }
+              }
               if (kb == 2) mbar_wait(&x_free[1], xph ^ 1);
               if (rank == 0) mbar_expect_tx(&x_full[kb], 2u * CH_SLOT);
               tma_load_2d_pair(smem + (CH_X0 + kb) * CH_SLOT, &a.x, mapa_u32(smem_u32(&x_full[kb]), 0), kb * TC_BK, m0);
@@ -280,7 +315,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
           }
       }
       // every commit the leader multicast to this CTA has landed before the CTA may exit
-      for (int i = 0; i < CH_RING; ++i, ++it) mbar_wait(&ring_empty[it & (CH_RING - 1)], ((it / CH_RING) & 1) ^ 1);
+      for (int i = 0; i < CH_RING; ++i) {
+        mbar_wait(&ring_empty[rs], rph ^ 1);
+        if (++rs == CH_RING) { rs = 0; rph ^= 1; }
+      }
       if (ti > 0) {
         mbar_wait(&x_free[0], uint32_t((ti - 1) & 1));
         mbar_wait(&x_free[1], uint32_t((ti - 1) & 1));
@@ -292,9 +330,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
       constexpr uint32_t ID_N256 = ID_BASE | (uint32_t(256 >> 3) << 17);
       constexpr uint32_t ID_N256_BMN = ID_N256 | (1u << 16);
       constexpr uint32_t ID_N32 = ID_BASE | (uint32_t(32 >> 3) << 17), ID_N16 = ID_BASE | (uint32_t(16 >> 3) << 17);
-      uint32_t it = 0, g = 0;
+      uint32_t rs = 0, rph = 0, g = 0;
       auto step_begin = [&]() -> uint32_t {  // the epilogue of step g - 2 has drained this accumulator and written this step's A operand
-        mbar_wait_cluster(&epi_done[g & 1], ((g >> 1) & 1) ^ 1);
+        mbar_wait(&epi_done[g & 1], ((g >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (a.trace != nullptr && blockIdx.x == 0 && g < 60) a.trace[g * 8 + 0] = clock64();
         return tmem_base + (g & 1) * 256u;
@@ -305,14 +343,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
         ++g;
       };
       auto ring_wait = [&]() -> uint32_t {
-        const uint32_t s = it & (CH_RING - 1), ph = (it / CH_RING) & 1;
-        mbar_wait(&ring_full[s], ph);
+        mbar_wait(&ring_full[rs], rph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        return smem_base + (CH_RING0 + s) * CH_SLOT;
+        return smem_base + (CH_RING0 + rs) * CH_SLOT;
       };
       auto ring_release = [&]() {
-        umma2_commit(&ring_empty[it & (CH_RING - 1)]);
-        ++it;
+        umma2_commit(&ring_empty[rs]);
+        if (++rs == CH_RING) { rs = 0; rph ^= 1; }
       };
       int ti = 0;
       for (int tile = pair_local; tile < tiles2; tile += pairs, ++ti) {
@@ -398,8 +435,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
         b3_s[32] = __ldg(a.net[1].b3);
       }
       for (int i = t; i < 4 * 34; i += CH_EPI_WARPS * 32) red_s[i] = 0.f;
+      float* bias_dst = reinterpret_cast<float*>(smem + CH_AUX * CH_SLOT + CH_AUX_BIAS);
+      for (int i = t; i < 4 * H; i += CH_EPI_WARPS * 32) {  // [net][layer][256]
+        const int nl = i / H, c = i - nl * H;
+        const ChainNet& N = a.net[nl >> 1];
+        bias_dst[i] = __ldg(((nl & 1) ? N.b2 : N.b1) + c);
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_WARPS * 32) : "memory");
     }
+    const uint32_t aux_s = smem_base + CH_AUX * CH_SLOT;
+    const uint32_t bias_chunk_s = aux_s + CH_AUX_BIAS + uint32_t(chunk) * 256u;  // + (net * 2 + layer) * 1024
+    uint32_t aux_n = 0;  // staged tiles so far (phase of aux_full)
     const uint32_t lead_done0 = mapa_u32(smem_u32(&epi_done[0]), 0), lead_done1 = mapa_u32(smem_u32(&epi_done[1]), 0);
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
     // this warp's 32 x 64 sub-tile (4 KB, one swizzle-atom column of a k-block) of the actor / critic tile, and this thread's row in it
@@ -425,7 +471,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"((g & 1) ? lead_done1 : lead_done0) : "memory");
+        // relaxed: a release here is MEMBAR.ALL.GPU in front of every arrive (19 % of the kernel's stall samples); the
+        // proxy fence above has already completed this warp's shared-memory writes, which is all the issuer's MMAs read
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"((g & 1) ? lead_done1 : lead_done0) : "memory");
         if (store_map != nullptr) {
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(store_map)),
                        "r"(sub), "r"(chunk * 64), "r"(row0)
@@ -437,10 +485,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
       }
       ++g;
     };
-    // before this warp overwrites a sub-tile: the bulk store that last read it has drained it (every store of this warp
-    // is older than anything it overwrites by at least one step, so this rarely waits)
+    // before this warp overwrites a sub-tile: the bulk store that last read it has drained it.  The stores of a warp
+    // alternate between its actor and its critic sub-tile, so the one that matters is always the second youngest.
     auto stores_drained = [&]() {
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       __syncwarp();
     };
     for (int tile = pair_local; tile < tiles2; tile += pairs) {
@@ -450,20 +498,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
       const int64_t mm = row_ok ? m : 0;
       for (int n = 0; n < 2; ++n) {  // steps 0, 1
         const ChainNet& N = a.net[n];
-        float b0[16];
-        ch_bias16(N.b1 + chunk * 64, b0);
         acc_wait();
         stores_drained();
-        ch_epi_forward(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), N.b1 + chunk * 64, b0, act, n ? row_c : row_a, sw);
+        ch_epi_forward(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), bias_chunk_s + uint32_t(n) * 2048u, act, n ? row_c : row_a, sw);
         step_done(&N.sH1, n ? sub_c : sub_a, row0);
       }
       for (int n = 0; n < 2; ++n) {  // steps 2, 3
         const ChainNet& N = a.net[n];
-        float b0[16];
-        ch_bias16(N.b2 + chunk * 64, b0);
         acc_wait();
         stores_drained();
-        ch_epi_forward(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), N.b2 + chunk * 64, b0, act, n ? row_c : row_a, sw);
+        ch_epi_forward(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), bias_chunk_s + uint32_t(n) * 2048u + 1024u, act, n ? row_c : row_a, sw);
         step_done(&N.sH2, n ? sub_c : sub_a, row0);
       }
       // step 4: actor output layer + loss.  A row's columns are split over the four warps of its TMEM lane quarter
@@ -471,12 +515,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
       // not use, then every warp finishes its own columns' seeds — one 16-byte unit of the K-major seed tile each.
       {
         const int j0 = chunk * 8;
-        float av[8];
-        const float* ap = a.ppo.action + mm * A + j0;
+        float av[8], old_lp, adv, tgt;  // tgt: for step 5
+        if (a.stage_loss && tile * 256 + int(rank) * 128 + 128 <= a.M) {  // the producer staged this CTA's rows (CTA-uniform)
+          mbar_wait(aux_full, aux_n & 1);
+          ++aux_n;
+          const uint32_t rs4 = aux_s + CH_AUX_ROW + uint32_t(r) * 4u;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old_lp) : "r"(rs4) : "memory");
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(adv) : "r"(rs4 + 512u) : "memory");
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tgt) : "r"(rs4 + 1024u) : "memory");
+          const uint32_t as4 = aux_s + CH_AUX_ACT + uint32_t(r * A + j0) * 4u;  // row stride A words: conflict-free for odd A
 #pragma unroll
-        for (int i = 0; i < 8; ++i) av[i] = (row_ok && j0 + i < A) ? __ldg(ap + i) : 0.f;
-        const float old_lp = row_ok ? __ldg(a.ppo.old_logp + mm) : 0.f, adv = row_ok ? __ldg(a.ppo.advantage + mm) : 0.f;
-        const float tgt = (chunk == 0 && row_ok) ? __ldg(a.ppo.target + mm) : 0.f;  // for step 5
+          for (int i = 0; i < 8; ++i) {
+            av[i] = 0.f;
+            if (j0 + i < A) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(av[i]) : "r"(as4 + 4u * i) : "memory");
+          }
+        } else {
+          const float* ap = a.ppo.action + mm * A + j0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) av[i] = (row_ok && j0 + i < A) ? __ldg(ap + i) : 0.f;
+          old_lp = row_ok ? __ldg(a.ppo.old_logp + mm) : 0.f;
+          adv = row_ok ? __ldg(a.ppo.advantage + mm) : 0.f;
+          tgt = row_ok ? __ldg(a.ppo.target + mm) : 0.f;
+        }
         acc_wait();
         const float scale = a.out_scale;
         const bool ft = a.ppo.final_tanh != 0;
@@ -580,9 +640,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
       }
       for (int n = 0; n < 2; ++n) {  // steps 8, 9
         const ChainNet& N = a.net[n];
-        // H1 left through the copy engine in step n: complete (not merely read) before it is loaded back
+        // H1 left through the copy engine in step n: its store must be complete (not merely read) before the row is
+        // loaded back; the 5 (4) younger stores of this warp may still be in flight
         if (lane == 0) {
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          if (n == 0) asm volatile("cp.async.bulk.wait_group 5;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
           asm volatile("fence.proxy.async.global;" ::: "memory");
         }
         __syncwarp();
@@ -595,8 +657,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
                        : "l"(hrow + s * 16)
                        : "memory");
         acc_wait();
-        ch_epi_dgrad_glob(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), act, ax, row_a, sw);  // both nets stage in the actor tile
-        step_done(&N.sZ1, sub_a, row0);
+        ch_epi_dgrad_glob(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), act, ax, N.dZ1 + mm * N.pZ1 + chunk * 64, row_ok);
+        step_done(nullptr, 0, 0);
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -63,8 +63,8 @@ class TensorDict:
         return TensorDict(out, batch_size=(self.batch_size.numel(),))
 
 
-def install():
-    """Register the shims and put the reference's `src/` on sys.path."""
+def install(src: str = REFERENCE_SRC):
+    """Register the shims and put the reference's `src/` (or its staged copy `oracle/_ref/src`) on sys.path."""
     from oracle.ppo_oracle import generalized_advantage_estimate
 
     def mod(name, **attrs):
@@ -83,5 +83,5 @@ def install():
     mod("mediapy", write_video=noop, show_video=noop)
     core = mod("gymnasium.core", Env=object)
     mod("gymnasium", core=core, Env=object)
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    if src not in sys.path:
+        sys.path.insert(0, src)
