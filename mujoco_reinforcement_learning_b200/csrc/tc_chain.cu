@@ -212,6 +212,10 @@ __device__ __forceinline__ float ch_red8(const float (&v)[8], int lane) {
   return y;
 }
 
+// ACT: the hidden activation as a compile-time constant, and the two networks of a step pair share ONE copy of every
+// epilogue body (loops over n not unrolled): the first version carried 64 KB of code — twice the instruction cache —
+// and every step of every tile started with instruction fetches from L2.
+template <int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_constant__ ChainArgs a) {
   constexpr uint32_t TMEM_COLS = 512;
   constexpr int H = kChainHidden;
@@ -419,7 +423,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
     const int q = warp & 3, chunk = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t sw = uint32_t(lane & 7);
-    const int act = a.act;
+    constexpr int act = ACT;
     const int A = a.ppo.act_dim;
     {  // constants of the output layers (written by the optimizer before this kernel: after the PDL wait)
       const int t = threadIdx.x - 64;
@@ -480,8 +484,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (a.trace != nullptr && blockIdx.x == 0 && g < 60)
+        if (a.trace != nullptr && blockIdx.x == 0 && g < 60) {
           atomicMax(reinterpret_cast<unsigned long long*>(a.trace) + g * 8 + 3, (unsigned long long)clock64());
+          if (warp == 2) a.trace[g * 8 + 6] = clock64();
+          if (warp == 17) a.trace[g * 8 + 7] = clock64();
+        }
       }
       ++g;
     };
@@ -496,18 +503,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
       const int64_t m = int64_t(row0) + lane;
       const bool row_ok = m < a.M;
       const int64_t mm = row_ok ? m : 0;
+#pragma unroll 1
       for (int n = 0; n < 2; ++n) {  // steps 0, 1
         const ChainNet& N = a.net[n];
         acc_wait();
         stores_drained();
+        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 4] = clock64();
         ch_epi_forward(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), bias_chunk_s + uint32_t(n) * 2048u, act, n ? row_c : row_a, sw);
+        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 5] = clock64();
         step_done(&N.sH1, n ? sub_c : sub_a, row0);
       }
+#pragma unroll 1
       for (int n = 0; n < 2; ++n) {  // steps 2, 3
         const ChainNet& N = a.net[n];
         acc_wait();
         stores_drained();
+        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 4] = clock64();
         ch_epi_forward(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), bias_chunk_s + uint32_t(n) * 2048u + 1024u, act, n ? row_c : row_a, sw);
+        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 5] = clock64();
         step_done(&N.sH2, n ? sub_c : sub_a, row0);
       }
       // step 4: actor output layer + loss.  A row's columns are split over the four warps of its TMEM lane quarter
@@ -631,13 +644,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
         }
         step_done(nullptr, 0, 0);
       }
+#pragma unroll 1
       for (int n = 0; n < 2; ++n) {  // steps 6, 7
         const ChainNet& N = a.net[n];
         acc_wait();
         stores_drained();
+        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 4] = clock64();
         ch_epi_dgrad_smem(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), act, n ? row_c : row_a, sw);
+        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 5] = clock64();
         step_done(&N.sZ2, n ? sub_c : sub_a, row0);
       }
+#pragma unroll 1
       for (int n = 0; n < 2; ++n) {  // steps 8, 9
         const ChainNet& N = a.net[n];
         // H1 left through the copy engine in step n: its store must be complete (not merely read) before the row is
@@ -648,6 +665,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
           asm volatile("fence.proxy.async.global;" ::: "memory");
         }
         __syncwarp();
+        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 4] = clock64();
         uint32_t ax[4][8];
         const __nv_bfloat16* hrow = N.H1 + mm * N.pH1 + chunk * 64;
 #pragma unroll
@@ -658,6 +676,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
                        : "memory");
         acc_wait();
         ch_epi_dgrad_glob(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), act, ax, N.dZ1 + mm * N.pZ1 + chunk * 64, row_ok);
+        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 5] = clock64();
         step_done(nullptr, 0, 0);
       }
     }
@@ -686,11 +705,13 @@ int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out) {
   B2_CHECK_ARG(a.M > 0 && a.KB1 >= 1 && a.KB1 <= 6 && a.tiles2 == (a.M + 255) / 256, "chain kernel: bad shape");
   static bool configured = false;
   if (!configured) {
-    B2_CUDA(cudaFuncSetAttribute(tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(tc_chain_kernel<B200PPO_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(tc_chain_kernel<B200PPO_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
     configured = true;
   }
   const int pairs = std::min(num_sms() / 2, a.tiles2);
   if (grid_out) *grid_out = 2 * pairs;
+  void (*kernel)(ChainArgs) = a.act == B200PPO_ACT_TANH ? tc_chain_kernel<B200PPO_ACT_TANH> : tc_chain_kernel<B200PPO_ACT_RELU>;
   // profiling aid: B200PPO_CHAIN_TRACE=<n> prints the clock64 timeline of pair 0 of the n-th launch (cycles since its
   // first step): when the issuer got its operands, when it had issued the step, when the epilogue saw the accumulator
   // and when the slowest epilogue warp of the leader was done with it
@@ -702,7 +723,7 @@ int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out) {
     B2_CUDA(cudaMemset(tr, 0, 60 * 8 * sizeof(long long)));
     ChainArgs b = a;
     b.trace = tr;
-    B2_CUDA(launch_pdl(tc_chain_kernel, dim3(2 * pairs), dim3(CH_THREADS), CH_SMEM, st, b));
+    B2_CUDA(launch_pdl(kernel, dim3(2 * pairs), dim3(CH_THREADS), CH_SMEM, st, b));
     B2_LAUNCH_CHECK();
     B2_CUDA(cudaStreamSynchronize(st));
     long long h[60 * 8];
@@ -711,11 +732,12 @@ int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out) {
     static const char* names[10] = {"L1a", "L1c", "L2a", "L2c", "L3a", "L3c", "D3a", "D3c", "D2a", "D2c"};
     fprintf(stderr, "chain kernel, pair 0 (M = %d, %d pairs): step | operands ready, issued | accumulator seen, epilogue done\n", a.M, pairs);
     for (int g = 0; g < 60 && h[g * 8] != 0; ++g)
-      fprintf(stderr, "  %2d %s | %7lld %7lld | %7lld %7lld\n", g, names[g % 10], h[g * 8] - h[0], h[g * 8 + 1] - h[0], h[g * 8 + 2] - h[0],
-              h[g * 8 + 3] - h[0]);
+      fprintf(stderr, "  %2d %s | %7lld %7lld | %7lld %7lld | warp 2: body %lld..%lld end %lld | warp 17 end %lld\n", g, names[g % 10], h[g * 8] - h[0],
+              h[g * 8 + 1] - h[0], h[g * 8 + 2] - h[0], h[g * 8 + 3] - h[0], h[g * 8 + 4] ? h[g * 8 + 4] - h[0] : 0,
+              h[g * 8 + 5] ? h[g * 8 + 5] - h[0] : 0, h[g * 8 + 6] ? h[g * 8 + 6] - h[0] : 0, h[g * 8 + 7] ? h[g * 8 + 7] - h[0] : 0);
     return B200PPO_OK;
   }
-  B2_CUDA(launch_pdl(tc_chain_kernel, dim3(2 * pairs), dim3(CH_THREADS), CH_SMEM, st, a));
+  B2_CUDA(launch_pdl(kernel, dim3(2 * pairs), dim3(CH_THREADS), CH_SMEM, st, a));
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }
