@@ -635,6 +635,7 @@ static int launch_chain(b200ppo_ctx* ctx, const float* params, const __nv_bfloat
     B2_TRY(tc_make_map(&c.w3m, bf.W[n][2], kChainHidden, out, bf.pitchW[n][2], 64, n ? 16 : 32));
     B2_TRY(tc_make_map(&c.sH1, bf.H[n][0], kChainHidden, B, bf.pitchH[n][0], 64, 32));
     B2_TRY(tc_make_map(&c.sH2, bf.H[n][1], kChainHidden, B, bf.pitchH[n][1], 64, 32));
+    B2_TRY(tc_make_map(&c.sZ1, bf.dZ[n][0], kChainHidden, B, bf.pitchZ[n][0], 64, 32));
     B2_TRY(tc_make_map(&c.sZ2, bf.dZ[n][1], kChainHidden, B, bf.pitchZ[n][1], 64, 32));
     c.b1 = params + N.b_off[0]; c.b2 = params + N.b_off[1]; c.b3 = params + N.b_off[2];
     c.H1 = bf.H[n][0]; c.H2 = bf.H[n][1]; c.dZ1 = bf.dZ[n][0]; c.dZ2 = bf.dZ[n][1]; c.dZ3 = bf.dZ[n][2];
@@ -652,7 +653,6 @@ static int launch_chain(b200ppo_ctx* ctx, const float* params, const __nv_bfloat
   a.KB1 = (D + TC_CHAIN_BK - 1) / TC_CHAIN_BK;
   a.act = ctx->net[0].d.activation;
   a.tiles2 = int((B + 255) / 256);
-  a.stage_loss = a.ppo.act_dim <= 20 && aligned16(action) && aligned16(old_logp) && aligned16(adv) && aligned16(tgt);
   a.trace = g_chain_trace;
   return launch_tc_chain(a, st, loss_ctas);
 }

@@ -43,19 +43,21 @@ constexpr int CH_EPI_WARPS = 16;
 constexpr int CH_THREADS = (2 + CH_EPI_WARPS) * 32;
 constexpr int CH_SLOT = 16384;  // one k-block of a 128-row operand tile: 128 rows x 128 B
 constexpr int CH_NSLOT = 14;
-constexpr int CH_RING = 3;
-// slot map: X k-blocks 0-5 | actor tile 6-9 | weight ring 10-12 | aux 13; the critic tile aliases X 2-5 (free once
-// L1c has read X), the output-layer seeds alias X 0-1
-constexpr int CH_X0 = 0, CH_HA0 = 6, CH_RING0 = 10, CH_AUX = 13, CH_HC0 = 2, CH_DZ3A = 0, CH_DZ3C = 1;
-// aux slot: the hidden-layer biases (the kernel leaves next to no L1: a bias load from global memory is an L2 round
-// trip in front of every accumulator slab) and the tile's loss operands, bulk-copied by the producer a tile ahead
-constexpr int CH_AUX_BIAS = 0;        // [net][layer][256] fp32
-constexpr int CH_AUX_ACT = 4096;      // [128][act_dim] fp32, act_dim <= kChainStageAct
-constexpr int CH_AUX_ROW = 14336;     // old_logp[128], advantage[128], target[128]
-constexpr int kChainStageAct = 20;
-constexpr int CH_MISC = 2048;
-constexpr int CH_SMEM = 1024 + CH_NSLOT * CH_SLOT + CH_MISC;  // = 227 KB
+constexpr int CH_RING = 4;
+// slot map: X k-blocks 0-5 | actor tile 6-9 | weight ring 10-13; the critic tile aliases X 2-5 (free once both first
+// layers have read X), the output-layer seeds alias X 0-1.  The ring must hold ~64 KB in flight: one 16 KB stage feeds
+// 512 tensor cycles and a refill (commit -> producer -> L2 -> shared memory) takes ~2 k cycles under load.
+constexpr int CH_X0 = 0, CH_HA0 = 6, CH_RING0 = 10, CH_HC0 = 2, CH_DZ3A = 0, CH_DZ3C = 1;
+// what is left of the 227 KB: barriers, the output layers' constants, running loss sums, bf16 hidden biases
+constexpr int kChainMaxAct = 24;
+constexpr int CH_RED_W = 2 + kChainMaxAct;
+constexpr int CH_MISC_B3 = 192, CH_MISC_CONST = 296, CH_MISC_RED = 488, CH_MISC_BIAS = 1024;
+constexpr int CH_MISC = 3072;
+constexpr int CH_SMEM = CH_NSLOT * CH_SLOT + CH_MISC;  // = 227 KB, the dynamic shared memory starts 1024-byte aligned (checked)
 static_assert(CH_SMEM <= 227 * 1024, "chain kernel shared memory");
+static_assert(CH_MISC_B3 + 4 * (kChainMaxAct + 1) <= CH_MISC_CONST && CH_MISC_CONST + 8 * kChainMaxAct <= CH_MISC_RED &&
+                  CH_MISC_RED + 16 * CH_RED_W <= CH_MISC_BIAS && CH_MISC_BIAS + 2048 <= CH_MISC,
+              "chain kernel misc layout");
 
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // arrivals come from the peer CTA too
   const uint32_t addr = smem_u32(bar);
@@ -106,10 +108,17 @@ __device__ __forceinline__ void ch_lds16(uint32_t srow, uint32_t sw, int s, uint
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(h[4]), "=r"(h[5]), "=r"(h[6]), "=r"(h[7]) : "r"(srow + (((2 * s + 1) ^ sw) << 4)) : "memory");
 }
 
-__device__ __forceinline__ void ch_lds_bias16(uint32_t saddr, float (&b)[16]) {  // broadcast reads: every lane the same 64 bytes
+__device__ __forceinline__ void ch_lds_bias16(uint32_t saddr, float (&b)[16]) {  // 16 bf16 biases; broadcast reads: every lane the same 32 bytes
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b[4 * u]), "=f"(b[4 * u + 1]), "=f"(b[4 * u + 2]), "=f"(b[4 * u + 3]) : "r"(saddr + 16u * u) : "memory");
+  for (int u = 0; u < 2; ++u) {
+    uint32_t w[4];
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(saddr + 16u * u) : "memory");
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      b[8 * u + 2 * j] = __uint_as_float(w[j] << 16);
+      b[8 * u + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    }
+  }
 }
 
 // Hidden-layer forward epilogue of this warp's 32 rows x 64 columns: TMEM -> bias (shared memory) + activation -> bf16
@@ -123,15 +132,15 @@ __device__ __forceinline__ void ch_epi_forward(uint32_t tcol, uint32_t bias_s, i
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   tmem_ld16_nowait(tcol + 16, vb);
   ch_act16(va, b, act, o); ch_sts16(srow, sw, 0, o);
-  ch_lds_bias16(bias_s + 64, b);
+  ch_lds_bias16(bias_s + 32, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   tmem_ld16_nowait(tcol + 32, va);
   ch_act16(vb, b, act, o); ch_sts16(srow, sw, 1, o);
-  ch_lds_bias16(bias_s + 128, b);
+  ch_lds_bias16(bias_s + 64, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   tmem_ld16_nowait(tcol + 48, vb);
   ch_act16(va, b, act, o); ch_sts16(srow, sw, 2, o);
-  ch_lds_bias16(bias_s + 192, b);
+  ch_lds_bias16(bias_s + 96, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   ch_act16(vb, b, act, o); ch_sts16(srow, sw, 3, o);
 }
@@ -181,6 +190,36 @@ __device__ __forceinline__ void ch_epi_dgrad_glob(uint32_t tcol, int act, const 
   if (row_ok) stg256(grow + 48, o);
 }
 
+// ... the actor's variant: staged in its (idle) tile so that it leaves through the bulk store
+__device__ __forceinline__ void ch_epi_dgrad_stage(uint32_t tcol, int act, const uint32_t (&ax)[4][8], uint32_t srow, uint32_t sw) {
+  uint32_t va[16], vb[16], o[8];
+  tmem_ld16_nowait(tcol, va);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 16, vb);
+  ws2_dgrad16(va, ax[0], act, o); ch_sts16(srow, sw, 0, o);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 32, va);
+  ws2_dgrad16(vb, ax[1], act, o); ch_sts16(srow, sw, 1, o);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(tcol + 48, vb);
+  ws2_dgrad16(va, ax[2], act, o); ch_sts16(srow, sw, 2, o);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  ws2_dgrad16(vb, ax[3], act, o); ch_sts16(srow, sw, 3, o);
+}
+
+__device__ __forceinline__ void ldg256_na(const void* p, uint32_t (&r)[8]) {  // coherent 256-bit load that does not linger in L1
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p)
+               : "memory");
+}
+
+__device__ __forceinline__ float ldg_f32_now(const float* p) {  // volatile: issued where it is written, not sunk to its use
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -213,37 +252,41 @@ __device__ __forceinline__ float ch_red8(const float (&v)[8], int lane) {
 }
 
 // ACT: the hidden activation as a compile-time constant, and the two networks of a step pair share ONE copy of every
-// epilogue body (loops over n not unrolled): the first version carried 64 KB of code — twice the instruction cache —
-// and every step of every tile started with instruction fetches from L2.
+// epilogue body (loops over the pair not unrolled): the first version carried ~100 KB of code — three times the
+// instruction cache — and every step of every tile started with instruction fetches from L2.
+//
+// Order inside a step pair: actor first in the forward half (steps 0-5), CRITIC first in the backward half (6-9).  The
+// critic's tile aliases X k-blocks 2-5: forward, its first epilogue may only write there once BOTH first-layer MMAs have
+// read X (so it goes second); backward, the earlier its last MMA (step 8) retires, the earlier the next tile's
+// observations can stream in behind the actor's step 9.  The one irregular dependency this creates: step 6 (critic)
+// needs the seeds of step 5, not of step 4.
 template <int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_constant__ ChainArgs a) {
   constexpr uint32_t TMEM_COLS = 512;
   constexpr int H = kChainHidden;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* misc = smem + CH_NSLOT * CH_SLOT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
   uint64_t* ring_full = bars;        // [4]  leader: both CTAs' TMA bytes
   uint64_t* ring_empty = bars + 4;   // [4]  commit multicast
   uint64_t* x_full = bars + 8;       // [6]  leader
-  uint64_t* x_free = bars + 14;      // [2]  slots 0-1 (after D3c), slots 2-5 (after D2c); commit multicast
+  uint64_t* x_free = bars + 14;      // [2]  slots 0-1 (after step 7), slots 2-5 (after step 8); commit multicast
   uint64_t* acc_full = bars + 16;    // [2]  commit multicast
   uint64_t* epi_done = bars + 18;    // [2]  leader: 2 x 16 epilogue warps
-  uint64_t* aux_full = bars + 20;    // [1]  this CTA's loss operands of the current tile have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
-  float* b3_s = reinterpret_cast<float*>(misc + 192);     // [0,32) actor output bias, [32] critic output bias
-  float* consts_s = reinterpret_cast<float*>(misc + 384); // [0,32) log sigma, [32,64) 1/var
-  float* red_s = reinterpret_cast<float*>(misc + 768);    // [4][34] running loss sums of the four loss warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* b3_s = reinterpret_cast<float*>(misc + CH_MISC_B3);        // [0,24) actor output bias, [24] critic output bias
+  float* consts_s = reinterpret_cast<float*>(misc + CH_MISC_CONST); // [0,24) log sigma, [24,48) 1/var
+  float* red_s = reinterpret_cast<float*>(misc + CH_MISC_RED);      // [4][26] running loss sums per TMEM lane quarter
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair_local = int(blockIdx.x) >> 1, pairs = int(gridDim.x) >> 1;
   const int KB1 = a.KB1, tiles2 = a.tiles2;
   const uint32_t smem_base = smem_u32(smem);
+  if ((smem_base & 1023u) != 0) __trap();  // the 128-byte swizzle atoms need it; there is no slack left to realign
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 18; ++i) mbar_init(&bars[i], 1);
-    mbar_init(aux_full, 1);
     mbar_init(&epi_done[0], 2 * CH_EPI_WARPS);
     mbar_init(&epi_done[1], 2 * CH_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -269,36 +312,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
         if (++rs == CH_RING) { rs = 0; rph ^= 1; }
         return dst;
       };
-      const int A = a.ppo.act_dim;
       int ti = 0;
       for (int tile = pair_local; tile < tiles2; tile += pairs, ++ti) {
         const int m0 = tile * 256 + int(rank) * 128;
         const uint32_t xph = uint32_t(ti & 1);
-        for (int n = 0; n < 2; ++n)
+        for (int o = 0; o < 2; ++o)
           for (int kb = 0; kb < KB1; ++kb) {
-            if (n == 0) {
-              if (kb == 0) {
-                mbar_wait(&x_free[0], xph ^ 1);  // ... which also says that the previous tile's loss steps are over
-                if (a.stage_loss && m0 + 128 <= a.M) {  // this CTA's loss operands (whole tiles only: 16-byte granules)
-                  uint8_t* aux = smem + CH_AUX * CH_SLOT;
-                  mbar_expect_tx(aux_full, uint32_t(128 * A * 4 + 3 * 512));
-                  bulk_load(aux + CH_AUX_ACT, a.ppo.action + int64_t(m0) * A, uint32_t(128 * A * 4), aux_full);
-                  bulk_load(aux + CH_AUX_ROW, a.ppo.old_logp + m0, 512u, aux_full);
-                  bulk_load(aux + CH_AUX_ROW + 512, a.ppo.advantage + m0, 512u, aux_full);
-                  bulk_load(aux + CH_AUX_ROW + 1024, a.ppo.target + m0, 512u, aux_full);
-                }
-              }
+            if (o == 0) {
+              if (kb == 0) mbar_wait(&x_free[0], xph ^ 1);
               if (kb == 2) mbar_wait(&x_free[1], xph ^ 1);
               if (rank == 0) mbar_expect_tx(&x_full[kb], 2u * CH_SLOT);
               tma_load_2d_pair(smem + (CH_X0 + kb) * CH_SLOT, &a.x, mapa_u32(smem_u32(&x_full[kb]), 0), kb * TC_BK, m0);
             }
             uint8_t* dst = ring_acquire(CH_SLOT);
-            tma_load_2d_pair(dst, &a.net[n].w1, cur_bar, kb * TC_BK, int(rank) * 128);
+            tma_load_2d_pair(dst, &a.net[o].w1, cur_bar, kb * TC_BK, int(rank) * 128);
           }
-        for (int n = 0; n < 2; ++n)
+        for (int o = 0; o < 2; ++o)
           for (int kb = 0; kb < H / TC_BK; ++kb) {
             uint8_t* dst = ring_acquire(CH_SLOT);
-            tma_load_2d_pair(dst, &a.net[n].w2k, cur_bar, kb * TC_BK, int(rank) * 128);
+            tma_load_2d_pair(dst, &a.net[o].w2k, cur_bar, kb * TC_BK, int(rank) * 128);
           }
         {  // output layers, K-major: 16 (actor) / 8 (critic) rows of W3 per CTA, all four k-blocks in one stage
           uint8_t* dst = ring_acquire(4 * 2048);
@@ -307,15 +339,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
           for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(dst + kb * 1024, &a.net[1].w3k, cur_bar, kb * TC_BK, int(rank) * 8);
         }
         {  // dgrad through the output layers: W3 as [K = out][N = hidden], this CTA's 128 hidden columns as two 64-wide atoms
-          uint8_t* dst = ring_acquire(2 * 4096);
-          for (int j = 0; j < 2; ++j) tma_load_2d_pair(dst + j * 4096, &a.net[0].w3m, cur_bar, int(rank) * 128 + 64 * j, 0);
-          dst = ring_acquire(2 * 2048);
+          uint8_t* dst = ring_acquire(2 * 2048);
           for (int j = 0; j < 2; ++j) tma_load_2d_pair(dst + j * 2048, &a.net[1].w3m, cur_bar, int(rank) * 128 + 64 * j, 0);
+          dst = ring_acquire(2 * 4096);
+          for (int j = 0; j < 2; ++j) tma_load_2d_pair(dst + j * 4096, &a.net[0].w3m, cur_bar, int(rank) * 128 + 64 * j, 0);
         }
-        for (int n = 0; n < 2; ++n)
+        for (int o = 0; o < 2; ++o)
           for (int kb = 0; kb < H / TC_BK; ++kb) {
             uint8_t* dst = ring_acquire(CH_SLOT);
-            for (int j = 0; j < 2; ++j) tma_load_2d_pair(dst + j * 8192, &a.net[n].w2m, cur_bar, int(rank) * 128 + 64 * j, kb * TC_BK);
+            for (int j = 0; j < 2; ++j) tma_load_2d_pair(dst + j * 8192, &a.net[1 - o].w2m, cur_bar, int(rank) * 128 + 64 * j, kb * TC_BK);
           }
       }
       // every commit the leader multicast to this CTA has landed before the CTA may exit
@@ -357,10 +389,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
       };
       int ti = 0;
       for (int tile = pair_local; tile < tiles2; tile += pairs, ++ti) {
-        for (int n = 0; n < 2; ++n) {  // steps 0, 1: first hidden layer
+        for (int o = 0; o < 2; ++o) {  // steps 0, 1: first hidden layer (actor, critic)
           const uint32_t d = step_begin();
           for (int kb = 0; kb < KB1; ++kb) {
-            if (n == 0) {
+            if (o == 0) {
               mbar_wait(&x_full[kb], uint32_t(ti & 1));
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
@@ -372,10 +404,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
           }
           step_end();
         }
-        for (int n = 0; n < 2; ++n) {  // steps 2, 3: second hidden layer
+        for (int o = 0; o < 2; ++o) {  // steps 2, 3: second hidden layer
           const uint32_t d = step_begin();
           for (int kb = 0; kb < H / TC_BK; ++kb) {
-            const uint32_t b = ring_wait(), aa = smem_base + ((n ? CH_HC0 : CH_HA0) + kb) * CH_SLOT;
+            const uint32_t b = ring_wait(), aa = smem_base + ((o ? CH_HC0 : CH_HA0) + kb) * CH_SLOT;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(b + k * 32, 0, 1024), ID_N256, (kb > 0 || k > 0) ? 1u : 0u);
@@ -383,38 +415,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
           }
           step_end();
         }
-        for (int n = 0; n < 2; ++n) {  // steps 4, 5: output layers (N = 32 / 16)
+        for (int o = 0; o < 2; ++o) {  // steps 4, 5: output layers (N = 32 actor / 16 critic)
           const uint32_t d = step_begin();
           const uint32_t b = ring_wait();
           for (int kb = 0; kb < H / TC_BK; ++kb) {
-            const uint32_t aa = smem_base + ((n ? CH_HC0 : CH_HA0) + kb) * CH_SLOT, bb = b + kb * (n ? 1024 : 2048);
+            const uint32_t aa = smem_base + ((o ? CH_HC0 : CH_HA0) + kb) * CH_SLOT, bb = b + kb * (o ? 1024 : 2048);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(bb + k * 32, 0, 1024), n ? ID_N16 : ID_N32, (kb > 0 || k > 0) ? 1u : 0u);
+              umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(bb + k * 32, 0, 1024), o ? ID_N16 : ID_N32, (kb > 0 || k > 0) ? 1u : 0u);
           }
           ring_release();
           step_end();
         }
-        for (int n = 0; n < 2; ++n) {  // steps 6, 7: dgrad through the output layers (K = 32 / 16)
+        for (int o = 0; o < 2; ++o) {  // steps 6, 7: dgrad through the output layers (K = 16 critic / 32 actor)
           const uint32_t d = step_begin();
-          const uint32_t b = ring_wait(), aa = smem_base + (n ? CH_DZ3C : CH_DZ3A) * CH_SLOT;
-          const int nk = n ? 1 : 2;
+          if (o == 0) {  // the critic's seeds come from step 5, the previous step (see the note on the order above)
+            mbar_wait(&epi_done[1], ((g - 1) >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const uint32_t b = ring_wait(), aa = smem_base + (o ? CH_DZ3A : CH_DZ3C) * CH_SLOT;
+          const int nk = o ? 2 : 1;
           for (int k = 0; k < nk; ++k)
-            umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(b + k * 2048, n ? 2048 : 4096, 1024), ID_N256_BMN, k > 0 ? 1u : 0u);
+            umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(b + k * 2048, o ? 4096 : 2048, 1024), ID_N256_BMN, k > 0 ? 1u : 0u);
           ring_release();
-          if (n == 1) umma2_commit(&x_free[0]);  // the seed tiles (X slots 0-1) have been read
+          if (o == 1) umma2_commit(&x_free[0]);  // both seed tiles (X slots 0-1) have been read
           step_end();
         }
-        for (int n = 0; n < 2; ++n) {  // steps 8, 9: dgrad through the second hidden layer
+        for (int o = 0; o < 2; ++o) {  // steps 8, 9: dgrad through the second hidden layer
           const uint32_t d = step_begin();
           for (int kb = 0; kb < H / TC_BK; ++kb) {
-            const uint32_t b = ring_wait(), aa = smem_base + ((n ? CH_HC0 : CH_HA0) + kb) * CH_SLOT;
+            const uint32_t b = ring_wait(), aa = smem_base + ((o ? CH_HA0 : CH_HC0) + kb) * CH_SLOT;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(b + k * 2048, 8192, 1024), ID_N256_BMN, (kb > 0 || k > 0) ? 1u : 0u);
             ring_release();
           }
-          if (n == 1) umma2_commit(&x_free[1]);  // the critic tile (X slots 2-5) has been read
+          if (o == 0) umma2_commit(&x_free[1]);  // the critic tile (X slots 2-5) has been read: the next observations may land
           step_end();
         }
       }
@@ -425,137 +461,136 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
     const uint32_t sw = uint32_t(lane & 7);
     constexpr int act = ACT;
     const int A = a.ppo.act_dim;
-    {  // constants of the output layers (written by the optimizer before this kernel: after the PDL wait)
+    {  // constants (written by the optimizer before this kernel: after the PDL wait)
       const int t = threadIdx.x - 64;
-      if (t < 32) {
+      if (t < kChainMaxAct) {
         b3_s[t] = t < A ? __ldg(a.net[0].b3 + t) : 0.f;
         float ls = 0.f, iv = 0.f;
         if (t < A) {
           const float sig = expf(__ldg(a.ppo.logstd + t));
           ls = logf(sig); iv = 1.f / (sig * sig);
         }
-        consts_s[t] = ls; consts_s[32 + t] = iv;
-      } else if (t == 32) {
-        b3_s[32] = __ldg(a.net[1].b3);
+        consts_s[t] = ls; consts_s[kChainMaxAct + t] = iv;
+      } else if (t == kChainMaxAct) {
+        b3_s[kChainMaxAct] = __ldg(a.net[1].b3);
       }
-      for (int i = t; i < 4 * 34; i += CH_EPI_WARPS * 32) red_s[i] = 0.f;
-      float* bias_dst = reinterpret_cast<float*>(smem + CH_AUX * CH_SLOT + CH_AUX_BIAS);
-      for (int i = t; i < 4 * H; i += CH_EPI_WARPS * 32) {  // [net][layer][256]
+      for (int i = t; i < 4 * CH_RED_W; i += CH_EPI_WARPS * 32) red_s[i] = 0.f;
+      // hidden-layer biases as bf16 [net][layer][256]: the kernel leaves next to no L1, so a bias load from global memory
+      // would be an L2 round trip in front of every accumulator slab; 2 KB is what is left of shared memory
+      __nv_bfloat16* bias_dst = reinterpret_cast<__nv_bfloat16*>(misc + CH_MISC_BIAS);
+      for (int i = t; i < 4 * H; i += CH_EPI_WARPS * 32) {
         const int nl = i / H, c = i - nl * H;
-        const ChainNet& N = a.net[nl >> 1];
-        bias_dst[i] = __ldg(((nl & 1) ? N.b2 : N.b1) + c);
+        const ChainNet& Nb = a.net[nl >> 1];
+        bias_dst[i] = __float2bfloat16_rn(__ldg(((nl & 1) ? Nb.b2 : Nb.b1) + c));
       }
       asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_WARPS * 32) : "memory");
     }
-    const uint32_t aux_s = smem_base + CH_AUX * CH_SLOT;
-    const uint32_t bias_chunk_s = aux_s + CH_AUX_BIAS + uint32_t(chunk) * 256u;  // + (net * 2 + layer) * 1024
-    uint32_t aux_n = 0;  // staged tiles so far (phase of aux_full)
+    const uint32_t bias_chunk_s = smem_base + CH_NSLOT * CH_SLOT + CH_MISC_BIAS + uint32_t(chunk) * 128u;  // + (net * 2 + layer) * 512
     const uint32_t lead_done0 = mapa_u32(smem_u32(&epi_done[0]), 0), lead_done1 = mapa_u32(smem_u32(&epi_done[1]), 0);
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
-    // this warp's 32 x 64 sub-tile (4 KB, one swizzle-atom column of a k-block) of the actor / critic tile, and this thread's row in it
+    // this warp's 32 x 64 sub-tile (4 KB) of the actor / critic tile, and this thread's row in it
     const uint32_t sub_a = smem_base + (CH_HA0 + chunk) * CH_SLOT + uint32_t(q) * 4096u;
     const uint32_t sub_c = smem_base + (CH_HC0 + chunk) * CH_SLOT + uint32_t(q) * 4096u;
     const uint32_t row_a = sub_a + uint32_t(lane) * 128u, row_c = sub_c + uint32_t(lane) * 128u;
     const uint32_t row_z3a = smem_base + CH_DZ3A * CH_SLOT + uint32_t(r) * 128u;
     const uint32_t row_z3c = smem_base + CH_DZ3C * CH_SLOT + uint32_t(r) * 128u;
-    float* red_row = red_s + q * 34;
+    float* red_row = red_s + q * CH_RED_W;
     uint32_t g = 0;
+    auto tr = [&](int slot) {
+      if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + slot] = clock64();
+    };
     auto acc_wait = [&]() {
       mbar_wait(&acc_full[g & 1], (g >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       __syncwarp();
-      if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 2] = clock64();
+      tr(2);
     };
     // End of a step for this warp: its shared-memory writes become visible to the async proxy (the tensor core's
-    // operand reads and the bulk store), the sub-tile it wrote leaves for global memory through the copy engine (one
-    // elected lane; rows past the batch are clipped by the tensor map), and the issuer learns that this warp has drained
-    // the accumulator and written its part of the next A operand.
-    auto step_done = [&](const CUtensorMap* store_map, uint32_t sub, int row0) {
+    // operand reads and the bulk store), the issuer learns that this warp has drained the accumulator and written its
+    // part of the next A operand, and the sub-tile it wrote leaves for global memory through the copy engine (one
+    // elected lane; rows past the batch are clipped by the tensor map).
+    auto step_done = [&](const CUtensorMap* store_map, uint32_t sub, int grow0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        // relaxed: a release here is MEMBAR.ALL.GPU in front of every arrive (19 % of the kernel's stall samples); the
-        // proxy fence above has already completed this warp's shared-memory writes, which is all the issuer's MMAs read
+        // relaxed: a release here is MEMBAR.ALL.GPU in front of every arrive (19 % of the first version's stall samples);
+        // the proxy fence above has already completed this warp's shared-memory writes, which is all the issuer's MMAs read
         asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"((g & 1) ? lead_done1 : lead_done0) : "memory");
         if (store_map != nullptr) {
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(store_map)),
-                       "r"(sub), "r"(chunk * 64), "r"(row0)
+                       "r"(sub), "r"(chunk * 64), "r"(grow0)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (a.trace != nullptr && blockIdx.x == 0 && g < 60) {
+        if (a.trace != nullptr && blockIdx.x == 0 && g < 60)
           atomicMax(reinterpret_cast<unsigned long long*>(a.trace) + g * 8 + 3, (unsigned long long)clock64());
-          if (warp == 2) a.trace[g * 8 + 6] = clock64();
-          if (warp == 17) a.trace[g * 8 + 7] = clock64();
-        }
       }
+      tr(6);
       ++g;
     };
-    // before this warp overwrites a sub-tile: the bulk store that last read it has drained it.  The stores of a warp
-    // alternate between its actor and its critic sub-tile, so the one that matters is always the second youngest.
-    auto stores_drained = [&]() {
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    // Bulk stores of a warp, in order: H1a H1c H2a H2c (steps 0-3), dZ2c dZ2a (6, 7), dZ1a (9).  Before a sub-tile is
+    // overwritten the store that last read it must have drained it: the youngest one in steps 0, 6 and 9, (at most) the
+    // second youngest elsewhere.
+    auto stores_drained = [&](bool youngest) {
+      if (lane == 0) {
+        if (youngest) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      }
       __syncwarp();
     };
+    // H1 of a network comes back from global memory for the last dgrad step: its bulk store (three / five groups back
+    // where the critic's / the actor's rows are requested) must be complete, not merely read
+    auto h1_visible = [&](bool critic) {
+      if (lane == 0) {
+        // (completion of a bulk group makes its writes visible to the waiting thread; __syncwarp orders the other lanes'
+        // loads after it.  A fence.proxy.async.global here was measured at ~4 k cycles per use.)
+        if (critic) asm volatile("cp.async.bulk.wait_group 3;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group 5;" ::: "memory");
+      }
+      __syncwarp();
+    };
+    uint32_t ax[4][8];  // this thread's 64 H1 values of the next dgrad step, requested one step ahead
     for (int tile = pair_local; tile < tiles2; tile += pairs) {
-      const int row0 = tile * 256 + int(rank) * 128 + q * 32;  // first global row of this warp's sub-tile
-      const int64_t m = int64_t(row0) + lane;
+      const int grow0 = tile * 256 + int(rank) * 128 + q * 32;  // first global row of this warp's sub-tile
+      const int64_t m = int64_t(grow0) + lane;
       const bool row_ok = m < a.M;
       const int64_t mm = row_ok ? m : 0;
+      float av[8], old_lp = 0.f, adv = 0.f, tgt = 0.f;  // loss operands of this row, requested two steps ahead
 #pragma unroll 1
-      for (int n = 0; n < 2; ++n) {  // steps 0, 1
-        const ChainNet& N = a.net[n];
-        acc_wait();
-        stores_drained();
-        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 4] = clock64();
-        ch_epi_forward(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), bias_chunk_s + uint32_t(n) * 2048u, act, n ? row_c : row_a, sw);
-        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 5] = clock64();
-        step_done(&N.sH1, n ? sub_c : sub_a, row0);
-      }
+      for (int layer = 0; layer < 2; ++layer) {
 #pragma unroll 1
-      for (int n = 0; n < 2; ++n) {  // steps 2, 3
-        const ChainNet& N = a.net[n];
-        acc_wait();
-        stores_drained();
-        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 4] = clock64();
-        ch_epi_forward(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), bias_chunk_s + uint32_t(n) * 2048u + 1024u, act, n ? row_c : row_a, sw);
-        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 5] = clock64();
-        step_done(&N.sH2, n ? sub_c : sub_a, row0);
-      }
-      // step 4: actor output layer + loss.  A row's columns are split over the four warps of its TMEM lane quarter
-      // (8 action columns each): partial log-probs meet in a 16-byte unit of the seed tile's row that the seeds do
-      // not use, then every warp finishes its own columns' seeds — one 16-byte unit of the K-major seed tile each.
-      {
-        const int j0 = chunk * 8;
-        float av[8], old_lp, adv, tgt;  // tgt: for step 5
-        if (a.stage_loss && tile * 256 + int(rank) * 128 + 128 <= a.M) {  // the producer staged this CTA's rows (CTA-uniform)
-          mbar_wait(aux_full, aux_n & 1);
-          ++aux_n;
-          const uint32_t rs4 = aux_s + CH_AUX_ROW + uint32_t(r) * 4u;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old_lp) : "r"(rs4) : "memory");
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(adv) : "r"(rs4 + 512u) : "memory");
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tgt) : "r"(rs4 + 1024u) : "memory");
-          const uint32_t as4 = aux_s + CH_AUX_ACT + uint32_t(r * A + j0) * 4u;  // row stride A words: conflict-free for odd A
+        for (int o = 0; o < 2; ++o) {  // steps 0-3: hidden layers forward (actor, critic)
+          const ChainNet& N = a.net[o];
+          if (layer == 1) {  // the loss operands of this row: requested now (volatile: not to be sunk to their use), needed in steps 4 / 5
+            if (o == 0) {
+              const float* ap = a.ppo.action + mm * A + chunk * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            av[i] = 0.f;
-            if (j0 + i < A) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(av[i]) : "r"(as4 + 4u * i) : "memory");
+              for (int i = 0; i < 8; ++i) av[i] = (row_ok && chunk * 8 + i < A) ? ldg_f32_now(ap + i) : 0.f;
+              if (row_ok) { old_lp = ldg_f32_now(a.ppo.old_logp + mm); adv = ldg_f32_now(a.ppo.advantage + mm); }
+            } else if (chunk == 0 && row_ok) {
+              tgt = ldg_f32_now(a.ppo.target + mm);
+            }
           }
-        } else {
-          const float* ap = a.ppo.action + mm * A + j0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) av[i] = (row_ok && j0 + i < A) ? __ldg(ap + i) : 0.f;
-          old_lp = row_ok ? __ldg(a.ppo.old_logp + mm) : 0.f;
-          adv = row_ok ? __ldg(a.ppo.advantage + mm) : 0.f;
-          tgt = row_ok ? __ldg(a.ppo.target + mm) : 0.f;
+          acc_wait();
+          stores_drained(layer == 0 && o == 0);
+          tr(4);
+          ch_epi_forward(lane_base + uint32_t(o) * 256u + uint32_t(chunk * 64), bias_chunk_s + uint32_t(o * 2 + layer) * 512u, act,
+                         o ? row_c : row_a, sw);
+          tr(5);
+          step_done(layer ? &N.sH2 : &N.sH1, o ? sub_c : sub_a, grow0);
         }
+      }
+      {  // step 4: actor output layer + loss.  A row's columns are split over the four warps of its TMEM lane quarter
+        // (8 action columns each): partial log-probs meet in a 16-byte unit of the seed tile's row that the seeds do
+        // not use, then every warp finishes its own columns' seeds — one 16-byte unit of the K-major seed tile each.
+        const int j0 = chunk * 8;
         acc_wait();
         const float scale = a.out_scale;
         const bool ft = a.ppo.final_tanh != 0;
         float d[8], th[8];
         float lp = 0.f;
-        if (j0 < A) {
+        if (j0 < A) {  // warp-uniform
           uint32_t v[8];
           tmem_ld8(lane_base + uint32_t(j0), v);
 #pragma unroll
@@ -567,13 +602,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
               th[i] = ft ? tanh_fast(pre) : pre;
               const float mean = ft ? scale * th[i] : pre;
               d[i] = av[i] - mean;
-              lp += -(d[i] * d[i]) * (0.5f * consts_s[32 + j]) - consts_s[j] - kTcLogSqrt2Pi;
+              lp += -(d[i] * d[i]) * (0.5f * consts_s[kChainMaxAct + j]) - consts_s[j] - kTcLogSqrt2Pi;
             }
           }
         }
         const uint32_t lp_unit = row_z3a + ((4u ^ sw) << 4);
+        tr(4);
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(lp_unit + uint32_t(chunk) * 4u), "f"(lp) : "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");  // the four warps of this lane quarter
+        tr(5);
         float l0, l1, l2, l3;
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(l0), "=f"(l1), "=f"(l2), "=f"(l3) : "r"(lp_unit) : "memory");
         const float lp_row = ((l0 + l1) + l2) + l3;  // same order in all four warps
@@ -596,11 +633,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
             const int j = j0 + i + u;
             dm[u] = 0.f;
             if (j < A) {
-              const float dn = d[i + u] * consts_s[32 + j];
+              const float dn = d[i + u] * consts_s[kChainMaxAct + j];
               float dmu = g_lp * dn;
               if (ft) dmu *= scale * (1.f - th[i + u] * th[i + u]);
-              dm[u] = dmu;                                      // g_lp = 0 for rows past the batch
-              d[i + u] = g_lp * (d[i + u] * dn - 1.f);          // this row's d loss / d logstd_j
+              dm[u] = dmu;                              // g_lp = 0 for rows past the batch
+              d[i + u] = g_lp * (d[i + u] * dn - 1.f);  // this row's d loss / d logstd_j
             }
           }
           pk[i >> 1] = pack_bf16(dm[0], dm[1]);
@@ -608,6 +645,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_z3a + ((uint32_t(chunk) ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         if (row_ok && j0 < a.net[0].pZ3)
           *reinterpret_cast<uint4*>(a.net[0].dZ3 + mm * a.net[0].pZ3 + j0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        tr(7);
         if (j0 < A) {  // warp-uniform
           const float tot = ch_red8(d, lane);
           const int col = j0 + ch_red8_col(lane);
@@ -618,14 +656,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
           if (lane == 0) red_row[0] += ssum;
         }
         step_done(nullptr, 0, 0);
-        // step 5: critic output + Huber loss (one value per row: the chunk-0 warps; the others only keep step)
+      }
+      {  // step 5: critic output + Huber loss (one value per row: the chunk-0 warps; the others only keep step)
         acc_wait();
         if (chunk == 0) {
           uint32_t v[8];
           tmem_ld8(lane_base + 256u, v);
           float dv = 0.f, hub = 0.f;
           if (row_ok) {
-            const float e = __uint_as_float(v[0]) + b3_s[32] - tgt;
+            const float e = __uint_as_float(v[0]) + b3_s[kChainMaxAct] - tgt;
             const float ae = fabsf(e);
             hub = ae < 1.f ? 0.5f * e * e : ae - 0.5f;
             dv = fminf(fmaxf(e, -1.f), 1.f) * a.ppo.inv_global_batch;
@@ -645,46 +684,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
         step_done(nullptr, 0, 0);
       }
 #pragma unroll 1
-      for (int n = 0; n < 2; ++n) {  // steps 6, 7
-        const ChainNet& N = a.net[n];
+      for (int o = 0; o < 2; ++o) {  // steps 6, 7: dgrad through the output layer, activation derivative from the tile in shared memory
+        const ChainNet& N = a.net[1 - o];
         acc_wait();
-        stores_drained();
-        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 4] = clock64();
-        ch_epi_dgrad_smem(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), act, n ? row_c : row_a, sw);
-        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 5] = clock64();
-        step_done(&N.sZ2, n ? sub_c : sub_a, row0);
-      }
-#pragma unroll 1
-      for (int n = 0; n < 2; ++n) {  // steps 8, 9
-        const ChainNet& N = a.net[n];
-        // H1 left through the copy engine in step n: its store must be complete (not merely read) before the row is
-        // loaded back; the 5 (4) younger stores of this warp may still be in flight
-        if (lane == 0) {
-          if (n == 0) asm volatile("cp.async.bulk.wait_group 5;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-        }
-        __syncwarp();
-        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 4] = clock64();
-        uint32_t ax[4][8];
-        const __nv_bfloat16* hrow = N.H1 + mm * N.pH1 + chunk * 64;
+        stores_drained(o == 0);
+        tr(4);
+        ch_epi_dgrad_smem(lane_base + uint32_t(o) * 256u + uint32_t(chunk * 64), act, o ? row_a : row_c, sw);
+        tr(5);
+        step_done(&N.sZ2, o ? sub_a : sub_c, grow0);
+        if (o == 0) {  // the critic's H1 row for step 8: in flight behind the actor's step 7
+          h1_visible(true);
+          const __nv_bfloat16* hrow = a.net[1].H1 + mm * a.net[1].pH1 + chunk * 64;
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
-          asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(ax[s][0]), "=r"(ax[s][1]), "=r"(ax[s][2]), "=r"(ax[s][3]), "=r"(ax[s][4]), "=r"(ax[s][5]), "=r"(ax[s][6]), "=r"(ax[s][7])
-                       : "l"(hrow + s * 16)
-                       : "memory");
+          for (int s4 = 0; s4 < 4; ++s4) ldg256_na(hrow + s4 * 16, ax[s4]);
+        }
+      }
+      {  // step 8: critic dgrad through the second hidden layer; the result only feeds the weight-gradient kernel and its
+        // tile (X slots 2-5) is about to take the next observations: straight from registers to global memory
         acc_wait();
-        ch_epi_dgrad_glob(lane_base + (g & 1) * 256u + uint32_t(chunk * 64), act, ax, N.dZ1 + mm * N.pZ1 + chunk * 64, row_ok);
-        if (a.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && g < 60) a.trace[g * 8 + 5] = clock64();
+        tr(4);
+        ch_epi_dgrad_glob(lane_base + uint32_t(chunk * 64), act, ax, a.net[1].dZ1 + mm * a.net[1].pZ1 + chunk * 64, row_ok);
+        tr(5);
         step_done(nullptr, 0, 0);
+        h1_visible(false);  // the actor's H1 row for step 9
+        const __nv_bfloat16* hrow = a.net[0].H1 + mm * a.net[0].pH1 + chunk * 64;
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) ldg256_na(hrow + s4 * 16, ax[s4]);
+      }
+      {  // step 9: actor dgrad through the second hidden layer, staged in the (now idle) actor tile for the bulk store
+        acc_wait();
+        stores_drained(true);
+        tr(4);
+        ch_epi_dgrad_stage(lane_base + 256u + uint32_t(chunk * 64), act, ax, row_a, sw);
+        tr(5);
+        step_done(&a.net[0].sZ1, sub_a, grow0);
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     // this CTA's row of loss partials: (sum surrogate, sum huber, sum d loss / d logstd_j)
     asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_WARPS * 32) : "memory");
     const int t = threadIdx.x - 64;
-    if (t < 2 + A) a.ppo.partials[int64_t(blockIdx.x) * (2 + A) + t] = red_s[t] + red_s[34 + t] + red_s[68 + t] + red_s[102 + t];
+    if (t < 2 + A)
+      a.ppo.partials[int64_t(blockIdx.x) * (2 + A) + t] = red_s[t] + red_s[CH_RED_W + t] + red_s[2 * CH_RED_W + t] + red_s[3 * CH_RED_W + t];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -698,7 +739,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
 long long* g_chain_trace = nullptr;
 
 bool tc_chain_shape_ok(int in_dim, int h1, int h2, int out_dim) {
-  return in_dim >= 1 && in_dim <= kChainMaxIn && h1 == kChainHidden && h2 == kChainHidden && out_dim >= 1 && out_dim <= 32;
+  return in_dim >= 1 && in_dim <= kChainMaxIn && h1 == kChainHidden && h2 == kChainHidden && out_dim >= 1 && out_dim <= kChainMaxAct;
 }
 
 int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out) {
@@ -729,10 +770,10 @@ int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out) {
     long long h[60 * 8];
     B2_CUDA(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(tr);
-    static const char* names[10] = {"L1a", "L1c", "L2a", "L2c", "L3a", "L3c", "D3a", "D3c", "D2a", "D2c"};
+    static const char* names[10] = {"L1a", "L1c", "L2a", "L2c", "L3a", "L3c", "D3c", "D3a", "D2c", "D2a"};
     fprintf(stderr, "chain kernel, pair 0 (M = %d, %d pairs): step | operands ready, issued | accumulator seen, epilogue done\n", a.M, pairs);
     for (int g = 0; g < 60 && h[g * 8] != 0; ++g)
-      fprintf(stderr, "  %2d %s | %7lld %7lld | %7lld %7lld | warp 2: body %lld..%lld end %lld | warp 17 end %lld\n", g, names[g % 10], h[g * 8] - h[0],
+      fprintf(stderr, "  %2d %s | %7lld %7lld | %7lld %7lld | warp 2: body %lld..%lld end %lld (%lld)\n", g, names[g % 10], h[g * 8] - h[0],
               h[g * 8 + 1] - h[0], h[g * 8 + 2] - h[0], h[g * 8 + 3] - h[0], h[g * 8 + 4] ? h[g * 8 + 4] - h[0] : 0,
               h[g * 8 + 5] ? h[g * 8 + 5] - h[0] : 0, h[g * 8 + 6] ? h[g * 8 + 6] - h[0] : 0, h[g * 8 + 7] ? h[g * 8 + 7] - h[0] : 0);
     return B200PPO_OK;

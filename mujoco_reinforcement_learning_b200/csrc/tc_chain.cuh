@@ -11,7 +11,7 @@ struct ChainNet {
   CUtensorMap w2m;  // W2 [256][256]  as [K = out][N = in], box 64 x 64      (dgrad, MN-major B operand)
   CUtensorMap w3k;  // W3 [out][256]  K-major, box 64 x (16 | 8) (forward; rows >= out zero-filled)
   CUtensorMap w3m;  // W3 [out][256]  as [K = out][N = hidden], box 64 x (32 | 16) (dgrad through the output layer)
-  CUtensorMap sH1, sH2, sZ2;  // bulk-store maps of the global copies [M][256], box 64 x 32 (rows past M clipped)
+  CUtensorMap sH1, sH2, sZ1, sZ2;  // bulk-store maps of the global copies [M][256], box 64 x 32 (rows past M clipped)
   const float *b1, *b2, *b3;
   __nv_bfloat16 *H1, *H2, *dZ1, *dZ2, *dZ3;  // global copies the weight-gradient kernel reads
   int pH1, pH2, pZ1, pZ2, pZ3;               // row pitches (elements)
@@ -23,7 +23,6 @@ struct ChainArgs {
   TcPpo ppo;         // loss operands (dz_out / dz_pitch unused: seeds go to net[n].dZ3)
   float out_scale;
   int M, KB1, act, tiles2;
-  int stage_loss;    // the loss operands are 16-byte aligned and act_dim <= 20: the producer stages them per tile
   long long* trace;  // debug: clock64 timeline of pair 0 (nullptr in production)
 };
 
@@ -32,7 +31,7 @@ constexpr int TC_CHAIN_BK = 64;
 extern long long* g_chain_trace;  // set by the debug entry point only
 constexpr int kChainMaxIn = 384;
 
-// in_dim <= 384, both hidden layers 256 wide, out <= 32, rows 32-byte aligned
+// in_dim <= 384, both hidden layers 256 wide, out <= 24, rows 32-byte aligned
 bool tc_chain_shape_ok(int in_dim, int h1, int h2, int out_dim);
 int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out);
 

@@ -58,7 +58,7 @@ SHAPES = [
     dict(D=376, A=17, B=500),              # the reference's default batch_size
     dict(D=27, A=8, B=4096),               # Ant: one k-block of observations
     dict(D=376, A=17, B=4096, act="relu"),
-    dict(D=100, A=32, B=300),              # widest action row the seed tile takes
+    dict(D=100, A=24, B=300),              # widest action row the chain kernel takes (wider ones use the per-layer launches)
     dict(D=64, A=1, B=77),
 ]
 
