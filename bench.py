@@ -13,8 +13,11 @@ slab of `envs` environments (weak scaling): the slabs are all-gathered after the
 1/N slice of every global minibatch (global permutation, as the reference indexes), gradients are summed by an
 NCCL all-reduce per minibatch.
 
-`--impl reference` times the CPU oracle port of the reference's path (`oracle/ppo_oracle.py`: the reference's
-own torch CPU operators) on the host cores, on a bounded sample of the same workload.
+`--impl reference` times the reference's OWN `PPO.calculate_advantages` + `PPO.train` (staged verbatim under
+`oracle/_ref` by `oracle/build_ref.py`, run behind `oracle/shims.py`) on the host cores, on a bounded sample of the same
+workload with the GPU arm's step definition; without `oracle/_ref` it falls back to the oracle port
+(`oracle/ppo_oracle.py`, `kind: "port"`).  `--scaling strong` keeps the TOTAL problem at `--envs` environments and
+`--minibatch` rows (each of N ranks owns 1/N of both) instead of the default weak scaling.
 """
 from __future__ import annotations
 
@@ -32,11 +35,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
 
 OBS_DIM, ACT_DIM, HIDDEN = 376, 17, [256, 256]
+TRAFFIC_BF16_B32768 = None  # filled in from profiles/r02_ncu_chain_wgrad_B32768.csv
 
 
 def peaks():
@@ -112,47 +113,119 @@ def flops_per_sample():
 
 
 # ------------------------------------------------------------------------------------------------------
+class CpuArm:
+    """The reference's CPU path on the host cores with the GPU arm's step definition: ONE advantage pass per step,
+    amortised over E epochs, and epochs of (randperm + gather of every leaf + all minibatches).  Runs the reference's
+    OWN code from `oracle/_ref` (kind "reference") or, where that is not staged, the oracle port (kind "port").
+    The reference's `train` (ppo.py:93-154) only runs whole epochs, so `n_ep` full epochs are timed per step and the
+    advantage pass is charged pro rata:  samples/s = n_ep * nb * B / (t_train + t_gae * n_ep / E)."""
+
+    def __init__(self, envs, T, B, E):
+        from oracle import build_ref
+        self.envs, self.T, self.B, self.E = envs, T, B, E
+        self.M, self.nb = envs * T, envs * T // B
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        roll = dict(make_rollout(envs, T, 1234 + 3))
+        roll["current_state"] = roll["current_state"].reshape(envs, T, OBS_DIM)
+        roll["action_log_prob"] = torch.zeros(envs, T)
+        self.roll = roll
+        if build_ref.available():
+            from oracle.ref_runner import ReferencePPO
+            self.ref = ReferencePPO(OBS_DIM, ACT_DIM, HIDDEN, B, 1, envs, T)
+            self.kind = "reference"
+            self.what = ("the reference's own PPO.calculate_advantages + PPO.train from oracle/_ref (verbatim sources behind "
+                         "oracle/shims.py; its Critic hard-codes 128x128 hidden layers, models/critic.py:13-14, so this arm does "
+                         "LESS arithmetic than the 256x256 GPU arm)")
+        else:
+            from oracle import ppo_oracle as O
+            torch.manual_seed(0)
+            self.O = O
+            self.agent = O.OracleAgent(O.OracleConfig(obs_dim=OBS_DIM, act_dim=ACT_DIM, actor_hidden=HIDDEN, critic_hidden=HIDDEN,
+                                                      batch_size=B, epochs=1))
+            self.kind = "port"
+            self.what = "oracle port of the reference path (oracle/ppo_oracle.py: the reference's torch CPU operators; oracle/_ref is not staged here)"
+
+    def gae(self):
+        r = self.roll
+        if self.kind == "reference":
+            mem = self.ref.memory(r)
+            self.ref.calculate_advantages(mem)
+            return mem
+        adv, tgt = self.O.calculate_advantages(r["reward"], r["current_state_value"], r["next_state_value"], r["terminated"], 0.99, 0.98)
+        return {"advantage": adv, "current_state_value_target": tgt}
+
+    def train(self, mem, epochs, n_envs=None, batch=None):
+        n_envs, batch = n_envs or self.envs, batch or self.B
+        T, r = self.T, self.roll
+        if self.kind == "reference":
+            if n_envs != self.envs:
+                mem = self.ref.TensorDict({k: mem[k][:n_envs] for k in mem.keys()}, batch_size=(n_envs, T))
+            self.ref.run.environment_config.num_envs = n_envs
+            self.ref.run.training_config.batch_size = batch
+            self.ref.train(mem, epochs=epochs)
+            return
+        m = n_envs * T
+        fm = {"current_state": r["current_state"].reshape(self.M, OBS_DIM)[:m], "action": r["action"].reshape(self.M, ACT_DIM)[:m],
+              "action_log_prob": r["action_log_prob"].reshape(self.M)[:m], "advantage": mem["advantage"].reshape(self.M, 1)[:m],
+              "current_state_value_target": mem["current_state_value_target"].reshape(self.M, 1)[:m]}
+        self.agent.cfg.batch_size = batch
+        self.O.ppo_train(self.agent, fm, [torch.randperm(m) for _ in range(epochs)])
+
+    def warm_up(self):
+        n = max(1, min(self.envs, (2 * self.B + self.T - 1) // self.T))  # two minibatches of one epoch
+        self.train(self.gae(), 1, n)
+
+    def timed_step(self, n_ep):
+        t0 = time.perf_counter()
+        mem = self.gae()
+        t_gae = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        self.train(mem, n_ep)
+        t_train = time.perf_counter() - t0
+        return t_gae, t_train, mem
+
+    def describe(self, t_gae, t_train, n_ep):
+        return (f"{self.what}; {self.cores} threads; per step: one advantage pass over {self.envs}x{self.T} ({t_gae * 1e3:.0f} ms, "
+                f"charged {n_ep}/{self.E}) + {n_ep} full epoch(s) of randperm + gather of every leaf + all {self.nb} minibatches "
+                f"of {self.B} ({t_train / n_ep * 1e3:.0f} ms per epoch)")
+
+    def b500(self, mem):
+        """The same code at the reference's default batch_size = 500 (main.py:44): 64 minibatches of one epoch."""
+        n = max(1, min(self.envs, 64 * 500 // self.T))
+        self.train(mem, 1, n, 500)  # warm-up of the small shapes
+        t0 = time.perf_counter()
+        self.train(mem, 1, n, 500)
+        dt = time.perf_counter() - t0
+        return (n * self.T // 500) * 500 / dt, f"{n * self.T // 500} minibatches of 500 (one epoch over {n} environments), same code"
+
+
 def run_reference(args, config):
-    """CPU arm: the oracle port of the reference path, all host threads, bounded sample per step."""
+    """CPU arm (rank 0 only).  Every timed step is the bounded sample CpuArm.timed_step describes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import ppo_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    B = args.minibatch
-    cfg = O.OracleConfig(obs_dim=OBS_DIM, act_dim=ACT_DIM, actor_hidden=HIDDEN, critic_hidden=HIDDEN, batch_size=B, epochs=1)
-    torch.manual_seed(0)
-    agent = O.OracleAgent(cfg)
-    roll = make_rollout(args.envs, args.rollout_steps, 1234 + 3)
-    M = args.envs * args.rollout_steps
-    with torch.no_grad():
-        mean, std = agent.networks["actor"](roll["current_state"].reshape(M, OBS_DIM))
-        logp = torch.distributions.Normal(mean, std).log_prob(roll["action"].reshape(M, ACT_DIM)).sum(1)
-    mb = max(1, min(M // B, args.ref_minibatches if args.ref_minibatches > 0 else max(1, (64 * 4096) // B)))
-
-    def step(seed):
-        adv, tgt = O.calculate_advantages(roll["reward"], roll["current_state_value"], roll["next_state_value"],
-                                          roll["terminated"], 0.99, 0.98)
-        fm = {"current_state": roll["current_state"].reshape(M, OBS_DIM), "action": roll["action"].reshape(M, ACT_DIM),
-              "action_log_prob": logp, "advantage": adv.reshape(M, 1), "current_state_value_target": tgt.reshape(M, 1)}
-        perm = torch.randperm(M, generator=torch.Generator().manual_seed(seed))
-        O.ppo_train(agent, fm, [perm], max_minibatches=mb)
-
-    for w in range(args.warmup):
-        step(w)
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        step(100 + k)
-    dt = time.perf_counter() - t0
-    value = args.steps * mb * B / dt
-    sample = (f"per step: full GAE over {args.envs}x{args.rollout_steps} + permutation gather of all leaves + the first "
-              f"{mb} of {M // B} minibatches of one epoch (torch CPU, {cores} threads)")
+    arm = CpuArm(args.envs, args.rollout_steps, args.minibatch, args.epochs)
+    arm.warm_up()
+    t_gae, t_train, mem = arm.timed_step(1)  # also sizes the sample: epochs per step within the budget
+    n_ep = max(1, min(args.epochs, args.ref_epochs, int(args.ref_budget / max(t_train, 1e-3))))
+    vals, wall = [], time.perf_counter()
+    for k in range(max(1, args.steps)):
+        t_gae, t_train, mem = arm.timed_step(n_ep)
+        vals.append(n_ep * arm.nb * arm.B / (t_train + t_gae * n_ep / arm.E))
+        if time.perf_counter() - wall > 180:  # whatever K is, the arm ends within a few minutes
+            break
+    value = sum(vals) / len(vals)
+    cb = {"value": value, "unit": "samples/s", "cores": arm.cores, "kind": arm.kind, "sample": arm.describe(t_gae, t_train, n_ep),
+          "gae_GBps": 21 * arm.M / 1e9 / t_gae}
+    if arm.B != 500:
+        cb["value_B500"], cb["sample_B500"] = arm.b500(mem)
+    samples_per_step = arm.E * arm.nb * arm.B
     line = {"impl": "reference", "metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "steps": len(vals), "warmup": args.warmup, "ms_per_step": samples_per_step / value * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "per_step_values": vals, "ms_per_step_note": "time of a full step (1 advantage pass + all epochs) at the measured rate"}
     print(json.dumps(line), flush=True)
 
 
@@ -170,6 +243,50 @@ def cuda_time(fn, iters, warm=3):
     return statistics.median(ts), min(ts)
 
 
+GAE_BYTES = 21  # read r, V, V' (12) + terminated (1), write advantage + target (8); `done` is implied (22 with it)
+
+
+def c5_sweep(pk, world=1, rank=0):
+    """BASELINE.json configs[4]: GAE / gather bandwidth over 256-65536 envs x 64-1024 steps.  With N ranks every rank owns
+    1/N of the environments (env-slab sharding, no communication): time = max over ranks, bytes = all ranks'."""
+    import mujoco_reinforcement_learning_b200 as pkg
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pts = []
+    for n, t in ((256, 64), (1024, 128), (4096, 128), (16384, 256), (65536, 256), (65536, 1024)):
+        nl = max(1, n // world)
+        r, v, vn = (torch.randn(nl, t, 1, device=dev) for _ in range(3))
+        term = torch.rand(nl, t, device=dev) < 0.01
+        med, _ = cuda_time(lambda: pkg.calculate_advantages(r, v, vn, term, 0.99, 0.98), 10)
+        m = nl * t
+        obs, act, s1 = torch.randn(m, OBS_DIM, device=dev), torch.randn(m, ACT_DIM, device=dev), torch.randn(m, device=dev)
+        idx = torch.randperm(m, device=dev)
+        medg, _ = cuda_time(lambda: pkg.gather_minibatch(idx, obs, act, s1, s1, s1, check=False), 5 if m > 4e6 else 10)
+        if world > 1:
+            tt = torch.tensor([med, medg], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            med, medg = float(tt[0]), float(tt[1])
+        gby = GAE_BYTES * nl * t * world
+        gaby = (2 * (4 * OBS_DIM + 4 * ACT_DIM + 12) + 8) * m * world
+        l2 = (gby / world) < 100e6
+        pts.append({"envs": n, "steps": t, "n_gpus": world, "gae_ms": med, "gae_GBps": gby / 1e9 / (med * 1e-3),
+                    "gae_frac_hbm": gby / 1e9 / (med * 1e-3) / (pk["hbm"] * world),
+                    "gather_ms": medg, "gather_GBps": gaby / 1e9 / (medg * 1e-3), "gather_frac_hbm": gaby / 1e9 / (medg * 1e-3) / (pk["hbm"] * world),
+                    "note": "GAE working set fits L2" if l2 else ""})
+        del r, v, vn, term, obs, act, s1, idx
+    return pts
+
+
+def k6_latency(agent, n_envs):
+    """Rollout inference (ppo.py:20-29: V(s), pi(s) sample, log-prob) for one environment step of `n_envs` environments."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    obs = torch.randn(n_envs, OBS_DIM, device=dev)
+    noise = torch.randn(n_envs, ACT_DIM, device=dev)
+    med, best = cuda_time(lambda: agent.act_fused(obs, noise=noise), 50, warm=5)
+    return {"envs": n_envs, "us_per_env_step_batch": med * 1e3, "best_us": best * 1e3,
+            "api": "PPOAgent.act_fused -> b200ppo_policy_infer (actor + critic forward, sample, log-prob)"}
+
+
 def hbm_kernel_lines(pk):
     """Roofline of the HBM-bound kernels at sizes that do not fit the 126 MB L2 (SURVEY.md §8d cache caveat)."""
     import mujoco_reinforcement_learning_b200 as pkg
@@ -180,17 +297,19 @@ def hbm_kernel_lines(pk):
     r, v, vn = (torch.randn(n, t, 1, device=dev) for _ in range(3))
     term = torch.rand(n, t, device=dev) < 0.01
     med, best = cuda_time(lambda: pkg.calculate_advantages(r, v, vn, term, 0.99, 0.98), 10)
-    gb = 22 * n * t / 1e9
-    out["gae_65536x1024"] = {"bytes": 22 * n * t, "ms": med, "GBps": gb / (med * 1e-3), "frac": gb / (med * 1e-3) / pk["hbm"]}
+    # 21 B per (env, step): PPO.calculate_advantages derives `done` from `terminated` (ppo.py:70-72), the kernel reads no done array
+    gb = GAE_BYTES * n * t / 1e9
+    out["gae_65536x1024"] = {"bytes": GAE_BYTES * n * t, "ms": med, "GBps": gb / (med * 1e-3), "frac": gb / (med * 1e-3) / pk["hbm"]}
     medn, _ = cuda_time(lambda: pkg.calculate_advantages(r, v, vn, term, 0.99, 0.98, normalize_advantage=True), 5)
-    out["gae_65536x1024_normalized"] = {"bytes": 22 * n * t, "ms": medn, "GBps": gb / (medn * 1e-3), "frac": gb / (medn * 1e-3) / pk["hbm"]}
+    out["gae_65536x1024_normalized"] = {"bytes": GAE_BYTES * n * t, "ms": medn, "GBps": gb / (medn * 1e-3), "frac": gb / (medn * 1e-3) / pk["hbm"]}
     del r, v, vn, term
+    out["c5_sweep"] = c5_sweep(pk)
     # K1 at the Humanoid shape (11.5 MB: L2 resident, reported as time)
     n, t = 4096, 128
     r, v, vn = (torch.randn(n, t, 1, device=dev) for _ in range(3))
     term = torch.rand(n, t, device=dev) < 0.01
     med, best = cuda_time(lambda: pkg.calculate_advantages(r, v, vn, term, 0.99, 0.98), 20)
-    out["gae_4096x128"] = {"bytes": 22 * n * t, "ms": med, "GBps": 22 * n * t / 1e9 / (med * 1e-3), "note": "L2-resident (11.5 MB)"}
+    out["gae_4096x128"] = {"bytes": GAE_BYTES * n * t, "ms": med, "GBps": GAE_BYTES * n * t / 1e9 / (med * 1e-3), "note": "L2-resident (11 MB)"}
     del r, v, vn, term
     # K2: one epoch's gather at the Humanoid shape, 1.665 GB algorithmic
     m = 4096 * 128
@@ -264,33 +383,16 @@ def hbm_kernel_lines(pk):
 
 
 def cpu_baseline(args):
-    """Bounded CPU sample of the same workload through the oracle port (rank 0, N=1 only)."""
-    from oracle import ppo_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    B = args.minibatch
-    M = args.envs * args.rollout_steps
-    cfg = O.OracleConfig(obs_dim=OBS_DIM, act_dim=ACT_DIM, actor_hidden=HIDDEN, critic_hidden=HIDDEN, batch_size=B, epochs=1)
-    torch.manual_seed(0)
-    agent = O.OracleAgent(cfg)
-    roll = make_rollout(args.envs, args.rollout_steps, 1234 + 3)
-    logp = torch.zeros(M)
-    mb = max(1, min(M // B, (48 * 4096) // B))
-    t0 = time.perf_counter()
-    adv, tgt = O.calculate_advantages(roll["reward"], roll["current_state_value"], roll["next_state_value"],
-                                      roll["terminated"], 0.99, 0.98)
-    t_gae = time.perf_counter() - t0
-    fm = {"current_state": roll["current_state"].reshape(M, OBS_DIM), "action": roll["action"].reshape(M, ACT_DIM),
-          "action_log_prob": logp, "advantage": adv.reshape(M, 1), "current_state_value_target": tgt.reshape(M, 1)}
-    perm = torch.randperm(M, generator=torch.Generator().manual_seed(1))
-    O.ppo_train(agent, fm, [perm], max_minibatches=2)  # warm-up
-    t0 = time.perf_counter()
-    O.ppo_train(agent, fm, [perm], max_minibatches=mb)
-    dt = time.perf_counter() - t0
-    return {"value": mb * B / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"oracle port (torch CPU ops of the reference), {cores} threads: gather of one epoch + first {mb} of "
-                      f"{M // B} minibatches; GAE {args.envs}x{args.rollout_steps} separately {t_gae * 1e3:.1f} ms "
-                      f"({22 * M / 1e9 / t_gae:.2f} GB/s)"}
+    """Bounded CPU sample of the same workload (rank 0, N=1 only): CpuArm, one timed step of <= 2 epochs."""
+    arm = CpuArm(args.envs, args.rollout_steps, args.minibatch, args.epochs)
+    arm.warm_up()
+    n_ep = 2 if arm.B >= 4096 else 1
+    t_gae, t_train, mem = arm.timed_step(n_ep)
+    out = {"value": n_ep * arm.nb * arm.B / (t_train + t_gae * n_ep / arm.E), "unit": "samples/s", "cores": arm.cores, "kind": arm.kind,
+           "sample": arm.describe(t_gae, t_train, n_ep), "gae_GBps": 21 * arm.M / 1e9 / t_gae}
+    if arm.B != 500:
+        out["value_B500"], out["sample_B500"] = arm.b500(mem)
+    return out
 
 
 def run_b200(args, config):
@@ -318,11 +420,14 @@ def run_b200(args, config):
     lib = _lib.load()
 
     n_envs, T, B, E = args.envs, args.rollout_steps, args.minibatch, args.epochs
+    if args.scaling == "strong":  # the named problem (4096 envs x 128 steps, 32768-row minibatches) split over the ranks
+        assert n_envs % world == 0 and B % world == 0, "--scaling strong: envs and minibatch must divide by the world size"
+        n_envs, B = n_envs // world, B // world
     M_local, M = n_envs * T, n_envs * T * world
     GB = B * world
     run = pkg.Run(training_config=pkg.TrainingConfig(learning_rate=1e-4, batch_size=GB, epochs_per_iteration=E),
                   ppo_config=pkg.PPOConfig(), environment_config=pkg.EnvironmentConfig(maximum_timesteps=T, num_envs=n_envs * world),
-                  network_config=pkg.NetworkConfig(input_shape=OBS_DIM, output_shape=ACT_DIM, linear_hidden_shapes=HIDDEN),
+                  network_config=pkg.NetworkConfig(input_shape=OBS_DIM, output_shape=ACT_DIM, linear_hidden_shapes=HIDDEN, critic_hidden_shapes=HIDDEN),
                   device=str(dev), gemm_precision=args.precision)
     torch.manual_seed(0)  # identical initial parameters on every rank
     agent = pkg.PPOAgent(run, max_batch=max(B, 4096))
@@ -398,31 +503,37 @@ def run_b200(args, config):
         pin = {k: v.pin_memory() for k, v in host.items()}
         pin_perms = [p.pin_memory() for p in perms_host]
         loss_host = torch.empty((E * nb, 2), dtype=torch.float32).pin_memory()
-        step_io = C.c_int64(eng.adam_step)
 
-        def step_host(i):
-            _lib.check(lib.b200ppo_update_host(eng._ctx, _lib.ptr(eng.flat), _lib.ptr(eng.exp_avg), _lib.ptr(eng.exp_avg_sq),
-                                               C.byref(step_io), C.c_void_p(pin["current_state"].data_ptr()),
-                                               C.c_void_p(pin["action"].data_ptr()), C.c_void_p(pin["action_log_prob"].data_ptr()),
-                                               C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["current_state_value"].data_ptr()),
-                                               C.c_void_p(pin["next_state_value"].data_ptr()),
-                                               C.c_void_p(pin["terminated"].data_ptr()), n_envs, T, 0.99, 0.98, 0, 0, 1.0,
-                                               C.c_void_p(pin_perms[i].data_ptr()), E, B, 0, C.byref(hp),
-                                               C.c_void_p(loss_host.data_ptr()), _lib.stream_ptr()), "b200ppo_update_host")
+        def time_e2e(engine, steps):
+            """`steps` calls of b200ppo_update_host (pinned host rollout -> losses on the host), wall clock around them."""
+            step_io = C.c_int64(engine.adam_step)
 
-        for i in range(max(1, min(args.warmup, 2))):
-            step_host(i)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            step_host(args.warmup + k)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        eng.adam_step = int(step_io.value)
+            def step_host(i):
+                _lib.check(lib.b200ppo_update_host(engine._ctx, _lib.ptr(engine.flat), _lib.ptr(engine.exp_avg), _lib.ptr(engine.exp_avg_sq),
+                                                   C.byref(step_io), C.c_void_p(pin["current_state"].data_ptr()),
+                                                   C.c_void_p(pin["action"].data_ptr()), C.c_void_p(pin["action_log_prob"].data_ptr()),
+                                                   C.c_void_p(pin["reward"].data_ptr()), C.c_void_p(pin["current_state_value"].data_ptr()),
+                                                   C.c_void_p(pin["next_state_value"].data_ptr()),
+                                                   C.c_void_p(pin["terminated"].data_ptr()), n_envs, T, 0.99, 0.98, 0, 0, 1.0,
+                                                   C.c_void_p(pin_perms[i % len(pin_perms)].data_ptr()), E, B, 0, C.byref(hp),
+                                                   C.c_void_p(loss_host.data_ptr()), _lib.stream_ptr()), "b200ppo_update_host")
+
+            for i in range(max(1, min(args.warmup, 2))):
+                step_host(i)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for k in range(steps):
+                step_host(args.warmup + k)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            engine.adam_step = int(step_io.value)
+            return dt / steps
+
+        dt_step = time_e2e(eng, args.steps)
         h2d = sum(v.numel() * v.element_size() for v in host.values()) + perms_host[0].numel() * 8
-        e2e = {"value": args.steps * samples_per_step / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": dt / args.steps * 1e3,
-               "api": "b200ppo_update_host (C ABI, pinned host buffers)"}
+        e2e = {"value": samples_per_step / dt_step, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": loss_host.numel() * 4, "ms_per_step": dt_step * 1e3,
+               "api": "b200ppo_update_host (C ABI, pinned host buffers)", "gemm": args.precision}
 
     else:
         # N > 1: the public Python API per rank — pinned host slab -> device, GAE, slab all-gather (NCCL), global-permutation
@@ -492,14 +603,15 @@ def run_b200(args, config):
         prof["gather"]["GBps"] = by / 1e9 / (prof["gather"]["ms"] * 1e-3)
         prof["gather"]["frac_hbm"] = prof["gather"]["GBps"] / pk["hbm"]
     roofline = {"kernel": "gemm_group_kernel (actor+critic MLP forward/dgrad/wgrad, fp32 FFMA)" if args.precision == "fp32"
-                else "tcgen05 bf16 GEMMs (actor+critic MLP forward/dgrad/wgrad)",
+                else "tcgen05 bf16 GEMMs: tc_chain_kernel (forward + losses + dgrads) and tc_wgrad2_kernel (weight gradients)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tensor_sustained"],
                 # DRAM bytes of the six GEMM launches of ONE 32768-row minibatch (sum of dram__bytes_read+write over
                 # profiles/r01_ncu_tc_kernels_B32768.csv); the HBM floor of the update is 1584 B/sample = 52 MB: the
                 # excess is activations crossing HBM between the per-layer kernels
-                "traffic": 389.6e6 if (args.precision == "bf16" and B == 32768) else None,
-                "traffic_note": "bytes per minibatch over 6 GEMM launches (ncu, profiles/r01_ncu_tc_kernels_B32768.csv)",
+                "traffic": TRAFFIC_BF16_B32768 if (args.precision == "bf16" and B == 32768) else None,
+                "traffic_note": "dram__bytes_read + write per 32768-row minibatch over its two GEMM launches, chain + weight gradients "
+                                "(ncu --set full, profiles/r02_ncu_chain_wgrad_B32768.csv); round 1: 389.6 MB over six launches",
                 "peak_source": pk["source"] + " bf16 sustained",
                 "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
                 "flops_per_sample": fl["total"], "launch_groups": sum(prof[k]["groups"] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad") if k in prof)}
@@ -511,7 +623,7 @@ def run_b200(args, config):
         for prec, vb in others:
             vrun = pkg.Run(training_config=pkg.TrainingConfig(learning_rate=1e-4, batch_size=vb, epochs_per_iteration=E),
                            ppo_config=pkg.PPOConfig(), environment_config=pkg.EnvironmentConfig(maximum_timesteps=T, num_envs=n_envs),
-                           network_config=pkg.NetworkConfig(input_shape=OBS_DIM, output_shape=ACT_DIM, linear_hidden_shapes=HIDDEN),
+                           network_config=pkg.NetworkConfig(input_shape=OBS_DIM, output_shape=ACT_DIM, linear_hidden_shapes=HIDDEN, critic_hidden_shapes=HIDDEN),
                            device=str(dev), gemm_precision=prec)
             torch.manual_seed(0)
             vagent = pkg.PPOAgent(vrun, max_batch=max(vb, 4096))
@@ -536,10 +648,27 @@ def run_b200(args, config):
             vms = a0.elapsed_time(a1) / 2
             variants.append({"gemm": prec, "minibatch": vb, "epochs_timed": vE, "ms_per_epoch": vms / vE,
                              "value": vE * vnb * vb / (vms * 1e-3), "unit": "samples/s (train() only, rollout resident)"})
+            if vb == B and e2e is not None and not args.no_e2e:  # the other precision end to end, same entry point, same bytes
+                dt_v = time_e2e(veng, 2)
+                variants[-1]["e2e"] = {"value": samples_per_step / dt_v, "unit": "samples/s", "ms_per_step": dt_v * 1e3,
+                                       "h2d_bytes_per_step": e2e["h2d_bytes_per_step"], "api": e2e["api"], "gemm": prec}
             del vagent, veng
 
+    # replicas must hold bit-identical parameters after the timed steps (outside the timed region)
+    replicas_identical = None
+    if world > 1:
+        bits = eng.flat.view(torch.int32).to(torch.int64)
+        digest = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=dev)).sum()])
+        every = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(every, digest)
+        replicas_identical = all(bool(torch.equal(every[0], e)) for e in every)
+        assert replicas_identical, "data-parallel replicas diverged"
+    k6 = k6_latency(agent, n_envs)
+    sweep_multi = c5_sweep(pk, world, rank) if (world > 1 and not args.no_kernels) else None
+
     line = {"metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
+            "replicas_identical": replicas_identical, "rollout_inference": k6,
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic", "config": config,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernel_classes": prof,
             "final_losses": final_losses, "samples_per_step": samples_per_step, "variants": variants}
@@ -548,6 +677,14 @@ def run_b200(args, config):
             line["hbm_kernels"] = hbm_kernel_lines(pk)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
+        if sweep_multi is not None:
+            line["hbm_kernels"] = {"c5_sweep": sweep_multi}
+        # the two precisions side by side: bf16 GEMMs are the 2e-2 variant, fp32 the reference's own precision
+        by_prec = {args.precision: {"value": value, "e2e": e2e["value"] if e2e else None}}
+        for v in variants:
+            if v["minibatch"] == B:
+                by_prec[v["gemm"]] = {"value": v["value"], "e2e": v.get("e2e", {}).get("value")}
+        line["headline_by_precision"] = by_prec
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -566,7 +703,10 @@ def main():
     ap.add_argument("--epochs", type=int, default=10, help="epochs_per_iteration (reference default, main.py:45)")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="GEMM arithmetic: bf16 tcgen05 (2e-2 parity, default) or fp32 FFMA (1e-5 parity)")
-    ap.add_argument("--ref-minibatches", type=int, default=0, help="reference arm: minibatches per step (0 = auto)")
+    ap.add_argument("--ref-epochs", type=int, default=4, help="reference arm: at most this many full epochs per timed step")
+    ap.add_argument("--ref-budget", type=float, default=20.0, help="reference arm: seconds of epochs per timed step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --envs / --minibatch are per GPU; strong: they are the TOTAL problem, split over the N ranks")
     ap.add_argument("--no-kernels", action="store_true", help="skip the HBM-kernel roofline mini-benchmarks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--no-variants", action="store_true", help="skip the secondary (precision, minibatch) settings")
@@ -580,6 +720,7 @@ def main():
               "envs_per_gpu": args.envs, "rollout_steps": args.rollout_steps, "obs_dim": OBS_DIM, "act_dim": ACT_DIM,
               "hidden": HIDDEN, "activation": "tanh", "gemm": args.precision, "minibatch_per_gpu": args.minibatch, "epochs_per_step": args.epochs,
               "parallelism": f"dp{max(world, 1)} (env-slab sharding, grad all-reduce)" if world > 1 else "single GPU",
+              "scaling": args.scaling,
               "cache": "inputs larger than L2 (788 MB observation buffer re-gathered every epoch); no explicit flush"}
     if args.impl == "reference":
         run_reference(args, config)

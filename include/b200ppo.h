@@ -32,7 +32,8 @@ extern "C" {
 #define B200PPO_ECUDA (-2)   /* CUDA runtime error, message in b200ppo_last_error() */
 #define B200PPO_ENOMEM (-3)
 #define B200PPO_ESTATE (-4)  /* call not valid for this context (e.g. batch larger than max_batch) */
-#define B200PPO_ENCCL (-5)
+#define B200PPO_ENCCL (-5)   /* collective / peer-exchange failure (NCCL error, a peer rank that did not arrive) */
+#define B200PPO_EINDEX (-6)  /* an index handed to a gather lies outside the table (the reference raises IndexError) */
 
 #define B200PPO_MAX_LAYERS 8
 
@@ -220,6 +221,13 @@ int b200ppo_normalize_obs(const void* obs, int obs_is_f64, int64_t n_envs, int32
 #define B200PPO_PROF_ALLREDUCE 6
 #define B200PPO_PROF_OTHER 7
 #define B200PPO_PROF_CLASSES 8
+/* Deferred device-side errors of the asynchronous entry points (b200ppo_train, the gathers inside it): synchronises
+ * `stream`, reads and clears the context's error word.  B200PPO_EINDEX: a permutation entry was outside [0, n_samples)
+ * (those rows were skipped; the reference raises IndexError at ppo.py:104).  B200PPO_ENCCL: the peer-memory gradient
+ * exchange timed out on a rank (B200PPO_PEER_TIMEOUT_MS, default 30000) — the optimizer step of that minibatch was NOT
+ * applied on this rank.  b200ppo_update_host polls by itself. */
+int b200ppo_poll_error(b200ppo_ctx* ctx, b200ppo_stream stream);
+
 int64_t b200ppo_launch_count(void);
 int b200ppo_profile_begin(b200ppo_ctx* ctx);
 int b200ppo_profile_end(b200ppo_ctx* ctx, double ms_out[B200PPO_PROF_CLASSES], int64_t launches_out[B200PPO_PROF_CLASSES]);

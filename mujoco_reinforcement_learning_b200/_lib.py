@@ -80,6 +80,7 @@ SIGNATURES = {
                                     c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_dbl, c_i32, c_i32, c_dbl, c_ptr, c_i32, c_i64,
                                     c_i64, C.POINTER(HParams), c_ptr, c_ptr]),
     "b200ppo_normalize_obs": (c_i32, [c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
+    "b200ppo_poll_error": (c_i32, [c_ptr, c_ptr]),
     "b200ppo_launch_count": (c_i64, []),
     "b200ppo_profile_begin": (c_i32, [c_ptr]),
     "b200ppo_profile_end": (c_i32, [c_ptr, C.POINTER(c_dbl), C.POINTER(c_i64)]),
@@ -128,9 +129,14 @@ def load() -> C.CDLL:
     return _LIB
 
 
+E_INDEX = -6
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().b200ppo_last_error().decode("utf-8", "replace")
+        if rc == E_INDEX:  # what the reference's `memory[idx]` raises (ppo.py:104)
+            raise IndexError(f"libb200ppo {what}: {msg}")
         raise RuntimeError(f"libb200ppo {what} failed (code {rc}): {msg}")
 
 

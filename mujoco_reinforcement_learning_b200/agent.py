@@ -38,12 +38,13 @@ class FusedAdam(torch.optim.Adam):
                     view.copy_(st[key].to(view.device))
                 st[key] = view
             if copy_from_state and "step" in st:
-                eng.adam_step = int(float(st["step"]))
-            st["step"] = torch.tensor(float(eng.adam_step))
+                eng.adam_steps[self.net_id] = int(float(st["step"]))
+            st["step"] = torch.tensor(float(eng.adam_steps[self.net_id]))
 
     def sync_step_from_engine(self):
+        """The per-parameter `step` entries torch's state_dict carries all mirror the engine's count for this optimiser."""
         for p, _ in self.engine.named_slots(self.net_id):
-            self.state[p]["step"] = torch.tensor(float(self.engine.adam_step))
+            self.state[p]["step"] = torch.tensor(float(self.engine.adam_steps[self.net_id]))
 
     def state_dict(self):
         self.sync_step_from_engine()
@@ -59,14 +60,19 @@ class FusedAdam(torch.optim.Adam):
         (`PPO.train`) does not come through here."""
         group = self.param_groups[0]
         b1, b2 = group["betas"]
+        t = self.engine.adam_steps[self.net_id] + 1  # one count per optimiser, kept in the engine (also what `train` continues from)
+        stepped = False
         for p, _ in self.engine.named_slots(self.net_id):
             if p.grad is None:
                 continue
             st = self.state[p]
-            t = int(float(st["step"])) + 1
             adam_step_(p.data.view(-1), p.grad.contiguous().view(-1), st["exp_avg"].view(-1), st["exp_avg_sq"].view(-1), t,
                        group["lr"], b1, b2, group["eps"])
             st["step"] = torch.tensor(float(t))
+            stepped = True
+        if stepped:
+            self.engine.adam_steps[self.net_id] = t
+
 
 
 class NormalLike:

@@ -60,7 +60,7 @@ class NetworkConfig:
     activation_class: type = torch.nn.Tanh
     num_linear_layers: int = 2
     linear_hidden_shapes: List[int] = field(default_factory=lambda: [256, 256])
-    critic_hidden_shapes: Optional[List[int]] = None  # None = same as the actor (the reference hard-codes [128,128])
+    critic_hidden_shapes: Optional[List[int]] = None  # None = [128, 128], what the reference hard-codes (models/critic.py:13-14)
     use_bias: bool = True
     use_batch_norm: bool = False
     last_layer_std: float = 0.01

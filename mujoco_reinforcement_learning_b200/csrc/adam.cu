@@ -83,8 +83,12 @@ __device__ __forceinline__ void combine_losses(const LossCombine& lc, float* s_l
 
 // Flag exchange of the peer-memory all-reduce: tell every peer that this rank's buffer of exchange `seq` is complete
 // (the kernel that wrote it finished before this one started), then wait until every peer has said the same.
-__device__ __forceinline__ void peer_exchange_barrier(const PeerSrc& ps) {
+// Returns false (for the whole block) when a peer did not show up within ps.timeout_cycles: the caller must then NOT
+// touch the parameters — whatever sits in that peer's exchange buffer is an older or half-written gradient — and the
+// error flag tells the host (b200ppo_poll_error), which fails the call instead of letting the replicas drift apart.
+__device__ __forceinline__ bool peer_exchange_barrier(const PeerSrc& ps) {
   const int q = threadIdx.x;
+  int timed_out = 0;
   if (q < ps.world && q != ps.rank) {
     if (blockIdx.x == 0) {
       __threadfence_system();
@@ -94,13 +98,14 @@ __device__ __forceinline__ void peer_exchange_barrier(const PeerSrc& ps) {
     unsigned v;
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ps.flags_local + q) : "memory");
-      if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer died; flag the error instead of hanging the GPU
-        if (ps.err != nullptr) *ps.err = 3;
+      if (clock64() - t0 > ps.timeout_cycles) {  // a peer died or stalled: flag the error instead of hanging the GPU
+        if (ps.err != nullptr) atomicMax(ps.err, B200PPO_ERRFLAG_PEER_TIMEOUT);
+        timed_out = 1;
         break;
       }
     } while (int(v - ps.seq) < 0);
   }
-  __syncthreads();
+  return __syncthreads_or(timed_out) == 0;
 }
 
 __device__ __forceinline__ float4 ld_peer4(const float* p) {  // peer memory: never through a stale L1 line
@@ -121,7 +126,7 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
   __shared__ float s_scr[256];
   pdl_wait_then_release();  // the gradient partials come from the kernel right before this one (common.cuh, PDL)
   if constexpr (PEERS) {
-    peer_exchange_barrier(ps);
+    if (!peer_exchange_barrier(ps)) return;  // no update from stale peer data; the host sees the flag
     if (blockIdx.x == 0 && threadIdx.x < 2 && ps.losses_out != nullptr) {
       float l = 0.f;
       for (int r = 0; r < ps.world; ++r) {

@@ -35,13 +35,16 @@ struct LossCombine {
 // optimizer kernel itself waits for the G flags and sums the G buffers in rank order (identical bits on every rank)
 // while applying Adam — the all-reduce, its launch and the separate reduction pass disappear from the critical path.
 constexpr int kMaxPeers = 8;
+constexpr int B200PPO_ERRFLAG_INDEX = 1;         // a gather met an index outside [0, n_rows)
+constexpr int B200PPO_ERRFLAG_PEER_TIMEOUT = 3;  // the peer-memory gradient exchange gave up on a peer
 struct PeerSrc {
   const float* src[kMaxPeers] = {};      // rank-ordered; src[rank] is the local buffer
   unsigned* flags_peer[kMaxPeers] = {};  // every rank's flag array [kMaxPeers] (slot q is written by rank q)
   unsigned* flags_local = nullptr;
   int world = 0, rank = 0;
   unsigned seq = 0;                      // value the flags must reach for this exchange
-  int32_t* err = nullptr;                // set to 3 when a peer does not show up within ~2 s
+  int32_t* err = nullptr;                // raised to B200PPO_ERRFLAG_PEER_TIMEOUT when a peer does not show up in time
+  long long timeout_cycles = 0;          // SM clocks to wait for a peer's flag (b200ppo_train: B200PPO_PEER_TIMEOUT_MS, default 30 s)
   float* losses_out = nullptr;           // [2] = sum over ranks of src[p][n + {0, 1}]
 };
 

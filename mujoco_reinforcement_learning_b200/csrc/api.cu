@@ -1118,6 +1118,8 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
         PROF(ctx, B200PPO_PROF_OTHER, st, launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, xb, st, &lc));
         PeerSrc ps{};
         ps.world = ctx->world; ps.rank = ctx->rank; ps.seq = seq; ps.err = ctx->err_flag; ps.losses_out = loss_slot;
+        static const long long timeout_ms = []() { const char* e = getenv("B200PPO_PEER_TIMEOUT_MS"); return e ? atoll(e) : 30000ll; }();
+        ps.timeout_cycles = timeout_ms * 2000000ll;  // ~2 GHz SM clock
         unsigned* flags0 = reinterpret_cast<unsigned*>(ctx->xbuf + 2 * ctx->xstride);
         ps.flags_local = flags0;
         for (int r = 0; r < ctx->world; ++r) {
@@ -1218,8 +1220,28 @@ extern "C" B2_EXPORT int b200ppo_update_host(b200ppo_ctx* ctx, float* params, fl
                        epochs, batch, max_minibatches_per_epoch, hp, h.losses, stream));
   if (losses_host && n_loss > 0)
     B2_CUDA(cudaMemcpyAsync(losses_host, h.losses, size_t(n_loss) * 4, cudaMemcpyDeviceToHost, st));
+  return b200ppo_poll_error(ctx, stream);  // synchronises the stream; bad permutation entries / peer time-outs fail the call
+}
+
+extern "C" B2_EXPORT int b200ppo_poll_error(b200ppo_ctx* ctx, b200ppo_stream stream) {
+  B2_CHECK_ARG(ctx, "b200ppo_poll_error: null context");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int32_t flag = 0;
+  B2_CUDA(cudaMemcpyAsync(&flag, ctx->err_flag, sizeof(flag), cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
-  return B200PPO_OK;
+  if (ctx->gather_stream != nullptr) {  // an epoch gather may still be running on the side stream
+    B2_CUDA(cudaStreamSynchronize(ctx->gather_stream));
+    B2_CUDA(cudaMemcpy(&flag, ctx->err_flag, sizeof(flag), cudaMemcpyDeviceToHost));
+  }
+  if (flag == 0) return B200PPO_OK;
+  B2_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(flag), st));
+  if (flag == B200PPO_ERRFLAG_PEER_TIMEOUT) {
+    set_error("gradient exchange: a peer rank did not arrive within the timeout (B200PPO_PEER_TIMEOUT_MS); the update of that "
+              "minibatch was skipped on this rank and the replicas are no longer in step");
+    return B200PPO_ENCCL;
+  }
+  set_error("index out of range: a permutation entry lies outside [0, n_samples)");
+  return B200PPO_EINDEX;
 }
 
 // ---- instrumentation -----------------------------------------------------------------------------------

@@ -104,8 +104,10 @@ class Actor(nn.Module):
         nc = run.network_config
         config = {"final_activation": nn.Tanh, "activation": nc.activation_class,
                   "hidden_layer_count": nc.num_linear_layers, "shapes": nc.linear_hidden_shapes}
+        # last_layer_std is NOT forwarded: the reference's Actor never passes it, so its last layer always gets the
+        # create_network default of 0.01 (linear/actor.py:17-23)
         self.actor = create_network(config, int(nc.input_shape * run.environment_config.window_length), nc.output_shape,
-                                    False, nc.use_bias, nc.use_batch_norm, nc.last_layer_std)
+                                    False, nc.use_bias, nc.use_batch_norm)
         self.actor_logstd = nn.Parameter(torch.zeros(nc.output_shape))
         self.output_max_value = float(nc.output_max_value)
         self.output_shape = int(nc.output_shape)
@@ -121,14 +123,16 @@ class Actor(nn.Module):
 
 
 class Critic(nn.Module):
-    """MLP value network — src/models/critic.py:6-25.  Hidden sizes come from the config (the reference
-    hard-codes [128, 128]); the input is flattened like the actor's so a [B, W, obs] window works."""
+    """MLP value network — src/models/critic.py:6-25.  Hidden sizes default to the reference's hard-coded [128, 128]
+    (so its `networks.pth` / `optimizer_critic.pth` load at default config); `critic_hidden_shapes` overrides them.  One
+    stated deviation: the input is flattened like the actor's, so a [B, W, obs] window works (the reference's critic takes
+    `input_shape` without the window factor and broadcasts)."""
 
     def __init__(self, run: Optional[Run] = None):
         super().__init__()
         run = run or Run.instance()
         nc = run.network_config
-        hidden = list(nc.critic_hidden_shapes if nc.critic_hidden_shapes is not None else nc.linear_hidden_shapes)
+        hidden = list(nc.critic_hidden_shapes if nc.critic_hidden_shapes is not None else [128, 128])
         config = {"final_activation": None, "activation": nc.activation_class, "hidden_layer_count": len(hidden),
                   "shapes": hidden}
         self.network = create_network(config, input_shape=int(nc.input_shape * run.environment_config.window_length),
@@ -178,7 +182,9 @@ class ActorCriticEngine:
         self.flat = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
-        self.adam_step = 0
+        # Adam step count per optimiser (0 actor, 1 critic): the ONE source of truth for both update paths — the fused
+        # trainer (`train`, which steps both optimisers once per minibatch) and `FusedAdam.step()`
+        self.adam_steps = [0, 0]
         self.obs_dim = actor.actor.in_dim
         self.act_dim = actor.output_shape
         # (parameter, element offset) in flat-buffer order == nn.Module.parameters() order
@@ -192,6 +198,18 @@ class ActorCriticEngine:
                                    int(self.lib.b200ppo_param_offset(self._ctx, 0, len(block.dims), 0))))
             block._engine, block._net_id = self, net_id
         self.bind_views(copy_from_modules=True)
+
+    @property
+    def adam_step(self) -> int:
+        """Common step count of the two optimisers (what the fused trainer continues from)."""
+        if self.adam_steps[0] != self.adam_steps[1]:
+            raise RuntimeError(f"actor and critic optimisers are at different Adam steps {self.adam_steps}: the fused trainer "
+                               "steps both per minibatch and needs them equal")
+        return self.adam_steps[0]
+
+    @adam_step.setter
+    def adam_step(self, value: int):
+        self.adam_steps = [int(value), int(value)]
 
     def __del__(self):
         try:
@@ -345,7 +363,7 @@ class ActorCriticEngine:
         return {n: grads[off[id(p)]:off[id(p)] + p.numel()].view(p.shape) for n, p in named_parameters}
 
     def train(self, obs, action, old_logp, advantage, target, perms, batch: int, hp: _lib.HParams,
-              max_minibatches_per_epoch: int = 0, rank_sliced_perms: bool = False) -> torch.Tensor:
+              max_minibatches_per_epoch: int = 0, rank_sliced_perms: bool = False, check_errors: bool = True) -> torch.Tensor:
         """`PPO.train` inner loops (ppo.py:101-140) in one native call.  Returns device losses [epochs*nb, 2].
         rank_sliced_perms: `perms` is [epochs, M // batch, batch // world] — only the permutation slots this rank
         consumes (`distributed.slice_perms_for_rank`) instead of the global [epochs, M]."""
@@ -385,4 +403,6 @@ class ActorCriticEngine:
             if rank_sliced_perms:
                 _lib.check(self.lib.b200ppo_set_perm_layout(self._ctx, 0), "b200ppo_set_perm_layout")
         self.adam_step = int(step.value)
+        if check_errors:  # deferred device-side errors (bad permutation entry, peer that never arrived): one stream sync per call
+            _lib.check(self.lib.b200ppo_poll_error(self._ctx, _lib.stream_ptr()), "b200ppo_train")
         return losses

@@ -37,7 +37,7 @@ elif which == "update":
     B, N, T = batch, max(512, batch // 64 * 2), 64
     run = pkg.Run(training_config=pkg.TrainingConfig(batch_size=B, epochs_per_iteration=1),
                   environment_config=pkg.EnvironmentConfig(maximum_timesteps=T, num_envs=N),
-                  network_config=pkg.NetworkConfig(input_shape=376, output_shape=17, linear_hidden_shapes=[256, 256]),
+                  network_config=pkg.NetworkConfig(input_shape=376, output_shape=17, linear_hidden_shapes=[256, 256], critic_hidden_shapes=[256, 256]),
                   gemm_precision=precision)
     agent = pkg.PPOAgent(run, max_batch=B)
     M = N * T

@@ -28,7 +28,7 @@ def main():
     def make_agent():
         run = pkg.Run(training_config=pkg.TrainingConfig(batch_size=GB, epochs_per_iteration=2),
                       environment_config=pkg.EnvironmentConfig(maximum_timesteps=T, num_envs=N),
-                      network_config=pkg.NetworkConfig(input_shape=Dm, output_shape=A, linear_hidden_shapes=H),
+                      network_config=pkg.NetworkConfig(input_shape=Dm, output_shape=A, linear_hidden_shapes=H, critic_hidden_shapes=H),
                       device=str(dev), gemm_precision=precision)
         torch.manual_seed(0)
         return run, pkg.PPOAgent(run, max_batch=GB)

@@ -335,3 +335,80 @@ def test_checkpoint_files_move_between_implementations(tmp_path):
     assert torch.equal(agent2.engine.exp_avg, agent.engine.exp_avg) and torch.equal(agent2.engine.exp_avg_sq, agent.engine.exp_avg_sq)
     assert agent2.engine.adam_step == agent.engine.adam_step == 2
     assert agent2.engine.params_are_bound()
+
+
+def test_adam_step_count_is_shared_by_both_update_paths(tmp_path):
+    """`FusedAdam.step()` (user-driven loss.backward(); opt.step()), `state_dict()`, `load_state_dict()` and the
+    fused trainer must agree on ONE step count per optimiser — checked against stock `torch.optim.Adam` on the same
+    gradients (bias correction restarts at t = 1 if a path loses the count)."""
+    oracle, agent, run = make_pair(11, 3, [32, 24], [32, 24], "tanh", batch=64, epochs=1, n_envs=4, steps=32, seed=5, max_batch=128)
+    ref_opt = {n: torch.optim.Adam(oracle.networks[n].parameters(), lr=1e-3, foreach=False) for n in ("actor", "critic")}
+    for opt in agent.optimizers.values():
+        opt.param_groups[0]["lr"] = 1e-3
+    g = torch.Generator().manual_seed(3)
+    for it in range(3):  # three manual steps of both optimisers with the same synthetic gradients
+        for (_, p_ref), (_, p) in zip(oracle.networks.named_parameters(), agent.networks.named_parameters()):
+            grad = torch.randn(p_ref.shape, generator=g)
+            p_ref.grad = grad.clone()
+            p.grad = grad.to(DEV)
+        for n in ("actor", "critic"):
+            ref_opt[n].step()
+            agent.optimizers[n].step()
+        sd = agent.optimizers["actor"].state_dict()
+        assert all(float(st["step"]) == it + 1 for st in sd["state"].values())  # state_dict keeps the manual count
+    assert agent.engine.adam_steps == [3, 3] and agent.engine.adam_step == 3
+    for (k, p_ref), (_, p) in zip(oracle.networks.named_parameters(), agent.networks.named_parameters()):
+        assert_close(p, p_ref.detach(), 1e-5, f"param {k} after manual steps")
+    # one optimiser ahead of the other: the fused trainer refuses to guess
+    agent.optimizers["critic"].step()
+    with pytest.raises(RuntimeError, match="different Adam steps"):
+        _ = agent.engine.adam_step
+    ref_opt["critic"].step()
+    agent.optimizers["actor"].step()
+    ref_opt["actor"].step()
+    # checkpoint round trip keeps the count, and the fused trainer continues from it
+    sd = {n: copy.deepcopy(agent.optimizers[n].state_dict()) for n in ("actor", "critic")}
+    agent.engine.adam_step = 0
+    for n in ("actor", "critic"):
+        agent.optimizers[n].load_state_dict(sd[n])
+    assert agent.engine.adam_steps == [4, 4]
+    roll = O.synthetic_rollout(4, 32, 11, 3, seed=5)
+    adv, tgt = O.calculate_advantages(roll["reward"], roll["current_state_value"], roll["next_state_value"], roll["terminated"], 0.99, 0.98)
+    memory = pkg.RolloutMemory({"current_state": roll["current_state"].to(DEV), "action": roll["action"].to(DEV),
+                                "action_log_prob": (torch.randn(4, 32) * 0.1 - 4).to(DEV), "advantage": adv.to(DEV),
+                                "current_state_value_target": tgt.to(DEV)}, (4, 32))
+    pkg.PPO(type("H", (), {"run": run})(), agent).train(memory, perms=torch.randperm(128)[None])
+    assert agent.engine.adam_steps == [6, 6]
+    assert all(float(st["step"]) == 6.0 for st in agent.optimizers["critic"].state_dict()["state"].values())
+
+
+def test_out_of_range_permutation_raises_index_error():
+    """the reference's `memory[idx]` raises IndexError on a bad index (ppo.py:104); the asynchronous CUDA path
+    must not train on stale shuffle-buffer rows and return OK."""
+    oracle, agent, run = make_pair(11, 3, [32, 24], [32, 24], "tanh", batch=64, epochs=1, n_envs=4, steps=32, seed=7, max_batch=128)
+    roll = O.synthetic_rollout(4, 32, 11, 3, seed=5)
+    adv, tgt = O.calculate_advantages(roll["reward"], roll["current_state_value"], roll["next_state_value"], roll["terminated"], 0.99, 0.98)
+    memory = pkg.RolloutMemory({"current_state": roll["current_state"].to(DEV), "action": roll["action"].to(DEV),
+                                "action_log_prob": (torch.randn(4, 32) * 0.1 - 4).to(DEV), "advantage": adv.to(DEV),
+                                "current_state_value_target": tgt.to(DEV)}, (4, 32))
+    perm = torch.randperm(128)[None].clone()
+    perm[0, 5] = 128  # one past the end
+    algo = pkg.PPO(type("H", (), {"run": run})(), agent)
+    with pytest.raises(IndexError):
+        algo.train(memory, perms=perm)
+    algo.train(memory, perms=torch.randperm(128)[None])  # the error word was cleared: a good call goes through
+
+
+def test_default_critic_loads_a_reference_checkpoint():
+    """with `critic_hidden_shapes` left at its default the critic is the reference's hard-coded 128x128 MLP
+    (models/critic.py:13-14), so a state_dict written by the reference's own agent loads without a shape mismatch."""
+    g = load_golden("train_tanh64")
+    init = sub(g, "init/")
+    D = init["actor.actor.first_layers.0.weight"].shape[1]
+    A = init["actor.actor_logstd"].shape[0]
+    run = pkg.Run(environment_config=pkg.EnvironmentConfig(maximum_timesteps=8, num_envs=2, window_length=1),
+                  network_config=pkg.NetworkConfig(input_shape=D, output_shape=A, activation_class=torch.nn.Tanh, num_linear_layers=2,
+                                                   linear_hidden_shapes=[int(h) for h in g["hidden"]]))
+    agent = pkg.PPOAgent(run, max_batch=64)
+    agent.networks.load_state_dict({k: torch.from_numpy(v) for k, v in init.items()})  # strict
+    assert tuple(agent.networks["critic"].network.dims) == (128, 128, 1)
