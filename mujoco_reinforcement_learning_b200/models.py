@@ -9,6 +9,7 @@ reference's key names (`actor.actor.first_layers.0.weight`, ..., `critic.network
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 from typing import List, Optional, Sequence
 
@@ -161,6 +162,16 @@ class _MLPFunction(torch.autograd.Function):
         return (None, None, gx, *gparams)
 
 
+def _on_engine_device(method):
+    """Run an engine entry point with the engine's GPU current: kernels launch on that device's current stream even when
+    the caller's current device is another one (a context on cuda:1 driven from cuda:0)."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 class ActorCriticEngine:
     """Owns the native context, the flat parameter buffer and the flat Adam state of one actor-critic pair."""
 
@@ -262,6 +273,7 @@ class ActorCriticEngine:
             raise RuntimeError(f"batch {x.shape[0]} exceeds the engine's max_batch {self.max_batch}")
         return x
 
+    @_on_engine_device
     def _mlp_forward_raw(self, net_id: int, x: torch.Tensor, need_saved: bool):
         self.ensure_bound()
         x = self._check_x(x)
@@ -276,6 +288,7 @@ class ActorCriticEngine:
                                                 _lib.ptr(saved), _lib.stream_ptr()), "b200ppo_mlp_forward")
         return out, saved
 
+    @_on_engine_device
     def _mlp_backward_raw(self, net_id, x, out, saved, grad_out, need_gx: bool):
         x = self._check_x(x)
         B = x.shape[0]
@@ -298,6 +311,7 @@ class ActorCriticEngine:
         return self._mlp_forward_raw(net_id, x, need_saved=False)[0]
 
     # -- fused paths -------------------------------------------------------------------------------------
+    @_on_engine_device
     def policy_infer(self, obs: torch.Tensor, noise: Optional[torch.Tensor], want_value: bool = True):
         """K6: one call for actor + critic forward, sampling and log-prob (ppo.py:22-26)."""
         self.ensure_bound()
@@ -315,6 +329,7 @@ class ActorCriticEngine:
                                                  _lib.stream_ptr()), "b200ppo_policy_infer")
         return action, logp, value, mean
 
+    @_on_engine_device
     def evaluate(self, obs: torch.Tensor, actions: torch.Tensor):
         """ppo.py:109-115,125: (new log-prob [B], entropy scalar, value [B,1]) without autograd."""
         self.ensure_bound()
@@ -333,6 +348,7 @@ class ActorCriticEngine:
         return _lib.HParams(float(lr_actor), float(lr_critic), float(betas[0]), float(betas[1]), float(eps),
                             float(clip_epsilon), float(entropy_eps))
 
+    @_on_engine_device
     def minibatch_grads(self, obs, action, old_logp, advantage, target, hp: _lib.HParams):
         """Losses and flat gradient of one minibatch (no optimiser step)."""
         self.ensure_bound()
@@ -349,6 +365,7 @@ class ActorCriticEngine:
                    "b200ppo_minibatch_grads")
         return losses, grads
 
+    @_on_engine_device
     def debug_activations(self, net: int, kind: int, layer: int, rows: int) -> torch.Tensor:
         """Test hook: bf16 intermediates of the last bf16 minibatch as fp32 (kind 0: H_layer, kind 1: dL/dz_layer)."""
         dims = (self.actor.actor if net == 0 else self.critic.network).dims
@@ -362,6 +379,7 @@ class ActorCriticEngine:
         off = {id(p): o for p, o in self.slots}
         return {n: grads[off[id(p)]:off[id(p)] + p.numel()].view(p.shape) for n, p in named_parameters}
 
+    @_on_engine_device
     def train(self, obs, action, old_logp, advantage, target, perms, batch: int, hp: _lib.HParams,
               max_minibatches_per_epoch: int = 0, rank_sliced_perms: bool = False, check_errors: bool = True) -> torch.Tensor:
         """`PPO.train` inner loops (ppo.py:101-140) in one native call.  Returns device losses [epochs*nb, 2].

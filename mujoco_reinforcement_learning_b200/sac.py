@@ -12,6 +12,7 @@ scalar glue (log-prob, min, TD target, MSE) is a handful of element-wise device 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -86,6 +87,42 @@ class _FlatAdam:
         eng, b, e = self.engine, self.begin, self.end
         adam_step_(eng.flat[b:e], self.grad[b:e], eng.exp_avg[b:e], eng.exp_avg_sq[b:e], self.step_count, self.lr)
 
+    # torch.optim.Adam's state_dict layout (state[i] = {step, exp_avg, exp_avg_sq}, one param group), so that the files
+    # `Agent.save` writes (agent.py:51-55) load into stock torch optimisers and back
+    def state_dict(self):
+        state = {}
+        if self.step_count > 0:
+            for i, (p, off) in enumerate(self.params):
+                sl = slice(off, off + p.numel())
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.engine.exp_avg[sl].view(p.shape).clone(),
+                            "exp_avg_sq": self.engine.exp_avg_sq[sl].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": False, "capturable": False, "differentiable": False, "fused": None, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        self.lr = float(sd["param_groups"][0]["lr"])
+        self.step_count = 0
+        for i, (p, off) in enumerate(self.params):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            sl = slice(off, off + p.numel())
+            self.engine.exp_avg[sl].copy_(st["exp_avg"].reshape(-1).to(self.engine.device))
+            self.engine.exp_avg_sq[sl].copy_(st["exp_avg_sq"].reshape(-1).to(self.engine.device))
+            self.step_count = int(float(st["step"]))
+
+
+class _ExponentialLR:
+    """`ExponentialLR(optimizer, gamma)` for a _FlatAdam: `step()` multiplies its learning rate (the reference steps one per
+    optimiser after every trained iteration, soft_actor_critic.py:199-201)."""
+
+    def __init__(self, optimizer: _FlatAdam, gamma: float):
+        self.optimizer, self.gamma = optimizer, gamma
+
+    def step(self):
+        self.optimizer.lr *= self.gamma
+
 
 class SoftActorCriticAgent:
     """networks: actor, online_critic, target_critic; optimizers: actor, online_critic (soft_actor_critic_agent.py:12-35)."""
@@ -120,8 +157,29 @@ class SoftActorCriticAgent:
             "actor": _FlatAdam(self.engine_pi, 0, self.engine_pi.n_actor, lr),
             "online_critic": _FlatAdam(self.engine_q, 0, self.engine_q.n_params, lr),
         }
+        self.schedulers = {name: _ExponentialLR(opt, 0.999) for name, opt in self.optimizers.items()}  # soft_actor_critic_agent.py:30-34
         for p in self.networks["target_critic"].parameters():
             p.requires_grad_(False)
+
+    # -- checkpoints (agent.py:47-72): same files, same state_dict keys as the reference's Agent.save / load ------------
+    def save(self):
+        run = self.run
+        ep = run.dynamic_config.current_episode
+        os.makedirs(f"{run.experiment_path}/networks/{ep}", exist_ok=True)
+        torch.save(self.networks.state_dict(), f"{run.experiment_path}/networks/{ep}/networks.pth")
+        for name, opt in self.optimizers.items():
+            torch.save(opt.state_dict(), f"{run.experiment_path}/networks/{ep}/optimizer_{name}.pth")
+
+    def load(self):
+        run = self.run
+        load_path = f"{run.experiment_path}/networks/{run.dynamic_config.current_episode}"
+        if not os.path.exists(load_path):
+            raise ValueError("the current path not exist!")
+        self.networks.load_state_dict(torch.load(f"{load_path}/networks.pth", map_location=run.device))
+        for eng in (self.engine_pi, self.engine_q, self.engine_qt):
+            eng.bind_views()
+        for name, opt in self.optimizers.items():
+            opt.load_state_dict(torch.load(f"{load_path}/optimizer_{name}.pth", map_location=run.device))
 
     def act(self, state: torch.Tensor, return_dist: bool = False, test_phase: bool = False, noise: Optional[torch.Tensor] = None):
         """agent.py:26-42 with `rsample()`: action = mean + std * eps."""

@@ -80,3 +80,41 @@ def test_polyak_update_is_bit_exact():
     ref = t * (1.0 - 0.005) + s * 0.005
     pkg.polyak_update_(t, s, 0.005)
     assert torch.equal(t, ref)
+
+
+def test_sac_checkpoint_round_trip_and_lr_schedule(tmp_path):
+    """the SAC agent keeps the reference's schedulers (ExponentialLR(0.999) per optimiser,
+    soft_actor_critic_agent.py:30-34) and `Agent.save` / `load` files (agent.py:47-72) in torch's Adam state layout."""
+    g = load_golden(SAC_CASES[0])
+    _, cfg = sac_agent_from_golden(g)
+    mem = sub(g, "mem/")
+    window, obs_dim = mem["current_state"].shape[2], mem["current_state"].shape[3]
+    run = _run_from_cfg(cfg, obs_dim, window)
+    run.experiment_path = str(tmp_path)
+    agent = pkg.SoftActorCriticAgent(run)
+    algo = pkg.SoftActorCritic(_Helper(run), agent)
+    memory = {k: torch.from_numpy(v).to(DEV) for k, v in mem.items()}
+    perms, eps = torch.from_numpy(g["perms"]), torch.from_numpy(g["eps"]).to(DEV)
+    algo.train(memory, 0, idx=perms[0], noise=eps[0:2])
+    lr0 = agent.optimizers["actor"].lr
+    for sch in agent.schedulers.values():
+        sch.step()
+    assert agent.optimizers["actor"].lr == pytest.approx(lr0 * 0.999) and set(agent.schedulers) == {"actor", "online_critic"}
+    agent.save()
+    d = tmp_path / "networks" / "0"
+    assert sorted(p.name for p in d.iterdir()) == ["networks.pth", "optimizer_actor.pth", "optimizer_online_critic.pth"]
+    # the optimizer file loads into a stock torch.optim.Adam over same-shaped parameters
+    osd = torch.load(d / "optimizer_actor.pth", map_location="cpu")
+    shapes = [st["exp_avg"].shape for st in osd["state"].values()]
+    stock = torch.optim.Adam([torch.nn.Parameter(torch.zeros(s)) for s in shapes], lr=1.0)
+    stock.load_state_dict(osd)
+    assert stock.param_groups[0]["lr"] == pytest.approx(lr0 * 0.999)
+    # and back into a fresh agent
+    run2 = _run_from_cfg(cfg, obs_dim, window)
+    run2.experiment_path = str(tmp_path)
+    agent2 = pkg.SoftActorCriticAgent(run2)
+    agent2.load()
+    for k, v in agent.networks.state_dict().items():
+        assert torch.equal(v, agent2.networks.state_dict()[k]), k
+    assert agent2.optimizers["online_critic"].step_count == 1
+    assert torch.equal(agent2.engine_q.exp_avg, agent.engine_q.exp_avg)
