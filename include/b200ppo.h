@@ -192,6 +192,22 @@ int b200ppo_update_host(b200ppo_ctx* ctx, float* params, float* exp_avg, float* 
                         int64_t max_minibatches_per_epoch, const b200ppo_hparams* hp, float* losses_host,
                         b200ppo_stream stream);
 
+/* The same in two halves, for a caller that can hand over rollout k + 1 while rollout k is still being trained on:
+ * `_begin` only enqueues the host->device copies of one rollout on the library's copy stream into staging set `slot`
+ * (0 or 1) and returns; `_end` makes `stream` wait for them (the advantage pass for the four small arrays only, so it
+ * runs while the observations still stream in), runs b200ppo_gae + b200ppo_train, copies the losses back and
+ * synchronises `stream`.  begin(k + 1, slot ^ 1) may be called before end(k, slot): the upload (875 MB at the bench
+ * shape, PCIe-bound) then hides behind the update.  The host buffers of a slot must stay valid until its `_end` returns.
+ * replaces: ppo.py:158-159 across consecutive iterations. */
+int b200ppo_update_host_begin(b200ppo_ctx* ctx, const float* obs_host, const float* action_host, const float* old_logp_host,
+                              const float* reward_host, const float* value_host, const float* next_value_host,
+                              const uint8_t* terminated_host, int64_t n_envs, int64_t n_steps, const int64_t* perms_host,
+                              int32_t epochs, int32_t slot);
+int b200ppo_update_host_end(b200ppo_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq, int64_t* adam_step_io,
+                            double gamma, double lmbda, int normalize_rewards, int normalize_advantage, double advantage_scaler,
+                            int64_t batch, int64_t max_minibatches_per_epoch, const b200ppo_hparams* hp, float* losses_host,
+                            int32_t slot, b200ppo_stream stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Observation normalisation feeding the policy.
  * replaces: EnvironmentHelper.normalize_state/_normalize/get_state,

@@ -79,6 +79,9 @@ SIGNATURES = {
     "b200ppo_update_host": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, C.POINTER(c_i64), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                     c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_dbl, c_i32, c_i32, c_dbl, c_ptr, c_i32, c_i64,
                                     c_i64, C.POINTER(HParams), c_ptr, c_ptr]),
+    "b200ppo_update_host_begin": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i32, c_i32]),
+    "b200ppo_update_host_end": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, C.POINTER(c_i64), c_dbl, c_dbl, c_i32, c_i32, c_dbl, c_i64, c_i64,
+                                        C.POINTER(HParams), c_ptr, c_i32, c_ptr]),
     "b200ppo_normalize_obs": (c_i32, [c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
     "b200ppo_poll_error": (c_i32, [c_ptr, c_ptr]),
     "b200ppo_launch_count": (c_i64, []),

@@ -142,13 +142,18 @@ struct b200ppo_ctx {
   cudaStream_t gather_stream = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
   // device staging of the host entry point
-  struct {
+  // two sets: b200ppo_update_host_begin(slot) uploads rollout k + 1 on the copy stream while _end(other slot) trains on rollout k
+  struct HostStage {
     float *obs = nullptr, *act = nullptr, *logp = nullptr, *rew = nullptr, *val = nullptr, *nval = nullptr;
     float *adv = nullptr, *tgt = nullptr, *losses = nullptr;
     uint8_t* term = nullptr;
     int64_t* perms = nullptr;
     int64_t rows = 0, perm_elems = 0, loss_elems = 0;
-  } host;
+    int64_t n_envs = 0, n_steps = 0;
+    int32_t epochs = 0;
+    cudaEvent_t ev_small = nullptr, ev_all = nullptr;  // scalars of the advantage pass uploaded / everything uploaded
+  } host[2];
+  cudaStream_t copy_stream = nullptr;
   // bf16 operands of the tensor-core path (precision == B200PPO_PREC_BF16); hidden layers only
   struct {
     __nv_bfloat16* H[2][B200PPO_MAX_LAYERS] = {};   // hidden activations [max_batch, pitchH], ones in column dims[l]
@@ -858,9 +863,14 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
     for (int l = 0; l < B200PPO_MAX_LAYERS; ++l) { dev_free(c->bf.H[n][l]); dev_free(c->bf.dZ[n][l]); dev_free(c->bf.W[n][l]); dev_free(c->bf.WT[n][l]); }
   dev_free(c->bf.X); dev_free(c->bf.sh_obs); dev_free(c->bf.obs_table);
   dev_free(c->sh_obs); dev_free(c->sh_act); dev_free(c->sh_logp); dev_free(c->sh_adv); dev_free(c->sh_tgt);
-  dev_free(c->host.obs); dev_free(c->host.act); dev_free(c->host.logp); dev_free(c->host.rew); dev_free(c->host.val);
-  dev_free(c->host.nval); dev_free(c->host.adv); dev_free(c->host.tgt); dev_free(c->host.losses); dev_free(c->host.term);
-  dev_free(c->host.perms);
+  for (auto& h : c->host) {
+    dev_free(h.obs); dev_free(h.act); dev_free(h.logp); dev_free(h.rew); dev_free(h.val);
+    dev_free(h.nval); dev_free(h.adv); dev_free(h.tgt); dev_free(h.losses); dev_free(h.term);
+    dev_free(h.perms);
+    if (h.ev_small) cudaEventDestroy(h.ev_small);
+    if (h.ev_all) cudaEventDestroy(h.ev_all);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (int r = 0; r < kMaxPeers; ++r) {
     if (c->peer_x[r] != nullptr && c->peer_x[r] != c->xbuf) cudaIpcCloseMemHandle(c->peer_x[r]);
     if (c->peer_table[r] != nullptr && c->peer_table[r] != c->bf.obs_table) cudaIpcCloseMemHandle(c->peer_table[r]);
@@ -1163,23 +1173,23 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
   return B200PPO_OK;
 }
 
-extern "C" B2_EXPORT int b200ppo_update_host(b200ppo_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq,
-                                   int64_t* adam_step_io, const float* obs_host, const float* action_host,
-                                   const float* old_logp_host, const float* reward_host, const float* value_host,
-                                   const float* next_value_host, const uint8_t* terminated_host, int64_t n_envs,
-                                   int64_t n_steps, double gamma, double lmbda, int normalize_rewards,
-                                   int normalize_advantage, double advantage_scaler, const int64_t* perms_host,
-                                   int32_t epochs, int64_t batch, int64_t max_minibatches_per_epoch,
-                                   const b200ppo_hparams* hp, float* losses_host, b200ppo_stream stream) {
+extern "C" B2_EXPORT int b200ppo_update_host_begin(b200ppo_ctx* ctx, const float* obs_host, const float* action_host,
+                                                   const float* old_logp_host, const float* reward_host, const float* value_host,
+                                                   const float* next_value_host, const uint8_t* terminated_host, int64_t n_envs,
+                                                   int64_t n_steps, const int64_t* perms_host, int32_t epochs, int32_t slot) {
   B2_CHECK_ARG(ctx == nullptr || !ctx->perm_rank_slices, "b200ppo_update_host: takes the global permutations (b200ppo_set_perm_layout(ctx, 0))");
   B2_CHECK_ARG(ctx && obs_host && action_host && old_logp_host && reward_host && value_host && next_value_host &&
-                   terminated_host && perms_host && hp,
+                   terminated_host && perms_host,
                "b200ppo_update_host: null pointer");
-  B2_CHECK_ARG(n_envs > 0 && n_steps > 0 && epochs > 0 && batch > 0, "b200ppo_update_host: bad sizes");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B2_CHECK_ARG(n_envs > 0 && n_steps > 0 && epochs > 0 && (slot == 0 || slot == 1), "b200ppo_update_host: bad sizes");
   const int64_t M = n_envs * n_steps;
   const int D = ctx->net[0].d.in_dim, A = ctx->net[0].out_dim();
-  auto& h = ctx->host;
+  auto& h = ctx->host[slot];
+  if (ctx->copy_stream == nullptr) B2_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (h.ev_small == nullptr) {
+    B2_CUDA(cudaEventCreateWithFlags(&h.ev_small, cudaEventDisableTiming));
+    B2_CUDA(cudaEventCreateWithFlags(&h.ev_all, cudaEventDisableTiming));
+  }
   if (h.rows < M) {
     B2_CUDA(cudaDeviceSynchronize());
     dev_free(h.obs); dev_free(h.act); dev_free(h.logp); dev_free(h.rew); dev_free(h.val); dev_free(h.nval);
@@ -1196,31 +1206,67 @@ extern "C" B2_EXPORT int b200ppo_update_host(b200ppo_ctx* ctx, float* params, fl
     B2_TRY(dev_alloc(&h.perms, int64_t(epochs) * M));
     h.perm_elems = int64_t(epochs) * M;
   }
+  h.n_envs = n_envs; h.n_steps = n_steps; h.epochs = epochs;
+  cudaStream_t cs = ctx->copy_stream;
+  const auto H2D = cudaMemcpyHostToDevice;
+  // the advantage pass only needs the four small arrays: they go first, so that it runs while the observations stream in
+  B2_CUDA(cudaMemcpyAsync(h.rew, reward_host, size_t(M) * 4, H2D, cs));
+  B2_CUDA(cudaMemcpyAsync(h.val, value_host, size_t(M) * 4, H2D, cs));
+  B2_CUDA(cudaMemcpyAsync(h.nval, next_value_host, size_t(M) * 4, H2D, cs));
+  B2_CUDA(cudaMemcpyAsync(h.term, terminated_host, size_t(M), H2D, cs));
+  B2_CUDA(cudaEventRecord(h.ev_small, cs));
+  B2_CUDA(cudaMemcpyAsync(h.obs, obs_host, size_t(M) * D * 4, H2D, cs));
+  B2_CUDA(cudaMemcpyAsync(h.act, action_host, size_t(M) * A * 4, H2D, cs));
+  B2_CUDA(cudaMemcpyAsync(h.logp, old_logp_host, size_t(M) * 4, H2D, cs));
+  B2_CUDA(cudaMemcpyAsync(h.perms, perms_host, size_t(epochs) * M * 8, H2D, cs));
+  B2_CUDA(cudaEventRecord(h.ev_all, cs));
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_update_host_end(b200ppo_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq,
+                                                 int64_t* adam_step_io, double gamma, double lmbda, int normalize_rewards,
+                                                 int normalize_advantage, double advantage_scaler, int64_t batch,
+                                                 int64_t max_minibatches_per_epoch, const b200ppo_hparams* hp, float* losses_host,
+                                                 int32_t slot, b200ppo_stream stream) {
+  B2_CHECK_ARG(ctx && params && exp_avg && exp_avg_sq && adam_step_io && hp && (slot == 0 || slot == 1), "b200ppo_update_host_end: bad argument");
+  auto& h = ctx->host[slot];
+  B2_CHECK_ARG(h.ev_all != nullptr && h.n_envs > 0 && batch > 0, "b200ppo_update_host_end: no upload was begun in slot %d", slot);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t M = h.n_envs * h.n_steps;
   int64_t nb = M / batch;
   if (max_minibatches_per_epoch > 0) nb = std::min(nb, max_minibatches_per_epoch);
-  const int64_t n_loss = int64_t(epochs) * nb * 2;
+  const int64_t n_loss = int64_t(h.epochs) * nb * 2;
   if (h.loss_elems < n_loss) {
     B2_CUDA(cudaDeviceSynchronize());
     dev_free(h.losses);
     B2_TRY(dev_alloc(&h.losses, n_loss));
     h.loss_elems = n_loss;
   }
-  const auto H2D = cudaMemcpyHostToDevice;
-  B2_CUDA(cudaMemcpyAsync(h.rew, reward_host, size_t(M) * 4, H2D, st));
-  B2_CUDA(cudaMemcpyAsync(h.val, value_host, size_t(M) * 4, H2D, st));
-  B2_CUDA(cudaMemcpyAsync(h.nval, next_value_host, size_t(M) * 4, H2D, st));
-  B2_CUDA(cudaMemcpyAsync(h.term, terminated_host, size_t(M), H2D, st));
-  B2_TRY(b200ppo_gae(h.rew, 0, h.val, h.nval, h.term, nullptr, n_envs, n_steps, gamma, lmbda, normalize_rewards,
+  B2_CUDA(cudaStreamWaitEvent(st, h.ev_small, 0));
+  B2_TRY(b200ppo_gae(h.rew, 0, h.val, h.nval, h.term, nullptr, h.n_envs, h.n_steps, gamma, lmbda, normalize_rewards,
                      normalize_advantage, advantage_scaler, h.adv, h.tgt, stream));
-  B2_CUDA(cudaMemcpyAsync(h.obs, obs_host, size_t(M) * D * 4, H2D, st));
-  B2_CUDA(cudaMemcpyAsync(h.act, action_host, size_t(M) * A * 4, H2D, st));
-  B2_CUDA(cudaMemcpyAsync(h.logp, old_logp_host, size_t(M) * 4, H2D, st));
-  B2_CUDA(cudaMemcpyAsync(h.perms, perms_host, size_t(epochs) * M * 8, H2D, st));
+  B2_CUDA(cudaStreamWaitEvent(st, h.ev_all, 0));
   B2_TRY(b200ppo_train(ctx, params, exp_avg, exp_avg_sq, adam_step_io, h.obs, h.act, h.logp, h.adv, h.tgt, M, h.perms,
-                       epochs, batch, max_minibatches_per_epoch, hp, h.losses, stream));
+                       h.epochs, batch, max_minibatches_per_epoch, hp, h.losses, stream));
   if (losses_host && n_loss > 0)
     B2_CUDA(cudaMemcpyAsync(losses_host, h.losses, size_t(n_loss) * 4, cudaMemcpyDeviceToHost, st));
+  h.n_envs = 0;  // consumed
   return b200ppo_poll_error(ctx, stream);  // synchronises the stream; bad permutation entries / peer time-outs fail the call
+}
+
+extern "C" B2_EXPORT int b200ppo_update_host(b200ppo_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq,
+                                   int64_t* adam_step_io, const float* obs_host, const float* action_host,
+                                   const float* old_logp_host, const float* reward_host, const float* value_host,
+                                   const float* next_value_host, const uint8_t* terminated_host, int64_t n_envs,
+                                   int64_t n_steps, double gamma, double lmbda, int normalize_rewards,
+                                   int normalize_advantage, double advantage_scaler, const int64_t* perms_host,
+                                   int32_t epochs, int64_t batch, int64_t max_minibatches_per_epoch,
+                                   const b200ppo_hparams* hp, float* losses_host, b200ppo_stream stream) {
+  B2_CHECK_ARG(hp && batch > 0, "b200ppo_update_host: bad argument");
+  B2_TRY(b200ppo_update_host_begin(ctx, obs_host, action_host, old_logp_host, reward_host, value_host, next_value_host,
+                                   terminated_host, n_envs, n_steps, perms_host, epochs, 0));
+  return b200ppo_update_host_end(ctx, params, exp_avg, exp_avg_sq, adam_step_io, gamma, lmbda, normalize_rewards, normalize_advantage,
+                                 advantage_scaler, batch, max_minibatches_per_epoch, hp, losses_host, 0, stream);
 }
 
 extern "C" B2_EXPORT int b200ppo_poll_error(b200ppo_ctx* ctx, b200ppo_stream stream) {

@@ -412,3 +412,60 @@ def test_default_critic_loads_a_reference_checkpoint():
     agent = pkg.PPOAgent(run, max_batch=64)
     agent.networks.load_state_dict({k: torch.from_numpy(v) for k, v in init.items()})  # strict
     assert tuple(agent.networks["critic"].network.dims) == (128, 128, 1)
+
+
+def _host_update(agent, roll, logp, perms, B, E, pipelined):
+    """One rollout through the host-buffer entry points of the C ABI; returns the losses [E * nb, 2]."""
+    import ctypes as C
+    from mujoco_reinforcement_learning_b200 import _lib
+    eng = agent.engine
+    lib = _lib.load()
+    N, T = roll["reward"].shape[0], roll["reward"].shape[1]
+    host = {k: roll[k].contiguous() for k in ("current_state", "action", "reward", "current_state_value", "next_state_value")}
+    term = roll["terminated"].to(torch.uint8).contiguous()
+    logp, perms = logp.contiguous(), perms.contiguous()
+    nb = (N * T) // B
+    losses = torch.empty(E * nb, 2)
+    hp = eng.hparams(1e-4, 1e-4, 0.1, 1e-4)
+    step = C.c_int64(eng.adam_step)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    if pipelined:
+        _lib.check(lib.b200ppo_update_host_begin(eng._ctx, p(host["current_state"]), p(host["action"]), p(logp), p(host["reward"]),
+                                                 p(host["current_state_value"]), p(host["next_state_value"]), p(term), N, T, p(perms), E, 1),
+                   "b200ppo_update_host_begin")
+        _lib.check(lib.b200ppo_update_host_end(eng._ctx, _lib.ptr(eng.flat), _lib.ptr(eng.exp_avg), _lib.ptr(eng.exp_avg_sq), C.byref(step),
+                                               0.99, 0.98, 0, 0, 1.0, B, 0, C.byref(hp), p(losses), 1, _lib.stream_ptr()),
+                   "b200ppo_update_host_end")
+    else:
+        _lib.check(lib.b200ppo_update_host(eng._ctx, _lib.ptr(eng.flat), _lib.ptr(eng.exp_avg), _lib.ptr(eng.exp_avg_sq), C.byref(step),
+                                           p(host["current_state"]), p(host["action"]), p(logp), p(host["reward"]),
+                                           p(host["current_state_value"]), p(host["next_state_value"]), p(term), N, T, 0.99, 0.98, 0, 0,
+                                           1.0, p(perms), E, B, 0, C.byref(hp), p(losses), _lib.stream_ptr()), "b200ppo_update_host")
+    eng.adam_step = int(step.value)
+    return losses
+
+
+def test_host_entry_points_match_the_oracle_and_each_other():
+    """`b200ppo_update_host` and its two-call form (`_begin` / `_end`, staging set 1) from HOST buffers: same losses and
+    parameters as the oracle's calculate_advantages + ppo_train (fp32, 1e-5), and bit-identical to each other."""
+    N, T, D, A, B, E = 8, 32, 11, 3, 64, 2
+    roll = O.synthetic_rollout(N, T, D, A, seed=21)
+    g = torch.Generator().manual_seed(4)
+    perms = torch.stack([torch.randperm(N * T, generator=g) for _ in range(E)])
+    results = []
+    for pipelined in (False, True):
+        oracle, agent, run = make_pair(D, A, [32, 24], [32, 24], "tanh", batch=B, epochs=E, n_envs=N, steps=T, seed=9, max_batch=128)
+        with torch.no_grad():
+            mean, std = oracle.networks["actor"](roll["current_state"].reshape(N * T, D))
+            logp = torch.distributions.Normal(mean, std).log_prob(roll["action"].reshape(N * T, A)).sum(1)
+        losses = _host_update(agent, roll, logp, perms, B, E, pipelined)
+        results.append((losses, agent.engine.flat.clone()))
+        adv, tgt = O.calculate_advantages(roll["reward"], roll["current_state_value"], roll["next_state_value"], roll["terminated"], 0.99, 0.98)
+        fm = {"current_state": roll["current_state"].reshape(N * T, D), "action": roll["action"].reshape(N * T, A), "action_log_prob": logp,
+              "advantage": adv.reshape(-1, 1), "current_state_value_target": tgt.reshape(-1, 1)}
+        ref_losses = np.array(O.ppo_train(oracle, fm, list(perms)))
+        np.testing.assert_allclose(losses.numpy(), ref_losses, rtol=1e-5, atol=1e-6)
+        for k, v in agent.networks.state_dict().items():
+            ref = oracle.networks.state_dict()[k]
+            assert (v.cpu() - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1e-3) + 2e-6, k
+    assert torch.equal(results[0][0], results[1][0]) and torch.equal(results[0][1], results[1][1])
