@@ -258,10 +258,11 @@ def c5_sweep(pk, world=1, rank=0):
         r, v, vn = (torch.randn(nl, t, 1, device=dev) for _ in range(3))
         term = torch.rand(nl, t, device=dev) < 0.01
         med, _ = cuda_time(lambda: pkg.calculate_advantages(r, v, vn, term, 0.99, 0.98), 10)
-        m = nl * t
+        del r, v, vn, term
+        m = min(nl * t, 4 * 1024 * 1024)  # the gather's tables are 1.5 KB per row: at most 4 M rows (13 GB in + out) per rank
         obs, act, s1 = torch.randn(m, OBS_DIM, device=dev), torch.randn(m, ACT_DIM, device=dev), torch.randn(m, device=dev)
         idx = torch.randperm(m, device=dev)
-        medg, _ = cuda_time(lambda: pkg.gather_minibatch(idx, obs, act, s1, s1, s1, check=False), 5 if m > 4e6 else 10)
+        medg, _ = cuda_time(lambda: pkg.gather_minibatch(idx, obs, act, s1, s1, s1, check=False), 5 if m > 2e6 else 10)
         if world > 1:
             tt = torch.tensor([med, medg], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -271,9 +272,11 @@ def c5_sweep(pk, world=1, rank=0):
         l2 = (gby / world) < 100e6
         pts.append({"envs": n, "steps": t, "n_gpus": world, "gae_ms": med, "gae_GBps": gby / 1e9 / (med * 1e-3),
                     "gae_frac_hbm": gby / 1e9 / (med * 1e-3) / (pk["hbm"] * world),
-                    "gather_ms": medg, "gather_GBps": gaby / 1e9 / (medg * 1e-3), "gather_frac_hbm": gaby / 1e9 / (medg * 1e-3) / (pk["hbm"] * world),
+                    "gather_rows_per_gpu": m, "gather_ms": medg, "gather_GBps": gaby / 1e9 / (medg * 1e-3),
+                    "gather_frac_hbm": gaby / 1e9 / (medg * 1e-3) / (pk["hbm"] * world),
                     "note": "GAE working set fits L2" if l2 else ""})
-        del r, v, vn, term, obs, act, s1, idx
+        del obs, act, s1, idx
+        torch.cuda.empty_cache()
     return pts
 
 
