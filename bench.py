@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 OBS_DIM, ACT_DIM, HIDDEN = 376, 17, [256, 256]
-TRAFFIC_BF16_B32768 = None  # filled in from profiles/r02_ncu_chain_wgrad_B32768.csv
+TRAFFIC_BF16_B32768 = 294.4e6  # 123.4 MB (tc_chain_kernel) + 171.0 MB (tc_wgrad2_kernel), profiles/r02_ncu_chain_wgrad_B32768.csv
 
 
 def peaks():
