@@ -58,6 +58,23 @@ adam_kernel(float* __restrict__ params, const float* __restrict__ grads, int n_p
   }
 }
 
+// g += grads[k][4i .. 4i+3] for k in [k0, n_partials), in index order (deterministic) — with the loads of up to eight
+// partials ISSUED before the first add.  Written as load-add-load-add (the first version) the compiler kept that order,
+// and the 9 split-K partials of the bench shape cost 9 dependent L2 round trips: 47 % of this kernel's stall samples sat
+// on those adds (profiles/r02_ncu_chain_wgrad_B32768.csv, 14.7 us for 329 k parameters).
+__device__ __forceinline__ void add_partials(float4& g, const float* __restrict__ grads, int k0, int n_partials, int64_t partial_stride, int64_t i) {
+  constexpr int NB = 8;  // + the first partial read by the caller = the 9 of the bench shape in one round; 85 registers keep the grid in one wave
+  for (; k0 < n_partials; k0 += NB) {
+    float4 h[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (k0 + j < n_partials) h[j] = __ldg(reinterpret_cast<const float4*>(grads + int64_t(k0 + j) * partial_stride + 4 * i));
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (k0 + j < n_partials) { g.x += h[j].x; g.y += h[j].y; g.z += h[j].z; g.w += h[j].w; }
+  }
+}
+
 struct CastTable {
   int64_t begin[2 * B200PPO_MAX_LAYERS], end[2 * B200PPO_MAX_LAYERS];  // element range of each matrix in the flat buffer
   __nv_bfloat16* dst[2 * B200PPO_MAX_LAYERS];
@@ -117,7 +134,7 @@ __device__ __forceinline__ float4 ld_peer4(const float* p) {  // peer memory: ne
 // PEERS: the gradient is the rank-ordered sum of every rank's exchange buffer (multi-GPU); kept out of the single-GPU
 // instantiation, whose register count (64) sets its occupancy.
 template <bool PEERS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, int n_partials, int64_t partial_stride,
                  float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t n, int64_t seg_split, AdamScalars s0,
                  AdamScalars s1, const __grid_constant__ CastTable ct, const __grid_constant__ LossCombine lc,
@@ -162,18 +179,7 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
       g = *reinterpret_cast<const float4*>(grads + 4 * i);
     }
     int k0 = PEERS ? n_partials : 1;
-    for (; k0 + 3 < n_partials; k0 += 4) {  // partials are added in index order (deterministic)
-      const float4 h0 = *reinterpret_cast<const float4*>(grads + (k0 + 0) * partial_stride + 4 * i);
-      const float4 h1 = *reinterpret_cast<const float4*>(grads + (k0 + 1) * partial_stride + 4 * i);
-      const float4 h2 = *reinterpret_cast<const float4*>(grads + (k0 + 2) * partial_stride + 4 * i);
-      const float4 h3 = *reinterpret_cast<const float4*>(grads + (k0 + 3) * partial_stride + 4 * i);
-      g.x = (((g.x + h0.x) + h1.x) + h2.x) + h3.x; g.y = (((g.y + h0.y) + h1.y) + h2.y) + h3.y;
-      g.z = (((g.z + h0.z) + h1.z) + h2.z) + h3.z; g.w = (((g.w + h0.w) + h1.w) + h2.w) + h3.w;
-    }
-    for (; k0 < n_partials; ++k0) {
-      const float4 h = *reinterpret_cast<const float4*>(grads + k0 * partial_stride + 4 * i);
-      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
-    }
+    add_partials(g, grads, k0, n_partials, partial_stride, i);
     if (lc_owner && 4 * i + 3 >= lc.logstd_off && 4 * i < lc.logstd_off + lc.act_dim) {
       const int64_t r = 4 * i - lc.logstd_off;
       if (r + 0 >= 0 && r + 0 < lc.act_dim) g.x = s_lc[2 + r + 0];
@@ -238,19 +244,7 @@ reduce_partials_kernel(const float* __restrict__ grads, int n_partials, int64_t 
   if (lc_owner) combine_losses(lc, s_lc, s_scr);
   for (int64_t i = tid; i < n4; i += nthreads) {
     float4 g = *reinterpret_cast<const float4*>(grads + 4 * i);
-    int k0 = 1;
-    for (; k0 + 3 < n_partials; k0 += 4) {
-      const float4 h0 = *reinterpret_cast<const float4*>(grads + (k0 + 0) * partial_stride + 4 * i);
-      const float4 h1 = *reinterpret_cast<const float4*>(grads + (k0 + 1) * partial_stride + 4 * i);
-      const float4 h2 = *reinterpret_cast<const float4*>(grads + (k0 + 2) * partial_stride + 4 * i);
-      const float4 h3 = *reinterpret_cast<const float4*>(grads + (k0 + 3) * partial_stride + 4 * i);
-      g.x = (((g.x + h0.x) + h1.x) + h2.x) + h3.x; g.y = (((g.y + h0.y) + h1.y) + h2.y) + h3.y;
-      g.z = (((g.z + h0.z) + h1.z) + h2.z) + h3.z; g.w = (((g.w + h0.w) + h1.w) + h2.w) + h3.w;
-    }
-    for (; k0 < n_partials; ++k0) {
-      const float4 h = *reinterpret_cast<const float4*>(grads + k0 * partial_stride + 4 * i);
-      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
-    }
+    add_partials(g, grads, 1, n_partials, partial_stride, i);
     if (lc_owner && 4 * i + 3 >= lc.logstd_off && 4 * i < lc.logstd_off + lc.act_dim) {
       const int64_t r = 4 * i - lc.logstd_off;
       if (r + 0 >= 0 && r + 0 < lc.act_dim) g.x = s_lc[2 + r + 0];
