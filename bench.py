@@ -35,6 +35,16 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout when the
+# environment says NCCL_DEBUG=VERSION, which is left as the launcher set it): file descriptor 1 is pointed at stderr for
+# the run and the JSON line goes to the saved original.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 
 OBS_DIM, ACT_DIM, HIDDEN = 376, 17, [256, 256]
 TRAFFIC_BF16_B32768 = 294.4e6  # 123.4 MB (tc_chain_kernel) + 171.0 MB (tc_wgrad2_kernel), profiles/r02_ncu_chain_wgrad_B32768.csv
@@ -226,7 +236,7 @@ def run_reference(args, config):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "per_step_values": vals, "ms_per_step_note": "time of a full step (1 advantage pass + all epochs) at the measured rate"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -722,7 +732,7 @@ def run_b200(args, config):
             if v["minibatch"] == B:
                 by_prec[v["gemm"]] = {"value": v["value"], "e2e": v.get("e2e", {}).get("value")}
         line["headline_by_precision"] = by_prec
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

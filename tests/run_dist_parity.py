@@ -22,6 +22,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     precision = sys.argv[1] if len(sys.argv) > 1 else "fp32"
     n_local, T, Dm, A, H, GB = 64, 32, 40, 6, [64, 64], 512
+    if len(sys.argv) > 2 and sys.argv[2] == "chain":  # 256-wide nets: every rank's slice of a minibatch goes through tc_chain_kernel
+        n_local, T, Dm, A, H, GB = 128, 32, 120, 6, [256, 256], 2048
     N = n_local * world
     M = N * T
 
