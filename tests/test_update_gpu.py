@@ -9,7 +9,7 @@ from oracle import ppo_oracle as O
 import copy
 
 from tests._util import (RTOL_BF16, RTOL_FP32, assert_close, assert_close_l2, assert_params_close, load_golden,
-                         sub)
+                         rel_l2, sub)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -289,19 +289,30 @@ def test_bf16_train_vs_oracle(shape):
     got = algo.last_losses.cpu().numpy()
     np.testing.assert_allclose(got, np.array(ref_losses), rtol=RTOL_BF16, atol=2e-3)
     ref_sd = oracle.networks.state_dict()
+    lr, steps = oracle.cfg.learning_rate, max_mb
+    print()
     for k, v in agent.networks.state_dict().items():
-        # zero-initialised biases are still O(lr) after two steps: their Adam step is sign(g)-like on entries whose
-        # gradient is bf16 rounding noise, so the first moments (below) are the meaningful comparison for them
-        if ref_sd[k].abs().max().item() > 1e-2:
-            assert_close_l2(v, ref_sd[k], RTOL_BF16, f"bf16 param {k}")
-    # ReLU: units whose pre-activation is within bf16 rounding of zero flip their gate, which switches that unit's
-    # whole per-sample gradient on or off; the actor's gradient is a heavily cancelling sum, so those flips show up
-    # at the ~5e-2 level in the first moments even though losses and parameters agree to 2e-2.
-    mom_tol = 1e-1 if shape.get("act") == "relu" else 1.5 * RTOL_BF16
+        e = rel_l2(v, ref_sd[k])
+        print(f"  bf16 param {k:48s} rel L2 err {e:.3e}  (max |ref| {ref_sd[k].abs().max().item():.2e})")
+        if ref_sd[k].abs().max().item() > 4 * lr * steps:
+            assert e <= RTOL_BF16, f"bf16 param {k}: relative L2 error {e:.3e} > {RTOL_BF16:.1e}"
+        else:
+            # A tensor that was zero-initialised (hidden biases, network_block_creator.py:51-52) consists, after two steps,
+            # of nothing but Adam's own first steps, and the first step of Adam is -lr * sign(g) whatever |g| is: every
+            # entry whose gradient is smaller than the bf16 GEMMs' rounding noise has an arbitrary sign in BOTH
+            # implementations.  With a fraction f of such entries the tensor's relative L2 error is ~2 sqrt(f) (measured
+            # 0.05-0.3 here, f ~ 0.1-2 %) — not an arithmetic error, and bounded by the step size per entry:
+            assert (v.cpu() - ref_sd[k]).abs().max().item() <= 2.0 * lr * steps * 1.001, k
+    # the gradients themselves (first moments after two steps) hold north_star's 2e-2 on every tensor.  ReLU: units whose
+    # pre-activation is within bf16 rounding of zero flip their gate, which switches that unit's whole per-sample gradient
+    # on or off (measured 4-6e-2 on the first-layer tensors, tests/test_chain_gpu.py): 1e-1 there.
+    mom_tol = 1e-1 if shape.get("act") == "relu" else RTOL_BF16
     for oname, opt in agent.optimizers.items():
         ref_state = oracle.optimizers[oname].state_dict()["state"]
         for pid, st in opt.state_dict()["state"].items():
-            assert_close_l2(st["exp_avg"], ref_state[pid]["exp_avg"], mom_tol, f"bf16 {oname}/{pid}/exp_avg")
+            e = rel_l2(st["exp_avg"], ref_state[pid]["exp_avg"])
+            print(f"  bf16 {oname}/{pid}/exp_avg rel L2 err {e:.3e}")
+            assert e <= mom_tol, f"bf16 {oname}/{pid}/exp_avg: relative L2 error {e:.3e} > {mom_tol:.1e}"
             assert float(st["step"]) == float(ref_state[pid]["step"])
 
 
