@@ -19,6 +19,10 @@ Contents
   dependencies and write its outputs to `tests/golden/*.npz`.  These two only run in
   the build container (the GPU box has no `/root/reference`); the fixtures travel.
 
+* `build_ref.py` + `ref_runner.py` — stage the reference's own sources VERBATIM under `oracle/_ref` (git-ignored; travels
+  to the GPU box with the snapshot) and run its `PPO.calculate_advantages` / `PPO.train` behind the shims: the timed CPU
+  arm of `bench.py` (`cpu_baseline.kind == "reference"`).
+
 Parity pinning status
 ---------------------
 * `PPO.calculate_advantages` pre/post-processing and `PPO.train` (forward, losses,
