@@ -108,6 +108,13 @@ __device__ __forceinline__ bool peer_exchange_barrier(const PeerSrc& ps) {
   int timed_out = 0;
   if (q < ps.world && q != ps.rank) {
     if (blockIdx.x == 0) {
+      if (ps.local_out != nullptr) {  // fused reduce: this rank's buffer is complete once every block of this grid has said so
+        const long long t0 = clock64();
+        unsigned d;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(d) : "l"(ps.done_counter) : "memory");
+        } while (int(d - ps.done_target) < 0 && clock64() - t0 <= ps.timeout_cycles);
+      }
       __threadfence_system();
       asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ps.flags_peer[q] + ps.rank), "r"(ps.seq) : "memory");
     }
@@ -142,7 +149,36 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
   __shared__ float s_lc[64];
   __shared__ float s_scr[256];
   pdl_wait_then_release();  // the gradient partials come from the kernel right before this one (common.cuh, PDL)
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  const int64_t n4 = n >> 2;  // the flat buffer is padded to a multiple of 32 elements
+  // the block whose grid-stride chunks contain actor_logstd finishes the loss partials (before anything is updated)
+  const bool lc_owner = lc.partials != nullptr && int64_t(blockIdx.x) == ((lc.logstd_off >> 2) / blockDim.x) % gridDim.x;
+  if (lc_owner) combine_losses(lc, s_lc, s_scr);
+  float4 g_local = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool fused = false;
   if constexpr (PEERS) {
+    fused = ps.local_out != nullptr;
+    if (fused) {
+      // Fused reduce (one element per thread): this rank's split-K partials are summed HERE, in index order, into its
+      // exchange buffer — the separate reduction launch in front of the exchange (11-13 us per minibatch) is gone.  Every
+      // block counts itself done; block 0 raises this rank's flag at the peers only when all have (see the barrier).
+      if (tid < n4) {
+        g_local = __ldg(reinterpret_cast<const float4*>(grads + 4 * tid));
+        add_partials(g_local, grads, 1, n_partials, partial_stride, tid);
+        if (lc_owner && 4 * tid + 3 >= lc.logstd_off && 4 * tid < lc.logstd_off + lc.act_dim) {
+          const int64_t r = 4 * tid - lc.logstd_off;
+          if (r + 0 >= 0 && r + 0 < lc.act_dim) g_local.x = s_lc[2 + r + 0];
+          if (r + 1 >= 0 && r + 1 < lc.act_dim) g_local.y = s_lc[2 + r + 1];
+          if (r + 2 >= 0 && r + 2 < lc.act_dim) g_local.z = s_lc[2 + r + 2];
+          if (r + 3 >= 0 && r + 3 < lc.act_dim) g_local.w = s_lc[2 + r + 3];
+        }
+        *reinterpret_cast<float4*>(ps.local_out + 4 * tid) = g_local;
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(ps.done_counter, 1u);
+    }
     if (!peer_exchange_barrier(ps)) return;  // no update from stale peer data; the host sees the flag
     if (blockIdx.x == 0 && threadIdx.x < 2 && ps.losses_out != nullptr) {
       float l = 0.f;
@@ -154,12 +190,6 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
       ps.losses_out[threadIdx.x] = l;
     }
   }
-  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
-  const int64_t n4 = n >> 2;  // the flat buffer is padded to a multiple of 32 elements
-  // the block whose grid-stride chunks contain actor_logstd finishes the loss partials (before anything is updated)
-  const bool lc_owner = lc.partials != nullptr && int64_t(blockIdx.x) == ((lc.logstd_off >> 2) / blockDim.x) % gridDim.x;
-  if (lc_owner) combine_losses(lc, s_lc, s_scr);
   for (int64_t i = tid; i < n4; i += nthreads) {
     // every load of this element is issued before the first use: the kernel is one L2 round trip deep, not n_partials
     const float4 p0 = *reinterpret_cast<float4*>(params + 4 * i);
@@ -170,7 +200,7 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
       float4 h[kMaxPeers];
 #pragma unroll
       for (int r = 0; r < kMaxPeers; ++r)
-        if (r < ps.world) h[r] = ld_peer4(ps.src[r] + 4 * i);
+        if (r < ps.world) h[r] = (fused && r == ps.rank) ? g_local : ld_peer4(ps.src[r] + 4 * i);  // own sum: still in the register
       g = h[0];
 #pragma unroll
       for (int r = 1; r < kMaxPeers; ++r)
@@ -178,9 +208,8 @@ adam_cast_kernel(float* __restrict__ params, const float* __restrict__ grads, in
     } else {
       g = *reinterpret_cast<const float4*>(grads + 4 * i);
     }
-    int k0 = PEERS ? n_partials : 1;
-    add_partials(g, grads, k0, n_partials, partial_stride, i);
-    if (lc_owner && 4 * i + 3 >= lc.logstd_off && 4 * i < lc.logstd_off + lc.act_dim) {
+    if constexpr (!PEERS) add_partials(g, grads, 1, n_partials, partial_stride, i);
+    if (!PEERS && lc_owner && 4 * i + 3 >= lc.logstd_off && 4 * i < lc.logstd_off + lc.act_dim) {
       const int64_t r = 4 * i - lc.logstd_off;
       if (r + 0 >= 0 && r + 0 < lc.act_dim) g.x = s_lc[2 + r + 0];
       if (r + 1 >= 0 && r + 1 < lc.act_dim) g.y = s_lc[2 + r + 1];
@@ -292,6 +321,8 @@ int launch_adam(float* params, const float* grads, int n_partials, int64_t parti
   return B200PPO_OK;
 }
 
+int adam_cast_grid(int64_t n) { return int(ew_grid(n / 4)); }
+
 int launch_adam_cast(float* params, const float* grads, int n_partials, int64_t partial_stride, float* exp_avg,
                      float* exp_avg_sq, int64_t n, int64_t seg_split, const AdamScalars& s0, const AdamScalars& s1,
                      const WeightCastGroup& casts, const LossCombine& lc, cudaStream_t st, const PeerSrc* peers) {
@@ -309,6 +340,8 @@ int launch_adam_cast(float* params, const float* grads, int n_partials, int64_t 
     ct.dst[k] = w.dst; ct.dst_t[k] = w.dst_t;
     ct.in[k] = w.in; ct.pitch[k] = w.pitch; ct.pitch_t[k] = w.pitch_t;
   }
+  B2_CHECK_ARG(peers == nullptr || peers->local_out == nullptr || int64_t(ew_grid(n / 4)) * 256 >= n / 4,
+               "fused reduce + exchange: one element per thread");
   if (peers != nullptr && peers->world > 0)
     B2_CUDA(launch_pdl(adam_cast_kernel<true>, dim3(ew_grid(n / 4)), dim3(256), 0, st, params, grads, n_partials, partial_stride, exp_avg,
                        exp_avg_sq, n, seg_split, s0, s1, ct, lc, *peers));

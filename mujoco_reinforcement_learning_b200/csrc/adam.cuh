@@ -46,6 +46,12 @@ struct PeerSrc {
   int32_t* err = nullptr;                // raised to B200PPO_ERRFLAG_PEER_TIMEOUT when a peer does not show up in time
   long long timeout_cycles = 0;          // SM clocks to wait for a peer's flag (b200ppo_train: B200PPO_PEER_TIMEOUT_MS, default 30 s)
   float* losses_out = nullptr;           // [2] = sum over ranks of src[p][n + {0, 1}]
+  // fused reduce (local_out != nullptr): the kernel's `grads` are this rank's split-K partials; it sums them into
+  // local_out (= src[rank]) itself, and block 0 raises the flag once done_counter has reached done_target (every block
+  // of the grid adds 1 per launch: the host passes launches * grid)
+  float* local_out = nullptr;
+  unsigned* done_counter = nullptr;
+  unsigned done_target = 0;
 };
 
 // Same update, and in the same pass the bf16 shadow copies of the hidden/output weight matrices that the tensor-core
@@ -54,6 +60,8 @@ struct PeerSrc {
 int launch_adam_cast(float* params, const float* grads, int n_partials, int64_t partial_stride, float* exp_avg,
                      float* exp_avg_sq, int64_t n, int64_t seg_split, const AdamScalars& s0, const AdamScalars& s1,
                      const WeightCastGroup& casts, const LossCombine& lc, cudaStream_t st, const PeerSrc* peers = nullptr);
+
+int adam_cast_grid(int64_t n);  // blocks launch_adam_cast uses for n parameters
 
 int launch_reduce_partials(const float* grads, int n_partials, int64_t partial_stride, int64_t n, float* out,
                            cudaStream_t st, const LossCombine* lc = nullptr);

@@ -121,6 +121,8 @@ struct b200ppo_ctx {
   float* loss_partials = nullptr;
   int64_t loss_partial_rows = 0;
   unsigned* ticket = nullptr;
+  unsigned* done_counter = nullptr;  // fused reduce of the peer exchange: blocks of the optimizer grid that have written their slice (monotone)
+  unsigned done_total = 0;           // what that counter reaches after the launches issued so far
   float* scratch = nullptr;     // [8] losses / entropy scratch
   int32_t* err_flag = nullptr;
   // shuffled-epoch buffers (train)
@@ -845,6 +847,7 @@ extern "C" B2_EXPORT int b200ppo_create(const b200ppo_mlp_desc* actor, const b20
   c->loss_partial_rows = std::max<int64_t>(std::max(loss_grid_size(Bm), 8 * num_sms()), 2 * ((Bm + 127) / 128) + 8);
   if (r == B200PPO_OK) r = dev_alloc(&c->loss_partials, c->loss_partial_rows * (2 + c->net[0].out_dim()), true);
   if (r == B200PPO_OK) r = dev_alloc(&c->ticket, 1, true);
+  if (r == B200PPO_OK) r = dev_alloc(&c->done_counter, 1, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->scratch, 8, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->err_flag, 1, true);
   if (r == B200PPO_OK && precision == B200PPO_PREC_BF16) r = alloc_bf16_workspaces(c);
@@ -857,7 +860,7 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   if (!c) return;
   cudaDeviceSynchronize();
   for (int n = 0; n < 2; ++n) { dev_free(c->ws_act[n]); dev_free(c->ws_dz[n]); dev_free(c->ws_out[n]); }
-  dev_free(c->gpart); dev_free(c->grad_flat); dev_free(c->loss_partials); dev_free(c->ticket); dev_free(c->scratch);
+  dev_free(c->gpart); dev_free(c->grad_flat); dev_free(c->loss_partials); dev_free(c->ticket); dev_free(c->done_counter); dev_free(c->scratch);
   dev_free(c->err_flag);
   for (int n = 0; n < 2; ++n)
     for (int l = 0; l < B200PPO_MAX_LAYERS; ++l) { dev_free(c->bf.H[n][l]); dev_free(c->bf.dZ[n][l]); dev_free(c->bf.W[n][l]); dev_free(c->bf.WT[n][l]); }
@@ -1125,7 +1128,12 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
         B2_TRY(minibatch_fwd_bwd(ctx, params, nullptr, ctx->bf.sh_obs + r0 * PX, ctx->sh_act + r0 * A, ctx->sh_logp + r0,
                                  ctx->sh_adv + r0, ctx->sh_tgt + r0, lb, hp, red_losses, &split, &loss_ctas, st));
         const LossCombine lc = make_loss_combine(ctx, params, loss_ctas, lb, hp, red_losses);
-        PROF(ctx, B200PPO_PROF_OTHER, st, launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, xb, st, &lc));
+        // the sum of this rank's split-K partials into its exchange buffer happens inside the optimizer kernel (one
+        // element per thread); B200PPO_P2P_FUSED_REDUCE=0 keeps the separate launch in front of it
+        static const bool fused_env = []() { const char* e = getenv("B200PPO_P2P_FUSED_REDUCE"); return !(e != nullptr && e[0] == '0'); }();
+        const int agrid = adam_cast_grid(ctx->n_params);
+        const bool fused = fused_env && loss_ctas > 0 && int64_t(agrid) * 256 >= ctx->n_params / 4;
+        if (!fused) PROF(ctx, B200PPO_PROF_OTHER, st, launch_reduce_partials(ctx->gpart, split, ctx->n_params, ctx->n_params, xb, st, &lc));
         PeerSrc ps{};
         ps.world = ctx->world; ps.rank = ctx->rank; ps.seq = seq; ps.err = ctx->err_flag; ps.losses_out = loss_slot;
         static const long long timeout_ms = []() { const char* e = getenv("B200PPO_PEER_TIMEOUT_MS"); return e ? atoll(e) : 30000ll; }();
@@ -1136,9 +1144,19 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
           ps.src[r] = ctx->peer_x[r] + xo;
           ps.flags_peer[r] = reinterpret_cast<unsigned*>(ctx->peer_x[r] + 2 * ctx->xstride);
         }
-        PROF(ctx, B200PPO_PROF_ADAM, st,
-             launch_adam_cast(params, xb, 1, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa, sc,
-                              cast_group(ctx, params), LossCombine{}, st, &ps));
+        if (fused) {
+          ps.local_out = xb;
+          ps.done_counter = ctx->done_counter;
+          ctx->done_total += unsigned(agrid);
+          ps.done_target = ctx->done_total;
+          PROF(ctx, B200PPO_PROF_ADAM, st,
+               launch_adam_cast(params, ctx->gpart, split, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa, sc,
+                                cast_group(ctx, params), lc, st, &ps));
+        } else {
+          PROF(ctx, B200PPO_PROF_ADAM, st,
+               launch_adam_cast(params, xb, 1, ctx->n_params, exp_avg, exp_avg_sq, ctx->n_params, ctx->n_actor, sa, sc,
+                                cast_group(ctx, params), LossCombine{}, st, &ps));
+        }
       } else {
         float* red_losses = ctx->grad_flat + ctx->n_params;
         B2_TRY(minibatch_fwd_bwd(ctx, params, tc ? nullptr : ctx->sh_obs + r0 * D, tc ? ctx->bf.sh_obs + r0 * PX : nullptr,
