@@ -28,12 +28,16 @@ constexpr int WG2_ONES_BYTES = 4096;
 
 struct Wg2Tile {
   int prob, m0, n0, nw, bias;  // nw: MMA N of this block (128 or 256); bias: this block also produces db
+  // split-K of THIS block: the blocks stream different byte counts per k-tile (a 256 x 256 block 64 KB per pair, a
+  // 256 x 128 one 48 KB, the 17-row output-layer block 33 KB), and the kernel is bound by that stream, so the batch is
+  // cut into more pieces for the heavier blocks; pairs [pair_begin, pair_begin + splits) work on this block
+  int pair_begin, splits, k_tiles_per_split;
 };
 
 struct Wg2Group {
   TcProblem p[kMaxTcProblems];
   Wg2Tile tile[kWg2MaxTiles];
-  int count, n_tiles, splits, k_tiles_per_split;
+  int count, n_tiles, max_splits;  // max_splits: partial slots the consumer sums; blocks with fewer splits zero-fill the rest
 };
 
 __device__ __forceinline__ uint32_t wg2_ctarank() {
@@ -86,12 +90,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_wg
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = wg2_ctarank();
   const int pair = int(blockIdx.x) >> 1;
-  const int ti = pair % grp.n_tiles, split = pair / grp.n_tiles;
+  int ti = 0;
+#pragma unroll 1
+  for (int i = 1; i < grp.n_tiles; ++i)
+    if (pair >= grp.tile[i].pair_begin) ti = i;
   const Wg2Tile T = grp.tile[ti];
+  const int split = pair - T.pair_begin;
   const TcProblem& P = grp.p[T.prob];
   const int total_kt = (P.K + TC_BK - 1) / TC_BK;
-  const int kt_begin = split * grp.k_tiles_per_split;
-  const int kt_end = min(total_kt, kt_begin + grp.k_tiles_per_split);
+  const int kt_begin = split * T.k_tiles_per_split;
+  const int kt_end = min(total_kt, kt_begin + T.k_tiles_per_split);
   const bool has_k = kt_end > kt_begin;
   const int nw_half = T.nw >> 1;  // H columns staged by each CTA
   const uint32_t stage_tx = 2u * uint32_t(TC_A_BYTES + nw_half * TC_BK * 2);
@@ -198,6 +206,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_wg
       }
       if (row_ok) P.bias_grad[int64_t(split) * P.split_stride + m] = __uint_as_float(v[0]);
     }
+    // the consumer sums grp.max_splits partial slots: the ones this block has no split for are zero-filled by its pairs
+    for (int z = split + T.splits; z < grp.max_splits; z += T.splits) {
+      if (!row_ok) break;
+      float* zp = P.out_f32 + int64_t(z) * P.split_stride + int64_t(m) * P.ld_f32;
+      for (int c = c_begin; c < c_end; c += 4) {
+        const int n = T.n0 + c;
+        if (n >= P.N) break;
+        if (vec && n + 4 <= P.N) *reinterpret_cast<float4*>(zp + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else
+          for (int j = 0; j < 4; ++j)
+            if (n + j < P.N) zp[n + j] = 0.f;
+      }
+      if (T.bias && half == 0 && P.bias_grad != nullptr) P.bias_grad[int64_t(z) * P.split_stride + m] = 0.f;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -231,19 +253,61 @@ int launch_tc_wgrad2(const TcGroup& g, int max_split, cudaStream_t st, int* spli
   if (w.n_tiles == 0) return B200PPO_OK;
   const int total_kt = int((K + TC_BK - 1) / TC_BK);
   const int pairs = num_sms() / 2;
-  int split = std::max(1, std::min({pairs / w.n_tiles, max_split, total_kt}));
-  w.k_tiles_per_split = (total_kt + split - 1) / split;
-  split = (total_kt + w.k_tiles_per_split - 1) / w.k_tiles_per_split;  // no empty trailing splits
-  w.splits = split;
+  // bytes a pair streams per k-tile for every block (rows / columns past the matrix are zero-filled without traffic)
+  double weight[kWg2MaxTiles], wsum = 0.0;
+  for (int t = 0; t < w.n_tiles; ++t) {
+    const Wg2Tile& T = w.tile[t];
+    const TcProblem& p = w.p[T.prob];
+    const int rows = std::min(2 * TC_BM, p.M - T.m0), cols = std::min(T.nw, p.N - T.n0);
+    weight[t] = double(rows + cols) * TC_BK * 2 + 2048.0;  // + a little for the per-k-tile fixed cost
+    wsum += weight[t];
+  }
+  // Measured (profiles/README.md, round 2): splits in proportion to the bytes a block streams are SLOWER than the same
+  // split for every block (8.28 vs 7.07 ms per 160 launches) — with a common split all blocks walk the batch in step, so
+  // the operands two blocks share (dZ1 of the two dW1 blocks, every k-tile of X / H) meet in L2.  Uniform is the default;
+  // B200PPO_WGRAD_UNIFORM=0 selects the weighted split.
+  static const char* uni_env = getenv("B200PPO_WGRAD_UNIFORM");
+  const bool uniform = !(uni_env != nullptr && uni_env[0] == '0');
+  const char* uni = uniform ? "1" : nullptr;
+  int used = 0, max_sp = 1;
+  for (int t = 0; t < w.n_tiles; ++t) {
+    int sp = (uni != nullptr && uni[0] == '1') ? pairs / w.n_tiles : int(pairs * weight[t] / wsum);
+    sp = std::max(1, std::min({sp, max_split, total_kt}));
+    w.tile[t].splits = sp;
+    used += sp;
+  }
+  // hand the pairs the rounding left over to the blocks with the most bytes per pair
+  while (used < pairs && !(uni != nullptr && uni[0] == '1')) {
+    int best = -1;
+    double worst = 0.0;
+    for (int t = 0; t < w.n_tiles; ++t) {
+      const double per_pair = weight[t] / w.tile[t].splits;
+      if (w.tile[t].splits < std::min(max_split, total_kt) && per_pair > worst) { worst = per_pair; best = t; }
+    }
+    if (best < 0) break;
+    ++w.tile[best].splits;
+    ++used;
+  }
+  int begin = 0;
+  for (int t = 0; t < w.n_tiles; ++t) {
+    Wg2Tile& T = w.tile[t];
+    T.k_tiles_per_split = (total_kt + T.splits - 1) / T.splits;
+    T.splits = (total_kt + T.k_tiles_per_split - 1) / T.k_tiles_per_split;  // no empty trailing splits
+    T.pair_begin = begin;
+    begin += T.splits;
+    max_sp = std::max(max_sp, T.splits);
+  }
+  w.max_splits = max_sp;
+  const int total_pairs = begin;
   constexpr int smem = 1024 + WG2_STAGES * WG2_STAGE_BYTES + WG2_ONES_BYTES + 256;
   static bool configured = false;
   if (!configured) {
     B2_CUDA(cudaFuncSetAttribute(tc_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  B2_CUDA(launch_pdl(tc_wgrad2_kernel, dim3(2 * w.n_tiles * split), dim3(TC_THREADS), smem, st, w));
+  B2_CUDA(launch_pdl(tc_wgrad2_kernel, dim3(2 * total_pairs), dim3(TC_THREADS), smem, st, w));
   B2_LAUNCH_CHECK();
-  if (split_out) *split_out = split;
+  if (split_out) *split_out = max_sp;
   return B200PPO_OK;
 }
 
