@@ -140,6 +140,7 @@ struct b200ppo_ctx {
   int64_t shared_rows = 0;   // rows of every rank's table; 0 = tables not shared
   bool shared_filled = false;
   bool perm_rank_slices = false;  // b200ppo_set_perm_layout: `perms` holds only this rank's slots
+  bool in_epoch = false;          // inside b200ppo_train's minibatch loop: the minibatch operands predate the previous kernel
   unsigned p2p_seq = 0;
   cudaStream_t gather_stream = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
@@ -626,7 +627,7 @@ static bool chain_applicable(const b200ppo_ctx* ctx) {
 
 static int launch_chain(b200ppo_ctx* ctx, const float* params, const __nv_bfloat16* xb, int64_t B, const float* action,
                         const float* old_logp, const float* adv, const float* tgt, const b200ppo_hparams* hp, int* loss_ctas,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool x_early) {
   auto& bf = ctx->bf;
   ChainArgs a{};
   const int D = ctx->net[0].d.in_dim;
@@ -660,6 +661,7 @@ static int launch_chain(b200ppo_ctx* ctx, const float* params, const __nv_bfloat
   a.KB1 = (D + TC_CHAIN_BK - 1) / TC_CHAIN_BK;
   a.act = ctx->net[0].d.activation;
   a.tiles2 = int((B + 255) / 256);
+  a.x_early = x_early ? 1 : 0;
   a.trace = g_chain_trace;
   return launch_tc_chain(a, st, loss_ctas);
 }
@@ -695,7 +697,7 @@ static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float*
     // tcgen05 everywhere: forward (L launches; PPO loss fused into the output layers' epilogue), dgrads (L-1), wgrads (1)
     if (chain_applicable(ctx)) {  // one launch: forward, losses, dgrads (tc_chain.cu); then the weight gradients
       int grid = 0;
-      PROF(ctx, B200PPO_PROF_GEMM_FWD, st, launch_chain(ctx, params, obs_b, B, action, old_logp, adv, tgt, hp, &grid, st));
+      PROF(ctx, B200PPO_PROF_GEMM_FWD, st, launch_chain(ctx, params, obs_b, B, action, old_logp, adv, tgt, hp, &grid, st, ctx->in_epoch));
       *loss_ctas_out = grid;
       return backward_nets_bf16(ctx, obs_b, B, ctx->gpart, split_out, st, true);
     }
@@ -1100,6 +1102,10 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
     const int64_t so = int64_t(set) * cap;
     for (int64_t i = 0; i < nb; ++i) {
       const int64_t r0 = so + i * lb;
+      // from the second minibatch of an epoch on, the kernel in front of the chain kernel is this epoch's optimizer step
+      // and the minibatch's rows were gathered before it: the chain kernel may prefetch them across the PDL boundary
+      struct EpochFlag { bool& f; ~EpochFlag() { f = false; } } epoch_flag{ctx->in_epoch};
+      ctx->in_epoch = i > 0;
       float* loss_slot = losses_out ? losses_out + (int64_t(e) * nb + i) * 2 : ctx->scratch;
       int split = 1, loss_ctas = 0;
       ++step;

@@ -285,6 +285,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
   const uint32_t smem_base = smem_u32(smem);
   if ((smem_base & 1023u) != 0) __trap();  // the 128-byte swizzle atoms need it; there is no slack left to realign
 
+  if (warp == 0 && lane < 19) {  // the kernel walks nineteen tensor maps: fetch the descriptors before the first copy needs them
+    const CUtensorMap* tm = lane == 0 ? &a.x : nullptr;
+    if (lane >= 1 && lane < 11) {
+      const ChainNet& Np = a.net[(lane - 1) / 5];
+      const int w = (lane - 1) % 5;
+      tm = w == 0 ? &Np.w1 : (w == 1 ? &Np.w2k : (w == 2 ? &Np.w2m : (w == 3 ? &Np.w3k : &Np.w3m)));
+    } else if (lane >= 11) {
+      const ChainNet& Np = a.net[(lane - 11) / 4];
+      const int w = (lane - 11) % 4;
+      tm = w == 0 ? &Np.sH1 : (w == 1 ? &Np.sH2 : (w == 2 ? &Np.sZ1 : &Np.sZ2));
+    }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+  }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 18; ++i) mbar_init(&bars[i], 1);
     mbar_init(&epi_done[0], 2 * CH_EPI_WARPS);
@@ -299,6 +312,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // The observations of a minibatch were gathered before the epoch began — older than the previous kernel — so the
+  // producer may request its first tile's X k-blocks while that kernel (the optimizer) is still draining; the weights it
+  // has just re-cast are only touched after the wait (common.cuh, PDL rule 2).
+  const bool x_early = a.x_early != 0 && pair_local < tiles2;
+  if (warp == 0 && lane == 0 && x_early) {
+    const int m0 = pair_local * 256 + int(rank) * 128;
+    for (int kb = 0; kb < KB1; ++kb) {
+      if (rank == 0) mbar_expect_tx(&x_full[kb], 2u * CH_SLOT);
+      tma_load_2d_pair(smem + (CH_X0 + kb) * CH_SLOT, &a.x, mapa_u32(smem_u32(&x_full[kb]), 0), kb * TC_BK, m0);
+    }
+  }
   pdl_wait_then_release();  // the weights were re-cast by the optimizer kernel right before this one
 
   if (warp == 0) {
@@ -318,7 +342,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
         const uint32_t xph = uint32_t(ti & 1);
         for (int o = 0; o < 2; ++o)
           for (int kb = 0; kb < KB1; ++kb) {
-            if (o == 0) {
+            if (o == 0 && !(ti == 0 && x_early)) {
               if (kb == 0) mbar_wait(&x_free[0], xph ^ 1);
               if (kb == 2) mbar_wait(&x_free[1], xph ^ 1);
               if (rank == 0) mbar_expect_tx(&x_full[kb], 2u * CH_SLOT);

@@ -23,6 +23,7 @@ struct ChainArgs {
   TcPpo ppo;         // loss operands (dz_out / dz_pitch unused: seeds go to net[n].dZ3)
   float out_scale;
   int M, KB1, act, tiles2;
+  int x_early;       // the observations are older than the previous kernel of the stream: X may be requested before the PDL wait
   long long* trace;  // debug: clock64 timeline of pair 0 (nullptr in production)
 };
 
