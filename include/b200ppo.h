@@ -256,6 +256,13 @@ int b200ppo_profile_end(b200ppo_ctx* ctx, double ms_out[B200PPO_PROF_CLASSES], i
 int b200ppo_debug_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t a_mn_major,
                           int32_t b_mn_major, int32_t bn, int32_t split_k, b200ppo_stream stream);
 
+/* Test hook for the fp32-tolerance tensor-core GEMM (csrc/gemm_split.cu: three bf16 terms per operand value, six products):
+ * C[M,N] = A * B^T with the operand layouts of b200ppo_debug_tc_gemm, `split_k` split-K partials summed in order;
+ * bias_grad (nullable; both operands MN-major): bias_grad[m] = sum_k A(m,k), read off the ones-column the split appends.
+ * Allocates temporaries and synchronises `stream`. */
+int b200ppo_debug_gemm_split(const float* A, const float* B, float* C, float* bias_grad, int32_t M, int32_t N, int32_t K,
+                             int32_t a_mn_major, int32_t b_mn_major, int32_t split_k, b200ppo_stream stream);
+
 /* Test hook: the bf16 intermediates the last bf16 minibatch left in the context, as fp32 [rows][dims[layer]].
  * kind 0: hidden activation H_layer (layer < n_layers - 1); kind 1: dL/dz of `layer` (the seeds for the output layer). */
 int b200ppo_debug_activations(b200ppo_ctx* ctx, int32_t net, int32_t kind, int32_t layer, int64_t rows, float* out,

@@ -14,6 +14,7 @@
 #include "cast.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm_split.cuh"
 #include "heads.cuh"
 #include "ppo_loss.cuh"
 #include "tc_chain.cuh"
@@ -124,6 +125,9 @@ struct b200ppo_ctx {
   unsigned* done_counter = nullptr;  // fused reduce of the peer exchange: blocks of the optimizer grid that have written their slice (monotone)
   unsigned done_total = 0;           // what that counter reaches after the launches issued so far
   float* scratch = nullptr;     // [8] losses / entropy scratch
+  // three-term bf16 operands of the fp32-tolerance tensor-core GEMMs (gemm_split.cuh); allocated at first use
+  mutable SplitArena arena;
+  int64_t arena_need = 0;
   int32_t* err_flag = nullptr;
   // shuffled-epoch buffers (train)
   // two sets (rows [0, sh_cap) and [sh_cap, 2 sh_cap)): epoch e+1 is gathered on a side stream while epoch e trains
@@ -236,10 +240,21 @@ __global__ void copy2_kernel(const float* __restrict__ src, float* __restrict__ 
   if (threadIdx.x < 2) dst[threadIdx.x] = src[threadIdx.x];
 }
 
+// The arena of three-term operands, emptied: call where a new set of sources starts (a minibatch, an entry point).
+// nullptr when the context cannot use it — the callers then stay on the FFMA kernels.
+static SplitArena* fresh_arena(const b200ppo_ctx* ctx) {
+  if (ctx->precision != B200PPO_PREC_FP32 || ctx->arena_need <= 0) return nullptr;
+  if (ctx->arena.cap < ctx->arena_need && split_arena_reserve(ctx->arena, ctx->arena_need) != B200PPO_OK) return nullptr;
+  split_arena_reset(ctx->arena);
+  return &ctx->arena;
+}
+
 // ---- forward -----------------------------------------------------------------------------------------
 // nets: bit 0 actor, bit 1 critic.  acts[n]: hidden activations (dense for `B` rows); outs[n]: [B, out_dim].
+// arena (nullable): where the fp32-tolerance tensor-core GEMMs keep their three-term operands; nullptr = FFMA only.
 static int forward_nets(const b200ppo_ctx* ctx, const float* params, const float* x, int64_t B, int nets,
-                        float* const acts[2], float* const outs[2], cudaStream_t st, bool skip_last = false) {
+                        float* const acts[2], float* const outs[2], cudaStream_t st, bool skip_last = false,
+                        SplitArena* arena = nullptr) {
   int maxL = 0;
   for (int n = 0; n < 2; ++n)
     if (nets & (1 << n)) maxL = std::max(maxL, ctx->net[n].d.n_layers);
@@ -272,7 +287,8 @@ static int forward_nets(const b200ppo_ctx* ctx, const float* params, const float
     if (np == 0) continue;
     const bool large = large_tiles >= (2 * num_sms()) / 3;
     for (int i = 0; i < np; ++i) gemm_group_add(g, probs[i], large ? 128 : 64, large ? 128 : 64, 1);
-    B2_TRY(launch_gemm_group(g, large, st));
+    if (arena != nullptr && gemm_split_applicable(g)) B2_TRY(launch_gemm_group_split(g, *arena, st));
+    else B2_TRY(launch_gemm_group(g, large, st));
   }
   return B200PPO_OK;
 }
@@ -281,7 +297,7 @@ static int pick_split(const b200ppo_ctx* ctx, int64_t tiles, int64_t K) {
   if (tiles <= 0) return 1;
   int64_t s = (4ll * num_sms() + tiles - 1) / tiles;
   s = std::min<int64_t>(s, std::max<int64_t>(1, K / 64));
-  s = std::min<int64_t>(s, ctx->max_split);
+  s = std::min<int64_t>(s, std::min(ctx->max_split, 32));
   return int(std::max<int64_t>(1, s));
 }
 
@@ -290,7 +306,7 @@ static int pick_split(const b200ppo_ctx* ctx, int64_t tiles, int64_t K) {
 // to gpart as `*split_out` split-K partials laid out like the parameter buffer.  grad_x[n] (nullable): dL/dx.
 static int backward_nets(b200ppo_ctx* ctx, const float* params, const float* x, int64_t B, int nets,
                          float* const acts[2], float* const dz[2], float* gpart, int* split_out,
-                         float* const grad_x[2], cudaStream_t st, bool skip_last_dgrad = false) {
+                         float* const grad_x[2], cudaStream_t st, bool skip_last_dgrad = false, SplitArena* arena = nullptr) {
   int maxL = 0;
   for (int n = 0; n < 2; ++n)
     if (nets & (1 << n)) maxL = std::max(maxL, ctx->net[n].d.n_layers);
@@ -330,7 +346,8 @@ static int backward_nets(b200ppo_ctx* ctx, const float* params, const float* x, 
     const bool large = large_tiles >= (2 * num_sms()) / 3;
     GemmGroup g{};
     for (int i = 0; i < np; ++i) gemm_group_add(g, probs[i], large ? 128 : 64, large ? 128 : 64, 1);
-    PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, launch_gemm_group(g, large, st));
+    if (arena != nullptr && gemm_split_applicable(g)) PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, launch_gemm_group_split(g, *arena, st));
+    else PROF(ctx, B200PPO_PROF_GEMM_DGRAD, st, launch_gemm_group(g, large, st));
   }
   // every weight / bias gradient in one grouped split-K launch
   if (gpart != nullptr) {
@@ -356,10 +373,19 @@ static int backward_nets(b200ppo_ctx* ctx, const float* params, const float* x, 
         probs[np++] = p;
       }
     }
-    const int split = pick_split(ctx, tiles, B);
+    int split = pick_split(ctx, tiles, B);
     GemmGroup g{};
     for (int i = 0; i < np; ++i) gemm_group_add(g, probs[i], 64, 64, split);
-    PROF(ctx, B200PPO_PROF_GEMM_WGRAD, st, launch_gemm_group(g, false, st));
+    if (arena != nullptr && gemm_split_applicable(g)) {
+      // The tensor core truncates its fp32 accumulator after every K = 16 step (gemm_split.cu), so the number of samples one
+      // accumulator sums is kept to kSplitChain: more split-K partials, which the optimizer kernel adds in fp32 (round to nearest).
+      split = int(std::min<int64_t>(ctx->max_split, std::max<int64_t>(split, (B + kSplitChain - 1) / kSplitChain)));
+      g = GemmGroup{};
+      for (int i = 0; i < np; ++i) gemm_group_add(g, probs[i], 64, 64, split);
+      PROF(ctx, B200PPO_PROF_GEMM_WGRAD, st, launch_gemm_group_split(g, *arena, st));
+    } else {
+      PROF(ctx, B200PPO_PROF_GEMM_WGRAD, st, launch_gemm_group(g, false, st));
+    }
     if (split_out) *split_out = split;
   }
   return B200PPO_OK;
@@ -720,7 +746,8 @@ static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float*
     return backward_nets_bf16(ctx, obs_b, B, ctx->gpart, split_out, st);
   }
   const bool heads = La >= 2 && Lc >= 2 && heads_supported(Na.out_dim(), Na.d.dims[La - 2], Nc.d.dims[Lc - 2]);
-  PROF(ctx, B200PPO_PROF_GEMM_FWD, st, forward_nets(ctx, params, obs, B, 3, acts, outs, st, heads));
+  SplitArena* arena = fresh_arena(ctx);
+  PROF(ctx, B200PPO_PROF_GEMM_FWD, st, forward_nets(ctx, params, obs, B, 3, acts, outs, st, heads, arena));
   if (heads) {
     HeadsArgs h{};
     h.h_a = acts[0] + Na.act_off(La - 2, B); h.h_c = acts[1] + Nc.act_off(Lc - 2, B);
@@ -747,7 +774,7 @@ static int minibatch_fwd_bwd(b200ppo_ctx* ctx, const float* params, const float*
     la.losses = losses_dev; la.logstd_grad = ctx->gpart + ctx->logstd_off;
     PROF(ctx, B200PPO_PROF_LOSS, st, launch_ppo_loss(la, st));
   }
-  return backward_nets(ctx, params, obs, B, 3, acts, dz, ctx->gpart, split_out, nullptr, st, heads);
+  return backward_nets(ctx, params, obs, B, 3, acts, dz, ctx->gpart, split_out, nullptr, st, heads, arena);
 }
 
 static LossCombine make_loss_combine(const b200ppo_ctx* ctx, const float* params, int loss_ctas, int64_t B,
@@ -836,7 +863,7 @@ extern "C" B2_EXPORT int b200ppo_create(const b200ppo_mlp_desc* actor, const b20
   c->n_params = cursor;
   c->max_batch = max_batch;
   c->precision = precision;
-  c->max_split = 32;
+  c->max_split = precision == B200PPO_PREC_FP32 ? 64 : 32;
   const int64_t Bm = max_batch;
   for (int n = 0; n < 2 && r == B200PPO_OK; ++n) {
     const Net& N = c->net[n];
@@ -853,6 +880,17 @@ extern "C" B2_EXPORT int b200ppo_create(const b200ppo_mlp_desc* actor, const b20
   if (r == B200PPO_OK) r = dev_alloc(&c->scratch, 8, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->err_flag, 1, true);
   if (r == B200PPO_OK && precision == B200PPO_PREC_BF16) r = alloc_bf16_workspaces(c);
+  if (precision == B200PPO_PREC_FP32) {
+    // what one minibatch can put into the arena of three-term operands: per net the observations, every hidden activation,
+    // every dL/dz block and every weight matrix (reserved at first use: small problems never touch it)
+    for (int n = 0; n < 2; ++n) {
+      const Net& N = c->net[n];
+      c->arena_need += split_arena_elems(Bm, N.d.in_dim);
+      for (int l = 0; l < N.d.n_layers; ++l)
+        c->arena_need += 2 * split_arena_elems(Bm, N.d.dims[l]) + split_arena_elems(N.d.dims[l], N.in_dim(l)) +
+                         split_arena_elems(N.in_dim(l), N.d.dims[l]);
+    }
+  }
   if (r != B200PPO_OK) { b200ppo_destroy(c); return r; }
   *out = c;
   return B200PPO_OK;
@@ -864,6 +902,7 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   for (int n = 0; n < 2; ++n) { dev_free(c->ws_act[n]); dev_free(c->ws_dz[n]); dev_free(c->ws_out[n]); }
   dev_free(c->gpart); dev_free(c->grad_flat); dev_free(c->loss_partials); dev_free(c->ticket); dev_free(c->done_counter); dev_free(c->scratch);
   dev_free(c->err_flag);
+  split_arena_free(c->arena);
   for (int n = 0; n < 2; ++n)
     for (int l = 0; l < B200PPO_MAX_LAYERS; ++l) { dev_free(c->bf.H[n][l]); dev_free(c->bf.dZ[n][l]); dev_free(c->bf.W[n][l]); dev_free(c->bf.WT[n][l]); }
   dev_free(c->bf.X); dev_free(c->bf.sh_obs); dev_free(c->bf.obs_table);

@@ -1,0 +1,271 @@
+// fp32-tolerance variant of the actor/critic GEMMs on tcgen05 (north_star's 1e-5 variant on the tensor cores).
+//
+// replaces: the same aten::addmm / aten::mm calls as gemm.cu (src/models/network_block_creator.py:74-86 forward, autograd
+//           of ppo.py:121,134 backward) — gemm.cu does them with FFMA, this file with six bf16 MMAs per product.
+//
+// A bf16 value carries 8 significant bits, an fp32 value 24: x = a + b + c with a = bf16(x), b = bf16(x - a),
+// c = bf16(x - a - b) is exact to 2^-24 |x| (both subtractions are exact in fp32).  For a dot product
+//   sum x y = sum (a + b + c)(a' + b' + c') = aa' + ab' + ba' + bb' + ac' + ca'  +  O(2^-24 |x||y|)
+// — the three dropped products (bc', cb', cc') are below 2^-24 — and every bf16 x bf16 product is exact in the tensor
+// core's fp32 accumulator.  Measured against fp64 on the bench shapes (profiles/README.md): max error / max |C| 3e-7, the
+// same as an fp32 FFMA loop (8e-7); three products (aa' + ab' + ba') give 5e-6, too close to the 1e-5 tolerance.
+//
+// Data layout: a [rows][cols] fp32 operand becomes bf16 [rows][3 * cp], cp = pad64(cols + 1): the three terms of a row
+// side by side, each padded with zeros to a whole number of 64-element k tiles.  The contiguous dimension is K for a
+// K-major operand and M / N for an MN-major one; either way the tile kernel (tc_gemm.cu) reaches term t by adding t * cp
+// to the box coordinate along that dimension, so ONE split of an activation serves the forward (K-major A operand) and the
+// weight gradient (MN-major B operand).  Activations get a column of ones behind their last column (term a only): as the
+// weight gradient's B operand that column makes the bias gradient fall out of the same MMAs (TcProblem.bias_col).
+#include "gemm_split.cuh"
+
+#include "tc_gemm.cuh"
+
+namespace b200ppo {
+
+static inline int pad64(int x) { return (x + 63) / 64 * 64; }
+int64_t split_arena_elems(int64_t rows, int cols) { return (rows * 3 * pad64(cols + 1) + 511) / 512 * 512; }
+
+int split_arena_reserve(SplitArena& a, int64_t elems) {
+  if (elems <= a.cap) return B200PPO_OK;
+  B2_CUDA(cudaDeviceSynchronize());
+  if (a.base != nullptr) cudaFree(a.base);
+  a.base = nullptr;
+  a.cap = 0;
+  split_arena_reset(a);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&a.base), size_t(elems) * sizeof(__nv_bfloat16));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%lld bytes) for the three-term operand arena failed: %s", (long long)(elems * 2), cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? B200PPO_ENOMEM : B200PPO_ECUDA;
+  }
+  a.cap = elems;
+  return B200PPO_OK;
+}
+
+void split_arena_free(SplitArena& a) {
+  if (a.base != nullptr) cudaFree(a.base);
+  a.base = nullptr;
+  a.cap = a.used = 0;
+  a.n = 0;
+}
+
+// ---- the split pass ------------------------------------------------------------------------------------------------------
+struct SplitJob {
+  const float* src;
+  __nv_bfloat16* dst;
+  int64_t rows, ld, unit_begin;  // first 8-column unit of this job in the launch
+  int cols, cp, ones, vec;
+};
+constexpr int kMaxSplitJobs = 2 * kMaxGemmProblems;
+struct SplitJobs {
+  SplitJob j[kMaxSplitJobs];
+  int n;
+  int64_t units;
+};
+
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+  return uint32_t(__bfloat16_as_ushort(lo)) | (uint32_t(__bfloat16_as_ushort(hi)) << 16);
+}
+
+// one thread = 8 consecutive columns of one row: 32 bytes in, 3 x 16 bytes out
+__global__ void __launch_bounds__(256) split3_kernel(const __grid_constant__ SplitJobs jobs) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int64_t u = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (u >= jobs.units) return;
+  int ji = 0;
+#pragma unroll 1
+  for (int i = 1; i < jobs.n; ++i)
+    if (u >= jobs.j[i].unit_begin) ji = i;
+  const SplitJob& J = jobs.j[ji];
+  const int upr = J.cp >> 3;
+  const int64_t local = u - J.unit_begin;
+  const int64_t row = local / upr;
+  const int c0 = int(local - row * upr) * 8;
+  float x[8];
+  const float* sp = J.src + row * J.ld + c0;
+  if (J.vec && c0 + 8 <= J.cols) {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(sp)), q = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+    x[0] = p.x; x[1] = p.y; x[2] = p.z; x[3] = p.w; x[4] = q.x; x[5] = q.y; x[6] = q.z; x[7] = q.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = (c0 + j < J.cols) ? __ldg(sp + j) : ((c0 + j == J.cols && J.ones) ? 1.f : 0.f);
+  }
+  uint32_t o[3][4];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    __nv_bfloat16 t[3][2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float r = x[j + k];
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        t[p][k] = __float2bfloat16_rn(r);
+        r -= __bfloat162float(t[p][k]);  // exact: the term shares r's leading bits
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) o[p][j >> 1] = pack2(t[p][0], t[p][1]);
+  }
+  __nv_bfloat16* dp = J.dst + row * (3 * int64_t(J.cp)) + c0;
+#pragma unroll
+  for (int p = 0; p < 3; ++p) *reinterpret_cast<uint4*>(dp + int64_t(p) * J.cp) = make_uint4(o[p][0], o[p][1], o[p][2], o[p][3]);
+}
+
+// Finds the split of (src, rows, cols, ld) in the arena or queues the job that makes it.
+static int get_split(SplitArena& arena, SplitJobs& jobs, const float* src, int64_t rows, int cols, int64_t ld, int ones,
+                     const __nv_bfloat16** out, int* cp_out) {
+  for (int i = 0; i < arena.n; ++i) {
+    const SplitArena::Entry& e = arena.e[i];
+    if (e.src == src && e.rows == rows && e.cols == cols && e.ld == ld && e.ones >= ones) {
+      *out = e.dst;
+      *cp_out = e.cp;
+      return B200PPO_OK;
+    }
+  }
+  const int cp = pad64(cols + 1);
+  const int64_t elems = split_arena_elems(rows, cols);
+  if (arena.n >= SplitArena::kMaxEntries || arena.used + elems > arena.cap || jobs.n >= kMaxSplitJobs) {
+    set_error("three-term operand arena exhausted (%d entries, %lld of %lld elements used, %lld more asked)", arena.n,
+              (long long)arena.used, (long long)arena.cap, (long long)elems);
+    return B200PPO_EINVAL;
+  }
+  __nv_bfloat16* dst = arena.base + arena.used;
+  arena.used += elems;
+  arena.e[arena.n++] = SplitArena::Entry{src, rows, ld, cols, ones, cp, dst};
+  SplitJob& J = jobs.j[jobs.n++];
+  J.src = src; J.dst = dst; J.rows = rows; J.ld = ld; J.cols = cols; J.cp = cp; J.ones = ones;
+  J.vec = (aligned16(src) && ld % 4 == 0) ? 1 : 0;
+  J.unit_begin = jobs.units;
+  jobs.units += rows * (cp / 8);
+  *out = dst;
+  *cp_out = cp;
+  return B200PPO_OK;
+}
+
+bool gemm_split_applicable(const GemmGroup& g) {
+  static const bool on = []() {
+    const char* e = getenv("B200PPO_FP32_TC");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  static const double min_macs = []() {
+    const char* e = getenv("B200PPO_FP32_TC_MIN_MACS");
+    return e != nullptr ? atof(e) : double(1ll << 27);
+  }();
+  if (!on || g.count == 0 || g.count > kMaxTcProblems) return false;
+  double macs = 0;
+  for (int i = 0; i < g.count; ++i) {
+    const GemmProblem& p = g.p[i];
+    if (p.C_bf16 != nullptr) return false;
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0) return false;
+    const bool a_k = p.a_sk == 1 && p.a_sm >= p.K, a_mn = p.a_sm == 1 && p.a_sk >= p.M;
+    const bool b_k = p.b_sk == 1 && p.b_sn >= p.K, b_mn = p.b_sn == 1 && p.b_sk >= p.N;
+    if (!(a_k || a_mn) || !(b_k || b_mn)) return false;
+    if (p.bias_grad != nullptr && !((a_mn && !a_k) && (b_mn && !b_k))) return false;  // bias gradients only off the wgrad layout
+    macs += double(p.M) * p.N * p.K;
+  }
+  return macs >= min_macs;
+}
+
+int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t st) {
+  if (g.total_tiles == 0 || g.count == 0) return B200PPO_OK;
+  B2_TRY(tc_init());
+  SplitJobs jobs{};
+  TcGroup tg{};
+  constexpr int BN = 128;
+  for (int i = 0; i < g.count; ++i) {
+    const GemmProblem& p = g.p[i];
+    const bool a_mn = !(p.a_sk == 1 && p.a_sm >= p.K), b_mn = !(p.b_sk == 1 && p.b_sn >= p.K);
+    const bool wgrad = a_mn && b_mn, fwd = !a_mn && !b_mn;
+    const __nv_bfloat16 *As = nullptr, *Bs = nullptr;
+    int a_cp = 0, b_cp = 0;
+    // the arrays as stored: K-major [M or N][K], MN-major [K][M or N]
+    B2_TRY(get_split(arena, jobs, p.A, a_mn ? p.K : p.M, a_mn ? p.M : p.K, a_mn ? p.a_sk : p.a_sm, fwd ? 1 : 0, &As, &a_cp));
+    B2_TRY(get_split(arena, jobs, p.B, b_mn ? p.K : p.N, b_mn ? p.N : p.K, b_mn ? p.b_sk : p.b_sn, wgrad ? 1 : 0, &Bs, &b_cp));
+    TcProblem t{};
+    t.M = p.M; t.N = p.N; t.K = p.K;
+    t.parts = 3; t.a_part = a_cp; t.b_part = b_cp;
+    t.out_f32 = p.C; t.ld_f32 = p.ldc; t.split_stride = p.c_split_stride;
+    t.bias_col = -1;
+    t.out_scale = p.out_scale;
+    t.precise = 1;
+    switch (p.epilogue) {
+      case EPI_STORE:
+        t.epilogue = TC_EPI_STORE;
+        if (p.bias_grad != nullptr) {  // the ones-column behind the B operand's last column
+          t.N = p.N + 1;
+          t.bias_col = p.N;
+          t.bias_grad = p.bias_grad;
+        }
+        break;
+      case EPI_BIAS: t.epilogue = TC_EPI_FWD; t.act = TC_ACT_NONE; t.bias = p.bias; break;
+      case EPI_BIAS_TANH: t.epilogue = TC_EPI_FWD; t.act = B200PPO_ACT_TANH; t.bias = p.bias; break;
+      case EPI_BIAS_RELU: t.epilogue = TC_EPI_FWD; t.act = B200PPO_ACT_RELU; t.bias = p.bias; break;
+      case EPI_BIAS_TANH_SCALE: t.epilogue = TC_EPI_FWD; t.act = TC_ACT_TANH_SCALE; t.bias = p.bias; break;
+      case EPI_DTANH: t.epilogue = TC_EPI_DGRAD; t.act = B200PPO_ACT_TANH; t.aux_f32 = p.aux; t.ld_aux = p.ld_aux; break;
+      case EPI_DRELU: t.epilogue = TC_EPI_DGRAD; t.act = B200PPO_ACT_RELU; t.aux_f32 = p.aux; t.ld_aux = p.ld_aux; break;
+      default: set_error("gemm_split: unknown epilogue %d", p.epilogue); return B200PPO_EINVAL;
+    }
+    B2_TRY(tc_group_add(tg, t, TcOperand{As, 3 * int64_t(a_cp), a_mn ? 1 : 0}, TcOperand{Bs, 3 * int64_t(b_cp), b_mn ? 1 : 0}, BN,
+                        p.split_k));
+  }
+  if (jobs.n > 0) {
+    const unsigned blocks = unsigned((jobs.units + 255) / 256);
+    B2_CUDA(launch_pdl(split3_kernel, dim3(blocks), dim3(256), 0, st, jobs));
+    B2_LAUNCH_CHECK();
+  }
+  return launch_tc_group(tg, BN, st);
+}
+
+}  // namespace b200ppo
+
+// ---- test hook --------------------------------------------------------------------------------------------------------------
+namespace b200ppo {
+__global__ void sum_partials_kernel(const float* __restrict__ part, int splits, int64_t stride, int64_t n, float* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += part[k * stride + i];
+  out[i] = s;
+}
+}  // namespace b200ppo
+
+using namespace b200ppo;
+
+extern "C" B2_EXPORT int b200ppo_debug_gemm_split(const float* A, const float* B, float* C, float* bias_grad, int32_t M, int32_t N,
+                                                  int32_t K, int32_t a_mn_major, int32_t b_mn_major, int32_t split_k,
+                                                  b200ppo_stream stream) {
+  B2_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && split_k >= 1, "b200ppo_debug_gemm_split: bad argument");
+  B2_CHECK_ARG(bias_grad == nullptr || (a_mn_major && b_mn_major), "b200ppo_debug_gemm_split: bias_grad needs both operands MN-major");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SplitArena arena;
+  const int64_t need = split_arena_elems(a_mn_major ? K : M, a_mn_major ? M : K) + split_arena_elems(b_mn_major ? K : N, b_mn_major ? N : K);
+  B2_TRY(split_arena_reserve(arena, need));
+  const int64_t mn = int64_t(M) * N, stride = (mn + M + 3) / 4 * 4;
+  float* part = nullptr;
+  B2_CUDA(cudaMalloc(&part, size_t(split_k) * stride * 4));
+  GemmGroup g{};
+  GemmProblem p{};
+  p.A = A; p.B = B; p.C = part; p.ldc = N;
+  p.M = M; p.N = N; p.K = K;
+  p.a_sm = a_mn_major ? 1 : K; p.a_sk = a_mn_major ? M : 1;
+  p.b_sn = b_mn_major ? 1 : K; p.b_sk = b_mn_major ? N : 1;
+  p.epilogue = EPI_STORE;
+  p.c_split_stride = stride;
+  if (bias_grad != nullptr) p.bias_grad = part + mn;
+  gemm_group_add(g, p, 64, 64, split_k);
+  int rc = launch_gemm_group_split(g, arena, st);
+  if (rc == B200PPO_OK) {
+    sum_partials_kernel<<<unsigned((mn + 255) / 256), 256, 0, st>>>(part, split_k, stride, mn, C);
+    count_launch();
+    if (bias_grad != nullptr) {
+      sum_partials_kernel<<<unsigned((M + 255) / 256), 256, 0, st>>>(part + mn, split_k, stride, M, bias_grad);
+      count_launch();
+    }
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(part);
+  split_arena_free(arena);
+  if (rc != B200PPO_OK) return rc;
+  B2_CUDA(cudaGetLastError());
+  return B200PPO_OK;
+}

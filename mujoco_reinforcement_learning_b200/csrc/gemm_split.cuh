@@ -1,0 +1,38 @@
+// fp32-tolerance GEMMs on the tcgen05 tensor cores: every fp32 operand is written as three bf16 terms (x = a + b + c
+// to 2^-24 relative) and the products aa, ab, ba, bb, ac, ca accumulate in one fp32 TMEM accumulator (gemm_split.cu).
+#pragma once
+#include "gemm.cuh"
+
+namespace b200ppo {
+
+// Device arena of the three-term operands of ONE minibatch.  An operand split once (the observations, a hidden
+// activation, a weight matrix, a dL/dz block) is found again by source pointer and shape, so the forward's A operand is
+// the weight gradient's B operand without a second pass.  Reset whenever the sources may have changed.
+struct SplitArena {
+  struct Entry {
+    const float* src;
+    int64_t rows, ld;
+    int cols, ones, cp;
+    __nv_bfloat16* dst;
+  };
+  static constexpr int kMaxEntries = 48;
+  __nv_bfloat16* base = nullptr;
+  int64_t cap = 0, used = 0;  // elements
+  Entry e[kMaxEntries];
+  int n = 0;
+};
+
+int split_arena_reserve(SplitArena& a, int64_t elems);  // (re)allocates; synchronises the device when it has to grow
+inline void split_arena_reset(SplitArena& a) { a.used = 0; a.n = 0; }
+void split_arena_free(SplitArena& a);
+// samples one tensor-core accumulator of a weight gradient may sum (see backward_nets in api.cu)
+constexpr int kSplitChain = 512;
+// elements one [rows][cols] operand occupies in the arena
+int64_t split_arena_elems(int64_t rows, int cols);
+
+// Every problem K- or MN-contiguous on both operands, no bf16 mirror output, and enough arithmetic to pay for the splits.
+bool gemm_split_applicable(const GemmGroup& g);
+// Same contract as launch_gemm_group (gemm.cuh): C, bias_grad and split-K partials land where the FFMA kernel puts them.
+int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t st);
+
+}  // namespace b200ppo

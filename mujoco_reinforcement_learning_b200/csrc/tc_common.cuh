@@ -110,6 +110,8 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
     float* __restrict__ outf = P.out_f32 != nullptr ? P.out_f32 + int64_t(split) * P.split_stride : nullptr;
     float* __restrict__ bgrad = P.bias_grad != nullptr ? P.bias_grad + int64_t(split) * P.split_stride : nullptr;
     const __nv_bfloat16* __restrict__ auxp = P.aux;
+    const float* __restrict__ auxf = P.aux_f32;
+    const bool precise = P.precise != 0;
     const int ld_bf16 = P.ld_bf16, ld_f32 = P.ld_f32, ld_aux = P.ld_aux, bias_col = P.bias_col;
     const bool f32_vec = (P.ld_f32 % 4 == 0) && (P.split_stride % 4 == 0);
     const float out_scale = P.out_scale;
@@ -127,7 +129,7 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
     uint4 pre[2];  // prefetched 32 bytes of the dgrad's activation row for the NEXT step
     auto prefetch_aux = [&](int c) {
       const int nb = n0 + c * CW;
-      if (epi == TC_EPI_DGRAD && row_ok && c < c_end && nb + CW <= Ncols && aux_vec) {
+      if (epi == TC_EPI_DGRAD && auxf == nullptr && row_ok && c < c_end && nb + CW <= Ncols && aux_vec) {
         const uint4* ap = reinterpret_cast<const uint4*>(auxp + int64_t(m) * ld_aux + nb);
         pre[0] = __ldg(ap);
         pre[1] = __ldg(ap + 1);
@@ -159,7 +161,11 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
             const float4 t = *reinterpret_cast<const float4*>(bias_s + (nb - n0) + u * 4);
             h[u * 4] = t.x; h[u * 4 + 1] = t.y; h[u * 4 + 2] = t.z; h[u * 4 + 3] = t.w;
           }
-          if (act == B200PPO_ACT_TANH) {
+          if (precise && (act == B200PPO_ACT_TANH || act == TC_ACT_TANH_SCALE)) {
+            const float sc = act == TC_ACT_TANH_SCALE ? out_scale : 1.f;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) h[j] = sc * tanhf(__uint_as_float(v[j]) + h[j]);
+          } else if (act == B200PPO_ACT_TANH) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) h[j] = tanh_fast(__uint_as_float(v[j]) + h[j]);
           } else if (act == B200PPO_ACT_RELU) {
@@ -174,7 +180,21 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
           }
         }
       } else if (epi == TC_EPI_DGRAD) {
-        if (live && full && aux_vec) {
+        if (auxf != nullptr) {
+          if (live) {
+            const float* ap = auxf + int64_t(m) * ld_aux + nb;
+            if (full && (ld_aux % 4 == 0)) {
+#pragma unroll
+              for (int u = 0; u < CW / 4; ++u) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(ap) + u);
+                h[u * 4] = t.x; h[u * 4 + 1] = t.y; h[u * 4 + 2] = t.z; h[u * 4 + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) h[j] = (nb + j < Ncols) ? __ldg(ap + j) : 0.f;
+            }
+          }
+        } else if (live && full && aux_vec) {
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const uint32_t ww[4] = {pre[u].x, pre[u].y, pre[u].z, pre[u].w};

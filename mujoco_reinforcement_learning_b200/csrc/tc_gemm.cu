@@ -71,6 +71,9 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   const int kt_begin = split * P.k_tiles_per_split;
   const int kt_end = min(total_kt, kt_begin + P.k_tiles_per_split);
   const bool has_k = kt_end > kt_begin;
+  // fp32-tolerance mode: the six products run one after the other over this split's k range, smallest terms first
+  const int kt_len = kt_end - kt_begin;
+  const int n_it = P.parts ? kSplitProducts * kt_len : kt_len;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -96,24 +99,31 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
 
   if (warp == 0) {
     if (lane == 0 && has_k) {  // ===== TMA producer =====
-      for (int kt = kt_begin, it = 0; kt < kt_end; ++kt, ++it) {
+      for (int it = 0; it < n_it; ++it) {
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], TC_A_BYTES + B_BYTES);
         uint8_t* a = sA + s * TC_A_BYTES;
         uint8_t* b = sB + s * B_BYTES;
+        int kb = kt_begin + it, ao = 0, bo = 0;  // k tile, offsets of the product's terms along the contiguous dimension
+        if (P.parts) {
+          const int c = it / kt_len;
+          kb = kt_begin + (it - c * kt_len);
+          ao = int((kSplitTermsA >> (4 * c)) & 3u) * P.a_part;
+          bo = int((kSplitTermsB >> (4 * c)) & 3u) * P.b_part;
+        }
         if (!P.a_mn_major) {
-          tma_load_2d(a, &P.tmA, &full_bar[s], kt * TC_BK, m0);
+          tma_load_2d(a, &P.tmA, &full_bar[s], ao + kb * TC_BK, m0);
         } else {
-          tma_load_2d(a, &P.tmA, &full_bar[s], m0, kt * TC_BK);
-          tma_load_2d(a + 64 * TC_BK * 2, &P.tmA, &full_bar[s], m0 + 64, kt * TC_BK);
+          tma_load_2d(a, &P.tmA, &full_bar[s], ao + m0, kb * TC_BK);
+          tma_load_2d(a + 64 * TC_BK * 2, &P.tmA, &full_bar[s], ao + m0 + 64, kb * TC_BK);
         }
         if (!P.b_mn_major) {
-          tma_load_2d(b, &P.tmB, &full_bar[s], kt * TC_BK, n0);
+          tma_load_2d(b, &P.tmB, &full_bar[s], bo + kb * TC_BK, n0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b + j * 64 * TC_BK * 2, &P.tmB, &full_bar[s], n0 + 64 * j, kt * TC_BK);
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b + j * 64 * TC_BK * 2, &P.tmB, &full_bar[s], bo + n0 + 64 * j, kb * TC_BK);
         }
       }
     }
@@ -127,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
       //                 one K=16 step = +2048 B.
       const uint32_t a_lbo = P.a_mn_major ? TC_BK * 128 : 0, b_lbo = P.b_mn_major ? TC_BK * 128 : 0;
       const uint32_t a_kstep = P.a_mn_major ? 2048 : 32, b_kstep = P.b_mn_major ? 2048 : 32;
-      for (int kt = kt_begin, it = 0; kt < kt_end; ++kt, ++it) {
+      for (int it = 0; it < n_it; ++it) {
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
                       idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
-          if (kt == kt_end - 1) umma_commit(tmem_full_bar);
+          if (it == n_it - 1) umma_commit(tmem_full_bar);
         }
         __syncwarp();
       }
@@ -228,13 +238,16 @@ int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B
   B2_CHECK_ARG(g.count < kMaxTcProblems, "too many problems in one tensor-core group");
   p.a_mn_major = A.mn_major;
   p.b_mn_major = B.mn_major;
-  if (!A.mn_major) B2_TRY(tc_make_map(&p.tmA, A.ptr, p.K, p.M, A.pitch, TC_BK, TC_BM));
-  else B2_TRY(tc_make_map(&p.tmA, A.ptr, p.M, p.K, A.pitch, 64, TC_BK));
-  if (!B.mn_major) B2_TRY(tc_make_map(&p.tmB, B.ptr, p.K, p.N, B.pitch, TC_BK, bn));
-  else B2_TRY(tc_make_map(&p.tmB, B.ptr, p.N, p.K, B.pitch, 64, TC_BK));
+  // fp32-tolerance mode: the whole row (three terms) is addressable, the producer adds the term's offset to the coordinate
+  const int64_t a_inner = p.parts ? 3 * int64_t(p.a_part) : (A.mn_major ? p.M : p.K);
+  const int64_t b_inner = p.parts ? 3 * int64_t(p.b_part) : (B.mn_major ? p.N : p.K);
+  if (!A.mn_major) B2_TRY(tc_make_map(&p.tmA, A.ptr, a_inner, p.M, A.pitch, TC_BK, TC_BM));
+  else B2_TRY(tc_make_map(&p.tmA, A.ptr, a_inner, p.K, A.pitch, 64, TC_BK));
+  if (!B.mn_major) B2_TRY(tc_make_map(&p.tmB, B.ptr, b_inner, p.N, B.pitch, TC_BK, bn));
+  else B2_TRY(tc_make_map(&p.tmB, B.ptr, b_inner, p.K, B.pitch, 64, TC_BK));
   const int total_kt = (p.K + TC_BK - 1) / TC_BK;
   if (split_k < 1) split_k = 1;
-  if (split_k > total_kt) split_k = total_kt;
+  if (split_k > total_kt && !p.parts) split_k = total_kt;  // (fp32-tolerance mode: the caller sums exactly split_k partials; empty ones store zeros)
   p.split_k = split_k;
   p.k_tiles_per_split = (total_kt + split_k - 1) / split_k;
   p.tiles_m = (p.M + TC_BM - 1) / TC_BM;

@@ -54,8 +54,20 @@ struct TcProblem {
   int bias_col;  // -1: none
   float out_scale;
   int staged;  // epilogue goes through the shared-memory staging tile (set by tc_group_add)
+  // fp32-tolerance mode (gemm_split.cu): both operands are stored as three bf16 terms per value (x = a + b + c to 2^-24,
+  // the terms side by side along the contiguous dimension, `a_part` / `b_part` elements apart) and the K loop runs the six
+  // products ac ca bb ab ba aa into the same fp32 accumulator — smallest first: the tensor core TRUNCATES the fp32
+  // accumulator after every K = 16 step (measured, profiles/rz_probe.py: -0.47 ulp per step), so only the aa steps, which
+  // come last, may happen at the accumulator's full magnitude.  0: plain bf16 operands.
+  int parts, a_part, b_part;
+  const float* aux_f32;  // TC_EPI_DGRAD: activation operand in fp32 (instead of `aux`)
+  int precise;           // TC_EPI_FWD: tanhf instead of the MUFU approximation
   TcPpo ppo;
 };
+
+// the six (A term, B term) products of the fp32-tolerance mode, one nibble per product
+constexpr uint32_t kSplitTermsA = 0x010120u, kSplitTermsB = 0x001102u;
+constexpr int kSplitProducts = 6;
 
 // Fused PPO epilogue applies when a warp's action slab (32 x A floats) and bf16 seed slab (32 x pad8(A)) share its 4 KB
 // staging tile, i.e. A <= 21 (Humanoid 17, Ant 8, HalfCheetah 6, Hopper 3).

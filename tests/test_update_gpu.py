@@ -171,6 +171,7 @@ def test_train_matches_reference_outputs(name):
 
 @pytest.mark.parametrize("shape", [dict(D=376, A=17, H=[256, 256], N=16, T=64, B=500),    # Humanoid dims, reference B
                                    dict(D=27, A=8, H=[256, 256], N=32, T=32, B=256),      # Ant dims
+                                   dict(D=376, A=17, H=[256, 256], N=64, T=128, B=4096),  # fp32-tolerance GEMMs on the tensor cores
                                    dict(D=11, A=3, H=[64, 64], N=16, T=256, B=4096),      # Hopper config, one big batch
                                    dict(D=17, A=6, H=[64, 64], N=1, T=2048, B=500)])      # HalfCheetah config
 def test_train_vs_oracle_on_baseline_shapes(shape):
