@@ -243,7 +243,7 @@ __global__ void copy2_kernel(const float* __restrict__ src, float* __restrict__ 
 // The arena of three-term operands, emptied: call where a new set of sources starts (a minibatch, an entry point).
 // nullptr when the context cannot use it — the callers then stay on the FFMA kernels.
 static SplitArena* fresh_arena(const b200ppo_ctx* ctx) {
-  if (ctx->precision != B200PPO_PREC_FP32 || ctx->arena_need <= 0) return nullptr;
+  if (ctx->arena_need <= 0) return nullptr;
   if (ctx->arena.cap < ctx->arena_need && split_arena_reserve(ctx->arena, ctx->arena_need) != B200PPO_OK) return nullptr;
   split_arena_reset(ctx->arena);
   return &ctx->arena;
@@ -880,7 +880,8 @@ extern "C" B2_EXPORT int b200ppo_create(const b200ppo_mlp_desc* actor, const b20
   if (r == B200PPO_OK) r = dev_alloc(&c->scratch, 8, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->err_flag, 1, true);
   if (r == B200PPO_OK && precision == B200PPO_PREC_BF16) r = alloc_bf16_workspaces(c);
-  if (precision == B200PPO_PREC_FP32) {
+  {
+    // (the fp32 entry points of a bf16 context — rollout inference, evaluate — use it too)
     // what one minibatch can put into the arena of three-term operands: per net the observations, every hidden activation,
     // every dL/dz block and every weight matrix (reserved at first use: small problems never touch it)
     for (int n = 0; n < 2; ++n) {
@@ -954,7 +955,7 @@ extern "C" B2_EXPORT int b200ppo_mlp_forward(b200ppo_ctx* ctx, int32_t net, cons
   float* outs[2] = {nullptr, nullptr};
   if (saved) acts[net] = saved;
   outs[net] = out;
-  return forward_nets(ctx, params, x, batch, 1 << net, acts, outs, static_cast<cudaStream_t>(stream));
+  return forward_nets(ctx, params, x, batch, 1 << net, acts, outs, static_cast<cudaStream_t>(stream), false, fresh_arena(ctx));
 }
 
 extern "C" B2_EXPORT int b200ppo_mlp_backward(b200ppo_ctx* ctx, int32_t net, const float* params, const float* x,
@@ -985,7 +986,7 @@ extern "C" B2_EXPORT int b200ppo_mlp_backward(b200ppo_ctx* ctx, int32_t net, con
     B2_CUDA(cudaMemcpyAsync(dz_last, grad_out, size_t(n_out) * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   int split = 1;
-  B2_TRY(backward_nets(ctx, params, x, batch, 1 << net, acts, dz, ctx->gpart, &split, gx, st));
+  B2_TRY(backward_nets(ctx, params, x, batch, 1 << net, acts, dz, ctx->gpart, &split, gx, st, false, fresh_arena(ctx)));
   return launch_reduce_partials(ctx->gpart + N.seg_begin, split, ctx->n_params, n_seg, grad_params, st);
 }
 
@@ -1001,7 +1002,7 @@ extern "C" B2_EXPORT int b200ppo_policy_infer(b200ppo_ctx* ctx, const float* par
   const bool need_actor = mean || action || logp;
   const int nets = (need_actor ? 1 : 0) | (value ? 2 : 0);
   if (nets == 0) return B200PPO_OK;
-  B2_TRY(forward_nets(ctx, params, obs, batch, nets, acts, outs, st));
+  B2_TRY(forward_nets(ctx, params, obs, batch, nets, acts, outs, st, false, fresh_arena(ctx)));
   if (action || logp)
     B2_TRY(launch_sample_logp(outs[0], params + ctx->logstd_off, noise, batch, ctx->net[0].out_dim(), action, logp, st));
   return B200PPO_OK;
@@ -1014,7 +1015,7 @@ extern "C" B2_EXPORT int b200ppo_evaluate(b200ppo_ctx* ctx, const float* params,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* acts[2] = {ctx->ws_act[0], ctx->ws_act[1]};
   float* outs[2] = {ctx->ws_out[0], value ? value : ctx->ws_out[1]};
-  B2_TRY(forward_nets(ctx, params, obs, batch, 3, acts, outs, st));
+  B2_TRY(forward_nets(ctx, params, obs, batch, 3, acts, outs, st, false, fresh_arena(ctx)));
   LossArgs la{};
   la.mean = outs[0]; la.logstd = params + ctx->logstd_off; la.action = action; la.batch = batch;
   la.act_dim = ctx->net[0].out_dim(); la.final_tanh = ctx->net[0].d.final_tanh; la.out_scale = ctx->net[0].d.out_scale;

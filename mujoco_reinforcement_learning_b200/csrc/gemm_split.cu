@@ -18,6 +18,8 @@
 // weight gradient's B operand that column makes the bias gradient fall out of the same MMAs (TcProblem.bias_col).
 #include "gemm_split.cuh"
 
+#include <algorithm>
+
 #include "tc_gemm.cuh"
 
 namespace b200ppo {
@@ -171,7 +173,16 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
   B2_TRY(tc_init());
   SplitJobs jobs{};
   TcGroup tg{};
-  constexpr int BN = 128;
+  // N tile: 256 when the outputs are wide (the A tile is fetched once per 256 columns), 192 for the weight gradients
+  // (N = in + 1 = 377 or 257 columns: two 192-wide tiles instead of three 128-wide ones)
+  int maxN = 0;
+  bool any_wgrad = false;
+  for (int i = 0; i < g.count; ++i) {
+    maxN = std::max(maxN, g.p[i].N + (g.p[i].bias_grad != nullptr ? 1 : 0));
+    any_wgrad |= g.p[i].bias_grad != nullptr;
+  }
+  int BN = maxN <= 128 ? 128 : (any_wgrad ? 192 : 256);
+  if (const char* e = getenv(any_wgrad ? "B200PPO_SPLIT_BN_WGRAD" : "B200PPO_SPLIT_BN")) BN = atoi(e);
   for (int i = 0; i < g.count; ++i) {
     const GemmProblem& p = g.p[i];
     const bool a_mn = !(p.a_sk == 1 && p.a_sm >= p.K), b_mn = !(p.b_sk == 1 && p.b_sn >= p.K);
