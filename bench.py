@@ -649,7 +649,8 @@ def run_b200(args, config):
             by = (2 * (4 * OBS_DIM + 4 * ACT_DIM + 12) + 8) * (E * nb * B)
         prof["gather"]["GBps"] = by / 1e9 / (prof["gather"]["ms"] * 1e-3)
         prof["gather"]["frac_hbm"] = prof["gather"]["GBps"] / pk["hbm"]
-    roofline = {"kernel": "gemm_group_kernel (actor+critic MLP forward/dgrad/wgrad, fp32 FFMA)" if args.precision == "fp32"
+    roofline = {"kernel": "fp32-tolerance GEMMs on tcgen05: split3_kernel + tc_gemm_kernel in three-term mode, six bf16 products per "
+                          "fp32 product (gemm_split.cu); achieved counts the fp32 products once" if args.precision == "fp32"
                 else "tcgen05 bf16 GEMMs: tc_chain_kernel (forward + losses + dgrads) and tc_wgrad2_kernel (weight gradients)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tensor_sustained"],
@@ -749,7 +750,8 @@ def main():
     ap.add_argument("--minibatch", type=int, default=32768, help="minibatch rows per GPU (global = N x this)")
     ap.add_argument("--epochs", type=int, default=10, help="epochs_per_iteration (reference default, main.py:45)")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
-                    help="GEMM arithmetic: bf16 tcgen05 (2e-2 parity, default) or fp32 FFMA (1e-5 parity)")
+                    help="GEMM arithmetic: bf16 tcgen05 (2e-2 parity, default) or fp32 tolerance (1e-5 parity: six bf16 tcgen05 "
+                         "products per fp32 product at large minibatches, FFMA below)")
     ap.add_argument("--ref-epochs", type=int, default=4, help="reference arm: at most this many full epochs per timed step")
     ap.add_argument("--ref-budget", type=float, default=20.0, help="reference arm: seconds of epochs per timed step")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
