@@ -309,6 +309,11 @@ int b200ppo_p2p_enable(b200ppo_ctx* ctx, int32_t on);
 int b200ppo_table_export(b200ppo_ctx* ctx, int64_t rows_local, uint8_t handle_out[64]);
 int b200ppo_table_import(b200ppo_ctx* ctx, const uint8_t* handles, int32_t world_size, int64_t rows_local);
 int b200ppo_table_fill(b200ppo_ctx* ctx, const float* obs_local, int64_t rows_local, b200ppo_stream stream);
+/* Optional, after EVERY rank's b200ppo_table_fill has completed (e.g. behind a collective that follows the fill in stream
+ * order on all ranks): copies the peers' tables into local memory once ((world - 1) x rows x pitch bf16 over NVLink), so
+ * that the per-epoch gathers of b200ppo_train(obs = NULL, ...) read local HBM instead of pulling 1 - 1/world of every
+ * epoch's rows from the peers.  The next b200ppo_table_fill invalidates the copy. */
+int b200ppo_table_replicate(b200ppo_ctx* ctx, b200ppo_stream stream);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ SIGNATURES = {
     "b200ppo_table_export": (c_i32, [c_ptr, c_i64, c_ptr]),
     "b200ppo_table_import": (c_i32, [c_ptr, c_ptr, c_i32, c_i64]),
     "b200ppo_table_fill": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr]),
+    "b200ppo_table_replicate": (c_i32, [c_ptr, c_ptr]),
 }
 
 

@@ -143,6 +143,11 @@ struct b200ppo_ctx {
   __nv_bfloat16* peer_table[kMaxPeers] = {};
   int64_t shared_rows = 0;   // rows of every rank's table; 0 = tables not shared
   bool shared_filled = false;
+  // b200ppo_table_replicate: the peers' tables copied once per rollout into local memory, so that the per-epoch gathers
+  // read HBM and leave NVLink to the gradient exchange
+  __nv_bfloat16* replica = nullptr;
+  int64_t replica_cap = 0;   // elements
+  bool replicated = false;
   bool perm_rank_slices = false;  // b200ppo_set_perm_layout: `perms` holds only this rank's slots
   bool in_epoch = false;          // inside b200ppo_train's minibatch loop: the minibatch operands predate the previous kernel
   unsigned p2p_seq = 0;
@@ -906,7 +911,7 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   split_arena_free(c->arena);
   for (int n = 0; n < 2; ++n)
     for (int l = 0; l < B200PPO_MAX_LAYERS; ++l) { dev_free(c->bf.H[n][l]); dev_free(c->bf.dZ[n][l]); dev_free(c->bf.W[n][l]); dev_free(c->bf.WT[n][l]); }
-  dev_free(c->bf.X); dev_free(c->bf.sh_obs); dev_free(c->bf.obs_table);
+  dev_free(c->bf.X); dev_free(c->bf.sh_obs); dev_free(c->bf.obs_table); dev_free(c->replica);
   dev_free(c->sh_obs); dev_free(c->sh_act); dev_free(c->sh_logp); dev_free(c->sh_adv); dev_free(c->sh_tgt);
   for (auto& h : c->host) {
     dev_free(h.obs); dev_free(h.act); dev_free(h.logp); dev_free(h.rew); dev_free(h.val);
@@ -1103,7 +1108,9 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
     const int64_t cstride = sliced ? lb : batch, coff = sliced ? 0 : int64_t(ctx->rank) * lb;
     if (shared_obs) {  // rows pulled from every rank's table over NVLink by the copy engine
       const float* parts[kMaxPeers];
-      for (int r = 0; r < ctx->world; ++r) parts[r] = reinterpret_cast<const float*>(ctx->peer_table[r]);
+      for (int r = 0; r < ctx->world; ++r)
+        parts[r] = reinterpret_cast<const float*>((ctx->replicated && r != ctx->rank) ? ctx->replica + int64_t(r) * ctx->shared_rows * PX
+                                                                                        : ctx->peer_table[r]);
       return launch_gather_parts(idx, nb * lb, n_samples, lb, cstride, coff, parts, ctx->world, ctx->shared_rows, PX / 2,
                                  action, A, old_logp, advantage, target, reinterpret_cast<float*>(ctx->bf.sh_obs + o * PX),
                                  ctx->sh_act + o * A, ctx->sh_logp + o, ctx->sh_adv + o, ctx->sh_tgt + o, ctx->err_flag, gs);
@@ -1527,6 +1534,29 @@ extern "C" B2_EXPORT int b200ppo_table_fill(b200ppo_ctx* ctx, const float* obs_l
   B2_TRY(launch_cast_rows_ones(obs_local, rows_local, ctx->net[0].d.in_dim, ctx->bf.obs_table, ctx->bf.pitchX,
                                static_cast<cudaStream_t>(stream)));
   ctx->shared_filled = true;
+  ctx->replicated = false;
+  return B200PPO_OK;
+}
+
+extern "C" B2_EXPORT int b200ppo_table_replicate(b200ppo_ctx* ctx, b200ppo_stream stream) {
+  B2_CHECK_ARG(ctx, "b200ppo_table_replicate: null context");
+  B2_CHECK_ARG(ctx->shared_rows > 0 && ctx->shared_filled, "b200ppo_table_replicate: fill the shared tables first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t slab = ctx->shared_rows * ctx->bf.pitchX;
+  if (ctx->replica_cap < slab * ctx->world) {
+    B2_CUDA(cudaDeviceSynchronize());
+    dev_free(ctx->replica);
+    ctx->replica_cap = 0;
+    B2_TRY(dev_alloc(&ctx->replica, slab * ctx->world));
+    ctx->replica_cap = slab * ctx->world;
+  }
+  // start with the next rank so that the eight ranks do not all pull from rank 0 first
+  for (int k = 1; k < ctx->world; ++k) {
+    const int r = (ctx->rank + k) % ctx->world;
+    B2_CUDA(cudaMemcpyAsync(ctx->replica + int64_t(r) * slab, ctx->peer_table[r], size_t(slab) * sizeof(__nv_bfloat16),
+                            cudaMemcpyDeviceToDevice, st));
+  }
+  ctx->replicated = true;
   return B200PPO_OK;
 }
 
