@@ -296,8 +296,29 @@ def k6_latency(agent, n_envs):
     obs = torch.randn(n_envs, OBS_DIM, device=dev)
     noise = torch.randn(n_envs, ACT_DIM, device=dev)
     med, best = cuda_time(lambda: agent.act_fused(obs, noise=noise), 50, warm=5)
+    # the same C-ABI call with preallocated outputs, 100 calls back to back between two events: what the GPU needs per
+    # environment step once the Python wrapper (four allocations per call) is out of the way
+    from mujoco_reinforcement_learning_b200 import _lib
+    eng = agent.engine
+    lib = _lib.load()
+    mean = torch.empty(n_envs, ACT_DIM, device=dev)
+    action, logp, value = torch.empty_like(mean), torch.empty(n_envs, device=dev), torch.empty(n_envs, 1, device=dev)
+    args = (eng._ctx, _lib.ptr(eng.flat), _lib.ptr(obs), n_envs, _lib.ptr(noise), _lib.ptr(mean), _lib.ptr(value), _lib.ptr(action),
+            _lib.ptr(logp), _lib.stream_ptr())
+    launches0 = lib.b200ppo_launch_count()
+    _lib.check(lib.b200ppo_policy_infer(*args), "b200ppo_policy_infer")
+    launches = lib.b200ppo_launch_count() - launches0
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(100):
+        lib.b200ppo_policy_infer(*args)
+    e1.record()
+    torch.cuda.synchronize()
     return {"envs": n_envs, "us_per_env_step_batch": med * 1e3, "best_us": best * 1e3,
-            "api": "PPOAgent.act_fused -> b200ppo_policy_infer (actor + critic forward, sample, log-prob)"}
+            "us_c_abi_back_to_back": e0.elapsed_time(e1) * 10.0, "launches_per_call": int(launches),
+            "api": "PPOAgent.act_fused -> b200ppo_policy_infer (actor + critic forward, sample, log-prob); bf16 context: weights and "
+                   "observations to bf16 + the forward-only instance of tc_chain_kernel"}
 
 
 def hbm_kernel_lines(pk):

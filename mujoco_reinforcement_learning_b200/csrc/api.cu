@@ -656,9 +656,15 @@ static bool chain_applicable(const b200ppo_ctx* ctx) {
   return int64_t(num_sms()) + 8 <= ctx->loss_partial_rows;
 }
 
+// Outputs of the forward-only instance (rollout inference); nullptr members are skipped.
+struct ChainInfer {
+  const float* noise;
+  float *mean, *value, *action, *logp;
+};
+
 static int launch_chain(b200ppo_ctx* ctx, const float* params, const __nv_bfloat16* xb, int64_t B, const float* action,
                         const float* old_logp, const float* adv, const float* tgt, const b200ppo_hparams* hp, int* loss_ctas,
-                        cudaStream_t st, bool x_early) {
+                        cudaStream_t st, bool x_early, const ChainInfer* inf = nullptr) {
   auto& bf = ctx->bf;
   ChainArgs a{};
   const int D = ctx->net[0].d.in_dim;
@@ -685,16 +691,19 @@ static int launch_chain(b200ppo_ctx* ctx, const float* params, const __nv_bfloat
   a.ppo.partials = ctx->loss_partials;
   a.ppo.act_dim = ctx->net[0].out_dim();
   a.ppo.final_tanh = ctx->net[0].d.final_tanh;
-  a.ppo.clip_eps = float(hp->clip_epsilon);
+  a.ppo.clip_eps = hp != nullptr ? float(hp->clip_epsilon) : 0.f;
   a.ppo.inv_global_batch = 1.f / float(B * ctx->world);
+  if (inf != nullptr) {
+    a.inf_noise = inf->noise; a.inf_mean = inf->mean; a.inf_value = inf->value; a.inf_action = inf->action; a.inf_logp = inf->logp;
+  }
   a.out_scale = ctx->net[0].d.out_scale;
   a.M = int(B);
   a.KB1 = (D + TC_CHAIN_BK - 1) / TC_CHAIN_BK;
   a.act = ctx->net[0].d.activation;
   a.tiles2 = int((B + 255) / 256);
   a.x_early = x_early ? 1 : 0;
-  a.trace = g_chain_trace;
-  return launch_tc_chain(a, st, loss_ctas);
+  a.trace = inf != nullptr ? nullptr : g_chain_trace;
+  return launch_tc_chain(a, st, loss_ctas, inf != nullptr);
 }
 
 // forward + losses + backward of one minibatch; gradients left as split-K partials in ctx->gpart.
@@ -1007,6 +1016,18 @@ extern "C" B2_EXPORT int b200ppo_policy_infer(b200ppo_ctx* ctx, const float* par
   const bool need_actor = mean || action || logp;
   const int nets = (need_actor ? 1 : 0) | (value ? 2 : 0);
   if (nets == 0) return B200PPO_OK;
+  if (ctx->precision == B200PPO_PREC_BF16 && chain_applicable(ctx)) {
+    // the bf16 variant's rollout step: weights and observations to bf16, then ONE tensor-core launch (the forward half of the
+    // chain kernel) that leaves mean, sampled action, its log-probability and the value (B200PPO_CHAIN_INFER=0: fp32 path)
+    static const char* mode = getenv("B200PPO_CHAIN_INFER");
+    if (!(mode != nullptr && mode[0] == '0')) {
+      B2_TRY(cast_weights(ctx, params, st));
+      B2_TRY(launch_cast_rows_ones(obs, batch, ctx->net[0].d.in_dim, ctx->bf.X, ctx->bf.pitchX, st));
+      const ChainInfer inf{noise, mean, value, action, logp};
+      int grid = 0;
+      return launch_chain(ctx, params, ctx->bf.X, batch, nullptr, nullptr, nullptr, nullptr, nullptr, &grid, st, false, &inf);
+    }
+  }
   B2_TRY(forward_nets(ctx, params, obs, batch, nets, acts, outs, st, false, fresh_arena(ctx)));
   if (action || logp)
     B2_TRY(launch_sample_logp(outs[0], params + ctx->logstd_off, noise, batch, ctx->net[0].out_dim(), action, logp, st));

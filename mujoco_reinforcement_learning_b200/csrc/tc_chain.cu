@@ -260,7 +260,11 @@ __device__ __forceinline__ float ch_red8(const float (&v)[8], int lane) {
 // read X (so it goes second); backward, the earlier its last MMA (step 8) retires, the earlier the next tile's
 // observations can stream in behind the actor's step 9.  The one irregular dependency this creates: step 6 (critic)
 // needs the seeds of step 5, not of step 4.
-template <int ACT>
+//
+// INFER: the rollout's policy evaluation (K6: PPOAgent.act, src/entities/agents/ppo_agent.py:act) as the same pipeline cut
+// after step 5 — no dgrad steps, no global copies of the hidden activations; step 4 turns the actor's output row into
+// mean, sampled action and its log-probability, step 5 writes the value.
+template <int ACT, bool INFER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_constant__ ChainArgs a) {
   constexpr uint32_t TMEM_COLS = 512;
   constexpr int H = kChainHidden;
@@ -362,6 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
           dst = ring_acquire(4 * 1024);
           for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(dst + kb * 1024, &a.net[1].w3k, cur_bar, kb * TC_BK, int(rank) * 8);
         }
+        if constexpr (INFER) continue;
         {  // dgrad through the output layers: W3 as [K = out][N = hidden], this CTA's 128 hidden columns as two 64-wide atoms
           uint8_t* dst = ring_acquire(2 * 2048);
           for (int j = 0; j < 2; ++j) tma_load_2d_pair(dst + j * 2048, &a.net[1].w3m, cur_bar, int(rank) * 128 + 64 * j, 0);
@@ -449,8 +454,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
               umma2_bf16(d, umma_desc(aa + k * 32, 0, 1024), umma_desc(bb + k * 32, 0, 1024), o ? ID_N16 : ID_N32, (kb > 0 || k > 0) ? 1u : 0u);
           }
           ring_release();
+          if (INFER && o == 1) {  // nothing reads the observations or the critic tile after this step
+            umma2_commit(&x_free[0]);
+            umma2_commit(&x_free[1]);
+          }
           step_end();
         }
+        if constexpr (INFER) continue;
         for (int o = 0; o < 2; ++o) {  // steps 6, 7: dgrad through the output layers (K = 16 critic / 32 actor)
           const uint32_t d = step_begin();
           if (o == 0) {  // the critic's seeds come from step 5, the previous step (see the note on the order above)
@@ -586,7 +596,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
 #pragma unroll 1
         for (int o = 0; o < 2; ++o) {  // steps 0-3: hidden layers forward (actor, critic)
           const ChainNet& N = a.net[o];
-          if (layer == 1) {  // the loss operands of this row: requested now (volatile: not to be sunk to their use), needed in steps 4 / 5
+          if (INFER) {
+            // (the noise row is read in step 4 by the one warp per lane quarter that finishes the actor's outputs)
+          } else if (layer == 1) {  // the loss operands of this row: requested now (volatile: not to be sunk to their use), needed in steps 4 / 5
             if (o == 0) {
               const float* ap = a.ppo.action + mm * A + chunk * 8;
 #pragma unroll
@@ -602,8 +614,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
           ch_epi_forward(lane_base + uint32_t(o) * 256u + uint32_t(chunk * 64), bias_chunk_s + uint32_t(o * 2 + layer) * 512u, act,
                          o ? row_c : row_a, sw);
           tr(5);
-          step_done(layer ? &N.sH2 : &N.sH1, o ? sub_c : sub_a, grow0);
+          step_done(INFER ? nullptr : (layer ? &N.sH2 : &N.sH1), o ? sub_c : sub_a, grow0);
         }
+      }
+      if constexpr (INFER) {
+        {  // step 4: the actor's output row -> mean, action = mean + sigma * noise, log-prob of that action (one warp per lane quarter)
+          acc_wait();
+          if (chunk == 0) {
+            const float scale = a.out_scale;
+            const bool ft = a.ppo.final_tanh != 0;
+            float lp = 0.f;
+#pragma unroll 1
+            for (int j0 = 0; j0 < A; j0 += 8) {
+              uint32_t v[8];
+              tmem_ld8(lane_base + uint32_t(j0), v);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int j = j0 + i;
+                if (j < A && row_ok) {
+                  const float pre = __uint_as_float(v[i]) + b3_s[j];
+                  const float mean = ft ? scale * tanhf(pre) : pre;
+                  const float nz = a.inf_noise != nullptr ? __ldg(a.inf_noise + mm * A + j) : 0.f;
+                  if (a.inf_mean != nullptr) a.inf_mean[mm * A + j] = mean;
+                  if (a.inf_action != nullptr) a.inf_action[mm * A + j] = mean + expf(consts_s[j]) * nz;
+                  lp += -0.5f * nz * nz - consts_s[j] - kTcLogSqrt2Pi;
+                }
+              }
+            }
+            if (row_ok && a.inf_logp != nullptr) a.inf_logp[mm] = lp;
+          }
+          step_done(nullptr, 0, 0);
+        }
+        {  // step 5: the critic's value
+          acc_wait();
+          if (chunk == 0) {
+            uint32_t v[8];
+            tmem_ld8(lane_base + 256u, v);
+            if (row_ok && a.inf_value != nullptr) a.inf_value[mm] = __uint_as_float(v[0]) + b3_s[kChainMaxAct];
+          }
+          step_done(nullptr, 0, 0);
+        }
+        continue;
       }
       {  // step 4: actor output layer + loss.  A row's columns are split over the four warps of its TMEM lane quarter
         // (8 action columns each): partial log-probs meet in a 16-byte unit of the seed tile's row that the seeds do
@@ -748,7 +799,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
     // this CTA's row of loss partials: (sum surrogate, sum huber, sum d loss / d logstd_j)
     asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_WARPS * 32) : "memory");
     const int t = threadIdx.x - 64;
-    if (t < 2 + A)
+    if (!INFER && t < 2 + A)
       a.ppo.partials[int64_t(blockIdx.x) * (2 + A) + t] = red_s[t] + red_s[CH_RED_W + t] + red_s[2 * CH_RED_W + t] + red_s[3 * CH_RED_W + t];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -766,23 +817,27 @@ bool tc_chain_shape_ok(int in_dim, int h1, int h2, int out_dim) {
   return in_dim >= 1 && in_dim <= kChainMaxIn && h1 == kChainHidden && h2 == kChainHidden && out_dim >= 1 && out_dim <= kChainMaxAct;
 }
 
-int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out) {
+int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out, bool infer) {
   B2_CHECK_ARG(a.M > 0 && a.KB1 >= 1 && a.KB1 <= 6 && a.tiles2 == (a.M + 255) / 256, "chain kernel: bad shape");
   static bool configured = false;
   if (!configured) {
-    B2_CUDA(cudaFuncSetAttribute(tc_chain_kernel<B200PPO_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
-    B2_CUDA(cudaFuncSetAttribute(tc_chain_kernel<B200PPO_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(tc_chain_kernel<B200PPO_ACT_TANH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(tc_chain_kernel<B200PPO_ACT_RELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(tc_chain_kernel<B200PPO_ACT_TANH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(tc_chain_kernel<B200PPO_ACT_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
     configured = true;
   }
   const int pairs = std::min(num_sms() / 2, a.tiles2);
   if (grid_out) *grid_out = 2 * pairs;
-  void (*kernel)(ChainArgs) = a.act == B200PPO_ACT_TANH ? tc_chain_kernel<B200PPO_ACT_TANH> : tc_chain_kernel<B200PPO_ACT_RELU>;
+  void (*kernel)(ChainArgs);
+  if (infer) kernel = a.act == B200PPO_ACT_TANH ? tc_chain_kernel<B200PPO_ACT_TANH, true> : tc_chain_kernel<B200PPO_ACT_RELU, true>;
+  else kernel = a.act == B200PPO_ACT_TANH ? tc_chain_kernel<B200PPO_ACT_TANH, false> : tc_chain_kernel<B200PPO_ACT_RELU, false>;
   // profiling aid: B200PPO_CHAIN_TRACE=<n> prints the clock64 timeline of pair 0 of the n-th launch (cycles since its
   // first step): when the issuer got its operands, when it had issued the step, when the epilogue saw the accumulator
   // and when the slowest epilogue warp of the leader was done with it
   static const char* trace_env = getenv("B200PPO_CHAIN_TRACE");
   static int calls = 0;
-  if (trace_env != nullptr && ++calls == atoi(trace_env)) {
+  if (trace_env != nullptr && !infer && ++calls == atoi(trace_env)) {
     long long* tr = nullptr;
     B2_CUDA(cudaMalloc(&tr, 60 * 8 * sizeof(long long)));
     B2_CUDA(cudaMemset(tr, 0, 60 * 8 * sizeof(long long)));

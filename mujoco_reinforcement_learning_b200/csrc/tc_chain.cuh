@@ -24,6 +24,9 @@ struct ChainArgs {
   float out_scale;
   int M, KB1, act, tiles2;
   int x_early;       // the observations are older than the previous kernel of the stream: X may be requested before the PDL wait
+  // forward-only mode (rollout inference): outputs, each nullable; inf_noise [M][act] nullable (action = mean)
+  float *inf_mean, *inf_value, *inf_action, *inf_logp;
+  const float* inf_noise;
   long long* trace;  // debug: clock64 timeline of pair 0 (nullptr in production)
 };
 
@@ -34,6 +37,7 @@ constexpr int kChainMaxIn = 384;
 
 // in_dim <= 384, both hidden layers 256 wide, out <= 24, rows 32-byte aligned
 bool tc_chain_shape_ok(int in_dim, int h1, int h2, int out_dim);
-int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out);
+// infer: the forward-only instance (mean / action / log-prob / value instead of losses, seeds and dgrads)
+int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out, bool infer = false);
 
 }  // namespace b200ppo

@@ -117,3 +117,40 @@ def test_chain_intermediates_and_gradients_vs_oracle(shape):
     tol = 8e-2 if act == "relu" else RTOL_BF16
     bad = [(k, e) for k, e in report if not e <= tol]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("shape", [dict(D=376, A=17, B=4096), dict(D=376, A=17, B=700), dict(D=27, A=8, B=4096, act="relu"),
+                                   dict(D=100, A=24, B=300), dict(D=64, A=1, B=77)],
+                         ids=lambda s: "-".join(f"{k}{v}" for k, v in s.items()))
+def test_rollout_step_in_one_tensor_core_launch(shape):
+    """K6 in the bf16 variant (ppo_agent.py act / ppo.py:22-26): the forward-only instance of the chain kernel leaves mean,
+    the sampled action, its log-probability and the value — each at north_star's bf16 tolerance against the oracle."""
+    from mujoco_reinforcement_learning_b200 import _lib
+    D, A, B = shape["D"], shape["A"], shape["B"]
+    oracle, agent, run = make_pair(D, A, [256, 256], [256, 256], shape.get("act", "tanh"), batch=B, max_batch=B, precision="bf16", seed=21)
+    g = torch.Generator().manual_seed(6)
+    obs = torch.randn(B, D, generator=g)
+    noise = torch.randn(B, A, generator=g)
+    with torch.no_grad():
+        for n, p in oracle.networks.named_parameters():
+            if n.endswith("bias"):
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+        agent.networks.load_state_dict(oracle.networks.state_dict())
+        mean_ref, std_ref = oracle.networks["actor"](obs)
+        v_ref = oracle.networks["critic"](obs)
+    a_ref = mean_ref + std_ref * noise
+    lp_ref = torch.distributions.Normal(mean_ref, std_ref).log_prob(a_ref).sum(1)
+    lib = _lib.load()
+    n0 = lib.b200ppo_launch_count()
+    action, logp, value, mean = agent.engine.policy_infer(obs.to(DEV), noise.to(DEV))
+    torch.cuda.synchronize()
+    assert lib.b200ppo_launch_count() - n0 == 3  # weights -> bf16, observations -> bf16, the chain kernel
+    for name, got, ref in (("mean", mean, mean_ref), ("action", action, a_ref), ("logp", logp, lp_ref), ("value", value, v_ref)):
+        e = rel_l2(got, ref)
+        print(f"  {name:8s} rel L2 err {e:.3e}")
+        assert e <= RTOL_BF16, (name, e)
+    # test phase: no noise -> the action is the mean; the critic alone / the actor alone
+    a2, lp2, v2, m2 = agent.engine.policy_infer(obs.to(DEV), None)
+    assert torch.equal(a2, m2) and torch.equal(m2, mean) and torch.equal(v2, value)
+    a3, _, v3, _ = agent.engine.policy_infer(obs.to(DEV), noise.to(DEV), want_value=False)
+    assert v3 is None and torch.equal(a3, action)
