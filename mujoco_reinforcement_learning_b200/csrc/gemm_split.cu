@@ -224,7 +224,36 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
     B2_CUDA(launch_pdl(split3_kernel, dim3(blocks), dim3(256), 0, st, jobs));
     B2_LAUNCH_CHECK();
   }
-  return launch_tc_group(tg, BN, st);
+  // debug: B200PPO_SPLIT_TRACE=<n> prints phase marks (cycles) of every 37th CTA of the n-th launch
+  static const char* trace_env = getenv("B200PPO_SPLIT_TRACE");
+  static int calls = 0;
+  long long* trace = nullptr;
+  if (trace_env != nullptr && ++calls == atoi(trace_env)) {
+    B2_CUDA(cudaMalloc(&trace, 64 * 8 * sizeof(long long)));
+    B2_CUDA(cudaMemset(trace, 0, 64 * 8 * sizeof(long long)));
+    tg.trace = trace;
+  }
+  struct TraceDump {
+    long long* t; cudaStream_t st; int tiles;
+    ~TraceDump() {
+      if (t == nullptr) return;
+      cudaStreamSynchronize(st);
+      long long h[64 * 8];
+      cudaMemcpy(h, t, sizeof(h), cudaMemcpyDeviceToHost);
+      cudaFree(t);
+      long long t0 = h[0];
+      for (int i = 0; i < 64; ++i) if (h[i * 8] != 0 && h[i * 8] < t0) t0 = h[i * 8];
+      fprintf(stderr, "split GEMM launch, %d CTAs: cta | sm | entry, set-up done, first operands, last MMA issued, epilogue done (warp 2), end  (cycles since the first entry; clocks of different SMs are not aligned)\n", tiles);
+      for (int i = 0; i < 64 && h[i * 8] != 0; ++i)
+        fprintf(stderr, "  %4d | %3lld | %7lld %7lld %7lld %7lld %7lld %7lld   (own: set-up %lld, to first operands %lld, main loop %lld, epilogue %lld)\n", i * 37, h[i * 8 + 7],
+                h[i * 8] - t0, h[i * 8 + 1] - t0, h[i * 8 + 2] - t0, h[i * 8 + 3] - t0, h[i * 8 + 5] - t0, h[i * 8 + 6] - t0,
+                h[i * 8 + 1] - h[i * 8], h[i * 8 + 2] - h[i * 8 + 1], h[i * 8 + 3] - h[i * 8 + 2], h[i * 8 + 5] - h[i * 8 + 3]);
+    }
+  } dump{trace, st, tg.total_tiles};
+  // forward / dgrad: two CTAs per SM (two-stage rings); weight gradients: one CTA with the deep ring — measured, profiles/README.md
+  bool two = !any_wgrad;
+  if (const char* e = getenv(any_wgrad ? "B200PPO_SPLIT_OCC_WGRAD" : "B200PPO_SPLIT_OCC")) two = atoi(e) == 2;
+  return launch_tc_group(tg, BN, st, nullptr, two);
 }
 
 }  // namespace b200ppo

@@ -30,15 +30,18 @@ extern long long* g_ws_trace;
 // smem ring depth: K loops are 1-6 tiles for forward/dgrad, so for BN <= 128 two 32 KB stages + the 32 KB epilogue
 // staging area let two CTAs share an SM (one CTA's epilogue overlaps the other's TMA/MMA main loop); the wide tiles
 // used by the long-K weight-gradient GEMM run one CTA per SM with a deeper ring.
-template <int BN> struct TcCfg {
-  static constexpr int STAGES = BN <= 128 ? 2 : (BN <= 192 ? 4 : 3);
-  static constexpr int CTAS_PER_SM = BN <= 128 ? 2 : 1;
+// OCC = 2 with a wide tile (the fp32-tolerance GEMMs, whose K loops are six times as long as their epilogue is wide): two
+// stages and no staging area, 100 KB per CTA, so that here too one CTA's epilogue overlaps the other's main loop.
+template <int BN, int OCC> struct TcCfg {
+  static constexpr int STAGES = OCC == 2 ? 2 : (BN <= 192 ? 5 : 4);  // 200 / 192 KB of operands in flight per SM at one CTA
+  static constexpr int CTAS_PER_SM = OCC;
+  static constexpr int STAGE_AREA = BN <= 128 ? TC_EPI_WARPS * 4096 : 0;  // (TC_STAGE_BYTES per epilogue warp; BN > 128 never stages)
 };
 int tc_ctas_per_sm(int bn) { return bn <= 128 ? 2 : 1; }
 
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_kernel(const __grid_constant__ TcGroup grp) {
-  constexpr int TC_STAGES = TcCfg<BN>::STAGES;
+template <int BN, int OCC>
+__global__ void __launch_bounds__(TC_THREADS, OCC) tc_gemm_kernel(const __grid_constant__ TcGroup grp) {
+  constexpr int TC_STAGES = TcCfg<BN, OCC>::STAGES;
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));  // power of two
   extern __shared__ uint8_t smem_raw[];
@@ -56,6 +59,15 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   uint8_t* stage_area = reinterpret_cast<uint8_t*>(bias_s) + 3072;                        // TC_EPI_WARPS x 4 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // debug timeline: 0 entry, 1 set-up done (after the PDL wait), 2 first operands landed, 3 last MMA issued, 4 accumulator
+  // complete (seen by warp 2), 5 warp 2's epilogue done, 6 CTA end; %smid in slot 7
+  long long* const trc = (grp.trace != nullptr && blockIdx.x % 37 == 0 && blockIdx.x / 37 < 64) ? grp.trace + (blockIdx.x / 37) * 8 : nullptr;
+  if (trc != nullptr && threadIdx.x == 0) {
+    trc[0] = clock64();
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trc[7] = smid;
+  }
 
   int pi = 0;
 #pragma unroll 1
@@ -91,6 +103,7 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait_then_release();  // everything below reads what earlier kernels of the chain wrote
+  if (trc != nullptr && threadIdx.x == 0) trc[1] = clock64();
   if (warp >= 2) {          // epilogue warps stage their constants (named barrier 1: the other two warps are already streaming)
     tc_stage_bias(P, n0, BN, bias_s, threadIdx.x - 64, TC_THREADS - 64);
     tc_ppo_stage_consts(P, consts_s, threadIdx.x - 64);
@@ -142,6 +155,8 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
         const uint32_t ph = (it / TC_STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (trc != nullptr && lane == 0 && it == 0) trc[2] = clock64();
+        if (trc != nullptr && lane == 0 && it == n_it - 1) trc[3] = clock64();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(sA + s * TC_A_BYTES), b_addr = smem_u32(sB + s * B_BYTES);
 #pragma unroll
@@ -174,8 +189,10 @@ __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN>::CTAS_PER_SM) tc_gemm_ke
       }
     } else tc_epilogue<BN>(P, split, tmem_base, has_k, m0, n0, warp, lane, tmem_full_bar, 0, bias_s);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (trc != nullptr && warp == 2 && lane == 0) trc[5] = clock64();
   }
   __syncthreads();
+  if (trc != nullptr && threadIdx.x == 0) trc[6] = clock64();
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -259,27 +276,27 @@ int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B
   return B200PPO_OK;
 }
 
-template <int BN>
+template <int BN, int OCC>
 static int launch_bn(const TcGroup& g, cudaStream_t st) {
-  constexpr int smem = TcCfg<BN>::STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256 + 3072 + TC_EPI_WARPS * TC_STAGE_BYTES;
+  constexpr int smem = TcCfg<BN, OCC>::STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256 + 3072 + TcCfg<BN, OCC>::STAGE_AREA;
   static bool configured = false;
   if (!configured) {
-    B2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B2_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  B2_CUDA(launch_pdl(tc_gemm_kernel<BN>, dim3(g.total_tiles), dim3(TC_THREADS), smem, st, g));
+  B2_CUDA(launch_pdl(tc_gemm_kernel<BN, OCC>, dim3(g.total_tiles), dim3(TC_THREADS), smem, st, g));
   B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }
 
-int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st, int* grid_out) {
+int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st, int* grid_out, bool two_per_sm) {
   if (grid_out) *grid_out = g.total_tiles;
   if (g.total_tiles == 0) return B200PPO_OK;
   switch (bn) {
-    case 64: return launch_bn<64>(g, st);
-    case 128: return launch_bn<128>(g, st);
-    case 192: return launch_bn<192>(g, st);
-    case 256: return launch_bn<256>(g, st);
+    case 64: return launch_bn<64, 2>(g, st);
+    case 128: return launch_bn<128, 2>(g, st);
+    case 192: return two_per_sm ? launch_bn<192, 2>(g, st) : launch_bn<192, 1>(g, st);
+    case 256: return two_per_sm ? launch_bn<256, 2>(g, st) : launch_bn<256, 1>(g, st);
   }
   set_error("unsupported tensor-core N tile %d", bn);
   return B200PPO_EINVAL;

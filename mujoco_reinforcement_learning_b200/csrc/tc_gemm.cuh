@@ -79,6 +79,7 @@ struct TcGroup {
   TcProblem p[kMaxTcProblems];
   int count;
   int total_tiles;
+  long long* trace;  // debug: clock64 phase marks of every 37th CTA, 8 slots each (nullptr in production)
 };
 
 // Operand description handed to tc_group_add (device pointers to bf16, pitches in elements).
@@ -93,7 +94,8 @@ int tc_make_map(CUtensorMap* out, const __nv_bfloat16* ptr, int64_t inner, int64
 int tc_init();  // resolves cuTensorMapEncodeTiled; returns B200PPO_OK or an error
 // bn: N tile (64, 128 or 256).  Fills tensor maps (cached) and tile bookkeeping.
 int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B, int bn, int split_k);
-int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st, int* grid_out = nullptr);
+// two_per_sm: the 192- / 256-wide tiles with a two-stage ring and two CTAs per SM (default: deep ring, one CTA)
+int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st, int* grid_out = nullptr, bool two_per_sm = false);
 int tc_pick_bn(int64_t rows_total_tiles_m, int N);
 int tc_ctas_per_sm(int bn);
 // Persistent weights-stationary variant (tc_ws.cu) for forward / dgrad groups with many row tiles.
