@@ -18,6 +18,8 @@
 // weight gradient's B operand that column makes the bias gradient fall out of the same MMAs (TcProblem.bias_col).
 #include "gemm_split.cuh"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "tc_gemm.cuh"
@@ -34,6 +36,10 @@ int split_arena_reserve(SplitArena& a, int64_t elems) {
   a.base = nullptr;
   a.cap = 0;
   split_arena_reset(a);
+  if (a.amax == nullptr && cudaMalloc(reinterpret_cast<void**>(&a.amax), SplitArena::kMaxEntries * sizeof(float)) != cudaSuccess) {
+    set_error("cudaMalloc of the operand-scale array failed");
+    return B200PPO_ENOMEM;
+  }
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&a.base), size_t(elems) * sizeof(__nv_bfloat16));
   if (e != cudaSuccess) {
     set_error("cudaMalloc(%lld bytes) for the three-term operand arena failed: %s", (long long)(elems * 2), cudaGetErrorString(e));
@@ -45,7 +51,9 @@ int split_arena_reserve(SplitArena& a, int64_t elems) {
 
 void split_arena_free(SplitArena& a) {
   if (a.base != nullptr) cudaFree(a.base);
+  if (a.amax != nullptr) cudaFree(a.amax);
   a.base = nullptr;
+  a.amax = nullptr;
   a.cap = a.used = 0;
   a.n = 0;
 }
@@ -54,8 +62,9 @@ void split_arena_free(SplitArena& a) {
 struct SplitJob {
   const float* src;
   __nv_bfloat16* dst;
+  float* amax;                   // two-term mode: this operand's largest magnitude (filled by absmax_kernel)
   int64_t rows, ld, unit_begin;  // first 8-column unit of this job in the launch
-  int cols, cp, ones, vec;
+  int cols, cp, ones, vec, terms;
 };
 constexpr int kMaxSplitJobs = 2 * kMaxGemmProblems;
 struct SplitJobs {
@@ -68,7 +77,74 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
   return uint32_t(__bfloat16_as_ushort(lo)) | (uint32_t(__bfloat16_as_ushort(hi)) << 16);
 }
 
-// one thread = 8 consecutive columns of one row: 32 bytes in, 3 x 16 bytes out
+// one thread = 8 consecutive columns of one row
+__device__ __forceinline__ void split_load8(const SplitJob& J, int64_t row, int c0, float (&x)[8], float one) {
+  const float* sp = J.src + row * J.ld + c0;
+  if (J.vec && c0 + 8 <= J.cols) {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(sp)), q = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+    x[0] = p.x; x[1] = p.y; x[2] = p.z; x[3] = p.w; x[4] = q.x; x[5] = q.y; x[6] = q.z; x[7] = q.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = (c0 + j < J.cols) ? __ldg(sp + j) : ((c0 + j == J.cols && J.ones) ? one : 0.f);
+  }
+}
+
+__device__ __forceinline__ bool J_ones_first(const SplitJob& J, int64_t u) { return J.ones != 0 && u == J.unit_begin; }
+
+// Largest magnitude of every job's source (two-term mode), one atomicMax per warp on the float's bits; an operand that
+// carries the ones-column counts a 1.0, so that the column's scaled value 2^e stays inside fp16.
+__global__ void __launch_bounds__(256) absmax_kernel(const __grid_constant__ SplitJobs jobs) {
+  const int64_t u = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  float m = 0.f;
+  int ji = 0;
+  if (u < jobs.units) {
+#pragma unroll 1
+    for (int i = 1; i < jobs.n; ++i)
+      if (u >= jobs.j[i].unit_begin) ji = i;
+    const SplitJob& J = jobs.j[ji];
+    const int upr = J.cp >> 3;
+    const int64_t local = u - J.unit_begin;
+    const int64_t row = local / upr;
+    const int c0 = int(local - row * upr) * 8;
+    float x[8];
+    split_load8(J, row, c0, x, 1.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m = fmaxf(m, fabsf(x[j]));
+  }
+  // warp -> block -> one atomic per (block, job), and none at all when the block cannot raise the current value
+  __shared__ float wm[8];
+  __shared__ int wj[8];
+  const bool live = u < jobs.units;
+  const int key = live ? ji : -1;
+  const unsigned same = __match_any_sync(0xffffffffu, key);
+  const int wid = threadIdx.x >> 5;
+  if (same == 0xffffffffu) {
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) { wm[wid] = m; wj[wid] = key; }
+  } else {  // a warp that straddles a job boundary (or the end of the launch): lane by lane
+    if ((threadIdx.x & 31) == 0) { wm[wid] = 0.f; wj[wid] = -1; }
+    if (live && m > 0.f) atomicMax(reinterpret_cast<unsigned*>(jobs.j[ji].amax), __float_as_uint(m));
+  }
+  if (live && J_ones_first(jobs.j[ji], u)) atomicMax(reinterpret_cast<unsigned*>(jobs.j[ji].amax), __float_as_uint(1.f));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int cur = -1;
+    float best = 0.f;
+    for (int w = 0; w <= 8; ++w) {
+      const int j = w < 8 ? wj[w] : -2;
+      if (j != cur) {
+        if (cur >= 0 && best > 0.f) {
+          unsigned* dst = reinterpret_cast<unsigned*>(jobs.j[cur].amax);
+          if (__float_as_uint(best) > *reinterpret_cast<volatile unsigned*>(dst)) atomicMax(dst, __float_as_uint(best));
+        }
+        cur = j;
+        best = 0.f;
+      }
+      if (w < 8) best = fmaxf(best, wm[w]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) split3_kernel(const __grid_constant__ SplitJobs jobs) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -84,13 +160,29 @@ __global__ void __launch_bounds__(256) split3_kernel(const __grid_constant__ Spl
   const int64_t row = local / upr;
   const int c0 = int(local - row * upr) * 8;
   float x[8];
-  const float* sp = J.src + row * J.ld + c0;
-  if (J.vec && c0 + 8 <= J.cols) {
-    const float4 p = __ldg(reinterpret_cast<const float4*>(sp)), q = __ldg(reinterpret_cast<const float4*>(sp) + 1);
-    x[0] = p.x; x[1] = p.y; x[2] = p.z; x[3] = p.w; x[4] = q.x; x[5] = q.y; x[6] = q.z; x[7] = q.w;
-  } else {
+  split_load8(J, row, c0, x, 1.f);
+  if (J.terms == 2) {  // two fp16 terms of x * 2^e
+    const float sc = exp2f(float(split_exponent(__ldg(J.amax))));
+    uint32_t o[2][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = (c0 + j < J.cols) ? __ldg(sp + j) : ((c0 + j == J.cols && J.ones) ? 1.f : 0.f);
+    for (int j = 0; j < 8; j += 2) {
+      __half t[2][2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float r = x[j + k] * sc;  // exact: a power of two, no overflow by the choice of e
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          t[p][k] = __float2half_rn(r);
+          r -= __half2float(t[p][k]);  // exact
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) o[p][j >> 1] = uint32_t(__half_as_ushort(t[p][0])) | (uint32_t(__half_as_ushort(t[p][1])) << 16);
+    }
+    __nv_bfloat16* dp = J.dst + row * (2 * int64_t(J.cp)) + c0;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) *reinterpret_cast<uint4*>(dp + int64_t(p) * J.cp) = make_uint4(o[p][0], o[p][1], o[p][2], o[p][3]);
+    return;
   }
   uint32_t o[3][4];
 #pragma unroll
@@ -114,13 +206,14 @@ __global__ void __launch_bounds__(256) split3_kernel(const __grid_constant__ Spl
 }
 
 // Finds the split of (src, rows, cols, ld) in the arena or queues the job that makes it.
-static int get_split(SplitArena& arena, SplitJobs& jobs, const float* src, int64_t rows, int cols, int64_t ld, int ones,
-                     const __nv_bfloat16** out, int* cp_out) {
+static int get_split(SplitArena& arena, SplitJobs& jobs, const float* src, int64_t rows, int cols, int64_t ld, int ones, int terms,
+                     const __nv_bfloat16** out, int* cp_out, const float** amax_out) {
   for (int i = 0; i < arena.n; ++i) {
     const SplitArena::Entry& e = arena.e[i];
-    if (e.src == src && e.rows == rows && e.cols == cols && e.ld == ld && e.ones >= ones) {
+    if (e.src == src && e.rows == rows && e.cols == cols && e.ld == ld && e.ones >= ones && e.terms == terms) {
       *out = e.dst;
       *cp_out = e.cp;
+      *amax_out = arena.amax + i;
       return B200PPO_OK;
     }
   }
@@ -133,9 +226,11 @@ static int get_split(SplitArena& arena, SplitJobs& jobs, const float* src, int64
   }
   __nv_bfloat16* dst = arena.base + arena.used;
   arena.used += elems;
-  arena.e[arena.n++] = SplitArena::Entry{src, rows, ld, cols, ones, cp, dst};
+  *amax_out = arena.amax + arena.n;
+  arena.e[arena.n++] = SplitArena::Entry{src, rows, ld, cols, ones, cp, terms, dst};
   SplitJob& J = jobs.j[jobs.n++];
   J.src = src; J.dst = dst; J.rows = rows; J.ld = ld; J.cols = cols; J.cp = cp; J.ones = ones;
+  J.terms = terms; J.amax = arena.amax + (arena.n - 1);
   J.vec = (aligned16(src) && ld % 4 == 0) ? 1 : 0;
   J.unit_begin = jobs.units;
   jobs.units += rows * (cp / 8);
@@ -171,6 +266,11 @@ bool gemm_split_applicable(const GemmGroup& g) {
 int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t st) {
   if (g.total_tiles == 0 || g.count == 0) return B200PPO_OK;
   B2_TRY(tc_init());
+  // 2: two fp16 terms of the scaled value, three products (default); 3: three bf16 terms, six products
+  static const int terms = []() {
+    const char* e = getenv("B200PPO_SPLIT_TERMS");
+    return (e != nullptr && atoi(e) == 3) ? 3 : 2;
+  }();
   SplitJobs jobs{};
   TcGroup tg{};
   // N tile: 256 when the outputs are wide (the A tile is fetched once per 256 columns), 192 for the weight gradients
@@ -188,13 +288,15 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
     const bool a_mn = !(p.a_sk == 1 && p.a_sm >= p.K), b_mn = !(p.b_sk == 1 && p.b_sn >= p.K);
     const bool wgrad = a_mn && b_mn, fwd = !a_mn && !b_mn;
     const __nv_bfloat16 *As = nullptr, *Bs = nullptr;
+    const float *a_amax = nullptr, *b_amax = nullptr;
     int a_cp = 0, b_cp = 0;
     // the arrays as stored: K-major [M or N][K], MN-major [K][M or N]
-    B2_TRY(get_split(arena, jobs, p.A, a_mn ? p.K : p.M, a_mn ? p.M : p.K, a_mn ? p.a_sk : p.a_sm, fwd ? 1 : 0, &As, &a_cp));
-    B2_TRY(get_split(arena, jobs, p.B, b_mn ? p.K : p.N, b_mn ? p.N : p.K, b_mn ? p.b_sk : p.b_sn, wgrad ? 1 : 0, &Bs, &b_cp));
+    B2_TRY(get_split(arena, jobs, p.A, a_mn ? p.K : p.M, a_mn ? p.M : p.K, a_mn ? p.a_sk : p.a_sm, fwd ? 1 : 0, terms, &As, &a_cp, &a_amax));
+    B2_TRY(get_split(arena, jobs, p.B, b_mn ? p.K : p.N, b_mn ? p.N : p.K, b_mn ? p.b_sk : p.b_sn, wgrad ? 1 : 0, terms, &Bs, &b_cp, &b_amax));
     TcProblem t{};
     t.M = p.M; t.N = p.N; t.K = p.K;
-    t.parts = 3; t.a_part = a_cp; t.b_part = b_cp;
+    t.parts = terms; t.a_part = a_cp; t.b_part = b_cp;
+    t.amax_a = a_amax; t.amax_b = b_amax;
     t.out_f32 = p.C; t.ld_f32 = p.ldc; t.split_stride = p.c_split_stride;
     t.bias_col = -1;
     t.out_scale = p.out_scale;
@@ -216,11 +318,19 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
       case EPI_DRELU: t.epilogue = TC_EPI_DGRAD; t.act = B200PPO_ACT_RELU; t.aux_f32 = p.aux; t.ld_aux = p.ld_aux; break;
       default: set_error("gemm_split: unknown epilogue %d", p.epilogue); return B200PPO_EINVAL;
     }
-    B2_TRY(tc_group_add(tg, t, TcOperand{As, 3 * int64_t(a_cp), a_mn ? 1 : 0}, TcOperand{Bs, 3 * int64_t(b_cp), b_mn ? 1 : 0}, BN,
+    B2_TRY(tc_group_add(tg, t, TcOperand{As, terms * int64_t(a_cp), a_mn ? 1 : 0}, TcOperand{Bs, terms * int64_t(b_cp), b_mn ? 1 : 0}, BN,
                         p.split_k));
   }
   if (jobs.n > 0) {
     const unsigned blocks = unsigned((jobs.units + 255) / 256);
+    if (terms == 2) {
+      if (!arena.amax_zeroed) {
+        B2_CUDA(cudaMemsetAsync(arena.amax, 0, SplitArena::kMaxEntries * sizeof(float), st));
+        arena.amax_zeroed = true;
+      }
+      absmax_kernel<<<blocks, 256, 0, st>>>(jobs);
+      B2_LAUNCH_CHECK();
+    }
     B2_CUDA(launch_pdl(split3_kernel, dim3(blocks), dim3(256), 0, st, jobs));
     B2_LAUNCH_CHECK();
   }
@@ -234,13 +344,21 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
     tg.trace = trace;
   }
   struct TraceDump {
-    long long* t; cudaStream_t st; int tiles;
+    long long* t; cudaStream_t st; int tiles; bool persistent = false;
     ~TraceDump() {
       if (t == nullptr) return;
       cudaStreamSynchronize(st);
       long long h[64 * 8];
       cudaMemcpy(h, t, sizeof(h), cudaMemcpyDeviceToHost);
       cudaFree(t);
+      if (persistent) {  // tc_persist_kernel: the tiles of CTA 0 (slot 3 = epilogue enters, before it waits for the accumulator)
+        const long long t0 = h[5];
+        fprintf(stderr, "persistent split GEMM, %d tiles, CTA 0: tile | producer first, last load | issuer: accumulator, first operands, last MMA | epilogue: enters, done\n", tiles);
+        for (int i = 0; i < 64 && h[i * 8 + 5] != 0; ++i)
+          fprintf(stderr, "  %2d | %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld\n", i, h[i * 8 + 5] - t0, h[i * 8 + 6] - t0, h[i * 8] - t0,
+                  h[i * 8 + 1] - t0, h[i * 8 + 2] - t0, h[i * 8 + 3] - t0, h[i * 8 + 4] - t0);
+        return;
+      }
       long long t0 = h[0];
       for (int i = 0; i < 64; ++i) if (h[i * 8] != 0 && h[i * 8] < t0) t0 = h[i * 8];
       fprintf(stderr, "split GEMM launch, %d CTAs: cta | sm | entry, set-up done, first operands, last MMA issued, epilogue done (warp 2), end  (cycles since the first entry; clocks of different SMs are not aligned)\n", tiles);
@@ -253,6 +371,14 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
   // forward / dgrad: two CTAs per SM (two-stage rings); weight gradients: one CTA with the deep ring — measured, profiles/README.md
   bool two = !any_wgrad;
   if (const char* e = getenv(any_wgrad ? "B200PPO_SPLIT_OCC_WGRAD" : "B200PPO_SPLIT_OCC")) two = atoi(e) == 2;
+  static const bool persist = []() {
+    const char* e = getenv("B200PPO_SPLIT_PERSIST");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (persist && BN >= 192) {
+    dump.persistent = true;
+    return launch_tc_persist(tg, BN, st);
+  }
   return launch_tc_group(tg, BN, st, nullptr, two);
 }
 

@@ -12,18 +12,20 @@ struct SplitArena {
   struct Entry {
     const float* src;
     int64_t rows, ld;
-    int cols, ones, cp;
+    int cols, ones, cp, terms;
     __nv_bfloat16* dst;
   };
   static constexpr int kMaxEntries = 48;
   __nv_bfloat16* base = nullptr;
+  float* amax = nullptr;      // [kMaxEntries] largest magnitude of every entry's source (two-term mode: the scale comes from it)
+  bool amax_zeroed = false;   // since the last reset
   int64_t cap = 0, used = 0;  // elements
   Entry e[kMaxEntries];
   int n = 0;
 };
 
 int split_arena_reserve(SplitArena& a, int64_t elems);  // (re)allocates; synchronises the device when it has to grow
-inline void split_arena_reset(SplitArena& a) { a.used = 0; a.n = 0; }
+inline void split_arena_reset(SplitArena& a) { a.used = 0; a.n = 0; a.amax_zeroed = false; }
 void split_arena_free(SplitArena& a);
 // samples one tensor-core accumulator of a weight gradient may sum (see backward_nets in api.cu)
 constexpr int kSplitChain = 512;

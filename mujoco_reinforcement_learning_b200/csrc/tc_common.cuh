@@ -1,5 +1,7 @@
 // Device-side building blocks shared by the tcgen05 GEMM kernels (tc_gemm.cu, tc_ws.cu).
 #pragma once
+#include <string.h>
+
 #include "tc_gemm.cuh"
 
 namespace b200ppo {
@@ -97,8 +99,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ float split_unscale(float amax_a, float amax_b) {
+  return exp2f(float(-(split_exponent(amax_a) + split_exponent(amax_b))));
+}
+
 // Epilogue of one 128 x BN accumulator tile, executed by the 8 epilogue warps (warp index 2..9 of the CTA).
-template <int BN>
+// X32: the fp32-tolerance problems' extras, compiled only into the kernels those problems use (the two-CTAs-per-SM
+// instances keep their register budget): the fp32 activation operand of a dgrad is requested one chunk ahead, and full
+// chunks of an fp32 output leave as 32-byte pieces (st.global.v8: whole sectors, half as many store instructions).
+template <int BN, bool X32 = false>
 __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint32_t tmem_acc, bool has_k, int m0, int n0, int warp,
                                             int lane, uint64_t* tmem_full_bar, uint32_t full_parity, const float* bias_s) {
     // Problem fields into registers once (the indexed constant-bank loads of `P.` inside the column loop showed up
@@ -125,14 +134,26 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
     const int c_begin = ((warp - 2) >> 2) * CH_PER_WARP;
     const int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
     const bool aux_vec = (ld_aux % 8 == 0);
+    // two-term fp16 mode: the operands were scaled by 2^eA and 2^eB
+    const bool rescale = P.parts == 2;
+    const float acc_scale = rescale ? split_unscale(__ldg(P.amax_a), __ldg(P.amax_b)) : 1.f;
 
     uint4 pre[2];  // prefetched 32 bytes of the dgrad's activation row for the NEXT step
+    float4 pref[CW / 4];  // the same for an fp32 activation operand (64 bytes)
+    const bool auxf_vec = X32 && auxf != nullptr && (ld_aux % 4 == 0);
+    const bool f32_v8 = X32 && f32_vec && (P.ld_f32 % 8 == 0) && (P.split_stride % 8 == 0) && outf != nullptr &&
+                        ((reinterpret_cast<uintptr_t>(outf) & 31u) == 0);
     auto prefetch_aux = [&](int c) {
       const int nb = n0 + c * CW;
       if (epi == TC_EPI_DGRAD && auxf == nullptr && row_ok && c < c_end && nb + CW <= Ncols && aux_vec) {
         const uint4* ap = reinterpret_cast<const uint4*>(auxp + int64_t(m) * ld_aux + nb);
         pre[0] = __ldg(ap);
         pre[1] = __ldg(ap + 1);
+      }
+      if (X32 && epi == TC_EPI_DGRAD && auxf_vec && row_ok && c < c_end && nb + CW <= Ncols) {
+        const float4* ap = reinterpret_cast<const float4*>(auxf + int64_t(m) * ld_aux + nb);
+#pragma unroll
+        for (int u = 0; u < CW / 4; ++u) pref[u] = __ldg(ap + u);
       }
     };
     prefetch_aux(c_begin);
@@ -148,6 +169,10 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
       } else {
 #pragma unroll
         for (int j = 0; j < CW; ++j) v[j] = 0u;
+      }
+      if (rescale) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * acc_scale);
       }
       const int nb = n0 + c * CW;
       const bool live = row_ok && nb < Ncols;
@@ -183,7 +208,13 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
         if (auxf != nullptr) {
           if (live) {
             const float* ap = auxf + int64_t(m) * ld_aux + nb;
-            if (full && (ld_aux % 4 == 0)) {
+            if (X32 && full && auxf_vec) {
+#pragma unroll
+              for (int u = 0; u < CW / 4; ++u) {
+                const float4 t = pref[u];
+                h[u * 4] = t.x; h[u * 4 + 1] = t.y; h[u * 4 + 2] = t.z; h[u * 4 + 3] = t.w;
+              }
+            } else if (full && (ld_aux % 4 == 0)) {
 #pragma unroll
               for (int u = 0; u < CW / 4; ++u) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(ap) + u);
@@ -239,7 +270,13 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
       if (outf != nullptr) {
         const int ncols = bias_col >= 0 ? bias_col : Ncols;  // columns that belong to the matrix proper
         float* op = outf + int64_t(m) * ld_f32 + nb;
-        if (nb + CW <= ncols && f32_vec) {
+        if (X32 && nb + CW <= ncols && f32_v8) {
+#pragma unroll
+          for (int u = 0; u < CW / 8; ++u)
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op + u * 8), "f"(h[u * 8]), "f"(h[u * 8 + 1]),
+                         "f"(h[u * 8 + 2]), "f"(h[u * 8 + 3]), "f"(h[u * 8 + 4]), "f"(h[u * 8 + 5]), "f"(h[u * 8 + 6]), "f"(h[u * 8 + 7])
+                         : "memory");
+        } else if (nb + CW <= ncols && f32_vec) {
 #pragma unroll
           for (int u = 0; u < CW / 4; ++u) reinterpret_cast<float4*>(op)[u] = make_float4(h[u * 4], h[u * 4 + 1], h[u * 4 + 2], h[u * 4 + 3]);
         } else {

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_gemm_kernel(const __grid_c
   const bool has_k = kt_end > kt_begin;
   // fp32-tolerance mode: the six products run one after the other over this split's k range, smallest terms first
   const int kt_len = kt_end - kt_begin;
-  const int n_it = P.parts ? kSplitProducts * kt_len : kt_len;
+  const int n_it = P.parts ? split_products(P.parts) * kt_len : kt_len;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_gemm_kernel(const __grid_c
         if (P.parts) {
           const int c = it / kt_len;
           kb = kt_begin + (it - c * kt_len);
-          ao = int((kSplitTermsA >> (4 * c)) & 3u) * P.a_part;
-          bo = int((kSplitTermsB >> (4 * c)) & 3u) * P.b_part;
+          ao = int((split_terms_a(P.parts) >> (4 * c)) & 3u) * P.a_part;
+          bo = int((split_terms_b(P.parts) >> (4 * c)) & 3u) * P.b_part;
         }
         if (!P.a_mn_major) {
           tma_load_2d(a, &P.tmA, &full_bar[s], ao + kb * TC_BK, m0);
@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_gemm_kernel(const __grid_c
   } else if (warp == 1) {
     if (has_k) {  // ===== MMA issuer =====
       // instruction descriptor: D fp32, A/B bf16, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(P.a_mn_major != 0) << 15) |
+      const uint32_t fmt = P.parts == 2 ? 0u : 1u;  // operand format: F16 for the two-term mode, BF16 otherwise
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(P.a_mn_major != 0) << 15) |
                              (uint32_t(P.b_mn_major != 0) << 16) | (uint32_t(BN >> 3) << 17) | (uint32_t(TC_BM >> 4) << 24);
       // K-major SW128: 8-row groups 1024 B apart; one K=16 step = +32 B inside the swizzle row.
       // MN-major SW128: K atoms (8 k-rows x 128 B) 1024 B apart (SBO), 64-wide MN atoms BK*128 B apart (LBO);
@@ -256,8 +257,8 @@ int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B
   p.a_mn_major = A.mn_major;
   p.b_mn_major = B.mn_major;
   // fp32-tolerance mode: the whole row (three terms) is addressable, the producer adds the term's offset to the coordinate
-  const int64_t a_inner = p.parts ? 3 * int64_t(p.a_part) : (A.mn_major ? p.M : p.K);
-  const int64_t b_inner = p.parts ? 3 * int64_t(p.b_part) : (B.mn_major ? p.N : p.K);
+  const int64_t a_inner = p.parts ? p.parts * int64_t(p.a_part) : (A.mn_major ? p.M : p.K);
+  const int64_t b_inner = p.parts ? p.parts * int64_t(p.b_part) : (B.mn_major ? p.N : p.K);
   if (!A.mn_major) B2_TRY(tc_make_map(&p.tmA, A.ptr, a_inner, p.M, A.pitch, TC_BK, TC_BM));
   else B2_TRY(tc_make_map(&p.tmA, A.ptr, a_inner, p.K, A.pitch, 64, TC_BK));
   if (!B.mn_major) B2_TRY(tc_make_map(&p.tmB, B.ptr, b_inner, p.N, B.pitch, TC_BK, bn));

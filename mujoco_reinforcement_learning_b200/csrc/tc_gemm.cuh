@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -59,7 +60,11 @@ struct TcProblem {
   // products ac ca bb ab ba aa into the same fp32 accumulator — smallest first: the tensor core TRUNCATES the fp32
   // accumulator after every K = 16 step (measured, profiles/rz_probe.py: -0.47 ulp per step), so only the aa steps, which
   // come last, may happen at the accumulator's full magnitude.  0: plain bf16 operands.
+  // parts == 2: two fp16 terms of the SCALED value (x 2^e, e from the tensor's largest magnitude, split_exponent below:
+  // 11 + 11 significant bits), products ab' ba' aa' — half the tensor work and operand traffic of the three-term mode; the
+  // epilogue multiplies the accumulator by 2^-(eA + eB), read from amax_a / amax_b.
   int parts, a_part, b_part;
+  const float *amax_a, *amax_b;
   const float* aux_f32;  // TC_EPI_DGRAD: activation operand in fp32 (instead of `aux`)
   int precise;           // TC_EPI_FWD: tanhf instead of the MUFU approximation
   TcPpo ppo;
@@ -68,6 +73,29 @@ struct TcProblem {
 // the six (A term, B term) products of the fp32-tolerance mode, one nibble per product
 constexpr uint32_t kSplitTermsA = 0x010120u, kSplitTermsB = 0x001102u;
 constexpr int kSplitProducts = 6;
+// two-term mode: ab', ba', aa'
+constexpr uint32_t kSplit2TermsA = 0x010u, kSplit2TermsB = 0x001u;
+constexpr int kSplit2Products = 3;
+__host__ __device__ inline int split_products(int parts) { return parts == 2 ? kSplit2Products : kSplitProducts; }
+__host__ __device__ inline uint32_t split_terms_a(int parts) { return parts == 2 ? kSplit2TermsA : kSplitTermsA; }
+__host__ __device__ inline uint32_t split_terms_b(int parts) { return parts == 2 ? kSplit2TermsB : kSplitTermsB; }
+
+// Two-term fp16 mode of the fp32-tolerance GEMMs (gemm_split.cu): a tensor whose largest magnitude is amax is scaled by
+// 2^e with e = 14 - ceil(log2(amax)), so that its largest value lands in (2^13, 2^14] — inside fp16's range with the
+// residual terms still normal numbers.  Exact integer arithmetic on the float's bits; amax = 0 -> e = 0.
+__host__ __device__ inline int split_exponent(float amax) {
+  if (!(amax > 0.f)) return 0;
+#ifdef __CUDA_ARCH__
+  const uint32_t bits = __float_as_uint(amax);
+#else
+  uint32_t bits;
+  memcpy(&bits, &amax, 4);
+#endif
+  const int ex = int((bits >> 23) & 0xffu) - 127;          // floor(log2(amax)) for normal numbers
+  const int ceil_log2 = (bits & 0x7fffffu) ? ex + 1 : ex;
+  int e = 14 - ceil_log2;
+  return e > 100 ? 100 : (e < -100 ? -100 : e);
+}
 
 // Fused PPO epilogue applies when a warp's action slab (32 x A floats) and bf16 seed slab (32 x pad8(A)) share its 4 KB
 // staging tile, i.e. A <= 21 (Humanoid 17, Ant 8, HalfCheetah 6, Hopper 3).
@@ -96,6 +124,9 @@ int tc_init();  // resolves cuTensorMapEncodeTiled; returns B200PPO_OK or an err
 int tc_group_add(TcGroup& g, TcProblem p, const TcOperand& A, const TcOperand& B, int bn, int split_k);
 // two_per_sm: the 192- / 256-wide tiles with a two-stage ring and two CTAs per SM (default: deep ring, one CTA)
 int launch_tc_group(const TcGroup& g, int bn, cudaStream_t st, int* grid_out = nullptr, bool two_per_sm = false);
+// Persistent instance (tc_persist.cu): one CTA per SM walks the tiles, accumulators double-buffered in TMEM; bn 192 or 256,
+// plain epilogues (forward / dgrad / store).  Used by the fp32-tolerance GEMMs.
+int launch_tc_persist(const TcGroup& g, int bn, cudaStream_t st);
 int tc_pick_bn(int64_t rows_total_tiles_m, int N);
 int tc_ctas_per_sm(int bn);
 // Persistent weights-stationary variant (tc_ws.cu) for forward / dgrad groups with many row tiles.
