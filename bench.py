@@ -689,14 +689,17 @@ def run_b200(args, config):
     variants = []
     if world == 1 and not args.no_variants:
         others = [(p, b) for p in ("bf16", "fp32") for b in (32768, 4096, 500) if not (p == args.precision and b == B)]
+        others.append(("fp32x2", 32768))  # fp32 context with two scaled fp16 terms per operand value (22-bit operands)
         for prec, vb in others:
             vrun = pkg.Run(training_config=pkg.TrainingConfig(learning_rate=1e-4, batch_size=vb, epochs_per_iteration=E),
                            ppo_config=pkg.PPOConfig(), environment_config=pkg.EnvironmentConfig(maximum_timesteps=T, num_envs=n_envs),
                            network_config=pkg.NetworkConfig(input_shape=OBS_DIM, output_shape=ACT_DIM, linear_hidden_shapes=HIDDEN, critic_hidden_shapes=HIDDEN),
-                           device=str(dev), gemm_precision=prec)
+                           device=str(dev), gemm_precision="fp32" if prec == "fp32x2" else prec)
             torch.manual_seed(0)
             vagent = pkg.PPOAgent(vrun, max_batch=max(vb, 4096))
             veng = vagent.engine
+            if prec == "fp32x2":
+                veng.set_fp32_terms(2)
             vnb = M // vb
             vE = E if vb >= 4096 else 2  # 1048 minibatches/epoch at the reference's batch_size=500: two epochs suffice
             vperm = perms_dev[0][:vE]

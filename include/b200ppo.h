@@ -256,6 +256,13 @@ int b200ppo_profile_end(b200ppo_ctx* ctx, double ms_out[B200PPO_PROF_CLASSES], i
 int b200ppo_debug_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t a_mn_major,
                           int32_t b_mn_major, int32_t bn, int32_t split_k, b200ppo_stream stream);
 
+/* fp32-precision contexts, GEMMs large enough for the tensor-core route (csrc/gemm_split.cu): how an fp32 operand value is
+ * handed to tcgen05.  3 (default): three bf16 terms, six products per fp32 product — 24-bit operands, north_star's 1e-5
+ * variant.  2: two fp16 terms of the value scaled by a power of two taken from the tensor's largest magnitude, three
+ * products — 22-bit operands, about 1.3x faster; gradients stay within 1e-5 of their tensor's scale, sums that cancel
+ * 1000 : 1 do not.  Env B200PPO_SPLIT_TERMS overrides. */
+int b200ppo_set_fp32_terms(b200ppo_ctx* ctx, int32_t terms);
+
 /* Test hook for the fp32-tolerance tensor-core GEMM (csrc/gemm_split.cu: three bf16 terms per operand value, six products):
  * C[M,N] = A * B^T with the operand layouts of b200ppo_debug_tc_gemm, `split_k` split-K partials summed in order;
  * bias_grad (nullable; both operands MN-major): bias_grad[m] = sum_k A(m,k), read off the ones-column the split appends.

@@ -128,6 +128,8 @@ struct b200ppo_ctx {
   // three-term bf16 operands of the fp32-tolerance tensor-core GEMMs (gemm_split.cuh); allocated at first use
   mutable SplitArena arena;
   int64_t arena_need = 0;
+  float* obs_amax = nullptr;   // max |observation| of the rollout b200ppo_train is working on (a bound for every minibatch's rows)
+  bool obs_amax_ok = false;    // valid: inside b200ppo_train's minibatch loop
   int32_t* err_flag = nullptr;
   // shuffled-epoch buffers (train)
   // two sets (rows [0, sh_cap) and [sh_cap, 2 sh_cap)): epoch e+1 is gathered on a side stream while epoch e trains
@@ -276,6 +278,8 @@ static int forward_nets(const b200ppo_ctx* ctx, const float* params, const float
       GemmProblem p{};
       p.A = (l == 0) ? x : acts[n] + N.act_off(l - 1, B);
       p.a_sm = N.in_dim(l); p.a_sk = 1;
+      if (l == 0) p.a_bound_dev = ctx->obs_amax_ok ? ctx->obs_amax : nullptr;
+      else if (N.d.activation == B200PPO_ACT_TANH) p.a_bound = 1.f;  // |tanh| <= 1
       p.B = params + N.w_off[l];
       p.b_sn = N.in_dim(l); p.b_sk = 1;
       p.bias = params + N.b_off[l];
@@ -368,6 +372,8 @@ static int backward_nets(b200ppo_ctx* ctx, const float* params, const float* x, 
         p.a_sm = 1; p.a_sk = N.d.dims[l];
         p.B = (l == 0) ? x : acts[n] + N.act_off(l - 1, B);
         p.b_sn = 1; p.b_sk = N.in_dim(l);
+        if (l == 0) p.b_bound_dev = ctx->obs_amax_ok ? ctx->obs_amax : nullptr;
+        else if (N.d.activation == B200PPO_ACT_TANH) p.b_bound = 1.f;
         p.M = N.d.dims[l]; p.N = N.in_dim(l); p.K = int(B);
         p.C = gpart + N.w_off[l];
         p.ldc = N.in_dim(l);
@@ -893,6 +899,7 @@ extern "C" B2_EXPORT int b200ppo_create(const b200ppo_mlp_desc* actor, const b20
   if (r == B200PPO_OK) r = dev_alloc(&c->done_counter, 1, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->scratch, 8, true);
   if (r == B200PPO_OK) r = dev_alloc(&c->err_flag, 1, true);
+  if (r == B200PPO_OK) r = dev_alloc(&c->obs_amax, 1, true);
   if (r == B200PPO_OK && precision == B200PPO_PREC_BF16) r = alloc_bf16_workspaces(c);
   {
     // (the fp32 entry points of a bf16 context — rollout inference, evaluate — use it too)
@@ -900,9 +907,9 @@ extern "C" B2_EXPORT int b200ppo_create(const b200ppo_mlp_desc* actor, const b20
     // every dL/dz block and every weight matrix (reserved at first use: small problems never touch it)
     for (int n = 0; n < 2; ++n) {
       const Net& N = c->net[n];
-      c->arena_need += split_arena_elems(Bm, N.d.in_dim);
+      c->arena_need += split_arena_elems(Bm, N.d.in_dim) + 8 * (Bm + 4096);  // (+ the per-row / per-column scale vectors)
       for (int l = 0; l < N.d.n_layers; ++l)
-        c->arena_need += 2 * split_arena_elems(Bm, N.d.dims[l]) + split_arena_elems(N.d.dims[l], N.in_dim(l)) +
+        c->arena_need += 3 * split_arena_elems(Bm, N.d.dims[l]) + split_arena_elems(N.d.dims[l], N.in_dim(l)) +  // H_l, dL/dz_l by row and by column
                          split_arena_elems(N.in_dim(l), N.d.dims[l]);
     }
   }
@@ -917,6 +924,7 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   for (int n = 0; n < 2; ++n) { dev_free(c->ws_act[n]); dev_free(c->ws_dz[n]); dev_free(c->ws_out[n]); }
   dev_free(c->gpart); dev_free(c->grad_flat); dev_free(c->loss_partials); dev_free(c->ticket); dev_free(c->done_counter); dev_free(c->scratch);
   dev_free(c->err_flag);
+  dev_free(c->obs_amax);
   split_arena_free(c->arena);
   for (int n = 0; n < 2; ++n)
     for (int l = 0; l < B200PPO_MAX_LAYERS; ++l) { dev_free(c->bf.H[n][l]); dev_free(c->bf.dZ[n][l]); dev_free(c->bf.W[n][l]); dev_free(c->bf.WT[n][l]); }
@@ -942,6 +950,12 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   }
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   delete c;
+}
+
+extern "C" B2_EXPORT int b200ppo_set_fp32_terms(b200ppo_ctx* ctx, int32_t terms) {
+  B2_CHECK_ARG(ctx && (terms == 2 || terms == 3), "b200ppo_set_fp32_terms: terms must be 2 or 3");
+  ctx->arena.terms = terms;
+  return B200PPO_OK;
 }
 
 extern "C" B2_EXPORT int64_t b200ppo_param_count(const b200ppo_ctx* c) { return c ? c->n_params : 0; }
@@ -1097,6 +1111,13 @@ extern "C" B2_EXPORT int b200ppo_train(b200ppo_ctx* ctx, float* params, float* e
   const bool tc = ctx->precision == B200PPO_PREC_BF16;
   const int PX = ctx->bf.pitchX;
   if (tc) PROF(ctx, B200PPO_PROF_OTHER, st, cast_weights(ctx, params, st));
+  // fp32-tolerance tensor-core GEMMs: the largest observation of the rollout bounds every minibatch's rows, so their fp16
+  // scale needs no measuring pass per minibatch (gemm.cuh a_bound_dev)
+  struct BoundFlag { bool& f; ~BoundFlag() { f = false; } } bound_flag{ctx->obs_amax_ok};
+  if (!tc && !shared_obs && ctx->arena_need > 0 && lb * int64_t(D) >= (1 << 20)) {
+    PROF(ctx, B200PPO_PROF_OTHER, st, launch_absmax(obs, n_samples, D, D, ctx->obs_amax, st));
+    ctx->obs_amax_ok = true;
+  }
   // Every epoch gathers nb*lb observation rows.  Converting on the fly reads 4D and writes 2*pitch bytes per row and
   // epoch; converting the whole rollout ONCE and then gathering bf16 rows byte for byte (bulk-copy kernel) costs
   // n_samples*(4D + 2*pitch) up front and 4*pitch per row and epoch.  Same bits either way.

@@ -39,6 +39,11 @@ struct GemmProblem {
   int a_vec, b_vec;  // 128-bit loads legal for this operand
   int c_vec;
   float out_scale;
+  // Optional upper bounds of max |A| / max |B| (fp32-tolerance tensor-core path, gemm_split.cu: the operand's fp16 scale comes
+  // from its largest magnitude; a known bound — 1 for tanh activations, the rollout's maximum for observations — saves
+  // the pass that measures it).  0 / nullptr: unknown.  The device pointer wins over the constant.
+  float a_bound, b_bound;
+  const float *a_bound_dev, *b_bound_dev;
 };
 
 constexpr int kMaxGemmProblems = 2 * B200PPO_MAX_LAYERS;

@@ -62,7 +62,10 @@ void split_arena_free(SplitArena& a) {
 struct SplitJob {
   const float* src;
   __nv_bfloat16* dst;
-  float* amax;                   // two-term mode: this operand's largest magnitude (filled by absmax_kernel)
+  float* amax;                   // two-term mode: this operand's largest magnitude (filled by absmax_kernel, or from the bound)
+  const float* bound_dev;        // a caller-supplied upper bound of it (device value; nullptr: `bound`; both empty: measure)
+  float bound;
+  int axis;                      // 0: one scale for the operand; 1: amax[row]; 2: amax[column]
   int64_t rows, ld, unit_begin;  // first 8-column unit of this job in the launch
   int cols, cp, ones, vec, terms;
 };
@@ -145,6 +148,96 @@ __global__ void __launch_bounds__(256) absmax_kernel(const __grid_constant__ Spl
   }
 }
 
+// Bias gradients of the two-term mode: bias_grad[s][m] = sum over split s's rows k of A[k][m], fp32, fixed order (a thread
+// walks its rows in order, the eight row groups of a block meet in shared memory in order): deterministic.
+struct ColsumJob {
+  const float* src;   // [rows][ld], `cols` columns used
+  float* dst;         // [splits][split_stride], column m at dst[s * split_stride + m]
+  int64_t rows, ld, split_stride;
+  int cols, splits, block_begin;
+};
+struct ColsumJobs {
+  ColsumJob j[kMaxGemmProblems];
+  int n, blocks;
+};
+
+__global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ ColsumJobs jobs) {
+  int ji = 0;
+#pragma unroll 1
+  for (int i = 1; i < jobs.n; ++i)
+    if (int(blockIdx.x) >= jobs.j[i].block_begin) ji = i;
+  const ColsumJob& J = jobs.j[ji];
+  const int local = int(blockIdx.x) - J.block_begin;
+  const int strips = (J.cols + 31) / 32;
+  const int s = local / strips, c = (local - s * strips) * 32 + int(threadIdx.x & 31);
+  const int ty = threadIdx.x >> 5;
+  const int64_t per = (J.rows + J.splits - 1) / J.splits;
+  const int64_t r0 = int64_t(s) * per, r1 = min(r0 + per, J.rows);
+  float acc = 0.f;
+  if (c < J.cols) {
+    const float* sp = J.src + c;
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {  // four independent loads in flight
+      const float a0 = __ldg(sp + r * J.ld), a1 = __ldg(sp + (r + 8) * J.ld), a2 = __ldg(sp + (r + 16) * J.ld), a3 = __ldg(sp + (r + 24) * J.ld);
+      acc += a0; acc += a1; acc += a2; acc += a3;
+    }
+    for (; r < r1; r += 8) acc += __ldg(sp + r * J.ld);
+  }
+  __shared__ float part[8][32];
+  part[ty][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ty == 0 && c < J.cols) {
+    float t = part[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += part[i][threadIdx.x];
+    J.dst[int64_t(s) * J.split_stride + c] = t;
+  }
+}
+
+// Per-row / per-column magnitudes for operands whose rows (columns) differ by many powers of two — the dL/dz blocks: one
+// scale for the whole tensor would push the small rows' residual terms into fp16's subnormals, and what the optimizer sees
+// of a weight gradient is its error relative to ITS row, not to the tensor.  Units of these launches: axis 1 — one warp per
+// row; axis 2 — one thread per (four columns, 64 rows).
+__global__ void __launch_bounds__(256) axis_max_kernel(const __grid_constant__ SplitJobs jobs) {
+  const int64_t u = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (u >= jobs.units) return;
+  int ji = 0;
+#pragma unroll 1
+  for (int i = 1; i < jobs.n; ++i)
+    if (u >= jobs.j[i].unit_begin) ji = i;
+  const SplitJob& J = jobs.j[ji];
+  const int64_t local = u - J.unit_begin;
+  if (J.axis == 1) {  // unit_begin is a multiple of 32: whole warps
+    const int64_t row = local >> 5;
+    const int lane = int(local & 31);
+    float m = 0.f;
+    const float* sp = J.src + row * J.ld;
+    for (int c = lane; c < J.cols; c += 32) m = fmaxf(m, fabsf(__ldg(sp + c)));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) J.amax[row] = m;
+  } else {
+    const int groups = (J.cols + 3) >> 2;
+    const int64_t chunk = local / groups;
+    const int c0 = int(local - chunk * groups) * 4;
+    const int64_t r0 = chunk * 64, r1 = min(r0 + 64, J.rows);
+    float m[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t r = r0; r < r1; ++r) {
+      const float* sp = J.src + r * J.ld + c0;
+      if (J.vec && c0 + 4 <= J.cols) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(sp));
+        m[0] = fmaxf(m[0], fabsf(t.x)); m[1] = fmaxf(m[1], fabsf(t.y)); m[2] = fmaxf(m[2], fabsf(t.z)); m[3] = fmaxf(m[3], fabsf(t.w));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + j < J.cols) m[j] = fmaxf(m[j], fabsf(__ldg(sp + j)));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c0 + j < J.cols && m[j] > 0.f) atomicMax(reinterpret_cast<unsigned*>(J.amax + c0 + j), __float_as_uint(m[j]));
+  }
+}
+
 __global__ void __launch_bounds__(256) split3_kernel(const __grid_constant__ SplitJobs jobs) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -162,14 +255,27 @@ __global__ void __launch_bounds__(256) split3_kernel(const __grid_constant__ Spl
   float x[8];
   split_load8(J, row, c0, x, 1.f);
   if (J.terms == 2) {  // two fp16 terms of x * 2^e
-    const float sc = exp2f(float(split_exponent(__ldg(J.amax))));
+    float am;
+    if (J.axis == 1) {
+      am = __ldg(J.amax + row);
+    } else if (J.bound_dev != nullptr || J.bound > 0.f) {  // no measuring pass ran: publish the bound for the GEMM's epilogue
+      am = J.bound_dev != nullptr ? __ldg(J.bound_dev) : J.bound;
+      if (J.ones) am = fmaxf(am, 1.f);
+      if (u == J.unit_begin) *J.amax = am;
+    } else {
+      am = __ldg(J.amax);
+    }
+    float scv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      scv[j] = exp2f(float(split_exponent(J.axis == 2 ? ((c0 + j < J.cols) ? __ldg(J.amax + c0 + j) : 0.f) : am)));
     uint32_t o[2][4];
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       __half t[2][2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        float r = x[j + k] * sc;  // exact: a power of two, no overflow by the choice of e
+        float r = x[j + k] * scv[j + k];  // exact: a power of two, no overflow by the choice of e
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
           t[p][k] = __float2half_rn(r);
@@ -207,18 +313,21 @@ __global__ void __launch_bounds__(256) split3_kernel(const __grid_constant__ Spl
 
 // Finds the split of (src, rows, cols, ld) in the arena or queues the job that makes it.
 static int get_split(SplitArena& arena, SplitJobs& jobs, const float* src, int64_t rows, int cols, int64_t ld, int ones, int terms,
-                     const __nv_bfloat16** out, int* cp_out, const float** amax_out) {
+                     int axis, float bound, const float* bound_dev, const __nv_bfloat16** out, int* cp_out, const float** amax_out) {
+  if (terms != 2) axis = 0;
   for (int i = 0; i < arena.n; ++i) {
     const SplitArena::Entry& e = arena.e[i];
-    if (e.src == src && e.rows == rows && e.cols == cols && e.ld == ld && e.ones >= ones && e.terms == terms) {
+    if (e.src == src && e.rows == rows && e.cols == cols && e.ld == ld && e.ones >= ones && e.terms == terms && e.axis == axis) {
       *out = e.dst;
       *cp_out = e.cp;
-      *amax_out = arena.amax + i;
+      *amax_out = e.amax;
       return B200PPO_OK;
     }
   }
   const int cp = pad64(cols + 1);
-  const int64_t elems = split_arena_elems(rows, cols);
+  // per-row / per-column magnitudes live behind the terms, as floats
+  const int64_t vec_floats = axis == 1 ? rows : (axis == 2 ? cols : 0);
+  const int64_t elems = split_arena_elems(rows, cols) + (2 * vec_floats + 511) / 512 * 512;
   if (arena.n >= SplitArena::kMaxEntries || arena.used + elems > arena.cap || jobs.n >= kMaxSplitJobs) {
     set_error("three-term operand arena exhausted (%d entries, %lld of %lld elements used, %lld more asked)", arena.n,
               (long long)arena.used, (long long)arena.cap, (long long)elems);
@@ -226,11 +335,15 @@ static int get_split(SplitArena& arena, SplitJobs& jobs, const float* src, int64
   }
   __nv_bfloat16* dst = arena.base + arena.used;
   arena.used += elems;
-  *amax_out = arena.amax + arena.n;
-  arena.e[arena.n++] = SplitArena::Entry{src, rows, ld, cols, ones, cp, terms, dst};
+  float* am = axis == 0 ? arena.amax + arena.n : reinterpret_cast<float*>(dst + split_arena_elems(rows, cols));
+  *amax_out = am;
+  arena.e[arena.n++] = SplitArena::Entry{src, rows, ld, cols, ones, cp, terms, axis, dst, am};
   SplitJob& J = jobs.j[jobs.n++];
   J.src = src; J.dst = dst; J.rows = rows; J.ld = ld; J.cols = cols; J.cp = cp; J.ones = ones;
-  J.terms = terms; J.amax = arena.amax + (arena.n - 1);
+  J.terms = terms; J.amax = am; J.axis = axis;
+  J.bound = bound; J.bound_dev = bound_dev;
+  static const bool no_bounds = getenv("B200PPO_SPLIT_NOBOUND") != nullptr;  // debug: measure every operand
+  if (no_bounds) { J.bound = 0.f; J.bound_dev = nullptr; }
   J.vec = (aligned16(src) && ld % 4 == 0) ? 1 : 0;
   J.unit_begin = jobs.units;
   jobs.units += rows * (cp / 8);
@@ -266,22 +379,23 @@ bool gemm_split_applicable(const GemmGroup& g) {
 int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t st) {
   if (g.total_tiles == 0 || g.count == 0) return B200PPO_OK;
   B2_TRY(tc_init());
-  // 2: two fp16 terms of the scaled value, three products (default); 3: three bf16 terms, six products
-  static const int terms = []() {
+  static const int env_terms = []() {
     const char* e = getenv("B200PPO_SPLIT_TERMS");
-    return (e != nullptr && atoi(e) == 3) ? 3 : 2;
+    return e != nullptr ? atoi(e) : 0;
   }();
+  const int terms = (env_terms == 2 || env_terms == 3) ? env_terms : (arena.terms == 2 ? 2 : 3);
   SplitJobs jobs{};
+  ColsumJobs colsums{};
   TcGroup tg{};
   // N tile: 256 when the outputs are wide (the A tile is fetched once per 256 columns), 192 for the weight gradients
   // (N = in + 1 = 377 or 257 columns: two 192-wide tiles instead of three 128-wide ones)
   int maxN = 0;
   bool any_wgrad = false;
   for (int i = 0; i < g.count; ++i) {
-    maxN = std::max(maxN, g.p[i].N + (g.p[i].bias_grad != nullptr ? 1 : 0));
+    maxN = std::max(maxN, g.p[i].N + ((g.p[i].bias_grad != nullptr && terms == 3) ? 1 : 0));
     any_wgrad |= g.p[i].bias_grad != nullptr;
   }
-  int BN = maxN <= 128 ? 128 : (any_wgrad ? 192 : 256);
+  int BN = maxN <= 128 ? 128 : ((any_wgrad && terms == 3) ? 192 : 256);
   if (const char* e = getenv(any_wgrad ? "B200PPO_SPLIT_BN_WGRAD" : "B200PPO_SPLIT_BN")) BN = atoi(e);
   for (int i = 0; i < g.count; ++i) {
     const GemmProblem& p = g.p[i];
@@ -291,12 +405,19 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
     const float *a_amax = nullptr, *b_amax = nullptr;
     int a_cp = 0, b_cp = 0;
     // the arrays as stored: K-major [M or N][K], MN-major [K][M or N]
-    B2_TRY(get_split(arena, jobs, p.A, a_mn ? p.K : p.M, a_mn ? p.M : p.K, a_mn ? p.a_sk : p.a_sm, fwd ? 1 : 0, terms, &As, &a_cp, &a_amax));
-    B2_TRY(get_split(arena, jobs, p.B, b_mn ? p.K : p.N, b_mn ? p.N : p.K, b_mn ? p.b_sk : p.b_sn, wgrad ? 1 : 0, terms, &Bs, &b_cp, &b_amax));
+    // A operands of the backward GEMMs are dL/dz blocks: one scale per row of C (= per stored row for the dgrad's K-major view,
+    // per stored column for the weight gradient's MN-major view); everything else one scale per tensor
+    static const bool per_axis = getenv("B200PPO_SPLIT_AXIS") != nullptr;  // experiment switch; measured: no effect on parity, slower
+    const int a_axis = (fwd || !per_axis) ? 0 : (a_mn ? 2 : 1);
+    B2_TRY(get_split(arena, jobs, p.A, a_mn ? p.K : p.M, a_mn ? p.M : p.K, a_mn ? p.a_sk : p.a_sm, (fwd && terms == 3) ? 1 : 0, terms, a_axis, p.a_bound,
+                     p.a_bound_dev, &As, &a_cp, &a_amax));
+    B2_TRY(get_split(arena, jobs, p.B, b_mn ? p.K : p.N, b_mn ? p.N : p.K, b_mn ? p.b_sk : p.b_sn, (wgrad && terms == 3) ? 1 : 0, terms, 0, p.b_bound,
+                     p.b_bound_dev, &Bs, &b_cp, &b_amax));
     TcProblem t{};
     t.M = p.M; t.N = p.N; t.K = p.K;
     t.parts = terms; t.a_part = a_cp; t.b_part = b_cp;
     t.amax_a = a_amax; t.amax_b = b_amax;
+    t.a_scale_rows = (terms == 2 && a_axis != 0) ? 1 : 0;
     t.out_f32 = p.C; t.ld_f32 = p.ldc; t.split_stride = p.c_split_stride;
     t.bias_col = -1;
     t.out_scale = p.out_scale;
@@ -304,10 +425,19 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
     switch (p.epilogue) {
       case EPI_STORE:
         t.epilogue = TC_EPI_STORE;
-        if (p.bias_grad != nullptr) {  // the ones-column behind the B operand's last column
+        if (p.bias_grad != nullptr && terms == 3) {  // the ones-column behind the B operand's last column
           t.N = p.N + 1;
           t.bias_col = p.N;
           t.bias_grad = p.bias_grad;
+        } else if (p.bias_grad != nullptr) {
+          // Two fp16 terms carry 22 bits: enough for the products, not for a bias gradient that is the small difference of
+          // large sums (measured: 2.4e-4 relative on a critic bias whose terms cancel 1000 : 1).  Those are plain fp32 column
+          // sums (colsum_kernel), one partial per split like the weight gradient's.
+          ColsumJob& cj = colsums.j[colsums.n++];
+          cj.src = p.A; cj.rows = p.K; cj.cols = p.M; cj.ld = p.a_sk;
+          cj.dst = p.bias_grad; cj.splits = p.split_k; cj.split_stride = p.c_split_stride;
+          cj.block_begin = colsums.blocks;
+          colsums.blocks += p.split_k * ((p.M + 31) / 32);
         }
         break;
       case EPI_BIAS: t.epilogue = TC_EPI_FWD; t.act = TC_ACT_NONE; t.bias = p.bias; break;
@@ -328,8 +458,32 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
         B2_CUDA(cudaMemsetAsync(arena.amax, 0, SplitArena::kMaxEntries * sizeof(float), st));
         arena.amax_zeroed = true;
       }
-      absmax_kernel<<<blocks, 256, 0, st>>>(jobs);
-      B2_LAUNCH_CHECK();
+      SplitJobs measure{}, axes{};  // the operands nobody gave a bound for; the ones scaled per row / per column
+      for (int i = 0; i < jobs.n; ++i) {
+        const SplitJob& J = jobs.j[i];
+        if (J.axis != 0) {
+          SplitJob& Aj = axes.j[axes.n++];
+          Aj = J;
+          Aj.unit_begin = axes.units;
+          axes.units += J.axis == 1 ? J.rows * 32 : ((J.rows + 63) / 64) * ((J.cols + 3) / 4);
+          axes.units = (axes.units + 31) / 32 * 32;  // the next job starts on a warp
+          if (J.axis == 2) B2_CUDA(cudaMemsetAsync(J.amax, 0, size_t(J.cols) * sizeof(float), st));
+          continue;
+        }
+        if (J.bound_dev != nullptr || J.bound > 0.f) continue;
+        SplitJob& Mj = measure.j[measure.n++];
+        Mj = J;
+        Mj.unit_begin = measure.units;
+        measure.units += J.rows * (J.cp / 8);
+      }
+      if (measure.n > 0) {
+        absmax_kernel<<<unsigned((measure.units + 255) / 256), 256, 0, st>>>(measure);
+        B2_LAUNCH_CHECK();
+      }
+      if (axes.n > 0) {
+        axis_max_kernel<<<unsigned((axes.units + 255) / 256), 256, 0, st>>>(axes);
+        B2_LAUNCH_CHECK();
+      }
     }
     B2_CUDA(launch_pdl(split3_kernel, dim3(blocks), dim3(256), 0, st, jobs));
     B2_LAUNCH_CHECK();
@@ -371,6 +525,10 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
   // forward / dgrad: two CTAs per SM (two-stage rings); weight gradients: one CTA with the deep ring — measured, profiles/README.md
   bool two = !any_wgrad;
   if (const char* e = getenv(any_wgrad ? "B200PPO_SPLIT_OCC_WGRAD" : "B200PPO_SPLIT_OCC")) two = atoi(e) == 2;
+  if (colsums.n > 0) {
+    colsum_kernel<<<unsigned(colsums.blocks), 256, 0, st>>>(colsums);
+    B2_LAUNCH_CHECK();
+  }
   static const bool persist = []() {
     const char* e = getenv("B200PPO_SPLIT_PERSIST");
     return !(e != nullptr && e[0] == '0');
@@ -382,6 +540,22 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
   return launch_tc_group(tg, BN, st, nullptr, two);
 }
 
+}  // namespace b200ppo
+
+namespace b200ppo {
+int launch_absmax(const float* src, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return B200PPO_OK;
+  B2_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  SplitJobs jobs{};
+  SplitJob& J = jobs.j[jobs.n++];
+  J.src = src; J.rows = rows; J.ld = ld; J.cols = cols; J.cp = (cols + 1 + 63) / 64 * 64; J.ones = 0;
+  J.vec = (aligned16(src) && ld % 4 == 0) ? 1 : 0;
+  J.amax = out;
+  jobs.units = rows * (J.cp / 8);
+  absmax_kernel<<<unsigned((jobs.units + 255) / 256), 256, 0, st>>>(jobs);
+  B2_LAUNCH_CHECK();
+  return B200PPO_OK;
+}
 }  // namespace b200ppo
 
 // ---- test hook --------------------------------------------------------------------------------------------------------------
@@ -404,7 +578,9 @@ extern "C" B2_EXPORT int b200ppo_debug_gemm_split(const float* A, const float* B
   B2_CHECK_ARG(bias_grad == nullptr || (a_mn_major && b_mn_major), "b200ppo_debug_gemm_split: bias_grad needs both operands MN-major");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SplitArena arena;
-  const int64_t need = split_arena_elems(a_mn_major ? K : M, a_mn_major ? M : K) + split_arena_elems(b_mn_major ? K : N, b_mn_major ? N : K);
+  if (const char* e = getenv("B200PPO_DEBUG_SPLIT_TERMS")) arena.terms = atoi(e) == 2 ? 2 : 3;  // read per call (tests switch it)
+  const int64_t need = split_arena_elems(a_mn_major ? K : M, a_mn_major ? M : K) + split_arena_elems(b_mn_major ? K : N, b_mn_major ? N : K) +
+                       4 * (int64_t(M) + K + 2048);
   B2_TRY(split_arena_reserve(arena, need));
   const int64_t mn = int64_t(M) * N, stride = (mn + M + 3) / 4 * 4;
   float* part = nullptr;

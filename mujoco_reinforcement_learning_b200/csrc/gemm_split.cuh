@@ -12,8 +12,9 @@ struct SplitArena {
   struct Entry {
     const float* src;
     int64_t rows, ld;
-    int cols, ones, cp, terms;
+    int cols, ones, cp, terms, axis;
     __nv_bfloat16* dst;
+    float* amax;  // scale source: one float (axis 0), one per row (1) or one per column (2)
   };
   static constexpr int kMaxEntries = 48;
   __nv_bfloat16* base = nullptr;
@@ -22,6 +23,10 @@ struct SplitArena {
   int64_t cap = 0, used = 0;  // elements
   Entry e[kMaxEntries];
   int n = 0;
+  // 3: three bf16 terms per value, six products — 24-bit operands, the 1e-5 variant (default).  2: two fp16 terms of the
+  // scaled value, three products — 22-bit operands: 1.3x faster, every gradient tensor still within 1e-5 of its scale, but a
+  // sum that cancels 1000 : 1 (a zero-initialised bias after Adam) shows the two missing bits (b200ppo_set_fp32_terms).
+  int terms = 3;
 };
 
 int split_arena_reserve(SplitArena& a, int64_t elems);  // (re)allocates; synchronises the device when it has to grow
@@ -34,6 +39,8 @@ int64_t split_arena_elems(int64_t rows, int cols);
 
 // Every problem K- or MN-contiguous on both operands, no bf16 mirror output, and enough arithmetic to pay for the splits.
 bool gemm_split_applicable(const GemmGroup& g);
+// max |src[r][c]| over a [rows][cols] array with row pitch ld, into *out (device), on `st`
+int launch_absmax(const float* src, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t st);
 // Same contract as launch_gemm_group (gemm.cuh): C, bias_grad and split-K partials land where the FFMA kernel puts them.
 int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t st);
 

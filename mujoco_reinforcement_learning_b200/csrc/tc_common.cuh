@@ -136,7 +136,7 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
     const bool aux_vec = (ld_aux % 8 == 0);
     // two-term fp16 mode: the operands were scaled by 2^eA and 2^eB
     const bool rescale = P.parts == 2;
-    const float acc_scale = rescale ? split_unscale(__ldg(P.amax_a), __ldg(P.amax_b)) : 1.f;
+    const float acc_scale = rescale ? split_unscale(P.a_scale_rows ? (row_ok ? __ldg(P.amax_a + m) : 0.f) : __ldg(P.amax_a), __ldg(P.amax_b)) : 1.f;
 
     uint4 pre[2];  // prefetched 32 bytes of the dgrad's activation row for the NEXT step
     float4 pref[CW / 4];  // the same for an fp32 activation operand (64 bytes)

@@ -365,6 +365,11 @@ class ActorCriticEngine:
                    "b200ppo_minibatch_grads")
         return losses, grads
 
+    def set_fp32_terms(self, terms: int) -> None:
+        """fp32 contexts: 3 = three bf16 terms per operand value (24-bit operands, the 1e-5 variant, default); 2 = two scaled
+        fp16 terms (22-bit operands, faster; include/b200ppo.h)."""
+        _lib.check(self.lib.b200ppo_set_fp32_terms(self._ctx, int(terms)), "b200ppo_set_fp32_terms")
+
     @_on_engine_device
     def debug_activations(self, net: int, kind: int, layer: int, rows: int) -> torch.Tensor:
         """Test hook: bf16 intermediates of the last bf16 minibatch as fp32 (kind 0: H_layer, kind 1: dL/dz_layer)."""

@@ -38,8 +38,10 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("terms", [3, 2], ids=["bf16x3", "fp16x2"])
 @pytest.mark.parametrize("M,N,K,a_mn,b_mn,split", CASES)
-def test_gemm_split_matches_float64(M, N, K, a_mn, b_mn, split):
+def test_gemm_split_matches_float64(M, N, K, a_mn, b_mn, split, terms, monkeypatch):
+    monkeypatch.setenv("B200PPO_DEBUG_SPLIT_TERMS", str(terms))
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     A = torch.randn(M, K, generator=g) * torch.exp(torch.randn(M, 1, generator=g))  # rows of very different scale
     B = torch.randn(N, K, generator=g)
@@ -58,8 +60,10 @@ def test_gemm_split_matches_float64(M, N, K, a_mn, b_mn, split):
         assert errb < 3e-6, errb
 
 
-def test_gemm_split_keeps_small_values():
+@pytest.mark.parametrize("terms", [3, 2], ids=["bf16x3", "fp16x2"])
+def test_gemm_split_keeps_small_values(terms, monkeypatch):
     """Values 2^-20 below their row's scale survive (a plain bf16 operand would drop them)."""
+    monkeypatch.setenv("B200PPO_DEBUG_SPLIT_TERMS", str(terms))
     M, N, K = 128, 128, 64
     A = torch.ones(M, K)
     A[:, 1] = 2.0 ** -20
@@ -71,7 +75,8 @@ def test_gemm_split_keeps_small_values():
 
 @pytest.mark.parametrize("shape", [dict(D=376, A=17, B=4096), dict(D=376, A=17, B=2500, act="relu"), dict(D=27, A=8, B=8192)],
                          ids=lambda s: "-".join(f"{k}{v}" for k, v in s.items()))
-def test_fp32_minibatch_on_tensor_cores_vs_oracle(shape):
+@pytest.mark.parametrize("terms", [3, 2], ids=["bf16x3", "fp16x2"])
+def test_fp32_minibatch_on_tensor_cores_vs_oracle(shape, terms):
     """The fp32-precision minibatch at sizes where its GEMMs take the tensor-core route: losses and every gradient at
     north_star's fp32 tolerance (1e-5 of the tensor's scale) against the oracle's autograd (ppo.py:110-134)."""
     from tests._util import RTOL_FP32, assert_close
@@ -93,6 +98,7 @@ def test_fp32_minibatch_on_tensor_cores_vs_oracle(shape):
         old_logp = torch.distributions.Normal(mean, std).log_prob(action).sum(1) + 0.08 * torch.randn(B, generator=g)
     _, grads_ref, al, cl = reference_graph(oracle, obs, action, old_logp, adv, tgt)
     eng = agent.engine
+    eng.set_fp32_terms(terms)
     hp = eng.hparams(1e-4, 1e-4, oracle.cfg.clip_epsilon, oracle.cfg.entropy_eps)
     losses, grads = eng.minibatch_grads(obs.to(DEV), action.to(DEV), old_logp.to(DEV), adv.to(DEV), tgt.to(DEV), hp)
     assert abs(losses[0].item() - al) <= RTOL_FP32 * max(1.0, abs(al)), (losses[0].item(), al)
