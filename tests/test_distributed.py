@@ -113,15 +113,18 @@ def test_gloo_world2_allgather_and_gradient_sum():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision,exchange,shape", [("fp32", "nccl", ""), ("bf16", "nccl", ""), ("bf16", "p2p", ""), ("bf16", "p2p", "chain"),
-                                                      ("bf16", "nccl", "chain")])
+                                                      ("bf16", "nccl", "chain"), ("bf16", "p2p", "chain+replicate")])
 def test_nccl_data_parallel_matches_single_gpu(precision, exchange, shape):
     """exchange: the per-minibatch gradient sum through ncclAllReduce, or through peer-mapped memory fused into the
-    optimizer kernel (bf16 path)."""
+    optimizer kernel (bf16 path).  +replicate: the peers' observation tables copied once per rollout
+    (b200ppo_table_replicate) instead of gathered remotely every epoch."""
+    replicate = shape.endswith("+replicate")
+    shape = shape.replace("+replicate", "")
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29577", os.path.join(ROOT, "tests", "run_dist_parity.py"), precision] + ([shape] if shape else [])
-    env = dict(os.environ, B200PPO_P2P="1" if exchange == "p2p" else "0")
+    env = dict(os.environ, B200PPO_P2P="1" if exchange == "p2p" else "0", B200PPO_TABLE_REPLICATE="1" if replicate else "0")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert res.returncode == 0 and "DIST PARITY OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
     assert f"exchange {exchange}" in res.stdout, res.stdout[-2000:]
