@@ -397,6 +397,11 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
   }
   int BN = maxN <= 128 ? 128 : ((any_wgrad && terms == 3) ? 192 : 256);
   if (const char* e = getenv(any_wgrad ? "B200PPO_SPLIT_BN_WGRAD" : "B200PPO_SPLIT_BN")) BN = atoi(e);
+  static const bool persist = []() {
+    const char* e = getenv("B200PPO_SPLIT_PERSIST");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool use_persist = persist && BN >= 192;
   for (int i = 0; i < g.count; ++i) {
     const GemmProblem& p = g.p[i];
     const bool a_mn = !(p.a_sk == 1 && p.a_sm >= p.K), b_mn = !(p.b_sk == 1 && p.b_sn >= p.K);
@@ -447,6 +452,27 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
       case EPI_DTANH: t.epilogue = TC_EPI_DGRAD; t.act = B200PPO_ACT_TANH; t.aux_f32 = p.aux; t.ld_aux = p.ld_aux; break;
       case EPI_DRELU: t.epilogue = TC_EPI_DGRAD; t.act = B200PPO_ACT_RELU; t.aux_f32 = p.aux; t.ld_aux = p.ld_aux; break;
       default: set_error("gemm_split: unknown epilogue %d", p.epilogue); return B200PPO_EINVAL;
+    }
+    // Three-term mode: a hidden activation (forward) or a dL/dz block (dgrad) is the next GEMMs' operand — the epilogue writes
+    // its terms straight into the arena (the persistent kernel's epilogue hides behind the next tile's main loop), which
+    // saves the split pass over it.  (Two-term mode cannot: the scale is only known once the whole tensor exists.)
+    static const bool fuse_env = []() {
+      const char* e = getenv("B200PPO_SPLIT_FUSE");
+      return !(e != nullptr && e[0] == '0');
+    }();
+    const bool producer = p.epilogue == EPI_BIAS_TANH || p.epilogue == EPI_BIAS_RELU || p.epilogue == EPI_DTANH || p.epilogue == EPI_DRELU;
+    if (fuse_env && use_persist && terms == 3 && producer && p.N % 16 == 0 && arena.n < SplitArena::kMaxEntries) {
+      const int ocp = pad64(p.N + 1);
+      const int64_t oelems = split_arena_elems(p.M, p.N);
+      const int ones = (p.epilogue == EPI_BIAS_TANH || p.epilogue == EPI_BIAS_RELU) ? 1 : 0;
+      bool known = false;
+      for (int e = 0; e < arena.n; ++e) known |= arena.e[e].src == p.C && arena.e[e].rows == p.M && arena.e[e].cols == p.N;
+      if (!known && arena.used + oelems <= arena.cap) {
+        __nv_bfloat16* odst = arena.base + arena.used;
+        arena.used += oelems;
+        arena.e[arena.n++] = SplitArena::Entry{p.C, int64_t(p.M), int64_t(p.ldc), p.N, ones, ocp, 3, 0, odst, arena.amax};
+        t.out_split = odst; t.split_cp = ocp; t.split_ones = ones;
+      }
     }
     B2_TRY(tc_group_add(tg, t, TcOperand{As, terms * int64_t(a_cp), a_mn ? 1 : 0}, TcOperand{Bs, terms * int64_t(b_cp), b_mn ? 1 : 0}, BN,
                         p.split_k));
@@ -529,11 +555,7 @@ int launch_gemm_group_split(const GemmGroup& g, SplitArena& arena, cudaStream_t 
     colsum_kernel<<<unsigned(colsums.blocks), 256, 0, st>>>(colsums);
     B2_LAUNCH_CHECK();
   }
-  static const bool persist = []() {
-    const char* e = getenv("B200PPO_SPLIT_PERSIST");
-    return !(e != nullptr && e[0] == '0');
-  }();
-  if (persist && BN >= 192) {
+  if (use_persist) {
     dump.persistent = true;
     return launch_tc_persist(tg, BN, st);
   }

@@ -141,6 +141,8 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
     uint4 pre[2];  // prefetched 32 bytes of the dgrad's activation row for the NEXT step
     float4 pref[CW / 4];  // the same for an fp32 activation operand (64 bytes)
     const bool auxf_vec = X32 && auxf != nullptr && (ld_aux % 4 == 0);
+    __nv_bfloat16* __restrict__ osplit = X32 ? P.out_split : nullptr;
+    const int split_cp = P.split_cp;
     const bool f32_v8 = X32 && f32_vec && (P.ld_f32 % 8 == 0) && (P.split_stride % 8 == 0) && outf != nullptr &&
                         ((reinterpret_cast<uintptr_t>(outf) & 31u) == 0);
     auto prefetch_aux = [&](int c) {
@@ -254,6 +256,30 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
         for (int j = 0; j < CW; ++j) h[j] = __uint_as_float(v[j]);
       }
       if (!live) continue;
+      if (X32 && osplit != nullptr && full) {  // (the launcher only asks for this when N is a multiple of 16)
+        uint32_t w[3][CW / 2];
+#pragma unroll
+        for (int j = 0; j < CW; j += 2) {
+          __nv_bfloat16 t[3][2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            float r = h[j + k];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+              t[p][k] = __float2bfloat16_rn(r);
+              r -= __bfloat162float(t[p][k]);
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < 3; ++p) w[p][j >> 1] = uint32_t(__bfloat16_as_ushort(t[p][0])) | (uint32_t(__bfloat16_as_ushort(t[p][1])) << 16);
+        }
+        __nv_bfloat16* sp = osplit + int64_t(m) * (3 * int64_t(split_cp)) + nb;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(sp + int64_t(p) * split_cp), "r"(w[p][0]), "r"(w[p][1]),
+                       "r"(w[p][2]), "r"(w[p][3]), "r"(w[p][4]), "r"(w[p][5]), "r"(w[p][6]), "r"(w[p][7])
+                       : "memory");
+      }
       if (outb != nullptr) {
         __nv_bfloat16* op = outb + int64_t(m) * ld_bf16 + nb;
         if (full && (ld_bf16 % 8 == 0)) {
@@ -290,6 +316,18 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& P, int split, uint3
           for (int j = 0; j < CW; ++j)
             if (nb + j == bias_col) bg = h[j];
           bgrad[m] = bg;
+        }
+      }
+    }
+    // the terms' padding behind the last column: zeros, and the ones-column in the leading term (last N tile, the warps of
+    // the upper column half, one row per thread)
+    if (X32 && osplit != nullptr && row_ok && n0 + BN >= Ncols && c_end == CHUNKS) {
+      __nv_bfloat16* sp = osplit + int64_t(m) * (3 * int64_t(split_cp));
+      for (int pc = Ncols; pc < split_cp; pc += 16) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const uint32_t first = (p == 0 && pc == Ncols && P.split_ones) ? 0x00003f80u : 0u;  // bf16 1.0 in the low half
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%2,%2,%2,%2,%2,%2};" ::"l"(sp + int64_t(p) * split_cp + pc), "r"(first), "r"(0u) : "memory");
         }
       }
     }

@@ -65,6 +65,10 @@ struct TcProblem {
   // epilogue multiplies the accumulator by 2^-(eA + eB), read from amax_a / amax_b.
   int parts, a_part, b_part;
   const float *amax_a, *amax_b;
+  // three-term mode, forward / dgrad epilogues: the fp32 result is ALSO written as its three bf16 terms, [M][3 * split_cp] with
+  // the zero padding (and the ones-column, split_ones) of gemm_split.cu's layout — the next GEMM's operand without a split pass
+  __nv_bfloat16* out_split;
+  int split_cp, split_ones;
   int a_scale_rows;  // amax_a is a vector with one entry per row of C (the A operand was scaled per row / per column)
   const float* aux_f32;  // TC_EPI_DGRAD: activation operand in fp32 (instead of `aux`)
   int precise;           // TC_EPI_FWD: tanhf instead of the MUFU approximation
