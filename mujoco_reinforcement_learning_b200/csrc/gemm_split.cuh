@@ -16,7 +16,7 @@ struct SplitArena {
     __nv_bfloat16* dst;
     float* amax;  // scale source: one float (axis 0), one per row (1) or one per column (2)
   };
-  static constexpr int kMaxEntries = 48;
+  static constexpr int kMaxEntries = 96;  // 2 nets x B200PPO_MAX_LAYERS x (activation, two dL/dz views, weights) and room to spare
   __nv_bfloat16* base = nullptr;
   float* amax = nullptr;      // [kMaxEntries] largest magnitude of every entry's source (two-term mode: the scale comes from it)
   bool amax_zeroed = false;   // since the last reset

@@ -106,3 +106,49 @@ def test_fp32_minibatch_on_tensor_cores_vs_oracle(shape, terms):
     by_name = eng.grads_by_name(grads, agent.networks.named_parameters())
     for k, r in grads_ref.items():
         assert_close(by_name[k], r, RTOL_FP32, f"grad {k}")
+
+
+@pytest.mark.parametrize("hidden,critic_hidden", [([256, 192, 128], [128, 64]), ([320, 256], [256, 256])],
+                         ids=["3-layer-actor", "wide-first-layer"])
+def test_fp32_tensor_core_route_on_other_architectures(hidden, critic_hidden):
+    """Shapes that mix the routes inside one minibatch: 128-wide layers (the one-tile kernel in three-term mode), a
+    weight-gradient group with more problems than one tensor-core launch takes (falls back to the FFMA kernel), layers
+    below the size threshold — losses and every gradient still at 1e-5 against the oracle's autograd."""
+    from tests._util import RTOL_FP32, assert_close
+    from tests.test_update_gpu import make_pair
+    D, A, B = 200, 6, 4096
+    oracle, agent, run = make_pair(D, A, hidden, critic_hidden, "tanh", batch=B, max_batch=B, precision="fp32", seed=5)
+    g = torch.Generator().manual_seed(13)
+    obs = torch.randn(B, D, generator=g)
+    action = torch.randn(B, A, generator=g).clamp_(-3, 3)
+    adv = torch.randn(B, 1, generator=g)
+    tgt = torch.randn(B, 1, generator=g)
+    with torch.no_grad():
+        mean, std = oracle.networks["actor"](obs)
+        old_logp = torch.distributions.Normal(mean, std).log_prob(action).sum(1) + 0.05 * torch.randn(B, generator=g)
+        v_ref = oracle.networks["critic"](obs)
+    # losses and gradients through autograd on the oracle's own modules (ppo.py:110-134)
+    cfg = oracle.cfg
+    for p in oracle.networks.parameters():
+        p.grad = None
+    m2, s2 = oracle.networks["actor"](obs)
+    dist = torch.distributions.Normal(m2, s2)
+    ratio = (dist.log_prob(action).sum(1) - old_logp).exp()[:, None]
+    s1, s2_ = ratio * adv, torch.clamp(ratio, 1.0 - cfg.clip_epsilon, 1.0 + cfg.clip_epsilon) * adv
+    actor_loss = -torch.min(s1, s2_).mean() - dist.entropy().mean() * cfg.entropy_eps
+    from oracle import ppo_oracle as O
+    critic_loss = O.huber_loss(oracle.networks["critic"](obs), tgt, reduction="mean")
+    (actor_loss + critic_loss).backward()
+    grads_ref = {n: p.grad.detach().clone() for n, p in oracle.networks.named_parameters()}
+    eng = agent.engine
+    hp = eng.hparams(1e-4, 1e-4, cfg.clip_epsilon, cfg.entropy_eps)
+    losses, grads = eng.minibatch_grads(obs.to(DEV), action.to(DEV), old_logp.to(DEV), adv.to(DEV), tgt.to(DEV), hp)
+    assert abs(losses[0].item() - actor_loss.item()) <= RTOL_FP32 * max(1.0, abs(actor_loss.item()))
+    assert abs(losses[1].item() - critic_loss.item()) <= RTOL_FP32 * max(1.0, abs(critic_loss.item()))
+    by_name = eng.grads_by_name(grads, agent.networks.named_parameters())
+    for k, r in grads_ref.items():
+        assert_close(by_name[k], r, RTOL_FP32, f"grad {k}")
+    # and the forward-only entry point on the same context
+    action_o, logp_o, value_o, mean_o = eng.policy_infer(obs.to(DEV), None)
+    assert_close(mean_o, mean, RTOL_FP32, "mean")
+    assert_close(value_o, v_ref, RTOL_FP32, "value")
