@@ -108,15 +108,16 @@ def test_fp32_minibatch_on_tensor_cores_vs_oracle(shape, terms):
         assert_close(by_name[k], r, RTOL_FP32, f"grad {k}")
 
 
-@pytest.mark.parametrize("hidden,critic_hidden", [([256, 192, 128], [128, 64]), ([320, 256], [256, 256])],
-                         ids=["3-layer-actor", "wide-first-layer"])
-def test_fp32_tensor_core_route_on_other_architectures(hidden, critic_hidden):
+@pytest.mark.parametrize("hidden,critic_hidden,D,B", [([256, 192, 128], [128, 64], 200, 4096), ([320, 256], [256, 256], 200, 4096),
+                                                      ([250, 130], [250, 130], 377, 4097)],
+                         ids=["3-layer-actor", "wide-first-layer", "ragged-everything"])
+def test_fp32_tensor_core_route_on_other_architectures(hidden, critic_hidden, D, B):
     """Shapes that mix the routes inside one minibatch: 128-wide layers (the one-tile kernel in three-term mode), a
     weight-gradient group with more problems than one tensor-core launch takes (falls back to the FFMA kernel), layers
     below the size threshold — losses and every gradient still at 1e-5 against the oracle's autograd."""
     from tests._util import RTOL_FP32, assert_close
     from tests.test_update_gpu import make_pair
-    D, A, B = 200, 6, 4096
+    A = 6  # ragged-everything: widths that are no multiple of 16, an odd observation width (scalar split loads), one row past a tile
     oracle, agent, run = make_pair(D, A, hidden, critic_hidden, "tanh", batch=B, max_batch=B, precision="fp32", seed=5)
     g = torch.Generator().manual_seed(13)
     obs = torch.randn(B, D, generator=g)
