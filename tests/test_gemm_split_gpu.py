@@ -111,7 +111,8 @@ def test_fp32_minibatch_on_tensor_cores_vs_oracle(shape, terms):
 @pytest.mark.parametrize("hidden,critic_hidden,D,B", [([256, 192, 128], [128, 64], 200, 4096), ([320, 256], [256, 256], 200, 4096),
                                                       ([250, 130], [250, 130], 377, 4097)],
                          ids=["3-layer-actor", "wide-first-layer", "ragged-everything"])
-def test_fp32_tensor_core_route_on_other_architectures(hidden, critic_hidden, D, B):
+@pytest.mark.parametrize("terms", [3, 2], ids=["bf16x3", "fp16x2"])
+def test_fp32_tensor_core_route_on_other_architectures(hidden, critic_hidden, D, B, terms):
     """Shapes that mix the routes inside one minibatch: 128-wide layers (the one-tile kernel in three-term mode), a
     weight-gradient group with more problems than one tensor-core launch takes (falls back to the FFMA kernel), layers
     below the size threshold — losses and every gradient still at 1e-5 against the oracle's autograd."""
@@ -142,6 +143,7 @@ def test_fp32_tensor_core_route_on_other_architectures(hidden, critic_hidden, D,
     (actor_loss + critic_loss).backward()
     grads_ref = {n: p.grad.detach().clone() for n, p in oracle.networks.named_parameters()}
     eng = agent.engine
+    eng.set_fp32_terms(terms)
     hp = eng.hparams(1e-4, 1e-4, cfg.clip_epsilon, cfg.entropy_eps)
     losses, grads = eng.minibatch_grads(obs.to(DEV), action.to(DEV), old_logp.to(DEV), adv.to(DEV), tgt.to(DEV), hp)
     assert abs(losses[0].item() - actor_loss.item()) <= RTOL_FP32 * max(1.0, abs(actor_loss.item()))
