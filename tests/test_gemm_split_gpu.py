@@ -73,7 +73,8 @@ def test_gemm_split_keeps_small_values(terms, monkeypatch):
     assert torch.equal(C.cpu(), torch.full((M, N), 2.0 ** -20))
 
 
-@pytest.mark.parametrize("shape", [dict(D=376, A=17, B=4096), dict(D=376, A=17, B=2500, act="relu"), dict(D=27, A=8, B=8192)],
+@pytest.mark.parametrize("shape", [dict(D=376, A=17, B=4096), dict(D=376, A=17, B=2500, act="relu"), dict(D=27, A=8, B=8192),
+                                   dict(D=376, A=17, B=32768)],  # the bench minibatch: 64 split-K partials of 512 samples each
                          ids=lambda s: "-".join(f"{k}{v}" for k, v in s.items()))
 @pytest.mark.parametrize("terms", [3, 2], ids=["bf16x3", "fp16x2"])
 def test_fp32_minibatch_on_tensor_cores_vs_oracle(shape, terms):
