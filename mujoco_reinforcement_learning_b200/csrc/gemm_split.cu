@@ -16,6 +16,14 @@
 // to the box coordinate along that dimension, so ONE split of an activation serves the forward (K-major A operand) and the
 // weight gradient (MN-major B operand).  Activations get a column of ones behind their last column (term a only): as the
 // weight gradient's B operand that column makes the bias gradient fall out of the same MMAs (TcProblem.bias_col).
+//
+// Environment switches (read once per process; all for measurements, none needed in use):
+//   B200PPO_FP32_TC=0              keep every fp32 GEMM on the FFMA kernels       B200PPO_FP32_TC_MIN_MACS   size threshold of the route
+//   B200PPO_SPLIT_TERMS=2|3        operand mode for every context (default: per context, b200ppo_set_fp32_terms)
+//   B200PPO_SPLIT_PERSIST=0        one-tile CTAs (tc_gemm_kernel) instead of the persistent kernel; then B200PPO_SPLIT_OCC[_WGRAD]=1|2
+//   B200PPO_SPLIT_BN[_WGRAD]       N tile       B200PPO_SPLIT_FUSE=0  no terms from the producing epilogue
+//   B200PPO_SPLIT_AXIS=1           two-term mode: one scale per row / column of the dL/dz operands instead of per tensor
+//   B200PPO_SPLIT_TRACE=<n>        phase timeline of the n-th launch on stderr
 #include "gemm_split.cuh"
 
 #include <cuda_fp16.h>
@@ -342,8 +350,6 @@ static int get_split(SplitArena& arena, SplitJobs& jobs, const float* src, int64
   J.src = src; J.dst = dst; J.rows = rows; J.ld = ld; J.cols = cols; J.cp = cp; J.ones = ones;
   J.terms = terms; J.amax = am; J.axis = axis;
   J.bound = bound; J.bound_dev = bound_dev;
-  static const bool no_bounds = getenv("B200PPO_SPLIT_NOBOUND") != nullptr;  // debug: measure every operand
-  if (no_bounds) { J.bound = 0.f; J.bound_dev = nullptr; }
   J.vec = (aligned16(src) && ld % 4 == 0) ? 1 : 0;
   J.unit_begin = jobs.units;
   jobs.units += rows * (cp / 8);
