@@ -332,11 +332,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       uint32_t rs = 0, rph = 0, cur_bar = 0;  // ring stage and its phase bit
-      uint32_t rn = 0;                        // stages acquired so far (trace)
+#ifdef B200PPO_CHAIN_RING_TRACE  // per-stage timestamps of the weight ring (build with -DB200PPO_CHAIN_RING_TRACE; off in production:
+      uint32_t rn = 0;             // the producer and issuer threads are the latency-critical ones)
+#endif
       auto ring_acquire = [&](uint32_t bytes) -> uint8_t* {
         mbar_wait(&ring_empty[rs], rph ^ 1);
+#ifdef B200PPO_CHAIN_RING_TRACE
         if (a.trace != nullptr && blockIdx.x == 0 && rn < 64) a.trace[480 + rn * 4 + 0] = clock64();
         ++rn;
+#endif
         if (rank == 0) mbar_expect_tx(&ring_full[rs], 2u * bytes);
         cur_bar = mapa_u32(smem_u32(&ring_full[rs]), 0);
         uint8_t* dst = smem + (CH_RING0 + rs) * CH_SLOT;
@@ -410,17 +414,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
         if (a.trace != nullptr && blockIdx.x == 0 && g < 60) a.trace[g * 8 + 1] = clock64();
         ++g;
       };
-      uint32_t wn = 0;  // stages consumed so far (trace)
+#ifdef B200PPO_CHAIN_RING_TRACE
+      uint32_t wn = 0;
+#endif
       auto ring_wait = [&]() -> uint32_t {
         mbar_wait(&ring_full[rs], rph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef B200PPO_CHAIN_RING_TRACE
         if (a.trace != nullptr && blockIdx.x == 0 && wn < 64) a.trace[480 + wn * 4 + 1] = clock64();
+#endif
         return smem_base + (CH_RING0 + rs) * CH_SLOT;
       };
       auto ring_release = [&]() {
         umma2_commit(&ring_empty[rs]);
+#ifdef B200PPO_CHAIN_RING_TRACE
         if (a.trace != nullptr && blockIdx.x == 0 && wn < 64) a.trace[480 + wn * 4 + 2] = clock64();
         ++wn;
+#endif
         if (++rs == CH_RING) { rs = 0; rph ^= 1; }
       };
       int ti = 0;
@@ -862,11 +872,13 @@ int launch_tc_chain(const ChainArgs& a, cudaStream_t st, int* grid_out, bool inf
       fprintf(stderr, "  %2d %s | %7lld %7lld | %7lld %7lld | warp 2: body %lld..%lld end %lld (%lld)\n", g, names[g % 10], h[g * 8] - h[0],
               h[g * 8 + 1] - h[0], h[g * 8 + 2] - h[0], h[g * 8 + 3] - h[0], h[g * 8 + 4] ? h[g * 8 + 4] - h[0] : 0,
               h[g * 8 + 5] ? h[g * 8 + 5] - h[0] : 0, h[g * 8 + 6] ? h[g * 8 + 6] - h[0] : 0, h[g * 8 + 7] ? h[g * 8 + 7] - h[0] : 0);
+#ifdef B200PPO_CHAIN_RING_TRACE
     fprintf(stderr, "weight ring of CTA 0, stage n: producer saw it empty | issuer saw it full, committed its MMAs  (-> refill = full[n] - empty[n]; turn-around = empty[n + %d] - committed[n])\n", CH_RING);
     for (int n = 0; n < 64 && h[480 + n * 4 + 1] != 0; ++n)
       fprintf(stderr, "  %2d | %7lld | %7lld %7lld | refill %5lld  turn-around %5lld\n", n, h[480 + n * 4] - h[0], h[480 + n * 4 + 1] - h[0],
               h[480 + n * 4 + 2] - h[0], h[480 + n * 4 + 1] - h[480 + n * 4],
               (n + CH_RING < 64 && h[480 + (n + CH_RING) * 4] != 0) ? h[480 + (n + CH_RING) * 4] - h[480 + n * 4 + 2] : 0);
+#endif
     return B200PPO_OK;
   }
   B2_CUDA(launch_pdl(kernel, dim3(2 * pairs), dim3(CH_THREADS), CH_SMEM, st, a));
