@@ -315,8 +315,30 @@ def k6_latency(agent, n_envs):
         lib.b200ppo_policy_infer(*args)
     e1.record()
     torch.cuda.synchronize()
+    us_infer = e0.elapsed_time(e1) * 10.0
+    # the rollout's own entry point: the same step written straight into the [N, T, ...] buffers (state copy included), V(s') of
+    # step t - 1 taken from step t's critic evaluation — what replaces ppo.py:20-49's three MLP calls per environment step
+    Tb = 16
+    buf = {"current_state": torch.empty(n_envs, Tb, OBS_DIM, device=dev), "current_state_value": torch.empty(n_envs, Tb, 1, device=dev),
+           "next_state_value": torch.empty(n_envs, Tb, 1, device=dev), "action": torch.empty(n_envs, Tb, ACT_DIM, device=dev),
+           "action_log_prob": torch.empty(n_envs, Tb, device=dev)}
+    for t in range(Tb):
+        eng.rollout_step(obs, noise, t, buf)
+    torch.cuda.synchronize()
+    launches0 = lib.b200ppo_launch_count()
+    e0.record()
+    for rep in range(8):
+        for t in range(Tb):
+            eng.rollout_step(obs, noise, t, buf)
+    e1.record()
+    torch.cuda.synchronize()
+    us_step = e0.elapsed_time(e1) * 1e3 / (8 * Tb)
+    step_launches = (lib.b200ppo_launch_count() - launches0) / (8 * Tb)
     return {"envs": n_envs, "us_per_env_step_batch": med * 1e3, "best_us": best * 1e3,
-            "us_c_abi_back_to_back": e0.elapsed_time(e1) * 10.0, "launches_per_call": int(launches),
+            "us_c_abi_back_to_back": us_infer, "launches_per_call": int(launches),
+            "rollout_step": {"us": us_step, "launches": step_launches,
+                             "api": "ActorCriticEngine.rollout_step -> b200ppo_rollout_step: s_t, V(s_t), a_t, log pi(a_t) into slice [:, t] of "
+                                    "the rollout buffers and V(s_t) as next_state_value[:, t - 1]"},
             "api": "PPOAgent.act_fused -> b200ppo_policy_infer (actor + critic forward, sample, log-prob); bf16 context: weights and "
                    "observations to bf16 + the forward-only instance of tc_chain_kernel"}
 

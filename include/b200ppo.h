@@ -256,6 +256,17 @@ int b200ppo_profile_end(b200ppo_ctx* ctx, double ms_out[B200PPO_PROF_CLASSES], i
 int b200ppo_debug_tc_gemm(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t a_mn_major,
                           int32_t b_mn_major, int32_t bn, int32_t split_k, b200ppo_stream stream);
 
+/* One environment step of the rollout written straight into the env-major [N, T, ...] buffers (replaces the per-step
+ * get_state_value / act / log_prob calls and TensorDict appends of src/entities/algorithms/ppo.py:20-49): at time index t
+ * buf_state[:, t] = obs, buf_value[:, t] = V(obs), buf_action[:, t] = mean(obs) + sigma * noise (noise NULL: the mean),
+ * buf_logp[:, t] = log-prob of that action, and — for t > 0 — buf_next_value[:, t - 1] = V(obs): the reference's second critic
+ * call per step evaluates the tensor that becomes the next step's current_state (ppo.py:21,27-29), so T + 1 critic
+ * evaluations fill both value buffers instead of 2 T.  t == T: only buf_next_value[:, T - 1] (pass the final state).
+ * bf16 contexts with 256-wide nets: one tensor-core launch behind the two bf16 casts.  buf_state / buf_next_value nullable. */
+int b200ppo_rollout_step(b200ppo_ctx* ctx, const float* params, const float* obs, int64_t n_envs, const float* noise, int64_t t,
+                         int64_t T, float* buf_state, float* buf_value, float* buf_next_value, float* buf_action, float* buf_logp,
+                         b200ppo_stream stream);
+
 /* fp32-precision contexts, GEMMs large enough for the tensor-core route (csrc/gemm_split.cu): how an fp32 operand value is
  * handed to tcgen05.  3 (default): three bf16 terms, six products per fp32 product — 24-bit operands, north_star's 1e-5
  * variant.  2: two fp16 terms of the value scaled by a power of two taken from the tensor's largest magnitude, three

@@ -89,6 +89,7 @@ SIGNATURES = {
     "b200ppo_profile_end": (c_i32, [c_ptr, C.POINTER(c_dbl), C.POINTER(c_i64)]),
     "b200ppo_debug_tc_gemm": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "b200ppo_set_fp32_terms": (c_i32, [c_ptr, c_i32]),
+    "b200ppo_rollout_step": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "b200ppo_debug_gemm_split": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "b200ppo_debug_activations": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_i64, c_ptr, c_ptr]),
     "b200ppo_polyak_update": (c_i32, [c_ptr, c_ptr, c_i64, c_dbl, c_ptr]),

@@ -128,6 +128,8 @@ struct b200ppo_ctx {
   // three-term bf16 operands of the fp32-tolerance tensor-core GEMMs (gemm_split.cuh); allocated at first use
   mutable SplitArena arena;
   int64_t arena_need = 0;
+  float* rollout_tmp = nullptr;  // b200ppo_rollout_step, contexts without the one-launch path: value / action / log-prob of a step
+  int64_t rollout_tmp_rows = 0;
   float* obs_amax = nullptr;   // max |observation| of the rollout b200ppo_train is working on (a bound for every minibatch's rows)
   bool obs_amax_ok = false;    // valid: inside b200ppo_train's minibatch loop
   int32_t* err_flag = nullptr;
@@ -666,6 +668,8 @@ static bool chain_applicable(const b200ppo_ctx* ctx) {
 struct ChainInfer {
   const float* noise;
   float *mean, *value, *action, *logp;
+  int64_t ld_action = 0, ld_value = 1, ld_logp = 1;  // row strides (0: act_dim)
+  float* value2 = nullptr;
 };
 
 static int launch_chain(b200ppo_ctx* ctx, const float* params, const __nv_bfloat16* xb, int64_t B, const float* action,
@@ -701,6 +705,8 @@ static int launch_chain(b200ppo_ctx* ctx, const float* params, const __nv_bfloat
   a.ppo.inv_global_batch = 1.f / float(B * ctx->world);
   if (inf != nullptr) {
     a.inf_noise = inf->noise; a.inf_mean = inf->mean; a.inf_value = inf->value; a.inf_action = inf->action; a.inf_logp = inf->logp;
+    a.inf_ld_action = inf->ld_action > 0 ? inf->ld_action : ctx->net[0].out_dim();
+    a.inf_ld_value = inf->ld_value; a.inf_ld_logp = inf->ld_logp; a.inf_value2 = inf->value2;
   }
   a.out_scale = ctx->net[0].d.out_scale;
   a.M = int(B);
@@ -925,6 +931,7 @@ extern "C" B2_EXPORT void b200ppo_destroy(b200ppo_ctx* c) {
   dev_free(c->gpart); dev_free(c->grad_flat); dev_free(c->loss_partials); dev_free(c->ticket); dev_free(c->done_counter); dev_free(c->scratch);
   dev_free(c->err_flag);
   dev_free(c->obs_amax);
+  dev_free(c->rollout_tmp);
   split_arena_free(c->arena);
   for (int n = 0; n < 2; ++n)
     for (int l = 0; l < B200PPO_MAX_LAYERS; ++l) { dev_free(c->bf.H[n][l]); dev_free(c->bf.dZ[n][l]); dev_free(c->bf.W[n][l]); dev_free(c->bf.WT[n][l]); }
@@ -1037,7 +1044,8 @@ extern "C" B2_EXPORT int b200ppo_policy_infer(b200ppo_ctx* ctx, const float* par
     if (!(mode != nullptr && mode[0] == '0')) {
       B2_TRY(cast_weights(ctx, params, st));
       B2_TRY(launch_cast_rows_ones(obs, batch, ctx->net[0].d.in_dim, ctx->bf.X, ctx->bf.pitchX, st));
-      const ChainInfer inf{noise, mean, value, action, logp};
+      ChainInfer inf{};
+      inf.noise = noise; inf.mean = mean; inf.value = value; inf.action = action; inf.logp = logp;
       int grid = 0;
       return launch_chain(ctx, params, ctx->bf.X, batch, nullptr, nullptr, nullptr, nullptr, nullptr, &grid, st, false, &inf);
     }
@@ -1045,6 +1053,71 @@ extern "C" B2_EXPORT int b200ppo_policy_infer(b200ppo_ctx* ctx, const float* par
   B2_TRY(forward_nets(ctx, params, obs, batch, nets, acts, outs, st, false, fresh_arena(ctx)));
   if (action || logp)
     B2_TRY(launch_sample_logp(outs[0], params + ctx->logstd_off, noise, batch, ctx->net[0].out_dim(), action, logp, st));
+  return B200PPO_OK;
+}
+
+__global__ void rollout_scatter_kernel(const float* __restrict__ value, const float* __restrict__ action, const float* __restrict__ logp,
+                                       int64_t n, int A, int64_t t, int64_t T, float* __restrict__ buf_value,
+                                       float* __restrict__ buf_next_value, float* __restrict__ buf_action, float* __restrict__ buf_logp) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = value[i];
+  if (buf_value != nullptr) buf_value[i * T + t] = v;
+  if (buf_next_value != nullptr) buf_next_value[i * T + t - 1] = v;
+  if (buf_action != nullptr)
+    for (int j = 0; j < A; ++j) buf_action[(i * T + t) * A + j] = action[i * A + j];
+  if (buf_logp != nullptr) buf_logp[i * T + t] = logp[i];
+}
+
+// One environment step of the rollout (ppo.py:20-49) written straight into the [N, T, ...] buffers: state s_t, V(s_t),
+// the sampled action and its log-probability at time index t — and V(s_t) once more as next_state_value of step t - 1,
+// which the reference computes with a second critic call on the very same tensor (ppo.py:27-29: next_state of step t - 1
+// is cloned into current_state of step t).  t == T: only that last next_state_value (no action is sampled).
+extern "C" B2_EXPORT int b200ppo_rollout_step(b200ppo_ctx* ctx, const float* params, const float* obs, int64_t n_envs,
+                                              const float* noise, int64_t t, int64_t T, float* buf_state, float* buf_value,
+                                              float* buf_next_value, float* buf_action, float* buf_logp, b200ppo_stream stream) {
+  B2_TRY(check_batch(ctx, n_envs, "b200ppo_rollout_step"));
+  B2_CHECK_ARG(params && obs && n_envs > 0 && T > 0 && t >= 0 && t <= T, "b200ppo_rollout_step: bad argument");
+  B2_CHECK_ARG(t == T || (buf_value && buf_action && buf_logp), "b200ppo_rollout_step: null buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = ctx->net[0].d.in_dim, A = ctx->net[0].out_dim();
+  const bool last = t == T;
+  if (!last && buf_state != nullptr)
+    B2_CUDA(cudaMemcpy2DAsync(buf_state + t * D, size_t(T) * D * sizeof(float), obs, size_t(D) * sizeof(float), size_t(D) * sizeof(float),
+                              size_t(n_envs), cudaMemcpyDeviceToDevice, st));
+  float* nv = (t > 0 && buf_next_value != nullptr) ? buf_next_value + (t - 1) : nullptr;
+  if (ctx->precision == B200PPO_PREC_BF16 && chain_applicable(ctx)) {
+    static const char* mode = getenv("B200PPO_CHAIN_INFER");
+    if (!(mode != nullptr && mode[0] == '0')) {
+      B2_TRY(cast_weights(ctx, params, st));
+      B2_TRY(launch_cast_rows_ones(obs, n_envs, D, ctx->bf.X, ctx->bf.pitchX, st));
+      ChainInfer inf{};
+      inf.noise = last ? nullptr : noise;
+      inf.value = last ? nullptr : buf_value + t;
+      inf.value2 = nv;
+      inf.action = last ? nullptr : buf_action + t * A;
+      inf.logp = last ? nullptr : buf_logp + t;
+      inf.ld_action = T * A; inf.ld_value = T; inf.ld_logp = T;
+      int grid = 0;
+      return launch_chain(ctx, params, ctx->bf.X, n_envs, nullptr, nullptr, nullptr, nullptr, nullptr, &grid, st, false, &inf);
+    }
+  }
+  // other contexts: the plain inference into scratch, then one scatter into the buffers
+  if (ctx->rollout_tmp_rows < n_envs) {
+    B2_CUDA(cudaDeviceSynchronize());
+    dev_free(ctx->rollout_tmp);
+    ctx->rollout_tmp_rows = 0;
+    B2_TRY(dev_alloc(&ctx->rollout_tmp, ctx->max_batch * (A + 2)));
+    ctx->rollout_tmp_rows = ctx->max_batch;
+  }
+  float* tv = ctx->rollout_tmp;
+  float* ta = tv + ctx->max_batch;
+  float* tl = ta + ctx->max_batch * A;
+  B2_TRY(b200ppo_policy_infer(ctx, params, obs, n_envs, last ? nullptr : noise, nullptr, tv, last ? nullptr : ta, last ? nullptr : tl, stream));
+  rollout_scatter_kernel<<<unsigned((n_envs + 127) / 128), 128, 0, st>>>(tv, ta, tl, n_envs, A, t, T, last ? nullptr : buf_value,
+                                                                         (t > 0) ? buf_next_value : nullptr, last ? nullptr : buf_action,
+                                                                         last ? nullptr : buf_logp);
+  B2_LAUNCH_CHECK();
   return B200PPO_OK;
 }
 

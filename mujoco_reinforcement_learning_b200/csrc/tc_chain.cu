@@ -653,12 +653,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
                   const float mean = ft ? scale * tanhf(pre) : pre;
                   const float nz = a.inf_noise != nullptr ? __ldg(a.inf_noise + mm * A + j) : 0.f;
                   if (a.inf_mean != nullptr) a.inf_mean[mm * A + j] = mean;
-                  if (a.inf_action != nullptr) a.inf_action[mm * A + j] = mean + expf(consts_s[j]) * nz;
+                  if (a.inf_action != nullptr) a.inf_action[mm * a.inf_ld_action + j] = mean + expf(consts_s[j]) * nz;
                   lp += -0.5f * nz * nz - consts_s[j] - kTcLogSqrt2Pi;
                 }
               }
             }
-            if (row_ok && a.inf_logp != nullptr) a.inf_logp[mm] = lp;
+            if (row_ok && a.inf_logp != nullptr) a.inf_logp[mm * a.inf_ld_logp] = lp;
           }
           step_done(nullptr, 0, 0);
         }
@@ -667,7 +667,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) tc_ch
           if (chunk == 0) {
             uint32_t v[8];
             tmem_ld8(lane_base + 256u, v);
-            if (row_ok && a.inf_value != nullptr) a.inf_value[mm] = __uint_as_float(v[0]) + b3_s[kChainMaxAct];
+            if (row_ok) {
+              const float val = __uint_as_float(v[0]) + b3_s[kChainMaxAct];
+              if (a.inf_value != nullptr) a.inf_value[mm * a.inf_ld_value] = val;
+              if (a.inf_value2 != nullptr) a.inf_value2[mm * a.inf_ld_value] = val;
+            }
           }
           step_done(nullptr, 0, 0);
         }

@@ -27,6 +27,10 @@ struct ChainArgs {
   // forward-only mode (rollout inference): outputs, each nullable; inf_noise [M][act] nullable (action = mean)
   float *inf_mean, *inf_value, *inf_action, *inf_logp;
   const float* inf_noise;
+  // row strides (elements) of inf_action / inf_value / inf_logp — a rollout writes slice [:, t] of its [N, T, ...] buffers —
+  // and a second destination of the value (the previous step's next_state_value: V(s') of step t - 1 is V(s) of step t)
+  long long inf_ld_action, inf_ld_value, inf_ld_logp;
+  float* inf_value2;
   long long* trace;  // debug: clock64 timeline of pair 0 (nullptr in production)
 };
 

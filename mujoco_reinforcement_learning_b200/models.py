@@ -365,6 +365,23 @@ class ActorCriticEngine:
                    "b200ppo_minibatch_grads")
         return losses, grads
 
+    @_on_engine_device
+    def rollout_step(self, obs: torch.Tensor, noise: Optional[torch.Tensor], t: int, buf: dict) -> torch.Tensor:
+        """One environment step written into the rollout's [N, T, ...] buffers (ppo.py:20-49); returns buf['action'][:, t].
+        t == T: only next_state_value[:, T - 1] from the final state."""
+        self.ensure_bound()
+        obs = self._check_x(obs)
+        N, T = buf["action"].shape[0], buf["action"].shape[1]
+        if noise is not None:
+            noise = _lib.require_cuda(noise, "noise", torch.float32).contiguous()
+        for k in ("current_state", "current_state_value", "next_state_value", "action", "action_log_prob"):
+            assert buf[k].is_contiguous() and buf[k].dtype == torch.float32 and buf[k].device == obs.device, k
+        _lib.check(self.lib.b200ppo_rollout_step(self._ctx, _lib.ptr(self.flat), _lib.ptr(obs), N, _lib.ptr(noise), int(t), int(T),
+                                                 _lib.ptr(buf["current_state"]), _lib.ptr(buf["current_state_value"]),
+                                                 _lib.ptr(buf["next_state_value"]), _lib.ptr(buf["action"]),
+                                                 _lib.ptr(buf["action_log_prob"]), _lib.stream_ptr()), "b200ppo_rollout_step")
+        return buf["action"][:, t] if t < T else None
+
     def set_fp32_terms(self, terms: int) -> None:
         """fp32 contexts: 3 = three bf16 terms per operand value (24-bit operands, the 1e-5 variant, default); 2 = two scaled
         fp16 terms (22-bit operands, faster; include/b200ppo.h)."""

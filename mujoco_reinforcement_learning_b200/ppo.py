@@ -12,6 +12,10 @@ from .config import Run
 from .memory import RolloutMemory
 
 
+def eng_in_dim(engine) -> int:
+    return int(getattr(engine, "obs_dim", -1))
+
+
 class PPO:
 
     def __init__(self, environment_helper, agent: PPOAgent, match_reference_rng: bool = False):
@@ -51,20 +55,31 @@ class PPO:
             "terminated": torch.empty((n, steps), dtype=torch.bool, device=dev),
             "truncated": torch.empty((n, steps), dtype=torch.bool, device=dev),
         }
+        eng = self.agent.engine
+        # the native step writes s_t, V(s_t), a_t, log pi(a_t) and V(s') of step t - 1 straight into the buffers; it takes the
+        # state as the flat [N, window * obs] row the networks see (network_block_creator.py flattens the same way)
+        flat_state = next_state.reshape(n, -1).shape[1] == eng_in_dim(self.agent.engine)
         for t in range(steps):
             current_state = next_state
-            action, logp, value = self.agent.act_fused(current_state, None if noise is None else noise[t].to(dev))
+            if flat_state:
+                eps = torch.randn((n, eng.act_dim), dtype=torch.float32, device=dev) if noise is None else noise[t].to(dev)
+                action = eng.rollout_step(current_state.reshape(n, -1), eps, t, buf)
+            else:
+                action, logp, value = self.agent.act_fused(current_state, None if noise is None else noise[t].to(dev))
             helper.step(action)
             next_state = helper.get_state(test_phase=False).to(dev, torch.float32)
-            buf["current_state"][:, t] = current_state
-            buf["current_state_value"][:, t] = value
-            buf["action"][:, t] = action
-            buf["action_log_prob"][:, t] = logp
-            buf["next_state_value"][:, t] = self.agent.get_state_value(next_state)
+            if not flat_state:
+                buf["current_state"][:, t] = current_state
+                buf["current_state_value"][:, t] = value
+                buf["action"][:, t] = action
+                buf["action_log_prob"][:, t] = logp
+                buf["next_state_value"][:, t] = self.agent.get_state_value(next_state)
             ts = helper.timestep
             buf["reward"][:, t, 0] = torch.as_tensor(ts.reward, dtype=torch.float64).to(dev)
             buf["terminated"][:, t] = torch.as_tensor(ts.terminated, dtype=torch.bool).to(dev)
             buf["truncated"][:, t] = torch.as_tensor(ts.truncated, dtype=torch.bool).to(dev)
+        if flat_state:
+            eng.rollout_step(next_state.reshape(n, -1), None, steps, buf)  # V of the final state closes next_state_value
         return RolloutMemory(buf, (n, steps))
 
     # ------------------------------------------------------------------------------------------------

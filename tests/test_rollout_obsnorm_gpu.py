@@ -57,3 +57,21 @@ def test_rollout_writes_the_reference_buffer():
     run.training_config.epochs_per_iteration = 1
     algo.train(mem)
     assert np.isfinite(algo.last_episode_losses).all()
+
+
+def test_rollout_through_the_one_launch_step_bf16():
+    """bf16 context, 256-wide nets: every environment step is b200ppo_rollout_step's tensor-core launch writing slice [:, t]
+    of the buffers; V(s') of step t is the very value written as V(s) of step t + 1 (ppo.py:21,27-29)."""
+    from tests._util import RTOL_BF16, rel_l2
+    N, T, D, A = 300, 6, 40, 4
+    oracle, agent, run = make_pair(D, A, [256, 256], [256, 256], "tanh", n_envs=N, steps=T, max_batch=512, precision="bf16")
+    noise = torch.randn(T, N, A, generator=torch.Generator().manual_seed(5))
+    ref = O.rollout(oracle, FakeHelper(run, N, D, A, seed=3), T, noise)
+    algo = pkg.PPO(FakeHelper(run, N, D, A, seed=3), agent)
+    mem = algo.rollout(noise=noise)
+    assert torch.equal(mem["next_state_value"][:, :-1], mem["current_state_value"][:, 1:])
+    for k in ("current_state", "current_state_value", "next_state_value", "action", "action_log_prob", "reward"):
+        assert tuple(mem[k].shape) == tuple(ref[k].shape), k
+        e = rel_l2(mem[k], ref[k])
+        assert e <= 1.5 * RTOL_BF16, (k, e)  # six steps of closed-loop feedback through bf16 policies
+    assert torch.equal(mem["terminated"].cpu(), ref["terminated"])
